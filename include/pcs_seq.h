@@ -1,0 +1,262 @@
+/*
+ * pcs_seq.h -- C ABI of libpcs_seq: the B200-native read sampler that replaces
+ * RACES::Mutations::SequencingSimulations::ReadSimulator<>::operator() on the
+ * simulate_seq() / simulate_normal_seq() path of caravagnalab/ProCESS.
+ *
+ * Plain C: pointers and sizes only, no C++ types, no exceptions, no torch types.
+ * Every function returns 0 (PCS_OK) or a negative pcs_status; the text of the
+ * last error on the calling thread is available from pcs_last_error().
+ *
+ * Reference interfaces each entry point replaces (paths relative to the
+ * ProCESS source tree):
+ *   pcs_forest_upload        <- PhylogeneticForest::get_sample_mutations_list(),
+ *                               get_normal_sample()      src/seq_simulation.cpp:566,572,651
+ *                               (per-cell genome traversal idiom
+ *                               src/phylogenetic_forest.cpp:279-376)
+ *   pcs_forest_set_groups    <- apply_FACS_labels()/split_by_labels()
+ *                                                        src/seq_simulation.cpp:183-243
+ *   pcs_plan_create          <- ReadSimulator<> construction + get_bin_dist() +
+ *                               get_relevant_chr_set()   src/seq_simulation.cpp:551-564,431-451,299-352
+ *   pcs_plan_run / pcs_simulate
+ *                            <- simulator(sequencer, mutations_list, chr_ids,
+ *                               coverage, normal_sample, purity, ...)
+ *                                                        src/seq_simulation.cpp:371,413,423
+ *   occurrences[] / coverage[] output tables
+ *                            <- SampleStatistics::get_data() / get_coverage()
+ *                               as consumed by add_sample_statistics()
+ *                                                        src/seq_simulation.cpp:92-140
+ *   pcs_active_rows          <- get_active_mutations()   src/seq_simulation.cpp:142-167
+ *   pcs_count_injected       <- the counting half of the simulator applied to a
+ *                               caller-supplied read-placement list (parity mode;
+ *                               no counterpart is exported by the reference)
+ *
+ * Positions are 1-based chromosome coordinates (the `chr_pos` column of the
+ * reference's data frame, src/seq_simulation.cpp:68).
+ */
+#ifndef PCS_SEQ_H
+#define PCS_SEQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCS_ABI_VERSION 1
+
+typedef enum pcs_status {
+  PCS_OK = 0,
+  PCS_ERR_INVALID = -1,   /* bad argument / malformed forest  (std::domain_error in the shim) */
+  PCS_ERR_CUDA = -2,      /* CUDA runtime failure              (std::runtime_error) */
+  PCS_ERR_NOMEM = -3,
+  PCS_ERR_UNSUPPORTED = -4,
+  PCS_ERR_INTERNAL = -5
+} pcs_status;
+
+/* kinds of genomic events labelling a forest node, applied in array order */
+enum {
+  PCS_EV_SID = 0,      /* SNV / indel (RACES::Mutations::SID) placed on `allele` */
+  PCS_EV_CNA_AMP = 1,  /* amplification: copy [pos,pos+len) of `allele` into new allele `dest` */
+  PCS_EV_CNA_DEL = 2,  /* deletion of [pos,pos+len) from `allele` */
+  PCS_EV_WGD = 3       /* whole genome doubling: every allele of every chromosome is copied */
+};
+
+/* Mutation::Nature, in the order of the reference's class strings
+ * (src/sequencing.cpp:333-335): "driver", "passenger", "germinal", "preneoplastic" */
+enum {
+  PCS_NATURE_DRIVER = 0,
+  PCS_NATURE_PASSENGER = 1,
+  PCS_NATURE_GERMINAL = 2,
+  PCS_NATURE_PRENEOPLASTIC = 3
+};
+
+/* sequencer models (src/seq_simulation.cpp:386-428) */
+enum {
+  PCS_SEQ_ERRORLESS = 0,        /* ErrorlessIlluminaSequencer or sequencer=NULL */
+  PCS_SEQ_BASIC_CONSTANT = 1,   /* BasicSequencer<ConstantQualityScoreModel>    */
+  PCS_SEQ_BASIC_RANDOM = 2      /* BasicSequencer<QualityScoreModel>            */
+};
+
+/*
+ * Flat description of a phylogenetic forest whose nodes are labelled by the
+ * genomic events arising in them.  All pointers are HOST memory owned by the
+ * caller; the library never keeps them after pcs_forest_upload() returns.
+ *
+ * Mutation table: the distinct SIDs (chr, pos, ref, alt) of the forest and of
+ * the germline, sorted by (chr, pos) with ties in the caller's (ref, alt) order
+ * -- i.e. std::map<SID, ...> order (src/seq_simulation.cpp:148,176).  The row
+ * index in this table is the row index of every output table.
+ */
+typedef struct pcs_forest_desc {
+  /* chromosomes, in ChromosomeId order */
+  uint32_t n_chr;
+  const uint32_t* chr_len;        /* [n_chr] length in bp                                     */
+  const uint8_t*  chr_n_alleles;  /* [n_chr] alleles in the germline genome (2, or 1 for X/Y) */
+
+  /* cell tree: parent index < child index; -1 marks a root */
+  uint32_t n_nodes;
+  const int32_t* node_parent;     /* [n_nodes] */
+
+  /* sampled cells (forest leaves) and the sample each comes from */
+  uint32_t n_samples;
+  uint32_t n_leaves;
+  const uint32_t* leaf_node;      /* [n_leaves] node index; the node must have no children */
+  const uint32_t* leaf_sample;    /* [n_leaves] in [0, n_samples)                          */
+
+  /* events, CSR by node, in application order inside a node; pre-neoplastic
+   * SIDs must come first in a root's list */
+  uint64_t n_events;
+  const uint64_t* node_event_off; /* [n_nodes+1] */
+  const uint8_t*  ev_kind;        /* [n_events] PCS_EV_*                                   */
+  const uint16_t* ev_chr;         /* [n_events] chromosome index (ignored for WGD)         */
+  const uint32_t* ev_pos;         /* [n_events] CNA first position (SID: ignored)          */
+  const uint32_t* ev_len;         /* [n_events] CNA length (SID: ignored)                  */
+  const uint16_t* ev_allele;      /* [n_events] SID/DEL: target allele id; AMP: source     */
+  const uint16_t* ev_dest;        /* [n_events] AMP: id of the new allele                  */
+  const uint32_t* ev_mut;         /* [n_events] SID: row in the mutation table             */
+  const uint8_t*  ev_nature;      /* [n_events] PCS_NATURE_*                               */
+
+  /* mutation table */
+  uint32_t n_mut;
+  const uint16_t* mut_chr;        /* [n_mut] */
+  const uint32_t* mut_pos;        /* [n_mut] 1-based */
+  const uint8_t*  mut_ref_len;    /* [n_mut] length of `ref` (>= 1) */
+  const uint8_t*  mut_alt_len;    /* [n_mut] length of `alt` (>= 1) */
+
+  /* germline SIDs: row + bit mask of the germline alleles carrying it */
+  uint64_t n_germline;
+  const uint32_t* germ_mut;         /* [n_germline] */
+  const uint8_t*  germ_allele_mask; /* [n_germline] bit a set: allele a carries the SID */
+} pcs_forest_desc;
+
+/* arguments of one simulate_seq()/simulate_normal_seq() call
+ * (src/seq_simulation.hpp:28-54; defaults src/sequencing.cpp:193-209) */
+typedef struct pcs_seq_params {
+  int32_t  seed;                  /* resolved seed (utility.hpp:41-64)                     */
+  double   coverage;
+  double   purity;                /* in [0,1]; ignored when normal_only                    */
+  uint32_t read_size;
+  uint32_t insert_size_mean;      /* 0: single-end; >0: paired-end                         */
+  uint32_t insert_size_stddev;
+  uint32_t sequencer;             /* PCS_SEQ_*                                             */
+  double   error_rate;
+  uint8_t  with_normal_sample;    /* append "normal_sample" as last output sample          */
+  uint8_t  preneoplastic_in_normal;
+  uint8_t  normal_only;           /* simulate_normal_seq(): only the normal sample         */
+  uint8_t  reserved0;
+  const uint8_t* chr_mask;        /* [n_chr] 1 = sequence the chromosome; NULL = all       */
+  /* work sharding (one process per GPU): this call handles tiles of
+   * shard `shard_rank` out of `shard_count`; counts of all shards add up to
+   * the single-shard result bit for bit */
+  uint32_t shard_rank;
+  uint32_t shard_count;           /* 0 is read as 1 */
+} pcs_seq_params;
+
+/* one injected read placement (parity mode) */
+typedef struct pcs_read_placement {
+  uint32_t cell;     /* leaf index; for normal cells: root ordinal (PRENEO) or 0 (PLAIN) */
+  uint32_t start;    /* 1-based reference position of the first base of the read        */
+  uint16_t chr;
+  uint16_t allele;   /* allele id inside the cell                                       */
+  uint16_t sample;   /* output sample index                                             */
+  uint16_t flags;    /* PCS_PLACE_*                                                     */
+} pcs_read_placement;
+
+enum {
+  PCS_PLACE_TUMOUR = 0,
+  PCS_PLACE_NORMAL_PLAIN = 1,   /* contaminant/normal cell carrying the germline only */
+  PCS_PLACE_NORMAL_PRENEO = 2   /* normal cell carrying germline + pre-neoplastic SIDs */
+};
+
+#define PCS_ERRMASK_WORDS 8     /* 256 read offsets; bit i set = base i is a sequencing error */
+
+typedef struct pcs_plan_info {
+  uint32_t n_out_samples;   /* groups (+1 if with_normal_sample), or 1 if normal_only */
+  uint32_t n_mut;           /* rows of the output tables                              */
+  uint32_t n_loci;
+  uint64_t n_tiles;         /* tiles of THIS shard                                    */
+  uint64_t n_tiles_total;
+  uint64_t n_templates;     /* read templates of THIS shard                           */
+  uint64_t n_templates_total;
+  uint32_t reads_per_template; /* 1 or 2 */
+  uint32_t read_size;
+} pcs_plan_info;
+
+typedef struct pcs_run_stats {
+  double   kernel_ms;       /* device time of the sampler kernel(s), CUDA events on the launch stream */
+  double   total_ms;        /* zero + sample + finalise (+ copies when host output)                   */
+  uint64_t kernel_launches; /* kernels launched by this call                                          */
+  uint64_t n_templates;
+  uint64_t n_reads;         /* reads that were placed (templates not rejected x mates)                */
+  uint64_t sum_depth;       /* sum over samples and loci of depth  (k_bar   = sum_depth / n_reads)    */
+  uint64_t sum_occurrences; /* sum over samples and rows of occ.   (k_alt   = sum_occ   / n_reads)    */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+} pcs_run_stats;
+
+typedef struct pcs_ctx pcs_ctx;
+typedef struct pcs_forest pcs_forest;
+typedef struct pcs_plan pcs_plan;
+
+/* flags of pcs_plan_run */
+enum {
+  PCS_RUN_HOST_OUTPUT = 0,    /* occ/cov are host pointers  */
+  PCS_RUN_DEVICE_OUTPUT = 1   /* occ/cov are device pointers on the context's device */
+};
+
+int pcs_abi_version(void);
+const char* pcs_last_error(void);
+
+/* one context per GPU; `stream` is a cudaStream_t (NULL = a stream owned by the context) */
+int pcs_create(pcs_ctx** ctx, int device_id, void* stream);
+int pcs_destroy(pcs_ctx* ctx);
+int pcs_device_name(pcs_ctx* ctx, char* buf, size_t buf_len);
+
+/* flatten the forest (haplotype numbering, loci, fragment sets) and copy it to HBM */
+int pcs_forest_upload(pcs_ctx* ctx, const pcs_forest_desc* desc, pcs_forest** forest);
+int pcs_forest_free(pcs_forest* forest);
+/* repartition the sampled cells into `n_groups` output samples (FACS labelling);
+ * leaf_group == NULL restores the forest's own samples */
+int pcs_forest_set_groups(pcs_forest* forest, const uint32_t* leaf_group, uint32_t n_groups);
+/* sizes of the flattened view: out[0]=n_loci out[1]=n_instances out[2]=n_haplotypes
+ * out[3]=n_fragment_sets out[4]=n_pieces out[5]=device bytes */
+int pcs_forest_info(const pcs_forest* forest, uint64_t out[6]);
+
+/* tile grid, per-tile template counts (host multinomial), sampling tables -> HBM */
+int pcs_plan_create(pcs_forest* forest, const pcs_seq_params* params, pcs_plan** plan);
+int pcs_plan_info_get(const pcs_plan* plan, pcs_plan_info* info);
+int pcs_plan_free(pcs_plan* plan);
+
+/* run the sampler: occurrences[s*n_mut + row], coverage[s*n_mut + row]
+ * (uint32, n_out_samples x n_mut each).  stats may be NULL. */
+int pcs_plan_run(pcs_plan* plan, int flags, uint32_t* occurrences, uint32_t* coverage,
+                 pcs_run_stats* stats);
+
+/* debug/parity: re-run the plan emitting every placed read as a placement
+ * record (+ its error mask when the sequencer has errors) instead of counting.
+ * Host buffers of capacity `cap` records; *n_out receives the number written. */
+int pcs_plan_trace(pcs_plan* plan, pcs_read_placement* placements, uint32_t* err_masks,
+                   uint64_t cap, uint64_t* n_out);
+
+/* plan + run + free with host outputs: the call the Rcpp shim makes */
+int pcs_simulate(pcs_forest* forest, const pcs_seq_params* params,
+                 uint32_t* occurrences, uint32_t* coverage, pcs_run_stats* stats);
+
+/* parity mode: count a caller-supplied list of read placements.
+ * err_masks: NULL or n * PCS_ERRMASK_WORDS words.  Host pointers. */
+int pcs_count_injected(pcs_forest* forest, uint32_t n_out_samples, uint32_t read_size,
+                       const pcs_read_placement* placements, const uint32_t* err_masks,
+                       uint64_t n, uint32_t* occurrences, uint32_t* coverage,
+                       pcs_run_stats* stats);
+
+/* rows with occurrences > 0 in at least one sample (get_active_mutations);
+ * with include_non_sequenced != 0 also the rows carried by at least one cell of
+ * the sequenced samples.  rows_out has capacity n_mut; *n_rows receives the count. */
+int pcs_active_rows(pcs_forest* forest, const uint32_t* occurrences, uint32_t n_out_samples,
+                    int include_non_sequenced, uint32_t* rows_out, uint32_t* n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCS_SEQ_H */
