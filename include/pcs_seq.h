@@ -256,6 +256,27 @@ int pcs_count_injected(pcs_forest* forest, uint32_t n_out_samples, uint32_t read
 int pcs_active_rows(pcs_forest* forest, const uint32_t* occurrences, uint32_t n_out_samples,
                     int include_non_sequenced, uint32_t* rows_out, uint32_t* n_rows);
 
+/* ---- host-only introspection of the flattened view (no GPU needed).  Used by the
+ * CPU test-suite to check the haplotype-interval view against explicit per-cell
+ * genomes and the planner's shard partition; not needed by the Rcpp shim. ---- */
+typedef struct pcs_flat pcs_flat;
+int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** flat);
+int pcs_flat_free(pcs_flat* flat);
+int pcs_flat_set_groups(pcs_flat* flat, const uint32_t* leaf_group, uint32_t n_groups);
+int pcs_flat_info(const pcs_flat* flat, uint64_t out[6]);
+/* haplotypes (alleles) of one cell on one chromosome; kind: PCS_PLACE_* */
+int pcs_flat_cell_haps(pcs_flat* flat, uint32_t kind, uint32_t cell, uint32_t chr, uint32_t cap,
+                       uint16_t* allele, uint32_t* hap, uint32_t* fragset, uint32_t* n);
+int pcs_flat_fragset(const pcs_flat* flat, uint32_t fragset, uint32_t cap, uint32_t* begin,
+                     uint32_t* end, uint32_t* n);
+/* mutation rows carried by haplotype `hap` of chromosome `chr` (germline included) */
+int pcs_flat_hap_rows(const pcs_flat* flat, uint32_t chr, uint32_t hap, uint32_t cap, uint32_t* rows,
+                      uint32_t* n);
+/* host half of pcs_plan_create: tile grid of the shard named in params */
+int pcs_flat_plan(const pcs_flat* flat, const pcs_seq_params* params, pcs_plan_info* info, uint64_t cap,
+                  uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,
+                  uint32_t* tile_begin, uint32_t* tile_len);
+
 #ifdef __cplusplus
 }
 #endif

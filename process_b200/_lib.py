@@ -1,0 +1,237 @@
+"""ctypes loader and thin object wrappers of libpcs_seq.so (the C ABI of include/pcs_seq.h).
+
+There is no CPU fallback: every compute entry point needs a B200 and raises
+PcsError otherwise.  Only the pcs_flat_* introspection calls run without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcs_seq.so")
+_LIB = None
+
+EXPORTS = [
+    "pcs_abi_version", "pcs_last_error", "pcs_create", "pcs_destroy", "pcs_device_name",
+    "pcs_forest_upload", "pcs_forest_free", "pcs_forest_set_groups", "pcs_forest_info",
+    "pcs_plan_create", "pcs_plan_info_get", "pcs_plan_free", "pcs_plan_run", "pcs_plan_trace",
+    "pcs_simulate", "pcs_count_injected", "pcs_active_rows",
+    "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
+    "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan",
+]
+
+
+class PcsError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"libpcs_seq status {status}: {msg}")
+        self.status = status
+        self.message = msg
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C process_b200/csrc` "
+                "(or python -c 'import __graft_entry__ as g; g.build()'). There is no CPU fallback.")
+        _LIB = C.CDLL(LIB_PATH)
+        _LIB.pcs_last_error.restype = C.c_char_p
+        if _LIB.pcs_abi_version() != A.PCS_ABI_VERSION:
+            raise ImportError("libpcs_seq.so ABI version mismatch; rebuild it")
+    return _LIB
+
+
+def _ok(rc):
+    if rc != 0:
+        raise PcsError(rc, lib().pcs_last_error().decode())
+
+
+def _u32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
+
+
+# --------------------------------------------------------------------------- host-only view
+class Flat:
+    """flattened (haplotype-interval) view of a forest, host side only."""
+
+    def __init__(self, forest):
+        self.forest = forest
+        self._h = C.c_void_p()
+        d = forest.as_desc()
+        _ok(lib().pcs_flat_create(C.byref(d), C.byref(self._h)))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().pcs_flat_free(self._h)
+            self._h = None
+
+    def set_groups(self, leaf_group, n_groups):
+        lg = _u32(leaf_group)
+        _ok(lib().pcs_flat_set_groups(self._h, A.ptr(lg, C.c_uint32), C.c_uint32(n_groups)))
+
+    def info(self):
+        out = (C.c_uint64 * 6)()
+        _ok(lib().pcs_flat_info(self._h, out))
+        return dict(n_loci=out[0], n_instances=out[1], n_haplotypes=out[2], n_fragment_sets=out[3], n_pieces=out[4])
+
+    def cell_haps(self, kind, cell, chrom, cap=4096):
+        al = np.zeros(cap, np.uint16); hp = np.zeros(cap, np.uint32); fs = np.zeros(cap, np.uint32)
+        n = C.c_uint32(0)
+        _ok(lib().pcs_flat_cell_haps(self._h, C.c_uint32(kind), C.c_uint32(cell), C.c_uint32(chrom), C.c_uint32(cap),
+                                     A.ptr(al, C.c_uint16), A.ptr(hp, C.c_uint32), A.ptr(fs, C.c_uint32), C.byref(n)))
+        return [(int(al[i]), int(hp[i]), int(fs[i])) for i in range(n.value)]
+
+    def fragset(self, fs, cap=4096):
+        b = np.zeros(cap, np.uint32); e = np.zeros(cap, np.uint32); n = C.c_uint32(0)
+        _ok(lib().pcs_flat_fragset(self._h, C.c_uint32(fs), C.c_uint32(cap), A.ptr(b, C.c_uint32),
+                                   A.ptr(e, C.c_uint32), C.byref(n)))
+        return [(int(b[i]), int(e[i])) for i in range(n.value)]
+
+    def hap_rows(self, chrom, hap):
+        cap = max(1, self.forest.n_mut)
+        rows = np.zeros(cap, np.uint32); n = C.c_uint32(0)
+        _ok(lib().pcs_flat_hap_rows(self._h, C.c_uint32(chrom), C.c_uint32(hap), C.c_uint32(cap),
+                                    A.ptr(rows, C.c_uint32), C.byref(n)))
+        return rows[:n.value].copy()
+
+    def plan(self, params: A.SeqParams, cap=1 << 22):
+        info = A.PlanInfo()
+        arrs = [np.zeros(cap, np.uint32) for _ in range(6)]
+        _ok(lib().pcs_flat_plan(self._h, C.byref(params), C.byref(info), C.c_uint64(cap),
+                                *[A.ptr(a, C.c_uint32) for a in arrs]))
+        n = int(min(cap, info.n_tiles))
+        keys = ["id", "templates", "sample", "chr", "begin", "len"]
+        return info, {k: a[:n] for k, a in zip(keys, arrs)}
+
+
+# --------------------------------------------------------------------------- device objects
+class Context:
+    def __init__(self, device=0, stream=None):
+        self._h = C.c_void_p()
+        _ok(lib().pcs_create(C.byref(self._h), C.c_int(device), C.c_void_p(stream)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pcs_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def device_name(self):
+        buf = C.create_string_buffer(256)
+        _ok(lib().pcs_device_name(self._h, buf, C.c_size_t(256)))
+        return buf.value.decode()
+
+
+class Forest:
+    """a forest flattened and resident in HBM."""
+
+    def __init__(self, ctx: Context, forest):
+        self.ctx = ctx
+        self.forest = forest
+        self._h = C.c_void_p()
+        d = forest.as_desc()
+        _ok(lib().pcs_forest_upload(ctx._h, C.byref(d), C.byref(self._h)))
+        self.n_groups = forest.n_samples
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pcs_forest_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_groups(self, leaf_group, n_groups):
+        lg = _u32(leaf_group)
+        _ok(lib().pcs_forest_set_groups(self._h, A.ptr(lg, C.c_uint32), C.c_uint32(n_groups or 0)))
+        self.n_groups = n_groups if leaf_group is not None else self.forest.n_samples
+
+    def info(self):
+        out = (C.c_uint64 * 6)()
+        _ok(lib().pcs_forest_info(self._h, out))
+        return dict(n_loci=out[0], n_instances=out[1], n_haplotypes=out[2], n_fragment_sets=out[3],
+                    n_pieces=out[4], device_bytes=out[5])
+
+    def n_out_samples(self, params: A.SeqParams):
+        if params.normal_only:
+            return 1
+        return self.n_groups + (1 if params.with_normal_sample else 0)
+
+    def simulate(self, params: A.SeqParams):
+        """plan + run + free with host outputs (the call the Rcpp shim makes)."""
+        n_out = self.n_out_samples(params)
+        occ = np.zeros((n_out, self.forest.n_mut), np.uint32)
+        cov = np.zeros((n_out, self.forest.n_mut), np.uint32)
+        st = A.RunStats()
+        _ok(lib().pcs_simulate(self._h, C.byref(params), A.ptr(occ, C.c_uint32), A.ptr(cov, C.c_uint32), C.byref(st)))
+        return occ, cov, st
+
+    def count_injected(self, n_out, read_size, placements, err_masks=None):
+        placements = np.ascontiguousarray(placements, dtype=A.PLACEMENT_DTYPE)
+        occ = np.zeros((n_out, self.forest.n_mut), np.uint32)
+        cov = np.zeros((n_out, self.forest.n_mut), np.uint32)
+        em = _u32(err_masks)
+        st = A.RunStats()
+        _ok(lib().pcs_count_injected(self._h, C.c_uint32(n_out), C.c_uint32(read_size),
+                                     C.c_void_p(placements.ctypes.data), A.ptr(em, C.c_uint32),
+                                     C.c_uint64(len(placements)), A.ptr(occ, C.c_uint32), A.ptr(cov, C.c_uint32),
+                                     C.byref(st)))
+        return occ, cov, st
+
+    def active_rows(self, occ, include_non_sequenced=False):
+        occ = np.ascontiguousarray(occ, dtype=np.uint32)
+        rows = np.zeros(max(1, self.forest.n_mut), np.uint32)
+        n = C.c_uint32(0)
+        _ok(lib().pcs_active_rows(self._h, A.ptr(occ, C.c_uint32), C.c_uint32(occ.shape[0]),
+                                  C.c_int(1 if include_non_sequenced else 0), A.ptr(rows, C.c_uint32), C.byref(n)))
+        return rows[:n.value].copy()
+
+
+class Plan:
+    """tile grid + sampling tables of one simulate call, resident in HBM."""
+
+    def __init__(self, forest: Forest, params: A.SeqParams):
+        self.forest = forest
+        self.params = params
+        self._h = C.c_void_p()
+        _ok(lib().pcs_plan_create(forest._h, C.byref(params), C.byref(self._h)))
+        self.info = A.PlanInfo()
+        _ok(lib().pcs_plan_info_get(self._h, C.byref(self.info)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pcs_plan_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def run(self):
+        n_out, n_mut = self.info.n_out_samples, self.info.n_mut
+        occ = np.zeros((n_out, n_mut), np.uint32)
+        cov = np.zeros((n_out, n_mut), np.uint32)
+        st = A.RunStats()
+        _ok(lib().pcs_plan_run(self._h, C.c_int(A.PCS_RUN_HOST_OUTPUT), A.ptr(occ, C.c_uint32),
+                               A.ptr(cov, C.c_uint32), C.byref(st)))
+        return occ, cov, st
+
+    def run_device(self, occ_ptr: int, cov_ptr: int):
+        """occ_ptr / cov_ptr: device addresses of uint32 [n_out_samples, n_mut] buffers."""
+        st = A.RunStats()
+        _ok(lib().pcs_plan_run(self._h, C.c_int(A.PCS_RUN_DEVICE_OUTPUT), C.c_void_p(occ_ptr),
+                               C.c_void_p(cov_ptr), C.byref(st)))
+        return st
+
+    def trace(self, cap, with_masks=False):
+        rec = np.zeros(cap, A.PLACEMENT_DTYPE)
+        masks = np.zeros((cap, A.PCS_ERRMASK_WORDS), np.uint32) if with_masks else None
+        n = C.c_uint64(0)
+        _ok(lib().pcs_plan_trace(self._h, C.c_void_p(rec.ctypes.data), A.ptr(masks, C.c_uint32),
+                                 C.c_uint64(cap), C.byref(n)))
+        return rec[:n.value], (None if masks is None else masks[:n.value])

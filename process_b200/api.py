@@ -1,0 +1,315 @@
+"""Host-side mirror of the reference's R/Rcpp interface for the sequencing path.
+
+Same names, argument order, defaults and error behaviour as
+  simulate_seq()          src/sequencing.cpp:193-209, src/seq_simulation.cpp:517-601
+  simulate_normal_seq()   src/sequencing.cpp:268-282, src/seq_simulation.cpp:603-679
+  BasicIlluminaSequencer / ErrorlessIlluminaSequencer
+                          src/sequencers.hpp:25-72, src/sequencers.cpp:80-106
+(R is not available in this image; INTEGRATION.md shows the Rcpp shim that makes
+the same C-ABI calls.)  Everything below the argument handling runs on the GPU
+through libpcs_seq.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+import weakref
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi as A
+from . import _lib as L
+from .forest import PhylogeneticForest
+
+NORMAL_SAMPLE_NAME = "normal_sample"  # src/seq_simulation.cpp:572, 651
+
+
+# ------------------------------------------------------------------ sequencers
+class ErrorlessIlluminaSequencer:
+    """src/sequencers.hpp:25-38"""
+
+    @property
+    def error_rate(self):
+        return 0.0
+
+    def __repr__(self):
+        return 'Errorless Illumina (platform: "ILLUMINA")'
+
+
+class BasicIlluminaSequencer:
+    """src/sequencers.hpp:40-72; validation as build_sequencer(), src/sequencers.cpp:80-106"""
+
+    def __init__(self, error_rate, random_quality_scores=True):
+        if isinstance(error_rate, bool) or not isinstance(error_rate, (int, float, np.integer, np.floating)):
+            raise ValueError('The parameter "error_rate" must be a positive real number.')
+        if error_rate < 0:
+            raise ValueError('The parameter "error_rate" must be a positive real number.')
+        if not isinstance(random_quality_scores, (bool, np.bool_)):
+            raise ValueError('The parameter "random_quality_scores" must be a Boolean value.')
+        self.error_rate = float(error_rate)
+        self.random_quality_scores = bool(random_quality_scores)
+
+    def __repr__(self):
+        kind = "random quality scores" if self.random_quality_scores else "constant quality scores"
+        return f'Basic Illumina (platform: "ILLUMINA" error rate: {self.error_rate:f} {kind})'
+
+
+def _sequencer_model(sequencer):
+    """dispatch of src/seq_simulation.cpp:375-429"""
+    if sequencer is None or isinstance(sequencer, ErrorlessIlluminaSequencer):
+        return A.PCS_SEQ_ERRORLESS, 0.0
+    if isinstance(sequencer, BasicIlluminaSequencer):
+        kind = A.PCS_SEQ_BASIC_RANDOM if sequencer.random_quality_scores else A.PCS_SEQ_BASIC_CONSTANT
+        return kind, sequencer.error_rate
+    raise ValueError("Unsupported sequencer type")
+
+
+def _sequencer_data(sequencer):
+    """get_sequencer_data(), src/seq_simulation.cpp:453-515"""
+    if sequencer is None:
+        return None
+    if isinstance(sequencer, BasicIlluminaSequencer):
+        return dict(name="BasicIlluminaSequencer", error_rate=sequencer.error_rate,
+                    random_quality_scores=sequencer.random_quality_scores)
+    return dict(name="ErrorlessIlluminaSequencer", error_rate=0.0)
+
+
+# ------------------------------------------------------------------ cell labelling
+@dataclass
+class SampledCell:
+    """const view of a sampled cell for the labelling callback (src/sampled_cell.hpp:27-56)"""
+    cell_id: int
+    sample: str
+    epistate: str = ""
+    mutant: str = ""
+    species: str = ""
+    birth_time: float = 0.0
+
+
+def _apply_FACS_labels(forest: PhylogeneticForest, labelling):
+    """apply_FACS_labels()/split_by_labels(), src/seq_simulation.cpp:183-243: one
+    callback per sampled cell; cells of sample S labelled L go to sample "S_L"
+    (or "S" for the empty label), new samples in order of first appearance."""
+    if labelling is None:
+        return None, list(forest.sample_names)
+    if not callable(labelling):
+        raise ValueError("The FACs_labelling_function must be a function.")
+    attrs = getattr(forest, "leaf_attrs", None) or {}
+    names, index = [], {}
+    group = np.zeros(forest.n_leaves, np.uint32)
+    for s in range(forest.n_samples):
+        for l in np.flatnonzero(forest.leaf_sample == s):
+            cell = SampledCell(cell_id=int(forest.leaf_node[l]), sample=forest.sample_names[s],
+                               **{k: (v[l].item() if hasattr(v[l], "item") else v[l]) for k, v in attrs.items()})
+            label = labelling(cell)
+            if not isinstance(label, str):
+                raise ValueError("The labelling function must return a string.")
+            name = forest.sample_names[s] + ("_" + label if label != "" else "")
+            key = (s, label)
+            if key not in index:
+                index[key] = len(names)
+                names.append(name)
+            group[l] = index[key]
+    return group, names
+
+
+# ------------------------------------------------------------------ argument handling
+def _reference_genome(forest, reference_genome):
+    """get_reference_genome(), src/seq_simulation.cpp:245-280"""
+    if reference_genome is None:
+        path = forest.reference_path
+        if path is None or not os.path.exists(path):
+            raise RuntimeError(f'The reference genome file "{path}" does not exists anymore. Please, re-build '
+                               'the mutation engine or use the parameter "reference_genome".')
+        return path
+    if isinstance(reference_genome, str):
+        if not os.path.exists(reference_genome):
+            raise RuntimeError(f'The reference genome file "{reference_genome}" does not exists.')
+        return reference_genome
+    raise ValueError('The parameter "reference_genome" must be either NULL or a string.')
+
+
+def _ordinal(i):
+    suf = "th" if 10 <= i % 100 <= 20 else {1: "st", 2: "nd", 3: "rd"}.get(i % 10, "th")
+    return f"{i}{suf}"
+
+
+def _chr_mask(forest, chromosomes):
+    """get_relevant_chr_set(), src/seq_simulation.cpp:299-352"""
+    if chromosomes is None:
+        return None
+    if isinstance(chromosomes, str):
+        chromosomes = [chromosomes]
+    if not isinstance(chromosomes, (list, tuple, np.ndarray)):
+        raise ValueError("Unsupported chromosome list type")
+    mask = np.zeros(forest.n_chr, np.uint8)
+    for i, name in enumerate(chromosomes, 1):
+        if not isinstance(name, (str, np.str_)):
+            raise ValueError(f"Expected a list of string: the {_ordinal(i)} element of the list is not a string.")
+        if name not in forest.chr_names:
+            raise ValueError(f'Unknown chromosome "{name}"')
+        mask[forest.chr_names.index(name)] = 1
+    return mask
+
+
+def _resolve_seed(seed):
+    """get_random_seed<int>(), src/utility.hpp:41-64"""
+    if seed is None:
+        return int(np.random.default_rng().integers(-2**31, 2**31 - 1))
+    if isinstance(seed, bool) or not isinstance(seed, (int, float, np.integer, np.floating)):
+        raise ValueError("The seed must be a number or NULL.")
+    return int(seed)
+
+
+_ctx_cache = {}
+_forest_cache = weakref.WeakKeyDictionary()
+
+
+def _device_forest(forest: PhylogeneticForest, device: int, cache: bool):
+    ctx = _ctx_cache.get(device)
+    if ctx is None:
+        ctx = _ctx_cache[device] = L.Context(device)
+    if not cache:
+        return L.Forest(ctx, forest), True
+    key = (device,)
+    slot = _forest_cache.setdefault(forest, {})
+    if key not in slot:
+        slot[key] = L.Forest(ctx, forest)
+    return slot[key], False
+
+
+def release_device_cache():
+    for slot in list(_forest_cache.values()):
+        for f in slot.values():
+            f.close()
+    _forest_cache.clear()
+    for c in _ctx_cache.values():
+        c.close()
+    _ctx_cache.clear()
+
+
+def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced):
+    """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181.
+    Sample columns in name order (std::map iteration), rows in SID order."""
+    import pandas as pd
+    rows = dev.active_rows(occ, include_non_sequenced)
+    ref, alt = forest.row_strings(rows)
+    cols = {
+        "chr": [forest.chr_names[c] for c in forest.mut_chr[rows]],
+        "chr_pos": forest.mut_pos[rows].astype(np.int32),
+        "ref": ref, "alt": alt,
+        "causes": forest.row_causes(rows), "classes": forest.row_classes(rows),
+    }
+    for s in sorted(range(len(names)), key=lambda i: names[i]):
+        o = occ[s, rows].astype(np.int32)
+        c = cov[s, rows].astype(np.int32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            vaf = o.astype(np.float64) / c
+        cols[f"{names[s]}.occurrences"] = o
+        cols[f"{names[s]}.coverage"] = c
+        cols[f"{names[s]}.VAF"] = vaf
+    return pd.DataFrame(cols)
+
+
+def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
+         insert_size_stddev, write_SAM, group, names, purity, with_normal_sample, preneo, normal_only,
+         include_non_sequenced, c_seed, device, cache, shard):
+    if not isinstance(forest, PhylogeneticForest):
+        raise TypeError("phylo_forest must be a PhylogeneticForest")
+    _reference_genome(forest, reference_genome)
+    kind, rate = _sequencer_model(sequencer)
+    mask = _chr_mask(forest, chromosomes)
+    if not normal_only and not (0 <= purity <= 1):
+        raise ValueError("The purity must belong to the interval [0,1].")
+    if write_SAM:
+        warnings.warn("SAM output is not built yet (SURVEY.md 8 f3): simulating counts only", stacklevel=3)
+    P = A.SeqParams(seed=c_seed, coverage=float(coverage), purity=float(purity), read_size=int(read_size),
+                    insert_size_mean=int(insert_size_mean), insert_size_stddev=int(insert_size_stddev),
+                    sequencer=kind, error_rate=rate, with_normal_sample=int(bool(with_normal_sample)),
+                    preneoplastic_in_normal=int(bool(preneo)), normal_only=int(bool(normal_only)),
+                    shard_rank=shard[0], shard_count=shard[1])
+    if mask is not None:
+        import ctypes as C
+        P.chr_mask = A.ptr(mask, C.c_uint8)
+    dev, owned = _device_forest(forest, device, cache)
+    try:
+        if not normal_only:
+            dev.set_groups(group, len(names) if group is not None else None)
+        occ, cov, st = dev.simulate(P)
+        if shard[1] > 1:
+            occ, cov = _reduce_over_ranks(occ, cov)
+        out_names = [NORMAL_SAMPLE_NAME] if normal_only else list(names) + ([NORMAL_SAMPLE_NAME] if with_normal_sample else [])
+        df = _result_dataframe(forest, dev, occ, cov, out_names, include_non_sequenced)
+    finally:
+        if owned:
+            dev.close()
+    return df, st
+
+
+def _reduce_over_ranks(occ, cov):
+    """sum the per-rank count tables (torch.distributed: NCCL on GPU, gloo on CPU)."""
+    import torch
+    import torch.distributed as dist
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    out = []
+    for a in (occ, cov):
+        t = torch.from_numpy(a.astype(np.int32)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out.append(t.cpu().numpy().astype(np.uint32))
+    return out
+
+
+def _shard():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1
+
+
+def simulate_seq(phylo_forest, sequencer=None, reference_genome=None, chromosomes=None, coverage=10,
+                 read_size=150, insert_size_mean=0, insert_size_stddev=10, output_dir="ProCESS_SAM",
+                 write_SAM=False, update_SAM=False, cell_labelling=None, purity=1, with_normal_sample=True,
+                 preneoplastic_in_normal=False, filename_prefix="chr_", template_name_prefix="r",
+                 include_non_sequenced_mutations=False, seed=None, *, device=0, cache=True):
+    """Simulate the sequencing of the samples in a phylogenetic forest.
+
+    Returns {"mutations": DataFrame, "parameters": dict} with the reference's schema
+    (src/seq_simulation.cpp:84-89, 137-139, 586-600)."""
+    c_seed = _resolve_seed(seed)
+    group, names = _apply_FACS_labels(phylo_forest, cell_labelling)
+    df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
+                  insert_size_stddev, write_SAM, group, names, purity, with_normal_sample,
+                  preneoplastic_in_normal, False, include_non_sequenced_mutations, c_seed, device, cache, _shard())
+    parameters = dict(sequencer=_sequencer_data(sequencer), reference_genome=reference_genome,
+                      chromosomes=chromosomes, coverage=coverage, read_size=read_size,
+                      insert_size_mean=insert_size_mean, insert_size_stddev=insert_size_stddev,
+                      output_dir=output_dir, write_SAM=write_SAM, update_SAM=update_SAM,
+                      cell_labelling=cell_labelling, purity=purity, with_normal_sample=with_normal_sample,
+                      filename_prefix=filename_prefix, template_name_prefix=template_name_prefix,
+                      include_non_sequenced_mutations=include_non_sequenced_mutations, seed=c_seed)
+    return {"mutations": df, "parameters": parameters, "_stats": st.as_dict()}
+
+
+def simulate_normal_seq(phylo_forest, sequencer=None, reference_genome=None, chromosomes=None, coverage=10,
+                        read_size=150, insert_size_mean=0, insert_size_stddev=10,
+                        output_dir="ProCESS_normal_SAM", write_SAM=True, update_SAM=False,
+                        with_preneoplastic=False, filename_prefix="chr_", template_name_prefix="r",
+                        include_non_sequenced_mutations=False, seed=None, *, device=0, cache=True):
+    """Simulate the sequencing of a normal sample (purity forced to 1,
+    src/seq_simulation.cpp:650-657)."""
+    c_seed = _resolve_seed(seed)
+    df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
+                  insert_size_stddev, write_SAM, None, [], 1.0, False, with_preneoplastic, True,
+                  include_non_sequenced_mutations, c_seed, device, cache, _shard())
+    parameters = dict(sequencer=_sequencer_data(sequencer), reference_genome=reference_genome,
+                      chromosomes=chromosomes, coverage=coverage, read_size=read_size,
+                      insert_size_mean=insert_size_mean, insert_size_stddev=insert_size_stddev,
+                      output_dir=output_dir, write_SAM=write_SAM, update_SAM=update_SAM,
+                      with_preneoplastic=with_preneoplastic, filename_prefix=filename_prefix,
+                      template_name_prefix=template_name_prefix,
+                      include_non_sequenced_mutations=include_non_sequenced_mutations, seed=c_seed)
+    return {"mutations": df, "parameters": parameters, "_stats": st.as_dict()}

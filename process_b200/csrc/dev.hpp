@@ -1,0 +1,64 @@
+// dev.hpp -- POD records shared by the host planner and the CUDA kernels.
+#pragma once
+#include <cstdint>
+
+#include <vector_types.h>
+
+namespace pcs {
+
+// One way of drawing a haplotype for a read that starts inside a tile: the
+// haplotype leaves of one (sample group | normal cells, fragment set) list.
+struct Entry {
+  uint32_t thr;       // cumulative selection threshold: pick first entry with u32 draw <= thr
+  uint32_t list_off;  // into hap_list
+  uint32_t list_n;
+  uint32_t frag_end;  // last position of the fragment the tile lies in (reads never cross it)
+};
+
+// A tile: a stretch of one piece of one chromosome for one output sample.  Every
+// template whose start falls in [begin, begin+len) is drawn by the CTA owning it.
+struct Tile {
+  uint32_t chr;
+  uint32_t begin;
+  uint32_t len;
+  uint32_t n_templates;
+  uint32_t entry_off;
+  uint32_t n_entries;
+  uint32_t sample;   // output sample index
+  uint32_t id;       // global tile number: Philox key, independent of sharding
+  uint32_t l0, l1;   // loci with position in [begin, begin+len+reach): staged range
+  uint32_t pad0, pad1;
+};
+static_assert(sizeof(Tile) == 48, "Tile layout");
+
+struct DevForest {
+  const uint32_t* locus_pos;       // [L]
+  const uint32_t* chr_locus_off;   // [n_chr+1]
+  const uint32_t* locus_inst_off;  // [L+1]
+  const uint4* inst;               // [I] {lo, span, row, ref_len | alt_len<<8}
+  const uint32_t* hap_list;        // concatenated haplotype lists
+  uint32_t n_loci;
+  uint32_t n_mut;
+};
+
+struct SeqModel {
+  uint32_t read_size;
+  uint32_t paired;          // 0/1
+  uint32_t sequencer;       // PCS_SEQ_*
+  uint32_t err_thr;         // floor(error_rate * 2^32), constant-quality model
+  float error_rate;         // random-quality model
+  uint32_t insert_n;        // entries of the insert-size CDF (paired)
+  uint32_t insert_min;      // smallest insert with non-zero probability
+  const uint32_t* insert_cdf;  // [insert_n] cumulative thresholds over the u32 range
+  uint32_t seed;
+};
+
+// injected placement after host translation (cell, allele) -> haplotype index
+struct DevPlacement {
+  uint32_t hap;
+  uint32_t start;
+  uint32_t frag_end;
+  uint32_t chr_sample;  // chr | sample << 16
+};
+
+}  // namespace pcs

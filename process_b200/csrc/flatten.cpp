@@ -1,0 +1,422 @@
+// flatten.cpp -- forest description -> haplotype-interval view (see flat.hpp).
+//
+// Event semantics replayed here (they are the ones the CPU oracle replays on
+// explicit genomes; DESIGN.md "Semantics"):
+//   SID  on allele a : placed iff the lineage has allele a and a fragment of a holds the position
+//   AMP  a -> d      : allele d = fragments of a clipped to [pos, pos+len-1] (with the SIDs there)
+//   DEL  on allele a : [pos, pos+len-1] removed from the fragments of a
+//   WGD              : per chromosome, every allele in increasing id order is copied to id next_id++
+#include "flat.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <stdexcept>
+#include <thread>
+#include <unordered_map>
+
+namespace pcs {
+namespace {
+
+using FragKey = std::vector<std::pair<uint32_t, uint32_t>>;
+
+void check(bool ok, const char* msg) {
+  if (!ok) throw std::domain_error(msg);
+}
+
+FragKey clip(const FragKey& s, uint32_t lo, uint32_t hi) {
+  FragKey out;
+  if (lo > hi) return out;
+  for (const auto& f : s) {
+    if (f.second < lo || f.first > hi) continue;
+    out.emplace_back(std::max(f.first, lo), std::min(f.second, hi));
+  }
+  return out;
+}
+
+FragKey remove_range(const FragKey& s, uint32_t lo, uint32_t hi, uint32_t chr_len) {
+  FragKey out = lo > 1 ? clip(s, 1, lo - 1) : FragKey{};
+  if (hi < chr_len) {
+    FragKey r = clip(s, hi + 1, chr_len);
+    out.insert(out.end(), r.begin(), r.end());
+  }
+  return out;
+}
+
+bool holds(const FragKey& s, uint32_t pos) {
+  for (const auto& f : s)
+    if (pos >= f.first && pos <= f.second) return true;
+  return false;
+}
+
+struct Tree {
+  std::vector<uint32_t> child_off, child_idx, roots;
+  std::vector<int64_t> node_leaf;
+};
+
+struct ChrWork {
+  uint32_t chr = 0;
+  std::vector<uint64_t> ev;           // events of this chromosome (+ WGD), node-major
+  std::vector<uint32_t> node_ev_off;  // [n_nodes+1]
+  bool has_wgd = false;
+  std::vector<Inst> inst;
+  std::vector<HapRec> haps;           // fragset is a LOCAL id until merge
+  std::vector<FragKey> fragsets;
+  std::map<FragKey, uint32_t> intern;
+  std::unordered_map<uint64_t, std::vector<std::pair<uint16_t, uint16_t>>> wgd_map;
+  std::string error;
+
+  uint32_t intern_set(const FragKey& k) {
+    auto it = intern.find(k);
+    if (it != intern.end()) return it->second;
+    uint32_t id = static_cast<uint32_t>(fragsets.size());
+    fragsets.push_back(k);
+    intern.emplace(k, id);
+    return id;
+  }
+};
+
+// which allele ids exist where: only needed to give WGD copies their ids
+void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
+  struct AState {
+    std::vector<uint16_t> ids;
+    uint32_t next;
+  };
+  std::vector<AState> pool;
+  AState base;
+  for (uint16_t a = 0; a < d.chr_n_alleles[w.chr]; ++a) base.ids.push_back(a);
+  base.next = d.chr_n_alleles[w.chr];
+  pool.push_back(base);
+  std::vector<std::pair<uint32_t, uint32_t>> stack;
+  for (uint32_t r : t.roots) stack.emplace_back(r, 0u);
+  while (!stack.empty()) {
+    auto [v, si] = stack.back();
+    stack.pop_back();
+    uint32_t cur = si;
+    bool own = false;
+    auto make_own = [&]() {
+      if (!own) {
+        pool.push_back(pool[cur]);
+        cur = static_cast<uint32_t>(pool.size() - 1);
+        own = true;
+      }
+    };
+    for (uint32_t i = w.node_ev_off[v]; i < w.node_ev_off[v + 1]; ++i) {
+      uint64_t e = w.ev[i];
+      if (d.ev_kind[e] == PCS_EV_CNA_AMP) {
+        const auto& ids = pool[cur].ids;
+        if (!std::binary_search(ids.begin(), ids.end(), d.ev_allele[e])) continue;
+        uint16_t dest = d.ev_dest[e];
+        check(!std::binary_search(ids.begin(), ids.end(), dest), "amplification destination allele exists");
+        make_own();
+        auto& mid = pool[cur].ids;
+        mid.insert(std::upper_bound(mid.begin(), mid.end(), dest), dest);
+        pool[cur].next = std::max<uint32_t>(pool[cur].next, dest + 1u);
+      } else if (d.ev_kind[e] == PCS_EV_WGD) {
+        make_own();
+        std::vector<uint16_t> snapshot = pool[cur].ids;
+        auto& m = w.wgd_map[e];
+        for (uint16_t a : snapshot) {
+          check(pool[cur].next < 65535, "allele id overflow");
+          uint16_t nd = static_cast<uint16_t>(pool[cur].next++);
+          m.emplace_back(a, nd);
+          auto& mid = pool[cur].ids;
+          mid.insert(std::upper_bound(mid.begin(), mid.end(), nd), nd);
+        }
+      }
+    }
+    for (uint32_t c = t.child_off[v]; c < t.child_off[v + 1]; ++c) stack.emplace_back(t.child_idx[c], cur);
+  }
+}
+
+void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
+                 const std::vector<std::pair<uint32_t, uint8_t>>& germ /* (row, mask) of this chr */) {
+  const uint32_t chr = w.chr;
+  const uint32_t clen = d.chr_len[chr];
+  const uint8_t n0 = d.chr_n_alleles[chr];
+  check(n0 >= 1 && n0 <= 2, "chr_n_alleles must be 1 or 2");
+  if (w.has_wgd) wgd_prepass(d, t, w);
+
+  const uint32_t full = w.intern_set(FragKey{{1u, clen}});
+  uint32_t counter = 0;
+  uint32_t germ_lo[2] = {0, 0}, germ_hi[2] = {0, 0};
+
+  struct Frame {
+    uint32_t node, fragset, ev_i, child_i, open_base;
+    uint16_t allele;
+    bool root_base, preneo_done, leaf_done;
+  };
+  std::vector<Frame> stack;
+  std::vector<uint32_t> open;  // instances whose interval is still growing
+
+  for (uint16_t g = 0; g < n0; ++g) {
+    germ_lo[g] = counter;
+    w.haps.push_back({0u, full, g, HAP_NORMAL_PLAIN});
+    ++counter;
+    for (uint32_t ri = 0; ri < t.roots.size(); ++ri) {
+      uint32_t r = t.roots[ri];
+      stack.push_back({r, full, w.node_ev_off[r], 0u, static_cast<uint32_t>(open.size()), g, true, false, false});
+      while (!stack.empty()) {
+        Frame& f = stack.back();
+        const uint32_t v = f.node;
+        auto preneo_leaf = [&]() {
+          f.preneo_done = true;
+          w.haps.push_back({ri, f.fragset, f.allele, HAP_NORMAL_PRENEO});
+          ++counter;
+        };
+        if (f.ev_i < w.node_ev_off[v + 1]) {
+          uint64_t e = w.ev[f.ev_i++];
+          uint8_t kind = d.ev_kind[e];
+          if (f.root_base && !f.preneo_done &&
+              !(kind == PCS_EV_SID && d.ev_nature[e] == PCS_NATURE_PRENEOPLASTIC))
+            preneo_leaf();
+          if (kind == PCS_EV_WGD) {
+            auto it = w.wgd_map.find(e);
+            if (it == w.wgd_map.end()) continue;
+            for (const auto& [a, nd] : it->second)
+              if (a == f.allele) {
+                Frame nf{v, f.fragset, f.ev_i, 0u, static_cast<uint32_t>(open.size()), nd, false, true, false};
+                stack.push_back(nf);  // invalidates f; loop re-reads the top
+                break;
+              }
+            continue;
+          }
+          if (d.ev_allele[e] != f.allele) continue;
+          if (kind == PCS_EV_SID) {
+            uint32_t m = d.ev_mut[e];
+            check(m < d.n_mut && d.mut_chr[m] == chr, "SID event names a row of another chromosome");
+            if (holds(w.fragsets[f.fragset], d.mut_pos[m])) {
+              open.push_back(static_cast<uint32_t>(w.inst.size()));
+              w.inst.push_back({counter, 0u, m,
+                                static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8)});
+            }
+          } else if (kind == PCS_EV_CNA_DEL) {
+            check(d.ev_len[e] >= 1, "CNA length must be positive");
+            f.fragset = w.intern_set(remove_range(w.fragsets[f.fragset], d.ev_pos[e],
+                                                  d.ev_pos[e] + d.ev_len[e] - 1, clen));
+          } else if (kind == PCS_EV_CNA_AMP) {
+            check(d.ev_len[e] >= 1, "CNA length must be positive");
+            uint32_t fs = w.intern_set(clip(w.fragsets[f.fragset], d.ev_pos[e], d.ev_pos[e] + d.ev_len[e] - 1));
+            Frame nf{v, fs, f.ev_i, 0u, static_cast<uint32_t>(open.size()), d.ev_dest[e], false, true, false};
+            stack.push_back(nf);
+          } else {
+            throw std::domain_error("unknown event kind");
+          }
+          continue;
+        }
+        if (f.root_base && !f.preneo_done) preneo_leaf();
+        const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
+        const bool dead = w.fragsets[f.fragset].empty();  // no DNA left: nothing below can be read
+        if (nc == 0 && !f.leaf_done) {
+          f.leaf_done = true;
+          if (t.node_leaf[v] >= 0 && !dead) {
+            w.haps.push_back({static_cast<uint32_t>(t.node_leaf[v]), f.fragset, f.allele, HAP_TUMOUR});
+            ++counter;
+          }
+        }
+        if (!dead && f.child_i < nc) {
+          uint32_t c = t.child_idx[t.child_off[v] + f.child_i++];
+          Frame nf{c, f.fragset, w.node_ev_off[c], 0u, static_cast<uint32_t>(open.size()), f.allele, false, true, false};
+          stack.push_back(nf);
+          continue;
+        }
+        // frame done: every instance opened in it is carried by [lo, counter)
+        for (size_t k = f.open_base; k < open.size(); ++k) {
+          Inst& in = w.inst[open[k]];
+          in.span = counter - in.lo;
+        }
+        open.resize(f.open_base);
+        stack.pop_back();
+      }
+    }
+    germ_hi[g] = counter;
+  }
+
+  for (const auto& [row, mask] : germ) {
+    check(mask != 0 && (mask >> n0) == 0, "germ_allele_mask names a missing allele");
+    uint32_t meta = static_cast<uint32_t>(d.mut_ref_len[row]) | (static_cast<uint32_t>(d.mut_alt_len[row]) << 8);
+    if (mask == 3) {
+      w.inst.push_back({germ_lo[0], germ_hi[1] - germ_lo[0], row, meta});
+    } else {
+      uint32_t g = mask == 1 ? 0 : 1;
+      w.inst.push_back({germ_lo[g], germ_hi[g] - germ_lo[g], row, meta});
+    }
+  }
+  std::stable_sort(w.inst.begin(), w.inst.end(), [](const Inst& a, const Inst& b) { return a.row < b.row; });
+}
+
+}  // namespace
+
+void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads) {
+  check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
+  check(d.n_nodes >= 1, "the forest has no nodes");
+  out = FlatForest{};
+  out.n_chr = d.n_chr;
+  out.n_mut = d.n_mut;
+  out.n_leaves = d.n_leaves;
+  out.n_samples = d.n_samples;
+  out.chr_len.assign(d.chr_len, d.chr_len + d.n_chr);
+  out.chr_n_alleles.assign(d.chr_n_alleles, d.chr_n_alleles + d.n_chr);
+  out.leaf_sample.assign(d.leaf_sample, d.leaf_sample + d.n_leaves);
+  for (uint32_t c = 0; c < d.n_chr; ++c) check(d.chr_len[c] >= 1, "chromosome length must be positive");
+
+  // ---- cell tree
+  Tree t;
+  t.child_off.assign(d.n_nodes + 1, 0);
+  for (uint32_t v = 0; v < d.n_nodes; ++v) {
+    int32_t p = d.node_parent[v];
+    if (p < 0) {
+      t.roots.push_back(v);
+    } else {
+      check(static_cast<uint32_t>(p) < v, "node_parent must precede the child");
+      ++t.child_off[p + 1];
+    }
+  }
+  for (uint32_t v = 0; v < d.n_nodes; ++v) t.child_off[v + 1] += t.child_off[v];
+  t.child_idx.resize(t.child_off[d.n_nodes]);
+  {
+    std::vector<uint32_t> fill(t.child_off.begin(), t.child_off.end() - 1);
+    for (uint32_t v = 0; v < d.n_nodes; ++v)
+      if (d.node_parent[v] >= 0) t.child_idx[fill[d.node_parent[v]]++] = v;
+  }
+  out.n_roots = static_cast<uint32_t>(t.roots.size());
+  t.node_leaf.assign(d.n_nodes, -1);
+  for (uint32_t l = 0; l < d.n_leaves; ++l) {
+    check(d.leaf_node[l] < d.n_nodes, "leaf_node out of range");
+    check(t.child_off[d.leaf_node[l] + 1] == t.child_off[d.leaf_node[l]], "a sampled cell must be a leaf");
+    check(d.leaf_sample[l] < d.n_samples, "leaf_sample out of range");
+    t.node_leaf[d.leaf_node[l]] = l;
+  }
+
+  // ---- mutation table -> loci
+  out.chr_locus_off.assign(d.n_chr + 1, 0);
+  out.row_locus.resize(d.n_mut);
+  for (uint32_t m = 0; m < d.n_mut; ++m) {
+    check(d.mut_chr[m] < d.n_chr, "mut_chr out of range");
+    check(d.mut_pos[m] >= 1 && d.mut_pos[m] <= d.chr_len[d.mut_chr[m]], "mutation position outside the chromosome");
+    check(d.mut_ref_len[m] >= 1 && d.mut_alt_len[m] >= 1, "ref/alt must be non-empty");
+    bool same = false;
+    if (m > 0) {
+      bool ordered = d.mut_chr[m - 1] < d.mut_chr[m] ||
+                     (d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] <= d.mut_pos[m]);
+      check(ordered, "mutation table must be sorted by (chr, pos)");
+      same = d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] == d.mut_pos[m];
+    }
+    if (!same) {
+      out.locus_pos.push_back(d.mut_pos[m]);
+      out.chr_locus_off[d.mut_chr[m] + 1] = static_cast<uint32_t>(out.locus_pos.size());
+    }
+    out.row_locus[m] = static_cast<uint32_t>(out.locus_pos.size() - 1);
+  }
+  for (uint32_t c = 1; c <= d.n_chr; ++c) out.chr_locus_off[c] = std::max(out.chr_locus_off[c], out.chr_locus_off[c - 1]);
+
+  // ---- events by chromosome (node-major order is preserved)
+  std::vector<ChrWork> work(d.n_chr);
+  for (uint32_t c = 0; c < d.n_chr; ++c) {
+    work[c].chr = c;
+    work[c].node_ev_off.assign(d.n_nodes + 1, 0);
+  }
+  check(d.node_event_off[0] == 0 && d.node_event_off[d.n_nodes] == d.n_events, "node_event_off is not a CSR of the events");
+  for (uint32_t v = 0; v < d.n_nodes; ++v) {
+    check(d.node_event_off[v] <= d.node_event_off[v + 1], "node_event_off must be non-decreasing");
+    for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+      if (d.ev_kind[e] == PCS_EV_WGD) {
+        for (auto& w : work) {
+          w.ev.push_back(e);
+          w.has_wgd = true;
+        }
+      } else {
+        check(d.ev_kind[e] <= PCS_EV_CNA_DEL, "unknown event kind");
+        check(d.ev_chr[e] < d.n_chr, "event chromosome out of range");
+        work[d.ev_chr[e]].ev.push_back(e);
+      }
+    }
+    for (auto& w : work) w.node_ev_off[v + 1] = static_cast<uint32_t>(w.ev.size());
+  }
+  std::vector<std::vector<std::pair<uint32_t, uint8_t>>> germ(d.n_chr);
+  for (uint64_t i = 0; i < d.n_germline; ++i) {
+    check(d.germ_mut[i] < d.n_mut, "germ_mut out of range");
+    germ[d.mut_chr[d.germ_mut[i]]].emplace_back(d.germ_mut[i], d.germ_allele_mask[i]);
+  }
+
+  // ---- per-chromosome haplotype numbering, chromosomes in parallel
+  std::atomic<uint32_t> next{0};
+  auto run = [&]() {
+    for (;;) {
+      uint32_t c = next.fetch_add(1);
+      if (c >= d.n_chr) return;
+      try {
+        flatten_chr(d, t, work[c], germ[c]);
+      } catch (const std::exception& e) {
+        work[c].error = e.what();
+        if (work[c].error.empty()) work[c].error = "flatten failed";
+      }
+    }
+  };
+  n_threads = std::max(1u, std::min<unsigned>(n_threads, d.n_chr));
+  if (n_threads == 1) {
+    run();
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < n_threads; ++i) th.emplace_back(run);
+    for (auto& x : th) x.join();
+  }
+  for (auto& w : work)
+    if (!w.error.empty()) throw std::domain_error(w.error);
+
+  // ---- merge
+  out.chr_haps.resize(d.n_chr);
+  out.full_fragset.resize(d.n_chr);
+  out.chr_piece_off.assign(d.n_chr + 1, 0);
+  size_t n_inst = 0;
+  for (auto& w : work) n_inst += w.inst.size();
+  out.inst.reserve(n_inst);
+  for (uint32_t c = 0; c < d.n_chr; ++c) {
+    ChrWork& w = work[c];
+    const uint32_t fs_base = static_cast<uint32_t>(out.fragsets.size());
+    for (const auto& k : w.fragsets) {
+      std::vector<Frag> fr;
+      for (const auto& p : k) fr.push_back({p.first, p.second});
+      out.fragsets.push_back(std::move(fr));
+    }
+    out.full_fragset[c] = fs_base;  // interned first in flatten_chr
+    for (auto& h : w.haps) h.fragset += fs_base;
+    out.chr_haps[c] = std::move(w.haps);
+    for (const auto& in : w.inst)
+      if (in.span > 0) out.inst.push_back(in);  // a SID no sampled haplotype inherited
+
+    // pieces: maximal intervals on which the set of covering fragments is constant
+    std::vector<uint8_t> used(w.fragsets.size(), 0);
+    for (const auto& h : out.chr_haps[c]) used[h.fragset - fs_base] = 1;
+    std::vector<uint32_t> bp{1u, d.chr_len[c] + 1};
+    for (size_t k = 0; k < w.fragsets.size(); ++k)
+      if (used[k])
+        for (const auto& p : w.fragsets[k]) {
+          bp.push_back(p.first);
+          bp.push_back(p.second + 1);
+        }
+    std::sort(bp.begin(), bp.end());
+    bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
+    for (size_t i = 0; i + 1 < bp.size(); ++i) {
+      Piece pc{c, bp[i], bp[i + 1] - 1, static_cast<uint32_t>(out.covers.size()), 0};
+      for (size_t k = 0; k < w.fragsets.size(); ++k) {
+        if (!used[k]) continue;
+        for (const auto& p : w.fragsets[k])
+          if (p.first <= pc.begin && pc.end <= p.second) {
+            out.covers.push_back({fs_base + static_cast<uint32_t>(k), p.second});
+            ++pc.cover_n;
+            break;
+          }
+      }
+      if (pc.cover_n) out.pieces.push_back(pc);
+    }
+    out.chr_piece_off[c + 1] = static_cast<uint32_t>(out.pieces.size());
+  }
+
+  // ---- instances are sorted by row inside a chromosome and rows are chromosome-major
+  const uint32_t L = static_cast<uint32_t>(out.locus_pos.size());
+  out.locus_inst_off.assign(L + 1, 0);
+  for (const auto& in : out.inst) ++out.locus_inst_off[out.row_locus[in.row] + 1];
+  for (uint32_t l = 0; l < L; ++l) out.locus_inst_off[l + 1] += out.locus_inst_off[l];
+}
+
+}  // namespace pcs

@@ -1,0 +1,27 @@
+// kernels.hpp -- host-callable launchers of kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+
+#include "dev.hpp"
+
+namespace pcs {
+
+cudaError_t launch_sample_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
+                                unsigned long long* n_reads);
+cudaError_t launch_trace_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                               const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
+                               DevPlacement* trace, uint32_t* trace_masks, unsigned long long cap,
+                               unsigned long long* trace_n);
+cudaError_t launch_count_injected(cudaStream_t st, const DevPlacement* rec, const uint32_t* masks,
+                                  unsigned long long n, const DevForest& F, uint32_t R, uint32_t* depth,
+                                  uint32_t* alt);
+cudaError_t launch_finalize(cudaStream_t st, const uint32_t* depth, const uint32_t* row_locus, uint32_t n_samples,
+                            uint32_t n_loci, uint32_t n_mut, uint32_t* coverage);
+cudaError_t launch_sum_u32(cudaStream_t st, const uint32_t* v, size_t n, unsigned long long* out);
+
+}  // namespace pcs

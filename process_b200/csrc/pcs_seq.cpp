@@ -1,0 +1,913 @@
+// pcs_seq.cpp -- host side of libpcs_seq behind the C ABI (include/pcs_seq.h):
+// context, forest upload, sample groups, planner (tile grid + host multinomial),
+// run / trace / injected-count drivers.  No CPU fallback: every compute entry
+// point launches the sm_100a kernels of kernels.cu or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/pcs_seq.h"
+#include "dev.hpp"
+#include "flat.hpp"
+#include "kernels.hpp"
+
+namespace {
+
+thread_local std::string g_err;
+
+struct CudaError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define CUDA_OK(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));                   \
+  } while (0)
+
+void require(bool ok, const char* msg) {
+  if (!ok) throw std::domain_error(msg);
+}
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    n = count;
+    if (count) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+  }
+  size_t bytes() const { return n * sizeof(T); }
+  // synchronous w.r.t. the host buffer (pageable memory): safe to free `v` afterwards
+  size_t upload(const std::vector<T>& v, cudaStream_t st) {
+    alloc(v.size());
+    if (!v.empty()) {
+      CUDA_OK(cudaMemcpyAsync(p, v.data(), bytes(), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));
+    }
+    return bytes();
+  }
+};
+
+double now_ms() {
+  using namespace std::chrono;
+  return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct pcs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  void bind() const { CUDA_OK(cudaSetDevice(device)); }
+};
+
+// host half of an uploaded forest: flattened view + output sample groups
+struct HostForest {
+  pcs::FlatForest flat;
+  uint32_t n_groups = 0;
+  std::vector<uint32_t> leaf_group;
+  std::vector<uint32_t> group_cells;  // tumour cells per group
+  std::vector<uint32_t> hap_list;
+  std::unordered_map<uint64_t, std::pair<uint32_t, uint32_t>> list_index;  // (group<<32|fragset) -> (off,n)
+  // (kind, cell, allele) -> haplotype index, per chromosome; built on first use
+  std::vector<std::vector<std::pair<uint64_t, uint32_t>>> lookup;
+
+  static uint64_t list_key(uint32_t group, uint32_t fragset) { return (static_cast<uint64_t>(group) << 32) | fragset; }
+  static uint64_t hap_key(uint8_t kind, uint32_t cell, uint16_t allele) {
+    return (static_cast<uint64_t>(kind) << 56) | (static_cast<uint64_t>(cell) << 16) | allele;
+  }
+
+  void build_groups(const uint32_t* lg, uint32_t ng) {
+    n_groups = ng;
+    leaf_group.assign(lg, lg + flat.n_leaves);
+    group_cells.assign(ng, 0);
+    for (uint32_t l = 0; l < flat.n_leaves; ++l) {
+      require(leaf_group[l] < ng, "leaf group out of range");
+      ++group_cells[leaf_group[l]];
+    }
+    std::map<uint64_t, std::vector<uint32_t>> lists;
+    for (uint32_t c = 0; c < flat.n_chr; ++c) {
+      const auto& haps = flat.chr_haps[c];
+      for (uint32_t h = 0; h < haps.size(); ++h) {
+        const pcs::HapRec& r = haps[h];
+        uint32_t g = r.kind == pcs::HAP_TUMOUR ? leaf_group[r.cell] : ng + (r.kind == pcs::HAP_NORMAL_PRENEO ? 1u : 0u);
+        lists[list_key(g, r.fragset)].push_back(h);
+      }
+    }
+    hap_list.clear();
+    list_index.clear();
+    for (auto& [k, v] : lists) {
+      list_index[k] = {static_cast<uint32_t>(hap_list.size()), static_cast<uint32_t>(v.size())};
+      hap_list.insert(hap_list.end(), v.begin(), v.end());
+    }
+  }
+
+  void build_lookup() {
+    if (!lookup.empty()) return;
+    lookup.resize(flat.n_chr);
+    for (uint32_t c = 0; c < flat.n_chr; ++c) {
+      auto& v = lookup[c];
+      const auto& haps = flat.chr_haps[c];
+      v.reserve(haps.size());
+      for (uint32_t h = 0; h < haps.size(); ++h) v.emplace_back(hap_key(haps[h].kind, haps[h].cell, haps[h].allele), h);
+      std::sort(v.begin(), v.end());
+    }
+  }
+};
+
+struct pcs_flat {
+  HostForest host;
+};
+
+struct pcs_forest {
+  pcs_ctx* ctx = nullptr;
+  HostForest host;
+  DevBuf<uint32_t> d_locus_pos, d_chr_locus_off, d_locus_inst_off, d_row_locus, d_hap_list;
+  DevBuf<pcs::Inst> d_inst;
+  uint64_t h2d_bytes = 0;
+
+  pcs::DevForest dev() const {
+    pcs::DevForest F;
+    F.locus_pos = d_locus_pos.p;
+    F.chr_locus_off = d_chr_locus_off.p;
+    F.locus_inst_off = d_locus_inst_off.p;
+    F.inst = reinterpret_cast<const uint4*>(d_inst.p);
+    F.hap_list = d_hap_list.p;
+    F.n_loci = static_cast<uint32_t>(host.flat.locus_pos.size());
+    F.n_mut = host.flat.n_mut;
+    return F;
+  }
+
+  void set_groups(const uint32_t* lg, uint32_t ng) {
+    host.build_groups(lg, ng);
+    ctx->bind();
+    h2d_bytes += d_hap_list.upload(host.hap_list, ctx->stream);
+  }
+};
+
+// host half of a plan: tile grid of this shard, sampling tables, sequencer model
+struct HostPlan {
+  std::vector<pcs::Tile> tiles;  // this shard, heaviest first
+  std::vector<pcs::Entry> entries;
+  std::vector<uint32_t> insert_cdf;
+  pcs::SeqModel model{};
+  pcs_plan_info info{};
+};
+
+struct pcs_plan {
+  pcs_forest* forest = nullptr;
+  HostPlan host;
+  DevBuf<pcs::Tile> d_tiles;
+  DevBuf<pcs::Entry> d_entries;
+  DevBuf<uint32_t> d_insert_cdf;
+  DevBuf<uint32_t> d_depth, d_occ, d_cov;
+  DevBuf<unsigned long long> d_counters;  // [0] reads placed [1] sum depth [2] sum occ [3] trace count
+  uint64_t h2d_bytes = 0;
+};
+
+namespace {
+
+uint32_t tile_bp() {
+  const char* s = std::getenv("PCS_TILE_BP");
+  if (s) {
+    long v = std::atol(s);
+    if (v >= 1024) return static_cast<uint32_t>(v);
+  }
+  return 1u << 18;
+}
+
+// cumulative thresholds over the u32 range: pick the first i with draw <= thr[i]
+std::vector<uint32_t> thresholds(const std::vector<double>& w) {
+  double total = 0;
+  for (double x : w) total += x;
+  std::vector<uint32_t> thr(w.size());
+  double cum = 0;
+  for (size_t i = 0; i < w.size(); ++i) {
+    cum += w[i];
+    double b = std::floor(cum / total * 4294967296.0);
+    if (i + 1 == w.size() || b >= 4294967296.0) b = 4294967296.0;
+    thr[i] = b < 1.0 ? 0u : static_cast<uint32_t>(b - 1.0);
+  }
+  return thr;
+}
+
+void validate(const pcs_seq_params& P) {
+  require(P.read_size >= 1 && P.read_size <= 65535, "read_size must be in [1, 65535]");
+  require(P.coverage >= 0 && std::isfinite(P.coverage), "coverage must be a non-negative number");
+  require(P.normal_only || (P.purity >= 0 && P.purity <= 1), "purity must belong to [0,1]");
+  require(P.sequencer <= PCS_SEQ_BASIC_RANDOM, "Unsupported sequencer type");
+  require(P.error_rate >= 0 && std::isfinite(P.error_rate), "The parameter \"error_rate\" must be a positive real number.");
+  if (P.insert_size_mean > 0) {
+    // get_bin_dist(): src/seq_simulation.cpp:431-451
+    double q = static_cast<double>(P.insert_size_stddev) * P.insert_size_stddev / P.insert_size_mean;
+    if (1 - q < 0)
+      throw std::runtime_error("The insert size mean (" + std::to_string(P.insert_size_mean) +
+                               ") must be greater than or equal to its variance (" +
+                               std::to_string(P.insert_size_stddev) + "*" + std::to_string(P.insert_size_stddev) + "=" +
+                               std::to_string(P.insert_size_stddev * P.insert_size_stddev) + ").");
+  }
+  uint32_t sc = P.shard_count ? P.shard_count : 1;
+  require(P.shard_rank < sc, "shard_rank must be smaller than shard_count");
+}
+
+// Binomial(t, p) as selection thresholds over its support
+void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& cdf, uint32_t& kmin, uint32_t& kmax) {
+  double q = static_cast<double>(sd) * sd / mean;
+  double p = 1 - q;
+  uint32_t t = static_cast<uint32_t>(mean / p);
+  std::vector<double> pmf(t + 1);
+  if (p >= 1.0) {
+    std::fill(pmf.begin(), pmf.end(), 0.0);
+    pmf[t] = 1.0;
+  } else {
+    for (uint32_t k = 0; k <= t; ++k)
+      pmf[k] = std::exp(std::lgamma(t + 1.0) - std::lgamma(k + 1.0) - std::lgamma(t - k + 1.0) +
+                        k * std::log(p) + (t - k) * std::log1p(-p));
+  }
+  kmin = 0;
+  kmax = t;
+  while (kmin < kmax && pmf[kmin] < 1e-18) ++kmin;
+  while (kmax > kmin && pmf[kmax] < 1e-18) --kmax;
+  std::vector<double> w(pmf.begin() + kmin, pmf.begin() + kmax + 1);
+  cdf = thresholds(w);
+}
+
+struct OutSample {
+  bool is_normal;
+  uint32_t group;
+};
+
+HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
+  HostPlan pl;
+  const pcs::FlatForest& F = fo.flat;
+  std::vector<uint8_t> chr_mask;
+  if (P.chr_mask) chr_mask.assign(P.chr_mask, P.chr_mask + F.n_chr);
+  const uint32_t R = P.read_size;
+  const bool paired = P.insert_size_mean > 0;
+  const uint32_t mates = paired ? 2 : 1;
+
+  uint32_t kmin = 0, kmax = 0;
+  if (paired) insert_table(P.insert_size_mean, P.insert_size_stddev, pl.insert_cdf, kmin, kmax);
+  const uint64_t reach = paired ? 2ull * R + kmax : R;
+
+  std::vector<OutSample> samples;
+  if (!P.normal_only)
+    for (uint32_t g = 0; g < fo.n_groups; ++g) samples.push_back({false, g});
+  if (P.normal_only || P.with_normal_sample) samples.push_back({true, 0});
+
+  const uint32_t normal_group = fo.n_groups + (P.preneoplastic_in_normal ? 1u : 0u);
+  const uint32_t W = tile_bp();
+  const uint32_t shards = P.shard_count ? P.shard_count : 1;
+
+  std::vector<pcs::Entry>& entries = pl.entries;
+  std::vector<uint32_t>& cdf = pl.insert_cdf;
+  std::vector<pcs::Tile> all;
+  std::vector<double> tile_w;
+  uint64_t total_templates = 0;
+
+  for (uint32_t s = 0; s < samples.size(); ++s) {
+    double purity = samples[s].is_normal ? 0.0 : P.purity;
+    uint32_t nT = samples[s].is_normal ? 0 : fo.group_cells[samples[s].group];
+    if (nT == 0) purity = 0.0;
+    for (uint32_t c = 0; c < F.n_chr; ++c) {
+      if (!chr_mask.empty() && !chr_mask[c]) continue;
+      const size_t first_tile = all.size();
+      // normal cells: every one carries each germline allele whole
+      auto nit = fo.list_index.find(HostForest::list_key(normal_group, F.full_fragset[c]));
+      require(nit != fo.list_index.end(), "internal: normal haplotype list missing");
+      const uint32_t n_normal_cells = P.preneoplastic_in_normal ? F.n_roots : 1;
+      for (uint32_t pi = F.chr_piece_off[c]; pi < F.chr_piece_off[c + 1]; ++pi) {
+        const pcs::Piece& pc = F.pieces[pi];
+        std::vector<double> w;
+        std::vector<pcs::Entry> es;
+        for (uint32_t k = 0; k < pc.cover_n; ++k) {
+          const pcs::Cover& cv = F.covers[pc.cover_off + k];
+          if (purity > 0) {
+            auto it = fo.list_index.find(HostForest::list_key(samples[s].group, cv.fragset));
+            if (it != fo.list_index.end() && it->second.second > 0) {
+              w.push_back(purity / nT * it->second.second);
+              es.push_back({0u, it->second.first, it->second.second, cv.frag_end});
+            }
+          }
+          if (purity < 1 && cv.fragset == F.full_fragset[c]) {
+            w.push_back((1 - purity) / n_normal_cells * nit->second.second);
+            es.push_back({0u, nit->second.first, nit->second.second, cv.frag_end});
+          }
+        }
+        if (es.empty()) continue;
+        double wsum = 0;
+        for (double x : w) wsum += x;
+        std::vector<uint32_t> thr = thresholds(w);
+        const uint32_t entry_off = static_cast<uint32_t>(entries.size());
+        for (size_t i = 0; i < es.size(); ++i) {
+          es[i].thr = thr[i];
+          entries.push_back(es[i]);
+        }
+        for (uint64_t b = pc.begin; b <= pc.end; b += W) {
+          pcs::Tile t{};
+          t.chr = c;
+          t.begin = static_cast<uint32_t>(b);
+          t.len = static_cast<uint32_t>(std::min<uint64_t>(W, pc.end - b + 1));
+          t.entry_off = entry_off;
+          t.n_entries = static_cast<uint32_t>(es.size());
+          t.sample = s;
+          const uint32_t* lp = F.locus_pos.data();
+          t.l0 = static_cast<uint32_t>(std::lower_bound(lp + F.chr_locus_off[c], lp + F.chr_locus_off[c + 1], t.begin) - lp);
+          uint64_t last = std::min<uint64_t>(b + t.len + reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
+          t.l1 = static_cast<uint32_t>(std::lower_bound(lp + F.chr_locus_off[c], lp + F.chr_locus_off[c + 1],
+                                                        static_cast<uint32_t>(last)) - lp);
+          all.push_back(t);
+          tile_w.push_back(wsum * t.len);
+        }
+      }
+      // templates of this (sample, chromosome), multinomial over its tiles
+      uint64_t N = static_cast<uint64_t>(std::llround(P.coverage * F.chr_len[c] / (static_cast<double>(R) * mates)));
+      std::seed_seq sq{static_cast<uint32_t>(P.seed), s, c, 0x7115u};
+      std::mt19937_64 rng(sq);
+      double wleft = 0;
+      for (size_t i = first_tile; i < all.size(); ++i) wleft += tile_w[i];
+      uint64_t left = all.size() > first_tile ? N : 0;
+      for (size_t i = first_tile; i < all.size() && left > 0; ++i) {
+        double p = (i + 1 == all.size()) ? 1.0 : std::min(1.0, std::max(0.0, tile_w[i] / wleft));
+        uint64_t k = p >= 1.0 ? left : static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(left), p)(rng));
+        require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
+        all[i].n_templates = static_cast<uint32_t>(k);
+        left -= k;
+        wleft -= tile_w[i];
+        total_templates += k;
+      }
+    }
+  }
+  for (size_t i = 0; i < all.size(); ++i) all[i].id = static_cast<uint32_t>(i);
+
+  // shard: longest-processing-time greedy on templates; ties by tile id => deterministic
+  std::vector<uint32_t> order(all.size());
+  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return all[a].n_templates > all[b].n_templates; });
+  pl.tiles.clear();
+  uint64_t mine = 0;
+  if (shards == 1) {
+    for (uint32_t i : order)
+      if (all[i].n_templates) pl.tiles.push_back(all[i]);
+    mine = total_templates;
+  } else {
+    std::vector<uint64_t> load(shards, 0);
+    for (uint32_t i : order) {
+      if (!all[i].n_templates) continue;
+      uint32_t best = 0;
+      for (uint32_t r = 1; r < shards; ++r)
+        if (load[r] < load[best]) best = r;
+      load[best] += all[i].n_templates;
+      if (best == P.shard_rank) pl.tiles.push_back(all[i]);
+    }
+    mine = load[P.shard_rank];
+  }
+
+  pcs::SeqModel& M = pl.model;
+  M.insert_cdf = nullptr;
+  M.read_size = R;
+  M.paired = paired ? 1 : 0;
+  M.sequencer = P.sequencer;
+  M.err_thr = static_cast<uint32_t>(std::min(4294967295.0, std::floor(P.error_rate * 4294967296.0)));
+  M.error_rate = static_cast<float>(P.error_rate);
+  M.insert_n = static_cast<uint32_t>(cdf.size());
+  M.insert_min = kmin;
+  M.seed = static_cast<uint32_t>(P.seed);
+
+  pl.info.n_out_samples = static_cast<uint32_t>(samples.size());
+  pl.info.n_mut = F.n_mut;
+  pl.info.n_loci = static_cast<uint32_t>(F.locus_pos.size());
+  pl.info.n_tiles = pl.tiles.size();
+  pl.info.n_tiles_total = all.size();
+  pl.info.n_templates = mine;
+  pl.info.n_templates_total = total_templates;
+  pl.info.reads_per_template = mates;
+  pl.info.read_size = R;
+  return pl;
+}
+
+void upload_plan(pcs_plan& pl) {
+  pcs_forest& fo = *pl.forest;
+  fo.ctx->bind();
+  cudaStream_t st = fo.ctx->stream;
+  pl.h2d_bytes += pl.d_tiles.upload(pl.host.tiles, st);
+  pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
+  pl.h2d_bytes += pl.d_insert_cdf.upload(pl.host.insert_cdf, st);
+  pl.host.model.insert_cdf = pl.d_insert_cdf.p;
+  const size_t S = pl.host.info.n_out_samples;
+  pl.d_depth.alloc(S * pl.host.info.n_loci);
+  pl.d_occ.alloc(S * pl.host.info.n_mut);
+  pl.d_cov.alloc(S * pl.host.info.n_mut);
+  pl.d_counters.alloc(4);
+}
+
+void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  pcs_forest& fo = *pl.forest;
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  const bool dev_out = (flags & PCS_RUN_DEVICE_OUTPUT) != 0;
+  const size_t S = pl.host.info.n_out_samples, M = pl.host.info.n_mut, L = pl.host.info.n_loci;
+  uint32_t* d_occ = dev_out ? occ : pl.d_occ.p;
+  uint32_t* d_cov = dev_out ? cov : pl.d_cov.p;
+  require(S * M == 0 || (occ && cov), "occurrences/coverage output pointers are NULL");
+  const double t0 = now_ms();
+  uint64_t launches = 0;
+
+  CUDA_OK(cudaEventRecord(cx.ev[0], st));
+  if (S * L != 0) CUDA_OK(cudaMemsetAsync(pl.d_depth.p, 0, S * L * sizeof(uint32_t), st));
+  if (S * M != 0) CUDA_OK(cudaMemsetAsync(d_occ, 0, S * M * sizeof(uint32_t), st));
+  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_OK(cudaEventRecord(cx.ev[1], st));
+  const pcs::DevForest DF = fo.dev();
+  CUDA_OK(pcs::launch_sample_tiles(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p, DF,
+                                   pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
+  launches += pl.host.tiles.empty() ? 0 : 1;
+  CUDA_OK(cudaEventRecord(cx.ev[2], st));
+  CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
+                               static_cast<uint32_t>(M), d_cov));
+  CUDA_OK(pcs::launch_sum_u32(st, pl.d_depth.p, S * L, pl.d_counters.p + 1));
+  CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
+  launches += (S * M != 0 ? 2 : 0) + (S * L != 0 ? 1 : 0);
+  CUDA_OK(cudaEventRecord(cx.ev[3], st));
+  uint64_t d2h = 0;
+  if (!dev_out && S * M != 0) {
+    CUDA_OK(cudaMemcpyAsync(occ, d_occ, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(cov, d_cov, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    d2h += 2 * S * M * sizeof(uint32_t);
+  }
+  unsigned long long counters[4] = {0, 0, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  d2h += sizeof(counters);
+  if (stats) {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, cx.ev[1], cx.ev[2]));
+    stats->kernel_ms = ms;
+    stats->total_ms = now_ms() - t0;
+    stats->kernel_launches = launches;
+    stats->n_templates = pl.host.info.n_templates;
+    stats->n_reads = counters[0];
+    stats->sum_depth = counters[1];
+    stats->sum_occurrences = counters[2];
+    stats->h2d_bytes = 0;
+    stats->d2h_bytes = d2h;
+  }
+}
+
+template <class Fn>
+int guarded(Fn&& fn) {
+  try {
+    fn();
+    return PCS_OK;
+  } catch (const CudaError& e) {
+    g_err = e.what();
+    return PCS_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    g_err = "out of host memory";
+    return PCS_ERR_NOMEM;
+  } catch (const std::domain_error& e) {
+    g_err = e.what();
+    return PCS_ERR_INVALID;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return PCS_ERR_INTERNAL;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcs_abi_version(void) { return PCS_ABI_VERSION; }
+
+const char* pcs_last_error(void) { return g_err.c_str(); }
+
+int pcs_create(pcs_ctx** out, int device_id, void* stream) {
+  return guarded([&] {
+    require(out != nullptr, "ctx output pointer is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw CudaError(std::string("no CUDA device available (libpcs_seq has no CPU path): ") +
+                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    require(device_id >= 0 && device_id < n, "device_id out of range");
+    auto cx = std::make_unique<pcs_ctx>();
+    cx->device = device_id;
+    cx->bind();
+    cudaDeviceProp prop{};
+    CUDA_OK(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10)
+      throw CudaError(std::string("libpcs_seq is built for sm_100a only; device is ") + prop.name + " (sm_" +
+                      std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    if (stream) {
+      cx->stream = static_cast<cudaStream_t>(stream);
+    } else {
+      CUDA_OK(cudaStreamCreateWithFlags(&cx->stream, cudaStreamNonBlocking));
+      cx->own_stream = true;
+    }
+    for (auto& ev : cx->ev) CUDA_OK(cudaEventCreate(&ev));
+    *out = cx.release();
+  });
+}
+
+int pcs_destroy(pcs_ctx* cx) {
+  return guarded([&] {
+    if (!cx) return;
+    cudaSetDevice(cx->device);
+    for (auto& ev : cx->ev)
+      if (ev) cudaEventDestroy(ev);
+    if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
+    delete cx;
+  });
+}
+
+int pcs_device_name(pcs_ctx* cx, char* buf, size_t len) {
+  return guarded([&] {
+    require(cx && buf && len > 0, "bad arguments");
+    cudaDeviceProp prop{};
+    CUDA_OK(cudaGetDeviceProperties(&prop, cx->device));
+    std::strncpy(buf, prop.name, len - 1);
+    buf[len - 1] = 0;
+  });
+}
+
+int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out) {
+  return guarded([&] {
+    require(cx && desc && out, "bad arguments");
+    auto fo = std::make_unique<pcs_forest>();
+    fo->ctx = cx;
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    pcs::flatten_forest(*desc, fo->host.flat, nt);
+    cx->bind();
+    cudaStream_t st = cx->stream;
+    fo->h2d_bytes += fo->d_locus_pos.upload(fo->host.flat.locus_pos, st);
+    fo->h2d_bytes += fo->d_chr_locus_off.upload(fo->host.flat.chr_locus_off, st);
+    fo->h2d_bytes += fo->d_locus_inst_off.upload(fo->host.flat.locus_inst_off, st);
+    fo->h2d_bytes += fo->d_row_locus.upload(fo->host.flat.row_locus, st);
+    fo->h2d_bytes += fo->d_inst.upload(fo->host.flat.inst, st);
+    fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
+    *out = fo.release();
+  });
+}
+
+int pcs_forest_free(pcs_forest* fo) {
+  return guarded([&] {
+    if (!fo) return;
+    cudaSetDevice(fo->ctx->device);
+    delete fo;
+  });
+}
+
+int pcs_forest_set_groups(pcs_forest* fo, const uint32_t* leaf_group, uint32_t n_groups) {
+  return guarded([&] {
+    require(fo != nullptr, "forest is NULL");
+    if (leaf_group)
+      fo->set_groups(leaf_group, n_groups);
+    else
+      fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
+  });
+}
+
+int pcs_forest_info(const pcs_forest* fo, uint64_t out[6]) {
+  return guarded([&] {
+    require(fo && out, "bad arguments");
+    uint64_t haps = 0;
+    for (const auto& v : fo->host.flat.chr_haps) haps += v.size();
+    out[0] = fo->host.flat.locus_pos.size();
+    out[1] = fo->host.flat.inst.size();
+    out[2] = haps;
+    out[3] = fo->host.flat.fragsets.size();
+    out[4] = fo->host.flat.pieces.size();
+    out[5] = fo->d_locus_pos.bytes() + fo->d_chr_locus_off.bytes() + fo->d_locus_inst_off.bytes() +
+             fo->d_row_locus.bytes() + fo->d_inst.bytes() + fo->d_hap_list.bytes();
+  });
+}
+
+int pcs_plan_create(pcs_forest* fo, const pcs_seq_params* params, pcs_plan** out) {
+  return guarded([&] {
+    require(fo && params && out, "bad arguments");
+    validate(*params);
+    auto pl = std::make_unique<pcs_plan>();
+    pl->forest = fo;
+    pl->host = make_host_plan(fo->host, *params);
+    upload_plan(*pl);
+    *out = pl.release();
+  });
+}
+
+int pcs_plan_info_get(const pcs_plan* pl, pcs_plan_info* info) {
+  return guarded([&] {
+    require(pl && info, "bad arguments");
+    *info = pl->host.info;
+  });
+}
+
+int pcs_plan_free(pcs_plan* pl) {
+  return guarded([&] {
+    if (!pl) return;
+    cudaSetDevice(pl->forest->ctx->device);
+    delete pl;
+  });
+}
+
+int pcs_plan_run(pcs_plan* pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(pl != nullptr, "plan is NULL");
+    run_plan(*pl, flags, occ, cov, stats);
+  });
+}
+
+int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint64_t cap, uint64_t* n_out) {
+  return guarded([&] {
+    require(pl && rec && n_out, "bad arguments");
+    pcs_forest& fo = *pl->forest;
+    pcs_ctx& cx = *fo.ctx;
+    cx.bind();
+    cudaStream_t st = cx.stream;
+    DevBuf<pcs::DevPlacement> d_rec;
+    DevBuf<uint32_t> d_masks;
+    d_rec.alloc(cap);
+    if (masks) d_masks.alloc(cap * PCS_ERRMASK_WORDS);
+    CUDA_OK(cudaMemsetAsync(pl->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
+                                    fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p, cap,
+                                    pl->d_counters.p + 3));
+    unsigned long long counters[4];
+    CUDA_OK(cudaMemcpyAsync(counters, pl->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    *n_out = counters[3];
+    if (counters[3] > cap) throw std::domain_error("trace capacity too small");
+    std::vector<pcs::DevPlacement> h(counters[3]);
+    if (!h.empty()) CUDA_OK(cudaMemcpy(h.data(), d_rec.p, h.size() * sizeof(pcs::DevPlacement), cudaMemcpyDeviceToHost));
+    if (masks && !h.empty())
+      CUDA_OK(cudaMemcpy(masks, d_masks.p, h.size() * PCS_ERRMASK_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) {
+      uint32_t chr = h[i].chr_sample & 0xffffu;
+      const pcs::HapRec& hr = fo.host.flat.chr_haps[chr][h[i].hap];
+      rec[i].cell = hr.cell;
+      rec[i].start = h[i].start;
+      rec[i].chr = static_cast<uint16_t>(chr);
+      rec[i].allele = hr.allele;
+      rec[i].sample = static_cast<uint16_t>(h[i].chr_sample >> 16);
+      rec[i].flags = hr.kind == pcs::HAP_TUMOUR ? PCS_PLACE_TUMOUR
+                     : hr.kind == pcs::HAP_NORMAL_PLAIN ? PCS_PLACE_NORMAL_PLAIN : PCS_PLACE_NORMAL_PRENEO;
+    }
+  });
+}
+
+int pcs_simulate(pcs_forest* fo, const pcs_seq_params* params, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  pcs_plan* pl = nullptr;
+  int rc = pcs_plan_create(fo, params, &pl);
+  if (rc != PCS_OK) return rc;
+  rc = pcs_plan_run(pl, PCS_RUN_HOST_OUTPUT, occ, cov, stats);
+  if (rc == PCS_OK && stats) stats->h2d_bytes = pl->h2d_bytes;
+  std::string keep = g_err;
+  pcs_plan_free(pl);
+  g_err = keep;
+  return rc;
+}
+
+int pcs_count_injected(pcs_forest* fo, uint32_t n_out_samples, uint32_t read_size, const pcs_read_placement* rec,
+                       const uint32_t* masks, uint64_t n, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(fo && occ && cov && (rec || n == 0), "bad arguments");
+    require(read_size >= 1 && read_size <= 65535, "read_size must be in [1, 65535]");
+    require(n_out_samples >= 1 && n_out_samples <= 65535, "n_out_samples out of range");
+    const pcs::FlatForest& F = fo->host.flat;
+    fo->host.build_lookup();
+    std::vector<pcs::DevPlacement> h(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      const pcs_read_placement& r = rec[i];
+      require(r.chr < F.n_chr, "placement chromosome out of range");
+      require(r.sample < n_out_samples, "placement sample out of range");
+      require(r.flags <= PCS_PLACE_NORMAL_PRENEO, "unknown placement flags");
+      uint8_t kind = r.flags == PCS_PLACE_TUMOUR ? pcs::HAP_TUMOUR
+                     : r.flags == PCS_PLACE_NORMAL_PLAIN ? pcs::HAP_NORMAL_PLAIN : pcs::HAP_NORMAL_PRENEO;
+      uint64_t key = HostForest::hap_key(kind, r.cell, r.allele);
+      const auto& lk = fo->host.lookup[r.chr];
+      auto it = std::lower_bound(lk.begin(), lk.end(), std::make_pair(key, 0u));
+      require(it != lk.end() && it->first == key, "placement names a missing allele");
+      const pcs::HapRec& hr = F.chr_haps[r.chr][it->second];
+      uint32_t frag_end = 0;
+      for (const auto& fr : F.fragsets[hr.fragset])
+        if (r.start >= fr.b && r.start <= fr.e) frag_end = fr.e;
+      require(frag_end != 0, "placement starts outside every fragment of the allele");
+      h[i] = pcs::DevPlacement{it->second, r.start, frag_end, static_cast<uint32_t>(r.chr) | (static_cast<uint32_t>(r.sample) << 16)};
+    }
+    pcs_ctx& cx = *fo->ctx;
+    cx.bind();
+    cudaStream_t st = cx.stream;
+    const double t0 = now_ms();
+    const size_t S = n_out_samples, M = F.n_mut, L = F.locus_pos.size();
+    DevBuf<pcs::DevPlacement> d_rec;
+    DevBuf<uint32_t> d_masks, d_depth, d_occ, d_cov;
+    DevBuf<unsigned long long> d_cnt;
+    uint64_t h2d = d_rec.upload(h, st);
+    if (masks) {
+      d_masks.alloc(n * PCS_ERRMASK_WORDS);
+      if (n) CUDA_OK(cudaMemcpyAsync(d_masks.p, masks, d_masks.bytes(), cudaMemcpyHostToDevice, st));
+      h2d += d_masks.bytes();
+    }
+    d_depth.alloc(S * L);
+    d_occ.alloc(S * M);
+    d_cov.alloc(S * M);
+    d_cnt.alloc(4);
+    if (S * L != 0) CUDA_OK(cudaMemsetAsync(d_depth.p, 0, d_depth.bytes(), st));
+    if (S * M != 0) CUDA_OK(cudaMemsetAsync(d_occ.p, 0, d_occ.bytes(), st));
+    CUDA_OK(cudaMemsetAsync(d_cnt.p, 0, d_cnt.bytes(), st));
+    CUDA_OK(cudaEventRecord(cx.ev[1], st));
+    CUDA_OK(pcs::launch_count_injected(st, d_rec.p, masks ? d_masks.p : nullptr, n, fo->dev(), read_size, d_depth.p, d_occ.p));
+    CUDA_OK(cudaEventRecord(cx.ev[2], st));
+    CUDA_OK(pcs::launch_finalize(st, d_depth.p, fo->d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
+                                 static_cast<uint32_t>(M), d_cov.p));
+    CUDA_OK(pcs::launch_sum_u32(st, d_depth.p, S * L, d_cnt.p + 1));
+    CUDA_OK(pcs::launch_sum_u32(st, d_occ.p, S * M, d_cnt.p + 2));
+    if (S * M != 0) {
+      CUDA_OK(cudaMemcpyAsync(occ, d_occ.p, d_occ.bytes(), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaMemcpyAsync(cov, d_cov.p, d_cov.bytes(), cudaMemcpyDeviceToHost, st));
+    }
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    CUDA_OK(cudaMemcpyAsync(counters, d_cnt.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    if (stats) {
+      float ms = 0;
+      CUDA_OK(cudaEventElapsedTime(&ms, cx.ev[1], cx.ev[2]));
+      stats->kernel_ms = ms;
+      stats->total_ms = now_ms() - t0;
+      stats->kernel_launches = (n ? 1 : 0) + (S * M != 0 ? 2 : 0) + (S * L != 0 ? 1 : 0);
+      stats->n_templates = n;
+      stats->n_reads = n;
+      stats->sum_depth = counters[1];
+      stats->sum_occurrences = counters[2];
+      stats->h2d_bytes = h2d;
+      stats->d2h_bytes = 2 * S * M * sizeof(uint32_t) + sizeof(counters);
+    }
+  });
+}
+
+int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples, int include_non_sequenced,
+                    uint32_t* rows_out, uint32_t* n_rows) {
+  return guarded([&] {
+    require(fo && occ && rows_out && n_rows, "bad arguments");
+    const pcs::FlatForest& F = fo->host.flat;
+    std::vector<uint8_t> carried;
+    if (include_non_sequenced) {
+      carried.assign(F.n_mut, 0);
+      for (const auto& in : F.inst) carried[in.row] = 1;  // inherited by at least one sampled haplotype
+    }
+    uint32_t k = 0;
+    for (uint32_t m = 0; m < F.n_mut; ++m) {
+      bool on = include_non_sequenced && carried[m];
+      for (uint32_t s = 0; s < n_out_samples && !on; ++s) on = occ[static_cast<size_t>(s) * F.n_mut + m] > 0;
+      if (on) rows_out[k++] = m;
+    }
+    *n_rows = k;
+  });
+}
+
+// ------------------------------------------------ host-only introspection
+// No GPU needed: tests use these to check the flattened view against explicit
+// per-cell genomes, and the planner's shard partition at world_size > 1.
+
+int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** out) {
+  return guarded([&] {
+    require(desc && out, "bad arguments");
+    auto fl = std::make_unique<pcs_flat>();
+    pcs::flatten_forest(*desc, fl->host.flat, std::max(1u, std::thread::hardware_concurrency()));
+    fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
+    *out = fl.release();
+  });
+}
+
+int pcs_flat_free(pcs_flat* fl) {
+  delete fl;
+  return PCS_OK;
+}
+
+int pcs_flat_set_groups(pcs_flat* fl, const uint32_t* leaf_group, uint32_t n_groups) {
+  return guarded([&] {
+    require(fl != nullptr, "flat is NULL");
+    if (leaf_group)
+      fl->host.build_groups(leaf_group, n_groups);
+    else
+      fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
+  });
+}
+
+int pcs_flat_info(const pcs_flat* fl, uint64_t out[6]) {
+  return guarded([&] {
+    require(fl && out, "bad arguments");
+    const pcs::FlatForest& F = fl->host.flat;
+    uint64_t haps = 0;
+    for (const auto& v : F.chr_haps) haps += v.size();
+    out[0] = F.locus_pos.size();
+    out[1] = F.inst.size();
+    out[2] = haps;
+    out[3] = F.fragsets.size();
+    out[4] = F.pieces.size();
+    out[5] = 0;
+  });
+}
+
+int pcs_flat_cell_haps(pcs_flat* fl, uint32_t kind, uint32_t cell, uint32_t chr, uint32_t cap, uint16_t* allele,
+                       uint32_t* hap, uint32_t* fragset, uint32_t* n) {
+  return guarded([&] {
+    require(fl && n, "bad arguments");
+    const pcs::FlatForest& F = fl->host.flat;
+    require(chr < F.n_chr, "chromosome out of range");
+    fl->host.build_lookup();
+    const auto& lk = fl->host.lookup[chr];
+    auto it = std::lower_bound(lk.begin(), lk.end(), std::make_pair(HostForest::hap_key(static_cast<uint8_t>(kind), cell, 0), 0u));
+    uint32_t k = 0;
+    for (; it != lk.end() && (it->first >> 16) == (HostForest::hap_key(static_cast<uint8_t>(kind), cell, 0) >> 16); ++it) {
+      if (k < cap) {
+        allele[k] = static_cast<uint16_t>(it->first & 0xffffu);
+        hap[k] = it->second;
+        fragset[k] = F.chr_haps[chr][it->second].fragset;
+      }
+      ++k;
+    }
+    *n = k;
+  });
+}
+
+int pcs_flat_fragset(const pcs_flat* fl, uint32_t fragset, uint32_t cap, uint32_t* begin, uint32_t* end, uint32_t* n) {
+  return guarded([&] {
+    require(fl && n, "bad arguments");
+    const pcs::FlatForest& F = fl->host.flat;
+    require(fragset < F.fragsets.size(), "fragment set out of range");
+    uint32_t k = 0;
+    for (const auto& fr : F.fragsets[fragset]) {
+      if (k < cap) {
+        begin[k] = fr.b;
+        end[k] = fr.e;
+      }
+      ++k;
+    }
+    *n = k;
+  });
+}
+
+int pcs_flat_hap_rows(const pcs_flat* fl, uint32_t chr, uint32_t hap, uint32_t cap, uint32_t* rows, uint32_t* n) {
+  return guarded([&] {
+    require(fl && n, "bad arguments");
+    const pcs::FlatForest& F = fl->host.flat;
+    require(chr < F.n_chr, "chromosome out of range");
+    uint32_t k = 0;
+    for (uint32_t l = F.chr_locus_off[chr]; l < F.chr_locus_off[chr + 1]; ++l)
+      for (uint32_t i = F.locus_inst_off[l]; i < F.locus_inst_off[l + 1]; ++i)
+        if (hap - F.inst[i].lo < F.inst[i].span) {
+          if (k < cap) rows[k] = F.inst[i].row;
+          ++k;
+        }
+    *n = k;
+  });
+}
+
+int pcs_flat_plan(const pcs_flat* fl, const pcs_seq_params* params, pcs_plan_info* info, uint64_t cap,
+                  uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,
+                  uint32_t* tile_begin, uint32_t* tile_len) {
+  return guarded([&] {
+    require(fl && params && info, "bad arguments");
+    validate(*params);
+    HostPlan pl = make_host_plan(fl->host, *params);
+    *info = pl.info;
+    for (size_t i = 0; i < pl.tiles.size() && i < cap; ++i) {
+      if (tile_id) tile_id[i] = pl.tiles[i].id;
+      if (tile_templates) tile_templates[i] = pl.tiles[i].n_templates;
+      if (tile_sample) tile_sample[i] = pl.tiles[i].sample;
+      if (tile_chr) tile_chr[i] = pl.tiles[i].chr;
+      if (tile_begin) tile_begin[i] = pl.tiles[i].begin;
+      if (tile_len) tile_len[i] = pl.tiles[i].len;
+    }
+  });
+}
+
+}  // extern "C"

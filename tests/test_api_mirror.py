@@ -1,0 +1,64 @@
+"""Argument handling of the Python mirror of the Rcpp interface (no GPU needed):
+the error behaviour of src/seq_simulation.cpp and src/sequencers.cpp."""
+import numpy as np
+import pytest
+
+from process_b200 import api
+from process_b200 import _abi as A
+
+from golden import micro_forest as MF
+
+
+def test_sequencer_constructors_validate_like_build_sequencer():
+    s = api.BasicIlluminaSequencer(4e-3)
+    assert s.error_rate == 4e-3 and s.random_quality_scores is True
+    assert api._sequencer_model(s) == (A.PCS_SEQ_BASIC_RANDOM, 4e-3)
+    assert api._sequencer_model(api.BasicIlluminaSequencer(1e-3, False)) == (A.PCS_SEQ_BASIC_CONSTANT, 1e-3)
+    assert api._sequencer_model(None) == api._sequencer_model(api.ErrorlessIlluminaSequencer()) == (A.PCS_SEQ_ERRORLESS, 0.0)
+    for bad in (-1, "x", None, True):
+        with pytest.raises(ValueError, match="error_rate"):
+            api.BasicIlluminaSequencer(bad)
+    with pytest.raises(ValueError, match="random_quality_scores"):
+        api.BasicIlluminaSequencer(1e-3, "yes")
+    with pytest.raises(ValueError, match="Unsupported sequencer type"):
+        api._sequencer_model(object())
+    assert api._sequencer_data(None) is None
+    assert api._sequencer_data(s) == dict(name="BasicIlluminaSequencer", error_rate=4e-3, random_quality_scores=True)
+    assert api._sequencer_data(api.ErrorlessIlluminaSequencer()) == dict(name="ErrorlessIlluminaSequencer", error_rate=0.0)
+
+
+def test_reference_genome_must_exist(tmp_path):
+    f = MF.forest()
+    with pytest.raises(RuntimeError, match="does not exists anymore"):
+        api.simulate_seq(f)
+    with pytest.raises(RuntimeError, match="does not exists"):
+        api.simulate_seq(f, reference_genome=str(tmp_path / "nope.fa"))
+    with pytest.raises(ValueError, match="either NULL or a string"):
+        api.simulate_seq(f, reference_genome=3)
+
+
+def test_chromosome_list_handling():
+    f = MF.forest()
+    assert api._chr_mask(f, None) is None
+    assert api._chr_mask(f, ["1"]).tolist() == [1]
+    with pytest.raises(ValueError, match="2nd element of the list is not a string"):
+        api._chr_mask(f, ["1", 2])
+    with pytest.raises(ValueError, match="Unsupported chromosome list type"):
+        api._chr_mask(f, 22)
+
+
+def test_cell_labelling_splits_samples_in_order_of_first_appearance():
+    f = MF.forest()
+    group, names = api._apply_FACS_labels(f, lambda c: "" if c.cell_id == 1 else "B")
+    assert names == ["s0", "s1_B"] and group.tolist() == [0, 1]
+    group, names = api._apply_FACS_labels(f, None)
+    assert group is None and names == ["s0", "s1"]
+    with pytest.raises(ValueError, match="must be a function"):
+        api._apply_FACS_labels(f, 3)
+
+
+def test_seed_resolution():
+    assert api._resolve_seed(7) == 7 and api._resolve_seed(7.0) == 7
+    assert -2**31 <= api._resolve_seed(None) < 2**31
+    with pytest.raises(ValueError):
+        api._resolve_seed("x")

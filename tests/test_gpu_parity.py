@@ -1,0 +1,311 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI, against the CPU oracle.
+
+Bit-exact bar (integer count tables):
+  * oracle placements  -> pcs_count_injected == oracle's own counts
+  * GPU sampler counts == oracle.count_injected(GPU sampler's own placements)
+  * sum over shards == single-shard tables (1/2/4/8 GPU invariance)
+Distributional bar for the free-running sampler (north_star): KS p > 0.01 on
+per-locus depth and VAF, mean coverage within 0.5 %.
+"""
+import numpy as np
+import pytest
+from scipy import stats
+
+import oracle
+from process_b200 import _abi as A
+from process_b200 import _lib as L
+from process_b200.synth import synth_forest
+
+from conftest import make_params, small_spec
+
+pytestmark = pytest.mark.gpu
+
+SEQ = [(A.PCS_SEQ_ERRORLESS, 0.0), (A.PCS_SEQ_BASIC_CONSTANT, 0.02), (A.PCS_SEQ_BASIC_RANDOM, 0.02)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = L.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def forests():
+    return [synth_forest(small_spec(s)) for s in range(3)]
+
+
+@pytest.mark.parametrize("seqm,rate", SEQ)
+@pytest.mark.parametrize("insert", [0, 200])
+def test_injected_reads_bit_exact(ctx, forests, seqm, rate, insert):
+    for f in forests:
+        P = make_params(coverage=15.0, purity=0.7, sequencer=seqm, error_rate=rate, insert_size_mean=insert,
+                        preneoplastic_in_normal=1)
+        ref = oracle.simulate(f, P, trace_cap=600_000, trace_masks=True)
+        assert len(ref["trace"]) == ref["n_reads"] > 10_000
+        dev = L.Forest(ctx, f)
+        n_out = dev.n_out_samples(P)
+        occ, cov, st = dev.count_injected(n_out, P.read_size, ref["trace"], ref["masks"])
+        assert np.array_equal(occ, ref["occ"])
+        assert np.array_equal(cov, ref["cov"])
+        assert st.kernel_launches >= 1 and st.n_reads == ref["n_reads"]
+        assert st.sum_occurrences == int(ref["occ"].sum())
+        dev.close()
+
+
+@pytest.mark.parametrize("seqm,rate", SEQ)
+@pytest.mark.parametrize("insert", [0, 200])
+@pytest.mark.parametrize("preneo", [0, 1])
+def test_sampler_counts_match_oracle_recount_of_its_own_reads(ctx, forests, seqm, rate, insert, preneo):
+    f = forests[preneo]
+    P = make_params(coverage=12.0, purity=0.6, sequencer=seqm, error_rate=rate, insert_size_mean=insert,
+                    preneoplastic_in_normal=preneo, seed=11 + preneo)
+    dev = L.Forest(ctx, f)
+    plan = L.Plan(dev, P)
+    occ, cov, st = plan.run()
+    rec, masks = plan.trace(cap=int(st.n_reads) + 16, with_masks=True)
+    assert len(rec) == st.n_reads > 10_000
+    occ2, cov2 = oracle.count_injected(f, plan.info.n_out_samples, P.read_size, rec, masks)
+    assert np.array_equal(occ, occ2)
+    assert np.array_equal(cov, cov2)
+    # run twice: same seed, same tables (counter-based RNG, integer sums)
+    occ3, cov3, _ = plan.run()
+    assert np.array_equal(occ, occ3) and np.array_equal(cov, cov3)
+    plan.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_shards_add_up_bit_exact(ctx, forests, shards):
+    f = forests[0]
+    dev = L.Forest(ctx, f)
+    P = make_params(coverage=20.0, purity=0.8, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01)
+    occ, cov, st = dev.simulate(P)
+    occ_s = np.zeros_like(occ)
+    cov_s = np.zeros_like(cov)
+    reads = 0
+    for r in range(shards):
+        Pr = make_params(coverage=20.0, purity=0.8, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01,
+                         shard_rank=r, shard_count=shards)
+        o, c, s = dev.simulate(Pr)
+        occ_s += o
+        cov_s += c
+        reads += s.n_reads
+    assert reads == st.n_reads
+    assert np.array_equal(occ_s, occ) and np.array_equal(cov_s, cov)
+    dev.close()
+
+
+def _spaced(pos, gap):
+    keep, last = [], -10**9
+    for i, p in enumerate(pos):
+        if p - last >= gap:
+            keep.append(i)
+            last = p
+    return np.asarray(keep)
+
+
+DIST_CASES = [(A.PCS_SEQ_ERRORLESS, 0.0, 0), (A.PCS_SEQ_BASIC_CONSTANT, 0.05, 0),
+              (A.PCS_SEQ_BASIC_RANDOM, 0.05, 0), (A.PCS_SEQ_ERRORLESS, 0.0, 300)]
+
+
+def _dist_forest():
+    return synth_forest(small_spec(5, chr_names=["1"], chr_len=[3_000_000], chr_n_alleles=[2], sample_cells=[40, 60],
+                                   germline_density=1.5e-3, cna_len=(50_000, 400_000)))
+
+
+def _ks_pvalues(f, P, occ, cov, ref):
+    """KS p-values of per-locus depth and VAF, GPU vs oracle, on loci far enough
+    apart that no read covers two of them (independent observations)."""
+    sel = _spaced(f.mut_pos.astype(np.int64), 3 * (2 * P.read_size + P.insert_size_mean))
+    out = []
+    for s in range(occ.shape[0]):
+        out.append(stats.ks_2samp(cov[s, sel], ref["cov"][s, sel]).pvalue)
+        ok = (cov[s, sel] > 0) & (ref["cov"][s, sel] > 0)
+        out.append(stats.ks_2samp(occ[s, sel][ok] / cov[s, sel][ok],
+                                  ref["occ"][s, sel][ok] / ref["cov"][s, sel][ok]).pvalue)
+    return np.asarray(out)
+
+
+@pytest.mark.parametrize("seqm,rate,insert", DIST_CASES)
+def test_free_running_distributions_match_oracle(ctx, seqm, rate, insert):
+    """north_star: KS p > 0.01 on depth and VAF, mean coverage within 0.5 %, same forest,
+    GPU sampler (Philox, tiles) vs CPU oracle (mt19937_64, per-fragment loop)."""
+    f = _dist_forest()
+    P = make_params(coverage=120.0, purity=0.75, sequencer=seqm, error_rate=rate, insert_size_mean=insert,
+                    insert_size_stddev=12, seed=1)
+    ref = oracle.simulate(f, P, n_threads=8)
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.simulate(P)
+    dev.close()
+    G = float(f.chr_len.sum())
+    n_out = occ.shape[0]
+    assert abs(st.n_reads * P.read_size / (G * n_out) / P.coverage - 1) < 5e-3
+    assert abs(st.n_reads / ref["n_reads"] - 1) < 5e-3
+    assert abs(cov.mean() / ref["cov"].mean() - 1) < 5e-3
+    for s in range(n_out):
+        assert abs(cov[s].mean() / ref["cov"][s].mean() - 1) < 5e-3, s
+    p = _ks_pvalues(f, P, occ, cov, ref)
+    assert p.min() > 0.01, p
+    # per-row agreement in units of binomial noise: no systematic shift anywhere
+    tot_g, tot_o = occ.sum(axis=0).astype(float), ref["occ"].sum(axis=0).astype(float)
+    z = (tot_g - tot_o) / np.sqrt(np.maximum(tot_g + tot_o, 1.0))
+    assert abs(z.mean()) < 0.1 and z.std() < 1.2
+
+
+def test_ks_pvalues_are_calibrated_over_seeds(ctx):
+    """One seed can land in a tail.  Over 6 GPU seeds x 6 oracle seeds x 3 samples x
+    {depth, VAF} the p-values must look like draws under the null: few below 0.01,
+    median well away from 0."""
+    f = _dist_forest()
+    dev = L.Forest(ctx, f)
+    gpu, cpu = [], []
+    for seed in range(6):
+        P = make_params(coverage=120.0, purity=0.75, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.02, seed=seed)
+        occ, cov, _ = dev.simulate(P)
+        gpu.append((occ, cov))
+        cpu.append(oracle.simulate(f, make_params(coverage=120.0, purity=0.75, sequencer=A.PCS_SEQ_BASIC_CONSTANT,
+                                                  error_rate=0.02, seed=100 + seed), n_threads=8))
+    dev.close()
+    P = make_params(coverage=120.0)
+    ps = np.concatenate([_ks_pvalues(f, P, o, c, r) for o, c in gpu for r in cpu])
+    assert len(ps) == 6 * 6 * 3 * 2
+    assert (ps < 0.01).mean() <= 0.03, np.sort(ps)[:8]
+    assert np.median(ps) > 0.3
+
+
+def test_normal_only_and_chromosome_mask(ctx, forests):
+    f = forests[2]
+    dev = L.Forest(ctx, f)
+    P = make_params(coverage=25.0, normal_only=1, with_normal_sample=0, preneoplastic_in_normal=1,
+                    chr_mask=[1, 0, 1])
+    occ, cov, st = dev.simulate(P)
+    assert occ.shape[0] == 1
+    on_masked = f.mut_chr == 1
+    assert cov[0, on_masked].sum() == 0 and occ[0, on_masked].sum() == 0
+    assert cov[0, ~on_masked].sum() > 0
+    # a normal cell carries germline (+ pre-neoplastic) SIDs only
+    somatic = (f.mut_nature_mask & ((1 << A.PCS_NATURE_DRIVER) | (1 << A.PCS_NATURE_PASSENGER))) != 0
+    assert occ[0, somatic].sum() == 0
+    preneo = (f.mut_nature_mask >> A.PCS_NATURE_PRENEOPLASTIC) & 1 == 1
+    assert occ[0, preneo & ~on_masked].sum() > 0
+    rec, _ = L.Plan(dev, P).trace(cap=int(st.n_reads) + 8)
+    assert set(np.unique(rec["flags"])) == {A.PCS_PLACE_NORMAL_PRENEO}
+    o2, c2 = oracle.count_injected(f, 1, P.read_size, rec)
+    assert np.array_equal(o2, occ) and np.array_equal(c2, cov)
+    dev.close()
+
+
+def test_sample_groups_like_facs_labelling(ctx, forests):
+    f = forests[1]
+    dev = L.Forest(ctx, f)
+    rng = np.random.default_rng(1)
+    groups = rng.integers(0, 5, f.n_leaves).astype(np.uint32)
+    dev.set_groups(groups, 5)
+    P = make_params(coverage=10.0, purity=0.9, with_normal_sample=1)
+    plan = L.Plan(dev, P)
+    assert plan.info.n_out_samples == 6
+    occ, cov, st = plan.run()
+    rec, _ = plan.trace(cap=int(st.n_reads) + 8)
+    tum = rec[rec["flags"] == A.PCS_PLACE_TUMOUR]
+    assert np.array_equal(groups[tum["cell"]], tum["sample"])
+    o2, c2 = oracle.count_injected(f, 6, P.read_size, rec)
+    assert np.array_equal(o2, occ) and np.array_equal(c2, cov)
+    ref = oracle.simulate(f, P, leaf_group=groups, n_groups=5)
+    assert abs(cov.mean() / ref["cov"].mean() - 1) < 0.05
+    plan.close()
+    dev.close()
+
+
+def test_empty_and_ragged_inputs(ctx, forests):
+    f = forests[0]
+    dev = L.Forest(ctx, f)
+    # no reads at all
+    occ, cov, st = dev.simulate(make_params(coverage=0.0))
+    assert occ.sum() == 0 and cov.sum() == 0 and st.n_reads == 0
+    # empty injected list
+    occ, cov, st = dev.count_injected(2, 150, np.zeros(0, A.PLACEMENT_DTYPE))
+    assert occ.sum() == 0 and cov.sum() == 0
+    # reads longer than some fragments, read_size 1, maximum read size the masks cover
+    for R in (1, 37, 256):
+        P = make_params(coverage=3.0, read_size=R, purity=0.5, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.1)
+        plan = L.Plan(dev, P)
+        o, c, s = plan.run()
+        rec, masks = plan.trace(cap=int(s.n_reads) + 8, with_masks=True)
+        o2, c2 = oracle.count_injected(f, plan.info.n_out_samples, R, rec, masks)
+        assert np.array_equal(o, o2) and np.array_equal(c, c2)
+        plan.close()
+    # malformed placements are refused, not mis-counted
+    bad = np.zeros(1, A.PLACEMENT_DTYPE)
+    bad["allele"] = 999
+    bad["start"] = 5
+    with pytest.raises(L.PcsError):
+        dev.count_injected(2, 150, bad)
+    dev.close()
+
+
+# ------------------------------------------------------------------ golden vectors through the C ABI
+def test_micro_forest_hand_computed_counts_on_gpu(ctx):
+    from golden import micro_forest as MF
+    f = MF.forest()
+    rec, masks = MF.placements()
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.count_injected(3, MF.READ_SIZE, rec, masks)
+    assert occ.tolist() == MF.EXPECTED_OCC
+    assert cov.tolist() == MF.EXPECTED_COV
+    for i in range(len(rec)):  # every read alone as well
+        o1, c1, _ = dev.count_injected(3, MF.READ_SIZE, rec[i:i + 1], masks[i:i + 1])
+        o2, c2 = oracle.count_injected(f, 3, MF.READ_SIZE, rec[i:i + 1], masks[i:i + 1])
+        assert np.array_equal(o1, o2) and np.array_equal(c1, c2), i
+    dev.close()
+
+
+@pytest.mark.parametrize("name", ["errorless_single", "random_quality_paired"])
+def test_committed_vectors_on_gpu(ctx, name):
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"injected_{name}.npz"))
+    f = synth_forest(small_spec(int(z["forest_seed"])))
+    masks = np.zeros((len(z["trace"]), A.PCS_ERRMASK_WORDS), np.uint32)
+    masks[z["mask_rows"]] = z["mask_vals"]
+    dev = L.Forest(ctx, f)
+    occ, cov, _ = dev.count_injected(z["occ"].shape[0], int(z["read_size"]), z["trace"], masks)
+    assert np.array_equal(occ, z["occ"]) and np.array_equal(cov, z["cov"])
+    dev.close()
+
+
+def test_python_mirror_schema_and_parameters(ctx, tmp_path):
+    """simulate_seq()/simulate_normal_seq() through the mirror of the Rcpp interface."""
+    from process_b200 import api
+    f = synth_forest(small_spec(4))
+    ref = tmp_path / "ref.fa"
+    ref.write_text(">1\nACGT\n")
+    f.reference_path = str(ref)
+    r = api.simulate_seq(f, chromosomes=["1", "X"], coverage=20, purity=0.8, seed=5,
+                         sequencer=api.BasicIlluminaSequencer(1e-3))
+    df = r["mutations"]
+    names = sorted(f.sample_names + ["normal_sample"])
+    want = ["chr", "chr_pos", "ref", "alt", "causes", "classes"]
+    for n in names:
+        want += [f"{n}.occurrences", f"{n}.coverage", f"{n}.VAF"]
+    assert list(df.columns) == want
+    assert set(df["chr"]) <= {"1", "X"} and len(df) > 100
+    assert (df[[f"{n}.occurrences" for n in names]].sum(axis=1) > 0).all()
+    assert df[["chr_pos"]].dtypes.iloc[0] == np.int32 and df["normal_sample.VAF"].dtype == np.float64
+    key = list(zip(df["chr"].map(f.chr_names.index), df["chr_pos"]))
+    assert key == sorted(key)
+    assert r["parameters"]["seed"] == 5 and r["parameters"]["sequencer"]["name"] == "BasicIlluminaSequencer"
+    assert list(r["parameters"]) == ["sequencer", "reference_genome", "chromosomes", "coverage", "read_size",
+                                     "insert_size_mean", "insert_size_stddev", "output_dir", "write_SAM", "update_SAM",
+                                     "cell_labelling", "purity", "with_normal_sample", "filename_prefix",
+                                     "template_name_prefix", "include_non_sequenced_mutations", "seed"]
+    allrows = api.simulate_seq(f, coverage=0.01, seed=5, include_non_sequenced_mutations=True)["mutations"]
+    assert len(allrows) > len(df)
+    with pytest.warns(UserWarning):
+        n = api.simulate_normal_seq(f, coverage=20, seed=5)
+    assert [c for c in n["mutations"].columns if "." in c] == ["normal_sample.occurrences", "normal_sample.coverage",
+                                                              "normal_sample.VAF"]
+    assert "with_preneoplastic" in n["parameters"]
+    lab = api.simulate_seq(f, coverage=5, seed=5, with_normal_sample=False,
+                           cell_labelling=lambda cell: "odd" if cell.cell_id % 2 else "")["mutations"]
+    assert any(c.startswith(f.sample_names[0] + "_odd.") for c in lab.columns)
+    api.release_device_cache()

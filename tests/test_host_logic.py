@@ -1,0 +1,162 @@
+"""Host side of libpcs_seq without a GPU: the flattened (haplotype-interval) view
+against explicit per-cell genomes, and the planner (tile grid, multinomial, shards)."""
+import numpy as np
+import pytest
+
+import oracle
+from process_b200 import _abi as A
+from process_b200 import _lib as L
+from process_b200.synth import synth_forest
+
+from conftest import make_params, small_spec
+from golden import micro_forest as MF
+
+
+def check_flat_against_explicit_genomes(f):
+    fl = L.Flat(f)
+    germ = {}
+    for m, mask in zip(f.germ_mut, f.germ_allele_mask):
+        germ.setdefault(int(f.mut_chr[m]), []).append((int(m), int(mask)))
+    n_roots = int((f.node_parent < 0).sum())
+    cells = [(A.PCS_PLACE_TUMOUR, l) for l in range(f.n_leaves)] + [(A.PCS_PLACE_NORMAL_PLAIN, 0)] + \
+            [(A.PCS_PLACE_NORMAL_PRENEO, r) for r in range(n_roots)]
+    checked = 0
+    for c in range(f.n_chr):
+        for kind, cell in cells:
+            frags, sids = oracle.cell_genome(f, kind, cell, c)
+            haps = {a: (h, fs) for a, h, fs in fl.cell_haps(kind, cell, c)}
+            alleles = {}
+            for a, o, b, e in frags:
+                d = alleles.setdefault(a, dict(origin=o, frags=[], rows=set()))
+                if b > 0:
+                    d["frags"].append((b, e))
+            for a, r in sids:
+                alleles[a]["rows"].add(r)
+            assert set(haps) <= set(alleles)
+            for a, d in alleles.items():
+                if not d["frags"]:
+                    assert a not in haps  # an allele with no DNA left cannot be read
+                    continue
+                h, fs = haps[a]
+                assert fl.fragset(fs) == sorted(d["frags"])
+                inside = lambda m: any(b <= int(f.mut_pos[m]) <= e for b, e in d["frags"])  # noqa: E731
+                want = set(d["rows"]) | {m for m, mask in germ.get(c, []) if mask & (1 << d["origin"]) and inside(m)}
+                got = {int(m) for m in fl.hap_rows(c, h) if inside(m)}
+                assert got == want, (kind, cell, c, a)
+                checked += 1
+    return checked
+
+
+def test_flat_view_of_the_micro_forest():
+    f = MF.forest()
+    assert check_flat_against_explicit_genomes(f) == 2 + 3 + 2 + 2
+    info = L.Flat(f).info()
+    assert info["n_loci"] == 8 and info["n_haplotypes"] == 2 + 3 + 2 + 2
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flat_view_matches_explicit_genomes(seed):
+    f = synth_forest(small_spec(seed))
+    assert (f.ev_kind == A.PCS_EV_WGD).sum() >= 1 and (f.ev_kind == A.PCS_EV_CNA_AMP).sum() >= 3
+    assert check_flat_against_explicit_genomes(f) > 100
+
+
+def test_flat_view_with_two_roots_and_nested_copies():
+    """amplify, then WGD the copy, then delete inside the copy of the copy"""
+    F = dict(MF.FOREST)
+    F = {k: list(v) if isinstance(v, list) else v for k, v in F.items()}
+    # second root (node 3) with one sampled child (node 4)
+    F["node_parent"] = [-1, 0, 0, -1, 3]
+    F["leaf_node"] = [1, 2, 4]
+    F["leaf_sample"] = [0, 1, 1]
+    extra = [  # kind chr pos len allele dest mut nature
+        (0, 0, 0, 0, 0, 0, 4, 3),      # root 3: pre-neoplastic SID row 4 (pos 400) on allele 0
+        (1, 0, 350, 300, 0, 2, 0, 0),  # node 4: AMP [350,649] a0 -> a2
+        (3, 0, 0, 0, 0, 0, 0, 0),      #         WGD: a0->a3, a1->a4, a2->a5
+        (2, 0, 380, 40, 5, 0, 0, 0),   #         DEL [380,419] of a5
+        (0, 0, 0, 0, 5, 0, 5, 1),      #         SID row 5 (pos 600) on a5
+    ]
+    for i, k in enumerate(["ev_kind", "ev_chr", "ev_pos", "ev_len", "ev_allele", "ev_dest", "ev_mut", "ev_nature"]):
+        F[k] = F[k] + [e[i] for e in extra]
+    F["node_event_off"] = [0, 1, 2, 6, 7, 11]
+    from process_b200.forest import PhylogeneticForest
+    f = PhylogeneticForest(**{k: (v if k in ("chr_names", "sample_names") else np.asarray(v)) for k, v in F.items()}).normalise()
+    frags, sids = oracle.cell_genome(f, A.PCS_PLACE_TUMOUR, 2, 0)
+    assert (5, 0, 350, 379) in frags and (5, 0, 420, 649) in frags and (2, 0, 350, 649) in frags
+    # row 4 (pos 400) is copied to a2, a3 and a5, then deleted from a5 together with [380,419]
+    assert sorted(sids) == [(0, 4), (2, 4), (3, 4), (5, 5)]
+    assert check_flat_against_explicit_genomes(f) >= 10
+
+
+def test_malformed_forests_are_refused():
+    f = MF.forest()
+    f.mut_pos = f.mut_pos[::-1].copy()
+    with pytest.raises(L.PcsError):
+        L.Flat(f)
+    f = MF.forest()
+    f.node_parent = np.asarray([1, -1, 0], np.int32)
+    with pytest.raises(L.PcsError):
+        L.Flat(f)
+    f = MF.forest()
+    f.germ_allele_mask = np.asarray([1, 3, 4, 1], np.uint8)
+    with pytest.raises(L.PcsError):
+        L.Flat(f)
+
+
+def test_planner_tile_grid_and_template_counts():
+    f = synth_forest(small_spec(1))
+    fl = L.Flat(f)
+    P = make_params(coverage=40.0, purity=0.8)
+    info, t = fl.plan(P)
+    assert info.n_out_samples == f.n_samples + 1 and info.n_tiles == len(t["id"])
+    # A9: round(coverage * chr_len / read_size) templates per (sample, chromosome)
+    for s in range(info.n_out_samples):
+        for c in range(f.n_chr):
+            got = int(t["templates"][(t["sample"] == s) & (t["chr"] == c)].sum())
+            assert got == int(round(40.0 * int(f.chr_len[c]) / 150))
+    # heaviest first, tiles inside their chromosome, distinct ids
+    assert np.all(np.diff(t["templates"].astype(np.int64)) <= 0)
+    assert np.all(t["begin"] + t["len"] - 1 <= f.chr_len[t["chr"]])
+    assert len(np.unique(t["id"])) == len(t["id"])
+    # same seed -> same plan; other seed -> other counts
+    _, t2 = fl.plan(make_params(coverage=40.0, purity=0.8))
+    assert all(np.array_equal(t[k], t2[k]) for k in t)
+    _, t3 = fl.plan(make_params(coverage=40.0, purity=0.8, seed=8))
+    assert not np.array_equal(t["templates"], t3["templates"])
+    # paired reads: half as many templates
+    info_p, _ = fl.plan(make_params(coverage=40.0, insert_size_mean=300))
+    assert info_p.reads_per_template == 2
+    assert abs(info_p.n_templates_total * 2 - info.n_templates_total) <= info.n_out_samples * f.n_chr
+
+
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_planner_shards_partition_the_tile_grid(shards):
+    f = synth_forest(small_spec(2))
+    fl = L.Flat(f)
+    info, t = fl.plan(make_params(coverage=25.0, purity=0.7))
+    seen = {}
+    loads = []
+    for r in range(shards):
+        info_r, tr = fl.plan(make_params(coverage=25.0, purity=0.7, shard_rank=r, shard_count=shards))
+        assert info_r.n_templates_total == info.n_templates_total and info_r.n_tiles_total == info.n_tiles_total
+        for i, n in zip(tr["id"], tr["templates"]):
+            assert i not in seen
+            seen[int(i)] = int(n)
+        loads.append(int(tr["templates"].sum()))
+        assert loads[-1] == info_r.n_templates
+    assert seen == {int(i): int(n) for i, n in zip(t["id"], t["templates"])}
+    assert max(loads) - min(loads) <= int(t["templates"].max())  # LPT balance
+    with pytest.raises(L.PcsError):
+        fl.plan(make_params(shard_rank=shards, shard_count=shards))
+
+
+def test_parameter_validation_messages():
+    fl = L.Flat(MF.forest())
+    with pytest.raises(L.PcsError, match="must be greater than or equal to its variance"):
+        fl.plan(make_params(insert_size_mean=50, insert_size_stddev=10))
+    with pytest.raises(L.PcsError, match="purity"):
+        fl.plan(make_params(purity=1.5))
+    with pytest.raises(L.PcsError, match="Unsupported sequencer type"):
+        fl.plan(make_params(sequencer=9))
+    info, _ = fl.plan(make_params(normal_only=1, purity=7.0))  # purity is ignored for the normal sample
+    assert info.n_out_samples == 1
