@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- simulated Gbases/s of the simulate_seq() read sampler on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3]
+
+A step = one full pass of the hot path over the workload: every read of every
+sample of the synthetic forest is placed and counted (BASELINE.json config 3:
+GRCh38-length genome, 3 tumour samples x 1000 cells + normal sample, 80x WGS,
+read size 150, errorless Illumina).  N > 1: one process per GPU under torchrun,
+the tile grid is sharded over ranks (strong scaling of the same job) and the
+per-sample count tables are summed with NCCL inside the step.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the
+reference's RACES code is not in the image and ProCESS does not compile without
+Rcpp) with all host threads on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from process_b200 import _abi as A  # noqa: E402
+from process_b200.synth import config_spec, synth_forest  # noqa: E402
+
+METRIC = "simulated_gbases_per_s"
+UNIT = "Gbases/s"
+WORKLOADS = {
+    # name: (synth config, genome scale, params)
+    "C3": ("C3", 1.0, dict(coverage=80.0, purity=1.0, read_size=150)),
+    "C1": ("C1", 1.0, dict(coverage=50.0, purity=1.0, read_size=150)),
+    "C3-small": ("C3", 0.02, dict(coverage=80.0, purity=1.0, read_size=150)),
+}
+
+
+def make_params(shard_rank=0, shard_count=1, chr_mask=None, **kw):
+    d = dict(seed=0, coverage=80.0, purity=1.0, read_size=150, insert_size_mean=0, insert_size_stddev=10,
+             sequencer=A.PCS_SEQ_ERRORLESS, error_rate=0.0, with_normal_sample=1, preneoplastic_in_normal=0,
+             normal_only=0, shard_rank=shard_rank, shard_count=shard_count)
+    d.update(kw)
+    p = A.SeqParams(**d)
+    if chr_mask is not None:
+        import ctypes as C
+        p._keep = np.ascontiguousarray(chr_mask, dtype=np.uint8)
+        p.chr_mask = A.ptr(p._keep, C.c_uint8)
+    return p
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy burst)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """per-launch DRAM bytes of the sampler kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "sampler_traffic.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return None
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, p[2:]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample_params(forest, workload_params, budget_reads):
+    """bounded sample of the workload for the CPU legs: the smallest autosome(s) of the
+    same forest, all samples, coverage scaled so that about `budget_reads` reads are drawn."""
+    order = np.argsort(forest.chr_len)
+    mask = np.zeros(forest.n_chr, np.uint8)
+    mask[order[0]] = 1
+    n_out = forest.n_samples + 1
+    full = workload_params["coverage"]
+    reads_full = full * float(forest.chr_len[order[0]]) / workload_params["read_size"] * n_out
+    cov = full * min(1.0, budget_reads / reads_full)
+    kw = dict(workload_params)
+    kw["coverage"] = cov
+    desc = (f"chromosome {forest.chr_names[order[0]]} ({int(forest.chr_len[order[0]])} bp) of the same forest, "
+            f"{n_out} samples, coverage {cov:.2f}x of {full:g}x")
+    return make_params(chr_mask=mask, **kw), desc
+
+
+def run_reference(args, forest, wl_params):
+    import oracle
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    P, desc = cpu_sample_params(forest, wl_params, budget_reads=6e6 * min(threads, 8))
+    times, reads = [], 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = oracle.simulate(forest, P, n_threads=threads)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            reads = r["n_reads"]
+    sec = float(np.mean(times))
+    val = reads * P.read_size / sec / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": args.workload, "note": "CPU oracle (port of the RACES@1142937 semantics; the reference "
+                   "itself cannot be built here), bounded sample"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    cfg, scale, wl_params = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference" and rank != 0:
+        return
+    forest = synth_forest(config_spec(cfg, seed=0, scale=scale))
+    if args.impl == "reference":
+        run_reference(args, forest, wl_params)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from process_b200 import _lib as L
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    ctx = L.Context(local, stream.cuda_stream)
+    dev = L.Forest(ctx, forest)
+    P = make_params(shard_rank=rank, shard_count=world, **wl_params)
+    plan = L.Plan(dev, P)
+    S, M = plan.info.n_out_samples, plan.info.n_mut
+    occ = torch.zeros((S, M), dtype=torch.int32, device="cuda")
+    cov = torch.zeros((S, M), dtype=torch.int32, device="cuda")
+
+    def step():
+        st = plan.run_device(occ.data_ptr(), cov.data_ptr())
+        if world > 1:  # the path's one exchange step: sum the per-sample count tables
+            dist.all_reduce(occ, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cov, op=dist.ReduceOp.SUM)
+        return st
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    clocks = ClockSampler(local) if rank == 0 else None
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    stats = [step() for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    reads = torch.tensor([float(sum(s.n_reads for s in stats))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(reads, op=dist.ReduceOp.SUM)
+    total_ms = float(ms.item())
+    total_reads = float(reads.item())
+    clk = clocks.stop(t0, t1) if clocks else None
+    R = plan.info.read_size
+    value = total_reads * R / (total_ms * 1e-3) / 1e9
+
+    # roofline of the sampler kernel on this rank: algorithmic bytes per read
+    st = stats[-1]
+    kbar = st.sum_depth / max(1, st.n_reads)
+    kalt = st.sum_occurrences / max(1, st.n_reads)
+    b_read = 24.0 + 20.0 * kbar + 8.0 * kalt
+    kernel_ms = float(np.mean([s.kernel_ms for s in stats]))
+    achieved = st.n_reads * b_read / (kernel_ms * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    traffic = ncu_traffic()
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
+                "kernel": "pcs::sample_tiles_kernel", "kernel_ms": kernel_ms, "reads_per_launch": int(st.n_reads),
+                "bytes_per_read": b_read, "k_bar": kbar, "k_alt": kalt,
+                "algorithmic_bytes_per_launch": st.n_reads * b_read}
+
+    # end to end through the C ABI with host buffers: flatten + upload, plan, kernels, tables back to the host
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(1, min(args.steps, 3))
+        h2d = d2h = 0
+        barrier()
+        t_e = time.perf_counter()
+        e2e_reads = 0
+        for _ in range(e2e_steps):
+            d2 = L.Forest(ctx, forest)
+            if world == 1:
+                o, c, s2 = d2.simulate(make_params(**wl_params))
+                h2d += forest.host_bytes() + s2.h2d_bytes
+                d2h += s2.d2h_bytes
+            else:
+                p2 = L.Plan(d2, P)
+                s2 = p2.run_device(occ.data_ptr(), cov.data_ptr())
+                dist.all_reduce(occ, op=dist.ReduceOp.SUM)
+                dist.all_reduce(cov, op=dist.ReduceOp.SUM)
+                o, c = occ.cpu(), cov.cpu()
+                h2d += forest.host_bytes()
+                d2h += 2 * S * M * 4
+                p2.close()
+            e2e_reads += s2.n_reads
+            d2.close()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t_e], dtype=torch.float64, device="cuda")
+        er = torch.tensor([float(e2e_reads)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(er, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(er.item()) * R / float(dt.item()) / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+               "ms_per_step": float(dt.item()) * 1e3 / e2e_steps,
+               "what": "pcs_forest_upload (flatten + H2D) + pcs_simulate (plan, kernels, D2H of the tables), host buffers"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        Pc, desc = cpu_sample_params(forest, wl_params, budget_reads=2.5e7)
+        t_c = time.perf_counter()
+        r = oracle.simulate(forest, Pc, n_threads=1)
+        dt_c = time.perf_counter() - t_c
+        cpu = {"value": r["n_reads"] * R / dt_c / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": desc + f"; {r['n_reads']} reads in {dt_c:.1f} s, one thread (the reference is single-threaded)"}
+
+    if rank == 0:
+        info = dev.info()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: BASELINE.json configs[2], GRCh38-length genome, 3 tumour samples x "
+                                   "1000 cells + normal_sample, 80x WGS, read_size 150, ErrorlessIlluminaSequencer"
+                       if args.workload == "C3" else args.workload,
+                       "samples": S, "rows": M, "reads_per_step": total_reads / args.steps,
+                       "tiles_this_rank": int(plan.info.n_tiles), "parallelism": f"tile-sharded x{world}",
+                       "l2": f"working set {(info['device_bytes'] + 3 * S * M * 4) / 1e6:.0f} MB > 126 MB L2; "
+                             "count tables re-zeroed every step; no explicit flush"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    plan.close()
+    dev.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
