@@ -27,7 +27,8 @@ struct Tile {
   uint32_t sample;   // output sample index
   uint32_t id;       // global tile number: Philox key, independent of sharding
   uint32_t l0, l1;   // loci with position in [begin, begin+len+reach): staged range
-  uint32_t pad0, pad1;
+  uint32_t r0;       // first mutation row of locus l0
+  uint32_t n_rows;   // rows of the loci [l0, l1)
 };
 static_assert(sizeof(Tile) == 48, "Tile layout");
 
@@ -51,6 +52,16 @@ struct SeqModel {
   uint32_t insert_min;      // smallest insert with non-zero probability
   const uint32_t* insert_cdf;  // [insert_n] cumulative thresholds over the u32 range
   uint32_t seed;
+  uint32_t reach;           // bases past a tile's last start position a template can span (without deletions)
+  uint32_t dir_shift;       // staged kernel: log2 of the bucket size of the in-tile locus directory
+};
+
+// shared-memory capacities of the staged sampler kernel for one plan (maxima over its staged tiles)
+struct StageDims {
+  uint32_t max_loci;
+  uint32_t max_inst;
+  uint32_t max_rows;
+  uint32_t max_buckets;
 };
 
 // injected placement after host translation (cell, allele) -> haplotype index

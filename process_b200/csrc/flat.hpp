@@ -48,6 +48,7 @@ struct FlatForest {
   std::vector<uint32_t> chr_locus_off;   // [n_chr+1]
   std::vector<uint32_t> locus_inst_off;  // [L+1]
   std::vector<uint32_t> row_locus;       // [n_mut]
+  std::vector<uint32_t> locus_first_row; // [L+1]
   std::vector<Inst> inst;                // sorted by row
 
   // haplotype leaves, per chromosome (index inside a chromosome = haplotype index)

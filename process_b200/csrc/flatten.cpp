@@ -308,6 +308,8 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     out.row_locus[m] = static_cast<uint32_t>(out.locus_pos.size() - 1);
   }
   for (uint32_t c = 1; c <= d.n_chr; ++c) out.chr_locus_off[c] = std::max(out.chr_locus_off[c], out.chr_locus_off[c - 1]);
+  out.locus_first_row.assign(out.locus_pos.size() + 1, d.n_mut);
+  for (uint32_t m = d.n_mut; m-- > 0;) out.locus_first_row[out.row_locus[m]] = m;
 
   // ---- events by chromosome (node-major order is preserved)
   std::vector<ChrWork> work(d.n_chr);

@@ -10,9 +10,13 @@
 
 namespace pcs {
 
-cudaError_t launch_sample_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
-                                unsigned long long* n_reads);
+size_t staged_smem_bytes(const StageDims& D);
+cudaError_t launch_sample_tiles_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                       const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                       uint32_t* alt, unsigned long long* n_reads);
+cudaError_t launch_sample_tiles_global(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                       const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
+                                       unsigned long long* n_reads);
 cudaError_t launch_trace_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
                                DevPlacement* trace, uint32_t* trace_masks, unsigned long long cap,

@@ -173,7 +173,9 @@ struct pcs_forest {
 
 // host half of a plan: tile grid of this shard, sampling tables, sequencer model
 struct HostPlan {
-  std::vector<pcs::Tile> tiles;  // this shard, heaviest first
+  std::vector<pcs::Tile> tiles;         // this shard, staged in shared memory, heaviest first
+  std::vector<pcs::Tile> tiles_global;  // this shard, too dense to stage
+  pcs::StageDims dims{};
   std::vector<pcs::Entry> entries;
   std::vector<uint32_t> insert_cdf;
   pcs::SeqModel model{};
@@ -183,7 +185,7 @@ struct HostPlan {
 struct pcs_plan {
   pcs_forest* forest = nullptr;
   HostPlan host;
-  DevBuf<pcs::Tile> d_tiles;
+  DevBuf<pcs::Tile> d_tiles, d_tiles_global;
   DevBuf<pcs::Entry> d_entries;
   DevBuf<uint32_t> d_insert_cdf;
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
@@ -200,6 +202,15 @@ uint32_t tile_bp() {
     if (v >= 1024) return static_cast<uint32_t>(v);
   }
   return 1u << 18;
+}
+
+uint32_t stage_loci_cap() {
+  const char* s = std::getenv("PCS_STAGE_LOCI");
+  if (s) {
+    long v = std::atol(s);
+    if (v >= 0 && v <= 8192) return static_cast<uint32_t>(v);
+  }
+  return 1024;
 }
 
 // cumulative thresholds over the u32 range: pick the first i with draw <= thr[i]
@@ -283,6 +294,7 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
 
   const uint32_t normal_group = fo.n_groups + (P.preneoplastic_in_normal ? 1u : 0u);
   const uint32_t W = tile_bp();
+  const uint32_t lcap = stage_loci_cap();
   const uint32_t shards = P.shard_count ? P.shard_count : 1;
 
   std::vector<pcs::Entry>& entries = pl.entries;
@@ -329,21 +341,30 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
           es[i].thr = thr[i];
           entries.push_back(es[i]);
         }
-        for (uint64_t b = pc.begin; b <= pc.end; b += W) {
+        const uint32_t* lp = F.locus_pos.data();
+        const uint32_t* c_lo = lp + F.chr_locus_off[c];
+        const uint32_t* c_hi = lp + F.chr_locus_off[c + 1];
+        for (uint64_t b = pc.begin; b <= pc.end;) {
           pcs::Tile t{};
           t.chr = c;
           t.begin = static_cast<uint32_t>(b);
-          t.len = static_cast<uint32_t>(std::min<uint64_t>(W, pc.end - b + 1));
           t.entry_off = entry_off;
           t.n_entries = static_cast<uint32_t>(es.size());
           t.sample = s;
-          const uint32_t* lp = F.locus_pos.data();
-          t.l0 = static_cast<uint32_t>(std::lower_bound(lp + F.chr_locus_off[c], lp + F.chr_locus_off[c + 1], t.begin) - lp);
-          uint64_t last = std::min<uint64_t>(b + t.len + reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
-          t.l1 = static_cast<uint32_t>(std::lower_bound(lp + F.chr_locus_off[c], lp + F.chr_locus_off[c + 1],
-                                                        static_cast<uint32_t>(last)) - lp);
+          t.l0 = static_cast<uint32_t>(std::lower_bound(c_lo, c_hi, t.begin) - lp);
+          uint64_t len = std::min<uint64_t>(W, pc.end - b + 1);
+          for (;;) {  // shrink the window until its loci fit the staging capacity
+            uint64_t last = std::min<uint64_t>(b + len + reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
+            t.l1 = static_cast<uint32_t>(std::lower_bound(c_lo, c_hi, static_cast<uint32_t>(last)) - lp);
+            if (t.l1 - t.l0 <= lcap || len <= 2048) break;
+            len = std::max<uint64_t>(2048, len / 2);
+          }
+          t.len = static_cast<uint32_t>(len);
+          t.r0 = F.locus_first_row[t.l0];
+          t.n_rows = F.locus_first_row[t.l1] - t.r0;
           all.push_back(t);
           tile_w.push_back(wsum * t.len);
+          b += len;
         }
       }
       // templates of this (sample, chromosome), multinomial over its tiles
@@ -370,11 +391,28 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   std::vector<uint32_t> order(all.size());
   for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return all[a].n_templates > all[b].n_templates; });
-  pl.tiles.clear();
+  // tiles whose loci / instances / rows fit the staging capacity go to the staged kernel
+  uint32_t dir_shift = 5;
+  while ((((static_cast<uint64_t>(W) + reach) >> dir_shift) + 1) > 4096) ++dir_shift;
+  auto stageable = [&](const pcs::Tile& t) {
+    const uint32_t n_inst = F.locus_inst_off[t.l1] - F.locus_inst_off[t.l0];
+    return lcap > 0 && t.l1 - t.l0 <= lcap && n_inst <= 2 * lcap && t.n_rows <= 2 * lcap;
+  };
+  auto take = [&](const pcs::Tile& t) {
+    if (stageable(t)) {
+      pl.tiles.push_back(t);
+      pl.dims.max_loci = std::max(pl.dims.max_loci, t.l1 - t.l0);
+      pl.dims.max_inst = std::max(pl.dims.max_inst, F.locus_inst_off[t.l1] - F.locus_inst_off[t.l0]);
+      pl.dims.max_rows = std::max(pl.dims.max_rows, t.n_rows);
+      pl.dims.max_buckets = std::max<uint32_t>(pl.dims.max_buckets, static_cast<uint32_t>(((t.len + reach) >> dir_shift) + 1));
+    } else {
+      pl.tiles_global.push_back(t);
+    }
+  };
   uint64_t mine = 0;
   if (shards == 1) {
     for (uint32_t i : order)
-      if (all[i].n_templates) pl.tiles.push_back(all[i]);
+      if (all[i].n_templates) take(all[i]);
     mine = total_templates;
   } else {
     std::vector<uint64_t> load(shards, 0);
@@ -384,10 +422,15 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
       for (uint32_t r = 1; r < shards; ++r)
         if (load[r] < load[best]) best = r;
       load[best] += all[i].n_templates;
-      if (best == P.shard_rank) pl.tiles.push_back(all[i]);
+      if (best == P.shard_rank) take(all[i]);
     }
     mine = load[P.shard_rank];
   }
+  // round the capacities so that plans of similar forests share one shared-memory footprint
+  pl.dims.max_loci = (pl.dims.max_loci + 63) & ~63u;
+  pl.dims.max_inst = (pl.dims.max_inst + 63) & ~63u;
+  pl.dims.max_rows = (pl.dims.max_rows + 63) & ~63u;
+  pl.dims.max_buckets = (pl.dims.max_buckets + 63) & ~63u;
 
   pcs::SeqModel& M = pl.model;
   M.insert_cdf = nullptr;
@@ -399,11 +442,13 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   M.insert_n = static_cast<uint32_t>(cdf.size());
   M.insert_min = kmin;
   M.seed = static_cast<uint32_t>(P.seed);
+  M.reach = static_cast<uint32_t>(reach);
+  M.dir_shift = dir_shift;
 
   pl.info.n_out_samples = static_cast<uint32_t>(samples.size());
   pl.info.n_mut = F.n_mut;
   pl.info.n_loci = static_cast<uint32_t>(F.locus_pos.size());
-  pl.info.n_tiles = pl.tiles.size();
+  pl.info.n_tiles = pl.tiles.size() + pl.tiles_global.size();
   pl.info.n_tiles_total = all.size();
   pl.info.n_templates = mine;
   pl.info.n_templates_total = total_templates;
@@ -417,6 +462,7 @@ void upload_plan(pcs_plan& pl) {
   fo.ctx->bind();
   cudaStream_t st = fo.ctx->stream;
   pl.h2d_bytes += pl.d_tiles.upload(pl.host.tiles, st);
+  pl.h2d_bytes += pl.d_tiles_global.upload(pl.host.tiles_global, st);
   pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
   pl.h2d_bytes += pl.d_insert_cdf.upload(pl.host.insert_cdf, st);
   pl.host.model.insert_cdf = pl.d_insert_cdf.p;
@@ -446,9 +492,11 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
   CUDA_OK(cudaEventRecord(cx.ev[1], st));
   const pcs::DevForest DF = fo.dev();
-  CUDA_OK(pcs::launch_sample_tiles(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p, DF,
-                                   pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
-  launches += pl.host.tiles.empty() ? 0 : 1;
+  CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
+                                          DF, pl.host.model, pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
+  CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
+                                          pl.d_entries.p, DF, pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
+  launches += (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
   CUDA_OK(cudaEventRecord(cx.ev[2], st));
   CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
                                static_cast<uint32_t>(M), d_cov));
@@ -659,6 +707,9 @@ int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint6
     CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
                                     fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p, cap,
                                     pl->d_counters.p + 3));
+    CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles_global.p, static_cast<uint32_t>(pl->host.tiles_global.size()),
+                                    pl->d_entries.p, fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p,
+                                    cap, pl->d_counters.p + 3));
     unsigned long long counters[4];
     CUDA_OK(cudaMemcpyAsync(counters, pl->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
@@ -899,13 +950,16 @@ int pcs_flat_plan(const pcs_flat* fl, const pcs_seq_params* params, pcs_plan_inf
     validate(*params);
     HostPlan pl = make_host_plan(fl->host, *params);
     *info = pl.info;
-    for (size_t i = 0; i < pl.tiles.size() && i < cap; ++i) {
-      if (tile_id) tile_id[i] = pl.tiles[i].id;
-      if (tile_templates) tile_templates[i] = pl.tiles[i].n_templates;
-      if (tile_sample) tile_sample[i] = pl.tiles[i].sample;
-      if (tile_chr) tile_chr[i] = pl.tiles[i].chr;
-      if (tile_begin) tile_begin[i] = pl.tiles[i].begin;
-      if (tile_len) tile_len[i] = pl.tiles[i].len;
+    std::vector<pcs::Tile> both = pl.tiles;
+    both.insert(both.end(), pl.tiles_global.begin(), pl.tiles_global.end());
+    std::stable_sort(both.begin(), both.end(), [](const pcs::Tile& a, const pcs::Tile& b) { return a.n_templates > b.n_templates; });
+    for (size_t i = 0; i < both.size() && i < cap; ++i) {
+      if (tile_id) tile_id[i] = both[i].id;
+      if (tile_templates) tile_templates[i] = both[i].n_templates;
+      if (tile_sample) tile_sample[i] = both[i].sample;
+      if (tile_chr) tile_chr[i] = both[i].chr;
+      if (tile_begin) tile_begin[i] = both[i].begin;
+      if (tile_len) tile_len[i] = both[i].len;
     }
   });
 }

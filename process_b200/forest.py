@@ -18,7 +18,7 @@ from . import _abi as A
 _BASES = np.array(list("ACGT"))
 
 
-@dataclass
+@dataclass(eq=False)
 class PhylogeneticForest:
     chr_names: list
     chr_len: np.ndarray          # u32 [n_chr]
@@ -49,6 +49,7 @@ class PhylogeneticForest:
     mut_nature_mask: np.ndarray = None # u8 bit set over PCS_NATURE_*
     cause_names: list = field(default_factory=list)
     reference_path: str | None = None
+    leaf_attrs: dict = field(default_factory=dict)   # per sampled cell: epistate, mutant, species, birth_time
     _keep: list = field(default_factory=list, repr=False)
 
     # ------------------------------------------------------------------ sizes
