@@ -8,12 +8,20 @@ namespace pcs {
 
 // One way of drawing a haplotype for a read that starts inside a tile: the
 // haplotype leaves of one (sample group | normal cells, fragment set) list.
+// A single 32-bit draw u picks the entry (first with u <= thr) and the leaf inside
+// it: leaf = umulhi(u - base, scale), scale = floor(list_n * 2^32 / (thr - base + 1)).
 struct Entry {
-  uint32_t thr;       // cumulative selection threshold: pick first entry with u32 draw <= thr
+  uint32_t thr;       // last draw value belonging to this entry (cumulative)
+  uint32_t base;      // first draw value belonging to this entry
+  uint32_t scale;
   uint32_t list_off;  // into hap_list
-  uint32_t list_n;
   uint32_t frag_end;  // last position of the fragment the tile lies in (reads never cross it)
+  uint32_t list_n;
+  uint32_t pad0, pad1;
 };
+static_assert(sizeof(Entry) == 32, "Entry layout");
+
+constexpr uint32_t kMaxStagedEntries = 16;  // tiles drawing from more lists use the global kernel
 
 // A tile: a stretch of one piece of one chromosome for one output sample.  Every
 // template whose start falls in [begin, begin+len) is drawn by the CTA owning it.
@@ -59,7 +67,6 @@ struct SeqModel {
 // shared-memory capacities of the staged sampler kernel for one plan (maxima over its staged tiles)
 struct StageDims {
   uint32_t max_loci;
-  uint32_t max_inst;
   uint32_t max_rows;
   uint32_t max_buckets;
 };

@@ -1,11 +1,12 @@
 // kernels.cu -- sm_100a kernels of the read sampler.
 //
-//   sample_tiles_staged_kernel  the hot kernel.  One CTA per tile: the tile's sorted
-//                         locus positions, SID instances and a bucket directory are
-//                         staged in shared memory; every thread draws templates with
-//                         Philox4x32-10 (start, haplotype, insert), walks the loci its
-//                         reads span and counts depth / occurrences with shared-memory
-//                         atomics; one coalesced red.global per touched counter at the end.
+//   sample_tiles_staged_kernel  the hot kernel.  One CTA per tile: the tile's sorted loci
+//                         are staged in shared memory as 16-byte records {position,
+//                         carrier interval, SID lengths, row} next to a bucket directory;
+//                         every thread draws templates with Philox4x32-10 (one block =
+//                         two single-end reads), walks the loci its reads span and counts
+//                         depth / occurrences with shared-memory atomics; one coalesced
+//                         red.global per touched counter at the end.
 //   sample_tiles_global_kernel  same walk straight from global memory (tiles too dense
 //                         to stage) and the read-tracing debug mode.
 //   count_injected_kernel the same locus walk over a caller-supplied placement list
@@ -28,6 +29,10 @@
 namespace pcs {
 
 // ------------------------------------------------------------------- Philox
+// Philox4x32-10.  The key is (seed, constant): uniform over the launch, so the key
+// schedule runs on the uniform datapath.  The counter carries (index, tile, purpose, base).
+constexpr uint32_t kPhiloxKey1 = 0xCA11AB1Eu;
+
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
@@ -51,18 +56,17 @@ __device__ __forceinline__ float ramp(uint32_t i, uint32_t R) {
 }
 
 // is any of the `n` read bases starting at `off` a sequencing error?  One Philox
-// block per tested base, keyed by (template, mate, hit, base) so the outcome does
-// not depend on scheduling.
+// block per tested base, counter (read, tile, 1 + hit, base): the outcome does not
+// depend on scheduling.
 struct ErrDraw {
   const SeqModel& M;
-  uint2 key;
-  uint32_t tmpl, mate;
+  uint32_t read, tile;
   uint32_t* mask;  // trace mode: error bits found, else nullptr
   __device__ bool operator()(uint32_t hit, uint32_t off, uint32_t n) const {
     if (M.sequencer == PCS_SEQ_ERRORLESS) return false;
     bool any = false;
     for (uint32_t b = 0; b < n; ++b) {
-      uint4 w = philox4x32_10(make_uint4(tmpl, 1u + mate, hit, b), key);
+      uint4 w = philox4x32_10(make_uint4(read, tile, 1u + hit, b), make_uint2(M.seed, kPhiloxKey1));
       bool e;
       if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
         e = w.x < M.err_thr;
@@ -96,13 +100,25 @@ struct ErrMaskLookup {
 };
 
 // ---------------------------------------------------------------- locus walk
-// State of one read of R bases from haplotype h: next reference position q,
-// bases still to place, carried SIDs met so far.
+// One read of R bases from haplotype h.  (q, rem): next reference position and
+// bases still to place as of the last carried indel; between indels the read
+// advances one reference base per read base, so the state need not be touched
+// at loci that carry nothing or an SNV.  stop = first position the read cannot reach.
 struct Walk {
-  uint32_t q, rem, hit;
+  uint32_t q, rem, stop, hit;
+  __device__ __forceinline__ void init(uint32_t x, uint32_t R, uint32_t frag_end) {
+    q = x;
+    rem = R;
+    hit = 0;
+    stop = min(x + R, frag_end + 1u);
+  }
 };
 
-// where the walk reads loci from / counts into
+// a locus as the walk sees it: one SID instance inline (the common case) or a list
+struct Locus {
+  uint32_t p, lo, span, lens, row, k0, n_multi;
+};
+
 struct GlobalView {
   const uint32_t* pos;       // locus_pos
   const uint32_t* ioff;      // locus_inst_off
@@ -110,60 +126,100 @@ struct GlobalView {
   uint32_t* depth;           // [L] of the sample (nullptr: trace mode)
   uint32_t* alt;             // [M] of the sample
   __device__ __forceinline__ uint32_t position(uint32_t i) const { return __ldg(pos + i); }
-  __device__ __forceinline__ uint32_t inst_begin(uint32_t i) const { return __ldg(ioff + i); }
-  __device__ __forceinline__ uint32_t inst_end(uint32_t i) const { return __ldg(ioff + i + 1); }
+  __device__ __forceinline__ void load(uint32_t i, uint32_t p, Locus& L) const {
+    L.p = p;
+    L.k0 = __ldg(ioff + i);
+    const uint32_t n = __ldg(ioff + i + 1) - L.k0;
+    L.span = 0;
+    L.n_multi = n;
+    if (n == 1) {
+      const uint4 in = __ldg(inst + L.k0);
+      L.lo = in.x; L.span = in.y; L.row = in.z; L.lens = in.w; L.n_multi = 0;
+    }
+  }
   __device__ __forceinline__ uint4 instance(uint32_t k) const { return __ldg(inst + k); }
   __device__ __forceinline__ void add_depth(uint32_t i) const { if (depth) atomicAdd(depth + i, 1u); }
   __device__ __forceinline__ void add_alt(uint32_t row) const { if (alt) atomicAdd(alt + row, 1u); }
+  __device__ __forceinline__ void add_alt_abs(uint32_t row) const { add_alt(row); }
 };
 
+// staged record: x = position, y = lo, z = span, w = ref_len | alt_len << 8 | relative row << 16;
+// z == 0: no inline instance, y = first instance (absolute index), w = how many
 struct SharedView {
-  const uint32_t* pos;   // [n] staged positions
-  const uint32_t* ioff;  // [n+1] instance offsets relative to the tile's first instance
-  const uint4* inst;     // staged instances; .z is the row relative to the tile's first row
+  const uint4* rec;      // [n]
+  const uint4* inst;     // global instances, for the rare multi-instance loci
   uint32_t* depth;       // [n]
   uint32_t* alt;         // [rows]
-  __device__ __forceinline__ uint32_t position(uint32_t i) const { return pos[i]; }
-  __device__ __forceinline__ uint32_t inst_begin(uint32_t i) const { return ioff[i]; }
-  __device__ __forceinline__ uint32_t inst_end(uint32_t i) const { return ioff[i + 1]; }
-  __device__ __forceinline__ uint4 instance(uint32_t k) const { return inst[k]; }
+  uint32_t r0;
   __device__ __forceinline__ void add_depth(uint32_t i) const { atomicAdd(depth + i, 1u); }
   __device__ __forceinline__ void add_alt(uint32_t row) const { atomicAdd(alt + row, 1u); }
+  __device__ __forceinline__ void add_alt_abs(uint32_t row) const { atomicAdd(alt + (row - r0), 1u); }
+  __device__ __forceinline__ uint4 instance(uint32_t k) const { return __ldg(inst + k); }
 };
 
-// Walk loci [i, end) of view V.  Returns the index it stopped at: `end` means the
-// view ran out before the read did (the caller may continue in another view).
+// a carried SID at position p: count it unless a sequencing error hides it, then let an
+// indel move the read's frame.  Returns false when the read is used up.
 template <class View, class Err>
-__device__ __forceinline__ uint32_t walk_loci(const View& V, uint32_t i, uint32_t end, uint32_t h, uint32_t R,
-                                              uint32_t frag_end, Walk& w, const Err& err, bool& done) {
-  done = true;
+__device__ __forceinline__ bool carried_sid(const View& V, uint32_t p, uint32_t lens, uint32_t row, bool abs_row,
+                                            uint32_t R, uint32_t frag_end, Walk& w, const Err& err) {
+  const uint32_t ref_len = lens & 0xffu, alt_len = (lens >> 8) & 0xffu;
+  const uint32_t rem_p = w.rem - (p - w.q);  // bases left when the read reaches p (>= 1)
+  const uint32_t consumed = min(alt_len, rem_p);
+  if (!err(w.hit, R - rem_p, consumed)) {
+    if (abs_row) V.add_alt_abs(row); else V.add_alt(row);
+  }
+  ++w.hit;
+  if (ref_len != 1u || alt_len != 1u) {
+    w.rem = rem_p - consumed;
+    w.q = p + ref_len;
+    w.stop = min(w.q + w.rem, frag_end + 1u);
+    return w.rem != 0;
+  }
+  return true;
+}
+
+// Walk loci [i, end) of the global arrays.  Returns false if the view ran out
+// before the read did.
+template <class Err>
+__device__ __forceinline__ bool walk_global(const GlobalView& V, uint32_t i, uint32_t end, uint32_t h, uint32_t R,
+                                            uint32_t frag_end, Walk& w, const Err& err) {
   for (; i < end; ++i) {
     const uint32_t p = V.position(i);
-    if (p > frag_end) return i;
+    if (p >= w.stop) return true;
     if (p < w.q) continue;  // inside the reference bases a carried SID replaced
-    const uint32_t gap = p - w.q;
-    if (gap >= w.rem) return i;
-    w.rem -= gap;
-    w.q = p;
     V.add_depth(i);
-    const uint32_t k1 = V.inst_end(i);
-    for (uint32_t k = V.inst_begin(i); k < k1; ++k) {
-      const uint4 in = V.instance(k);
-      if (h - in.x < in.y) {
-        const uint32_t ref_len = in.w & 0xffu, alt_len = (in.w >> 8) & 0xffu;
-        const uint32_t consumed = min(alt_len, w.rem);
-        if (!err(w.hit, R - w.rem, consumed)) V.add_alt(in.z);
-        ++w.hit;
-        if (ref_len != 1u || alt_len != 1u) {
-          w.rem -= consumed;
-          w.q = p + ref_len;
-        }
+    Locus L;
+    V.load(i, p, L);
+    if (L.span != 0) {
+      if (h - L.lo < L.span && !carried_sid(V, p, L.lens, L.row, false, R, frag_end, w, err)) return true;
+    } else {
+      for (uint32_t k = L.k0; k < L.k0 + L.n_multi; ++k) {
+        const uint4 in = V.instance(k);
+        if (h - in.x < in.y && !carried_sid(V, p, in.w, in.z, false, R, frag_end, w, err)) return true;
       }
     }
-    if (w.rem == 0) return i;
   }
-  done = false;
-  return end;
+  return false;
+}
+
+template <class Err>
+__device__ __forceinline__ bool walk_shared(const SharedView& V, uint32_t i, uint32_t end, uint32_t h, uint32_t R,
+                                            uint32_t frag_end, Walk& w, const Err& err) {
+  for (; i < end; ++i) {
+    const uint4 r = V.rec[i];
+    if (r.x >= w.stop) return true;
+    if (r.x < w.q) continue;
+    V.add_depth(i);
+    if (r.z != 0) {
+      if (h - r.y < r.z && !carried_sid(V, r.x, r.w & 0xffffu, r.w >> 16, false, R, frag_end, w, err)) return true;
+    } else {
+      for (uint32_t k = r.y; k < r.y + r.w; ++k) {
+        const uint4 in = V.instance(k);
+        if (h - in.x < in.y && !carried_sid(V, r.x, in.w, in.z, true, R, frag_end, w, err)) return true;
+      }
+    }
+  }
+  return false;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_pos(const uint32_t* pos, uint32_t lo, uint32_t hi, uint32_t x) {
@@ -174,34 +230,33 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const uint32_t* pos, uint32_
   return lo;
 }
 
-// draw of one template: start, haplotype, insert; false if it falls off its molecule
+// ------------------------------------------------------------ template draws
+// Single-end: Philox block j of a tile yields templates 2j and 2j+1 (two words
+// each: start, haplotype).  Paired-end: block j yields template j (start,
+// haplotype, insert).
 struct Template {
   uint32_t x, h, ins, frag_end;
 };
 
-template <bool PAIRED>
-__device__ __forceinline__ bool draw_template(const Tile& T, const Entry* __restrict__ ent, const DevForest& F,
-                                              const SeqModel& M, uint2 key, uint32_t t, Template& out) {
-  const uint4 w = philox4x32_10(make_uint4(t, 0u, 0u, 0u), key);
-  out.x = T.begin + __umulhi(w.x, T.len);
+template <class EntryPtr>
+__device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const DevForest& F, uint32_t u_start, uint32_t u_hap,
+                                      uint32_t tlen, Template& out) {
+  out.x = T.begin + __umulhi(u_start, T.len);
   uint32_t e = 0;
-  while (e + 1 < T.n_entries && w.y > ent[e].thr) ++e;
-  const Entry E = ent[e];
-  out.h = __ldg(F.hap_list + E.list_off + __umulhi(w.z, E.list_n));
-  out.frag_end = E.frag_end;
-  out.ins = 0;
-  uint32_t tlen = M.read_size;
-  if (PAIRED) {
-    uint32_t lo = 0, hi = M.insert_n - 1;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (w.w > __ldg(M.insert_cdf + mid)) lo = mid + 1; else hi = mid;
-    }
-    out.ins = M.insert_min + lo;
-    tlen = 2u * M.read_size + out.ins;
+  while (u_hap > ent[e].thr) ++e;  // the last entry's thr is 0xffffffff
+  const uint32_t leaf = __umulhi(u_hap - ent[e].base, ent[e].scale);
+  out.h = __ldg(F.hap_list + ent[e].list_off + leaf);
+  out.frag_end = ent[e].frag_end;
+  return out.x + (tlen - 1u) <= out.frag_end;  // else the template falls off its molecule
+}
+
+__device__ __forceinline__ uint32_t draw_insert(const SeqModel& M, uint32_t u) {
+  uint32_t lo = 0, hi = M.insert_n - 1;
+  while (lo < hi) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (u > __ldg(M.insert_cdf + mid)) lo = mid + 1; else hi = mid;
   }
-  // 64-bit: x + tlen may pass 2^32 only for absurd inputs, but stay exact
-  return static_cast<uint64_t>(out.x) + tlen - 1 <= E.frag_end;
+  return M.insert_min + lo;
 }
 
 __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* dst) {
@@ -219,40 +274,74 @@ __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* ds
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
 
+struct StagedTile {
+  SharedView SV;
+  const uint16_t* dir;
+  uint32_t n, shift, stage_end, chr_l1;
+};
+
+// one read through the staged loci (and past them, if a carried deletion stretches it that far)
+template <bool ERRORS>
+__device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
+                                            uint32_t* depth, uint32_t* alt, uint32_t read_id, uint32_t xs, uint32_t h,
+                                            uint32_t frag_end) {
+  const uint32_t R = M.read_size;
+  Walk w;
+  w.init(xs, R, frag_end);
+  const uint32_t i = S.dir[(xs - T.begin) >> S.shift];
+  bool done;
+  if (ERRORS) {
+    const ErrDraw err{M, read_id, T.id, nullptr};
+    done = walk_shared(S.SV, i, S.n, h, R, frag_end, w, err);
+    if (!done && w.stop > S.stage_end && T.l1 < S.chr_l1) {
+      const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
+                          alt + static_cast<size_t>(T.sample) * F.n_mut};
+      walk_global(GV, T.l1, S.chr_l1, h, R, frag_end, w, err);
+    }
+  } else {
+    const NoErr err;
+    done = walk_shared(S.SV, i, S.n, h, R, frag_end, w, err);
+    if (!done && w.stop > S.stage_end && T.l1 < S.chr_l1) {
+      const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
+                          alt + static_cast<size_t>(T.sample) * F.n_mut};
+      walk_global(GV, T.l1, S.chr_l1, h, R, frag_end, w, err);
+    }
+  }
+}
+
 template <bool PAIRED, bool ERRORS>
 __global__ void __launch_bounds__(kStagedThreads, 4)
 sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
                            StageDims D, uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
                            unsigned long long* __restrict__ n_reads) {
   extern __shared__ __align__(16) unsigned char smem[];
-  uint4* s_inst = reinterpret_cast<uint4*>(smem);
-  uint32_t* s_pos = reinterpret_cast<uint32_t*>(s_inst + D.max_inst);
-  uint32_t* s_ioff = s_pos + D.max_loci;
-  uint32_t* s_depth = s_ioff + D.max_loci + 1;
+  uint4* s_rec = reinterpret_cast<uint4*>(smem);
+  uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_rec + D.max_loci);
   uint32_t* s_alt = s_depth + D.max_loci;
   uint16_t* s_dir = reinterpret_cast<uint16_t*>(s_alt + D.max_rows);
-  __shared__ Entry s_ent[8];
+  __shared__ Entry s_ent[kMaxStagedEntries];
 
   const Tile T = tiles[blockIdx.x];
   const uint32_t n = T.l1 - T.l0;
-  const uint32_t i0 = __ldg(F.locus_inst_off + T.l0);
-  const uint32_t n_inst = __ldg(F.locus_inst_off + T.l1) - i0;
   const uint32_t shift = M.dir_shift;
   const uint32_t n_buckets = ((T.len + M.reach) >> shift) + 1;
 
-  // ---- stage the tile
+  // ---- stage the tile: locus records, zeroed counters, entries
   for (uint32_t i = threadIdx.x; i < n; i += kStagedThreads) {
-    s_pos[i] = __ldg(F.locus_pos + T.l0 + i);
+    const uint32_t l = T.l0 + i;
+    const uint32_t k0 = __ldg(F.locus_inst_off + l), k1 = __ldg(F.locus_inst_off + l + 1);
+    uint4 r = make_uint4(__ldg(F.locus_pos + l), k0, 0u, k1 - k0);
+    if (k1 - k0 == 1u) {
+      const uint4 in = __ldg(F.inst + k0);
+      r.y = in.x;
+      r.z = in.y;
+      r.w = (in.w & 0xffffu) | ((in.z - T.r0) << 16);
+    }
+    s_rec[i] = r;
     s_depth[i] = 0;
   }
-  for (uint32_t i = threadIdx.x; i <= n; i += kStagedThreads) s_ioff[i] = __ldg(F.locus_inst_off + T.l0 + i) - i0;
-  for (uint32_t k = threadIdx.x; k < n_inst; k += kStagedThreads) {
-    uint4 in = __ldg(F.inst + i0 + k);
-    in.z -= T.r0;
-    s_inst[k] = in;
-  }
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
-  if (threadIdx.x < T.n_entries && threadIdx.x < 8) s_ent[threadIdx.x] = entries[T.entry_off + threadIdx.x];
+  if (threadIdx.x < T.n_entries) s_ent[threadIdx.x] = entries[T.entry_off + threadIdx.x];
   __syncthreads();
   // directory: first staged locus at or after the start of each bucket
   for (uint32_t b = threadIdx.x; b < n_buckets; b += kStagedThreads) {
@@ -260,49 +349,47 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     uint32_t lo = 0, hi = n;
     while (lo < hi) {
       uint32_t mid = (lo + hi) >> 1;
-      if (s_pos[mid] < x) lo = mid + 1; else hi = mid;
+      if (s_rec[mid].x < x) lo = mid + 1; else hi = mid;
     }
     s_dir[b] = static_cast<uint16_t>(lo);
   }
   __syncthreads();
 
-  const SharedView SV{s_pos, s_ioff, s_inst, s_depth, s_alt};
-  const uint32_t chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
-  const uint2 key = make_uint2(M.seed, T.id);
+  StagedTile S;
+  S.SV = SharedView{s_rec, F.inst, s_depth, s_alt, T.r0};
+  S.dir = s_dir;
+  S.n = n;
+  S.shift = shift;
+  S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
+  S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
+  const uint2 key = make_uint2(M.seed, kPhiloxKey1);
   const uint32_t R = M.read_size;
-  const uint32_t stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
-  const Entry* ent = T.n_entries <= 8 ? s_ent : entries + T.entry_off;
   uint32_t placed = 0;
 
-  for (uint32_t t = threadIdx.x; t < T.n_templates; t += kStagedThreads) {
-    Template tp;
-    if (!draw_template<PAIRED>(T, ent, F, M, key, t, tp)) continue;
-#pragma unroll
-    for (uint32_t mate = 0; mate < (PAIRED ? 2u : 1u); ++mate) {
-      const uint32_t xs = mate == 0 ? tp.x : tp.x + R + tp.ins;
-      uint32_t i = s_dir[(xs - T.begin) >> shift];
-      while (i < n && s_pos[i] < xs) ++i;
-      Walk w{xs, R, 0u};
-      bool done;
-      if (ERRORS) {
-        const ErrDraw err{M, key, t, mate, nullptr};
-        i = walk_loci(SV, i, n, tp.h, R, tp.frag_end, w, err, done);
-        if (!done && T.l1 < chr_l1 && w.q + w.rem > stage_end) {  // a carried deletion stretched the read past the staged loci
-          const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
-                              alt + static_cast<size_t>(T.sample) * F.n_mut};
-          walk_loci(GV, T.l1, chr_l1, tp.h, R, tp.frag_end, w, err, done);
-        }
-      } else {
-        const NoErr err;
-        i = walk_loci(SV, i, n, tp.h, R, tp.frag_end, w, err, done);
-        if (!done && T.l1 < chr_l1 && w.q + w.rem > stage_end) {
-          const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
-                              alt + static_cast<size_t>(T.sample) * F.n_mut};
-          walk_loci(GV, T.l1, chr_l1, tp.h, R, tp.frag_end, w, err, done);
-        }
+  if (PAIRED) {
+    for (uint32_t t = threadIdx.x; t < T.n_templates; t += kStagedThreads) {
+      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, 0u), key);
+      const uint32_t ins = draw_insert(M, u.z);
+      Template tp;
+      if (!place(T, s_ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
+      staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * t, tp.x, tp.h, tp.frag_end);
+      staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * t + 1u, tp.x + R + ins, tp.h, tp.frag_end);
+      placed += 2;
+    }
+  } else {
+    const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
+    for (uint32_t j = threadIdx.x; j < n_blocks; j += kStagedThreads) {
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, 0u), key);
+      Template tp;
+      if (place(T, s_ent, F, u.x, u.y, R, tp)) {
+        staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j, tp.x, tp.h, tp.frag_end);
+        ++placed;
+      }
+      if (2u * j + 1u < T.n_templates && place(T, s_ent, F, u.z, u.w, R, tp)) {
+        staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j + 1u, tp.x, tp.h, tp.frag_end);
+        ++placed;
       }
     }
-    placed += PAIRED ? 2u : 1u;
   }
   __syncthreads();
 
@@ -322,6 +409,30 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
 
 // ------------------------------------------- global-memory sampler (fallback, trace)
 template <bool TRACE>
+__device__ __forceinline__ void global_read(const Tile& T, const DevForest& F, const SeqModel& M, const GlobalView& GV,
+                                            uint32_t chr_l1, uint32_t read_id, uint32_t xs, uint32_t h,
+                                            uint32_t frag_end, DevPlacement* trace, uint32_t* trace_masks,
+                                            unsigned long long trace_cap, unsigned long long* trace_n) {
+  uint32_t mask[PCS_ERRMASK_WORDS];
+  if (TRACE) {
+#pragma unroll
+    for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) mask[i] = 0;
+  }
+  const ErrDraw err{M, read_id, T.id, TRACE ? mask : nullptr};
+  Walk w;
+  w.init(xs, M.read_size, frag_end);
+  walk_global(GV, lower_bound_pos(F.locus_pos, T.l0, chr_l1, xs), chr_l1, h, M.read_size, frag_end, w, err);
+  if (TRACE) {
+    unsigned long long idx = atomicAdd(trace_n, 1ull);
+    if (idx < trace_cap) {
+      trace[idx] = DevPlacement{h, xs, frag_end, T.chr | (T.sample << 16)};
+      if (trace_masks)
+        for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) trace_masks[idx * PCS_ERRMASK_WORDS + i] = mask[i];
+    }
+  }
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(256)
 sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
                            uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
@@ -333,37 +444,37 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst,
                       TRACE ? nullptr : depth + static_cast<size_t>(T.sample) * F.n_loci,
                       TRACE ? nullptr : alt + static_cast<size_t>(T.sample) * F.n_mut};
-  const uint2 key = make_uint2(M.seed, T.id);
+  const uint2 key = make_uint2(M.seed, kPhiloxKey1);
   const uint32_t R = M.read_size;
-  const uint32_t mates = M.paired ? 2u : 1u;
   const Entry* ent = entries + T.entry_off;
   uint32_t placed = 0;
 
-  for (uint32_t t = threadIdx.x; t < T.n_templates; t += blockDim.x) {
-    Template tp;
-    const bool ok = M.paired ? draw_template<true>(T, ent, F, M, key, t, tp) : draw_template<false>(T, ent, F, M, key, t, tp);
-    if (!ok) continue;
-    for (uint32_t mate = 0; mate < mates; ++mate) {
-      const uint32_t xs = mate == 0 ? tp.x : tp.x + R + tp.ins;
-      uint32_t mask[PCS_ERRMASK_WORDS];
-      if (TRACE) {
-#pragma unroll
-        for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) mask[i] = 0;
+  if (M.paired) {
+    for (uint32_t t = threadIdx.x; t < T.n_templates; t += blockDim.x) {
+      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, 0u), key);
+      const uint32_t ins = draw_insert(M, u.z);
+      Template tp;
+      if (!place(T, ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
+      global_read<TRACE>(T, F, M, GV, chr_l1, 2u * t, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
+      global_read<TRACE>(T, F, M, GV, chr_l1, 2u * t + 1u, tp.x + R + ins, tp.h, tp.frag_end, trace, trace_masks,
+                         trace_cap, trace_n);
+      placed += 2;
+    }
+  } else {
+    const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
+    for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, 0u), key);
+      Template tp;
+      if (place(T, ent, F, u.x, u.y, R, tp)) {
+        global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
+        ++placed;
       }
-      const ErrDraw err{M, key, t, mate, TRACE ? mask : nullptr};
-      Walk w{xs, R, 0u};
-      bool done;
-      walk_loci(GV, lower_bound_pos(F.locus_pos, T.l0, chr_l1, xs), chr_l1, tp.h, R, tp.frag_end, w, err, done);
-      if (TRACE) {
-        unsigned long long idx = atomicAdd(trace_n, 1ull);
-        if (idx < trace_cap) {
-          trace[idx] = DevPlacement{tp.h, xs, tp.frag_end, T.chr | (T.sample << 16)};
-          if (trace_masks)
-            for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) trace_masks[idx * PCS_ERRMASK_WORDS + i] = mask[i];
-        }
+      if (2u * j + 1u < T.n_templates && place(T, ent, F, u.z, u.w, R, tp)) {
+        global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j + 1u, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap,
+                           trace_n);
+        ++placed;
       }
     }
-    placed += mates;
   }
   block_add_u64(placed, n_reads);
 }
@@ -381,9 +492,9 @@ count_injected_kernel(const DevPlacement* __restrict__ rec, const uint32_t* __re
   const ErrMaskLookup err{masks ? masks + i * PCS_ERRMASK_WORDS : nullptr};
   const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(sample) * F.n_loci,
                       alt + static_cast<size_t>(sample) * F.n_mut};
-  Walk w{p.start, R, 0u};
-  bool done;
-  walk_loci(GV, lower_bound_pos(F.locus_pos, l0, l1, p.start), l1, p.hap, R, p.frag_end, w, err, done);
+  Walk w;
+  w.init(p.start, R, p.frag_end);
+  walk_global(GV, lower_bound_pos(F.locus_pos, l0, l1, p.start), l1, p.hap, R, p.frag_end, w, err);
 }
 
 // ------------------------------------------------------------------ finalize
@@ -409,8 +520,8 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
 
 // ----------------------------------------------------------------- launchers
 size_t staged_smem_bytes(const StageDims& D) {
-  size_t b = static_cast<size_t>(D.max_inst) * sizeof(uint4);
-  b += (static_cast<size_t>(D.max_loci) * 3 + 1 + D.max_rows) * sizeof(uint32_t);
+  size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
+  b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint16_t);
   return (b + 15) & ~static_cast<size_t>(15);
 }

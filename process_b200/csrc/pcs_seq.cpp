@@ -324,12 +324,12 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
             auto it = fo.list_index.find(HostForest::list_key(samples[s].group, cv.fragset));
             if (it != fo.list_index.end() && it->second.second > 0) {
               w.push_back(purity / nT * it->second.second);
-              es.push_back({0u, it->second.first, it->second.second, cv.frag_end});
+              es.push_back(pcs::Entry{0u, 0u, 0u, it->second.first, cv.frag_end, it->second.second, 0u, 0u});
             }
           }
           if (purity < 1 && cv.fragset == F.full_fragset[c]) {
             w.push_back((1 - purity) / n_normal_cells * nit->second.second);
-            es.push_back({0u, nit->second.first, nit->second.second, cv.frag_end});
+            es.push_back(pcs::Entry{0u, 0u, 0u, nit->second.first, cv.frag_end, nit->second.second, 0u, 0u});
           }
         }
         if (es.empty()) continue;
@@ -337,9 +337,22 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
         for (double x : w) wsum += x;
         std::vector<uint32_t> thr = thresholds(w);
         const uint32_t entry_off = static_cast<uint32_t>(entries.size());
-        for (size_t i = 0; i < es.size(); ++i) {
-          es[i].thr = thr[i];
-          entries.push_back(es[i]);
+        {
+          // entries whose share of the draw range is empty can never be picked: drop them
+          std::vector<pcs::Entry> kept;
+          uint64_t base = 0;
+          for (size_t i = 0; i < es.size(); ++i) {
+            if (static_cast<uint64_t>(thr[i]) + 1 <= base) continue;
+            const uint64_t width = static_cast<uint64_t>(thr[i]) + 1 - base;
+            es[i].thr = thr[i];
+            es[i].base = static_cast<uint32_t>(base);
+            // leaf = umulhi(u - base, scale) < list_n
+            es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es[i].list_n) << 32) / width));
+            kept.push_back(es[i]);
+            base = static_cast<uint64_t>(thr[i]) + 1;
+          }
+          es.swap(kept);
+          for (const auto& e : es) entries.push_back(e);
         }
         const uint32_t* lp = F.locus_pos.data();
         const uint32_t* c_lo = lp + F.chr_locus_off[c];
@@ -395,14 +408,12 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   uint32_t dir_shift = 5;
   while ((((static_cast<uint64_t>(W) + reach) >> dir_shift) + 1) > 4096) ++dir_shift;
   auto stageable = [&](const pcs::Tile& t) {
-    const uint32_t n_inst = F.locus_inst_off[t.l1] - F.locus_inst_off[t.l0];
-    return lcap > 0 && t.l1 - t.l0 <= lcap && n_inst <= 2 * lcap && t.n_rows <= 2 * lcap;
+    return lcap > 0 && t.l1 - t.l0 <= lcap && t.n_rows <= 2 * lcap && t.n_entries <= pcs::kMaxStagedEntries;
   };
   auto take = [&](const pcs::Tile& t) {
     if (stageable(t)) {
       pl.tiles.push_back(t);
       pl.dims.max_loci = std::max(pl.dims.max_loci, t.l1 - t.l0);
-      pl.dims.max_inst = std::max(pl.dims.max_inst, F.locus_inst_off[t.l1] - F.locus_inst_off[t.l0]);
       pl.dims.max_rows = std::max(pl.dims.max_rows, t.n_rows);
       pl.dims.max_buckets = std::max<uint32_t>(pl.dims.max_buckets, static_cast<uint32_t>(((t.len + reach) >> dir_shift) + 1));
     } else {
@@ -428,7 +439,6 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   }
   // round the capacities so that plans of similar forests share one shared-memory footprint
   pl.dims.max_loci = (pl.dims.max_loci + 63) & ~63u;
-  pl.dims.max_inst = (pl.dims.max_inst + 63) & ~63u;
   pl.dims.max_rows = (pl.dims.max_rows + 63) & ~63u;
   pl.dims.max_buckets = (pl.dims.max_buckets + 63) & ~63u;
 
