@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "../../include/pcs_seq.h"
 #include "dev.hpp"
@@ -29,12 +30,15 @@
 namespace pcs {
 
 // ------------------------------------------------------------------- Philox
-// Philox4x32-10.  The key is (seed, constant): uniform over the launch, so the key
-// schedule runs on the uniform datapath.  The counter carries (index, tile, purpose, base).
-constexpr uint32_t kPhiloxKey1 = 0xCA11AB1Eu;
+// Philox4x32-10 as a keyed bijection of its 128-bit counter.  The key is a
+// compile-time constant, so the ten round keys fold into immediates; everything
+// that varies -- (index, tile, purpose, seed) -- rides in the counter, and distinct
+// tuples are distinct counters.
+constexpr uint32_t kPhiloxKey0 = 0x5EEDC0DEu, kPhiloxKey1 = 0xCA11AB1Eu;
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c) {
   constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint2 k = make_uint2(kPhiloxKey0, kPhiloxKey1);
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
@@ -56,8 +60,8 @@ __device__ __forceinline__ float ramp(uint32_t i, uint32_t R) {
 }
 
 // is any of the `n` read bases starting at `off` a sequencing error?  One Philox
-// block per tested base, counter (read, tile, 1 + hit, base): the outcome does not
-// depend on scheduling.
+// block per tested base, counter (read, tile, (1 + hit) | base << 20, seed): the
+// outcome does not depend on scheduling.
 struct ErrDraw {
   const SeqModel& M;
   uint32_t read, tile;
@@ -66,7 +70,7 @@ struct ErrDraw {
     if (M.sequencer == PCS_SEQ_ERRORLESS) return false;
     bool any = false;
     for (uint32_t b = 0; b < n; ++b) {
-      uint4 w = philox4x32_10(make_uint4(read, tile, 1u + hit, b), make_uint2(M.seed, kPhiloxKey1));
+      uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), M.seed));
       bool e;
       if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
         e = w.x < M.err_thr;
@@ -145,15 +149,26 @@ struct GlobalView {
 
 // staged record: x = position, y = lo, z = span, w = ref_len | alt_len << 8 | relative row << 16;
 // z == 0: no inline instance, y = first instance (absolute index), w = how many
+// The three arrays are addressed with 32-bit shared-window addresses computed once
+// per CTA (ld.shared / red.shared on a register address).
 struct SharedView {
-  const uint4* rec;      // [n]
+  uint32_t rec;          // shared address of uint4 [n]
+  uint32_t depth;        // shared address of uint32 [n]
+  uint32_t alt;          // shared address of uint32 [rows]
   const uint4* inst;     // global instances, for the rare multi-instance loci
-  uint32_t* depth;       // [n]
-  uint32_t* alt;         // [rows]
   uint32_t r0;
-  __device__ __forceinline__ void add_depth(uint32_t i) const { atomicAdd(depth + i, 1u); }
-  __device__ __forceinline__ void add_alt(uint32_t row) const { atomicAdd(alt + row, 1u); }
-  __device__ __forceinline__ void add_alt_abs(uint32_t row) const { atomicAdd(alt + (row - r0), 1u); }
+  __device__ __forceinline__ uint4 record(uint32_t i) const {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(rec + i * 16u));
+    return r;
+  }
+  __device__ __forceinline__ void add_depth(uint32_t i) const {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(depth + i * 4u) : "memory");
+  }
+  __device__ __forceinline__ void add_alt(uint32_t row) const {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(alt + row * 4u) : "memory");
+  }
+  __device__ __forceinline__ void add_alt_abs(uint32_t row) const { add_alt(row - r0); }
   __device__ __forceinline__ uint4 instance(uint32_t k) const { return __ldg(inst + k); }
 };
 
@@ -169,7 +184,7 @@ __device__ __forceinline__ bool carried_sid(const View& V, uint32_t p, uint32_t 
     if (abs_row) V.add_alt_abs(row); else V.add_alt(row);
   }
   ++w.hit;
-  if (ref_len != 1u || alt_len != 1u) {
+  if ((lens & 0xffffu) != 0x0101u) {
     w.rem = rem_p - consumed;
     w.q = p + ref_len;
     w.stop = min(w.q + w.rem, frag_end + 1u);
@@ -206,7 +221,7 @@ template <class Err>
 __device__ __forceinline__ bool walk_shared(const SharedView& V, uint32_t i, uint32_t end, uint32_t h, uint32_t R,
                                             uint32_t frag_end, Walk& w, const Err& err) {
   for (; i < end; ++i) {
-    const uint4 r = V.rec[i];
+    const uint4 r = V.record(i);
     if (r.x >= w.stop) return true;
     if (r.x < w.q) continue;
     V.add_depth(i);
@@ -273,11 +288,17 @@ __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* ds
 
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
+constexpr int kDefaultMinCtas = 4;
 
 struct StagedTile {
   SharedView SV;
-  const uint16_t* dir;
+  uint32_t dir;  // shared address of uint16 [buckets]
   uint32_t n, shift, stage_end, chr_l1;
+  __device__ __forceinline__ uint32_t first_locus(uint32_t bucket) const {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(dir + bucket * 2u));
+    return v;
+  }
 };
 
 // one read through the staged loci (and past them, if a carried deletion stretches it that far)
@@ -288,7 +309,7 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   const uint32_t R = M.read_size;
   Walk w;
   w.init(xs, R, frag_end);
-  const uint32_t i = S.dir[(xs - T.begin) >> S.shift];
+  const uint32_t i = S.first_locus((xs - T.begin) >> S.shift);
   bool done;
   if (ERRORS) {
     const ErrDraw err{M, read_id, T.id, nullptr};
@@ -309,8 +330,8 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   }
 }
 
-template <bool PAIRED, bool ERRORS>
-__global__ void __launch_bounds__(kStagedThreads, 4)
+template <bool PAIRED, bool ERRORS, int MIN_CTAS>
+__global__ void __launch_bounds__(kStagedThreads, MIN_CTAS)
 sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
                            StageDims D, uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
                            unsigned long long* __restrict__ n_reads) {
@@ -356,19 +377,20 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   __syncthreads();
 
   StagedTile S;
-  S.SV = SharedView{s_rec, F.inst, s_depth, s_alt, T.r0};
-  S.dir = s_dir;
+  S.SV = SharedView{static_cast<uint32_t>(__cvta_generic_to_shared(s_rec)),
+                    static_cast<uint32_t>(__cvta_generic_to_shared(s_depth)),
+                    static_cast<uint32_t>(__cvta_generic_to_shared(s_alt)), F.inst, T.r0};
+  S.dir = static_cast<uint32_t>(__cvta_generic_to_shared(s_dir));
   S.n = n;
   S.shift = shift;
   S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
   S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
-  const uint2 key = make_uint2(M.seed, kPhiloxKey1);
   const uint32_t R = M.read_size;
   uint32_t placed = 0;
 
   if (PAIRED) {
     for (uint32_t t = threadIdx.x; t < T.n_templates; t += kStagedThreads) {
-      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, 0u), key);
+      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, M.seed));
       const uint32_t ins = draw_insert(M, u.z);
       Template tp;
       if (!place(T, s_ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
@@ -379,15 +401,15 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   } else {
     const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
     for (uint32_t j = threadIdx.x; j < n_blocks; j += kStagedThreads) {
-      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, 0u), key);
-      Template tp;
-      if (place(T, s_ent, F, u.x, u.y, R, tp)) {
-        staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j, tp.x, tp.h, tp.frag_end);
-        ++placed;
-      }
-      if (2u * j + 1u < T.n_templates && place(T, s_ent, F, u.z, u.w, R, tp)) {
-        staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j + 1u, tp.x, tp.h, tp.frag_end);
-        ++placed;
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+      const uint32_t n_here = 2u * j + 1u < T.n_templates ? 2u : 1u;
+#pragma unroll 1
+      for (uint32_t k = 0; k < n_here; ++k) {
+        Template tp;
+        if (place(T, s_ent, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) {
+          staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j + k, tp.x, tp.h, tp.frag_end);
+          ++placed;
+        }
       }
     }
   }
@@ -444,14 +466,13 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst,
                       TRACE ? nullptr : depth + static_cast<size_t>(T.sample) * F.n_loci,
                       TRACE ? nullptr : alt + static_cast<size_t>(T.sample) * F.n_mut};
-  const uint2 key = make_uint2(M.seed, kPhiloxKey1);
   const uint32_t R = M.read_size;
   const Entry* ent = entries + T.entry_off;
   uint32_t placed = 0;
 
   if (M.paired) {
     for (uint32_t t = threadIdx.x; t < T.n_templates; t += blockDim.x) {
-      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, 0u), key);
+      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, M.seed));
       const uint32_t ins = draw_insert(M, u.z);
       Template tp;
       if (!place(T, ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
@@ -463,7 +484,7 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   } else {
     const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
     for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
-      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, 0u), key);
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
       Template tp;
       if (place(T, ent, F, u.x, u.y, R, tp)) {
         global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
@@ -526,16 +547,38 @@ size_t staged_smem_bytes(const StageDims& D) {
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
-template <bool PAIRED, bool ERRORS>
-static cudaError_t launch_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                 const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
-                                 uint32_t* alt, unsigned long long* n_reads) {
+static int staged_min_ctas() {
+  static const int v = [] {
+    const char* s = std::getenv("PCS_MIN_CTAS");
+    const int x = s ? std::atoi(s) : 0;
+    return (x >= 3 && x <= 8) ? x : kDefaultMinCtas;
+  }();
+  return v;
+}
+
+template <bool PAIRED, bool ERRORS, int MIN_CTAS>
+static cudaError_t launch_staged_occ(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                     const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                     uint32_t* alt, unsigned long long* n_reads) {
   const size_t smem = staged_smem_bytes(D);
-  auto kern = sample_tiles_staged_kernel<PAIRED, ERRORS>;
+  auto kern = sample_tiles_staged_kernel<PAIRED, ERRORS, MIN_CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
   kern<<<n_tiles, kStagedThreads, smem, st>>>(tiles, entries, F, M, D, depth, alt, n_reads);
   return cudaGetLastError();
+}
+
+template <bool PAIRED, bool ERRORS>
+static cudaError_t launch_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                 const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                 uint32_t* alt, unsigned long long* n_reads) {
+  switch (staged_min_ctas()) {
+    case 3: return launch_staged_occ<PAIRED, ERRORS, 3>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    case 5: return launch_staged_occ<PAIRED, ERRORS, 5>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    case 6: return launch_staged_occ<PAIRED, ERRORS, 6>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    case 8: return launch_staged_occ<PAIRED, ERRORS, 8>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    default: return launch_staged_occ<PAIRED, ERRORS, 4>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+  }
 }
 
 cudaError_t launch_sample_tiles_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
