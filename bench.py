@@ -192,7 +192,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    stream = torch.cuda.current_stream()
+    # one explicit stream for everything: the library launches on it, torch events are recorded on it and
+    # NCCL orders its collectives against it (torch's default stream has handle 0, which pcs_create reads
+    # as "make your own stream" -- that would leave the sampler and the all_reduce unordered)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = L.Context(local, stream.cuda_stream)
     dev = L.Forest(ctx, forest)
     P = make_params(shard_rank=rank, shard_count=world, **wl_params)
@@ -231,6 +236,11 @@ def main():
         dist.all_reduce(reads, op=dist.ReduceOp.SUM)
     total_ms = float(ms.item())
     total_reads = float(reads.item())
+    # the reduced tables must hold exactly what the ranks counted
+    want = torch.tensor([float(stats[-1].sum_occurrences)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+    tables_ok = bool(int(occ.sum(dtype=torch.int64).item()) == int(want.item()))
     clk = clocks.stop(t0, t1) if clocks else None
     R = plan.info.read_size
     value = total_reads * R / (total_ms * 1e-3) / 1e9
@@ -246,7 +256,7 @@ def main():
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic["dram_bytes_per_launch"] if traffic else None, "peak_source": peak_src,
-                "kernel": "pcs::sample_tiles_kernel", "kernel_ms": kernel_ms, "reads_per_launch": int(st.n_reads),
+                "kernel": "pcs::sample_tiles_staged_kernel", "kernel_ms": kernel_ms, "reads_per_launch": int(st.n_reads),
                 "bytes_per_read": b_read, "k_bar": kbar, "k_alt": kalt,
                 "algorithmic_bytes_per_launch": st.n_reads * b_read}
 
@@ -311,6 +321,7 @@ def main():
                              "count tables re-zeroed every step; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+            "checks": {"reduced_tables_equal_sum_of_rank_counts": tables_ok},
             "clocks": clk,
         }
         print(json.dumps(line))

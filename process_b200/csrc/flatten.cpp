@@ -10,6 +10,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <thread>
 #include <unordered_map>
@@ -246,7 +249,21 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
 
 }  // namespace
 
+namespace {
+struct PhaseTimer {
+  bool on = std::getenv("PCS_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[pcs flatten] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads) {
+  PhaseTimer timer;
   check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
   check(d.n_nodes >= 1, "the forest has no nodes");
   out = FlatForest{};
@@ -287,6 +304,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     t.node_leaf[d.leaf_node[l]] = l;
   }
 
+  timer.lap("cell tree");
   // ---- mutation table -> loci
   out.chr_locus_off.assign(d.n_chr + 1, 0);
   out.row_locus.resize(d.n_mut);
@@ -311,6 +329,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   out.locus_first_row.assign(out.locus_pos.size() + 1, d.n_mut);
   for (uint32_t m = d.n_mut; m-- > 0;) out.locus_first_row[out.row_locus[m]] = m;
 
+  timer.lap("loci");
   // ---- events by chromosome (node-major order is preserved)
   std::vector<ChrWork> work(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) {
@@ -340,6 +359,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     germ[d.mut_chr[d.germ_mut[i]]].emplace_back(d.germ_mut[i], d.germ_allele_mask[i]);
   }
 
+  timer.lap("events by chromosome");
   // ---- per-chromosome haplotype numbering, chromosomes in parallel
   std::atomic<uint32_t> next{0};
   auto run = [&]() {
@@ -365,6 +385,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   for (auto& w : work)
     if (!w.error.empty()) throw std::domain_error(w.error);
 
+  timer.lap("haplotype numbering");
   // ---- merge
   out.chr_haps.resize(d.n_chr);
   out.full_fragset.resize(d.n_chr);
@@ -414,11 +435,13 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     out.chr_piece_off[c + 1] = static_cast<uint32_t>(out.pieces.size());
   }
 
+  timer.lap("merge + pieces");
   // ---- instances are sorted by row inside a chromosome and rows are chromosome-major
   const uint32_t L = static_cast<uint32_t>(out.locus_pos.size());
   out.locus_inst_off.assign(L + 1, 0);
   for (const auto& in : out.inst) ++out.locus_inst_off[out.row_locus[in.row] + 1];
   for (uint32_t l = 0; l < L; ++l) out.locus_inst_off[l + 1] += out.locus_inst_off[l];
+  timer.lap("instance offsets");
 }
 
 }  // namespace pcs
