@@ -289,10 +289,35 @@ __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* ds
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
 constexpr int kDefaultMinCtas = 4;
+constexpr uint32_t kQueueSlots = 64;  // per warp: < 32 waiting + <= 32 pushed in one go
+
+// hide where a shared-window address came from, so the compiler keeps it in a register
+// instead of rebuilding it from SR_CgaCtaId inside every loop
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+  return v;
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
+  return r;
+}
 
 struct StagedTile {
   SharedView SV;
-  uint32_t dir;  // shared address of uint16 [buckets]
+  uint32_t dir;    // shared address of uint16 [buckets]
+  uint32_t ent;    // shared address of the tile's entries (32 bytes each)
   uint32_t n, shift, stage_end, chr_l1;
   __device__ __forceinline__ uint32_t first_locus(uint32_t bucket) const {
     uint16_t v;
@@ -301,15 +326,31 @@ struct StagedTile {
   }
 };
 
-// one read through the staged loci (and past them, if a carried deletion stretches it that far)
+// start and haplotype of one template from two 32-bit draws; entries read from shared memory
+__device__ __forceinline__ bool place_staged(const StagedTile& S, const Tile& T, const DevForest& F, uint32_t u_start,
+                                             uint32_t u_hap, uint32_t tlen, uint32_t& x, uint32_t& h, uint32_t& e,
+                                             uint32_t& frag_end) {
+  x = T.begin + __umulhi(u_start, T.len);
+  e = 0;
+  uint4 a = lds128(S.ent);
+  while (u_hap > a.x) {  // the last entry's thr is 0xffffffff
+    ++e;
+    a = lds128(S.ent + e * 32u);
+  }
+  h = __ldg(F.hap_list + a.w + __umulhi(u_hap - a.y, a.z));
+  frag_end = lds32(S.ent + e * 32u + 16u);
+  return x + (tlen - 1u) <= frag_end;  // else the template falls off its molecule
+}
+
+// one queued read through the staged loci (and past them, if a carried deletion stretches it that far)
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
-                                            uint32_t* depth, uint32_t* alt, uint32_t read_id, uint32_t xs, uint32_t h,
-                                            uint32_t frag_end) {
+                                            uint32_t* depth, uint32_t* alt, uint4 item) {
   const uint32_t R = M.read_size;
+  const uint32_t xs = item.x, h = item.y, read_id = item.z, i = item.w & 0xffffu;
+  const uint32_t frag_end = lds32(S.ent + (item.w >> 16) * 32u + 16u);
   Walk w;
   w.init(xs, R, frag_end);
-  const uint32_t i = S.first_locus((xs - T.begin) >> S.shift);
   bool done;
   if (ERRORS) {
     const ErrDraw err{M, read_id, T.id, nullptr};
@@ -330,6 +371,31 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   }
 }
 
+// Per-warp queue of reads that may span a locus.  Drawing and probing stay converged
+// (every lane works on its own read); the divergent part -- the walk, which four reads
+// out of five never need -- runs only when 32 reads are waiting, one per lane.
+struct HitQueue {
+  uint32_t base;  // shared address of this warp's kQueueSlots uint4 slots
+  uint32_t n;     // reads waiting (warp-uniform)
+};
+
+template <bool ERRORS>
+__device__ __forceinline__ void queue_push(HitQueue& Q, const StagedTile& S, const Tile& T, const DevForest& F,
+                                           const SeqModel& M, uint32_t* depth, uint32_t* alt, bool has, uint4 item,
+                                           uint32_t lane) {
+  const uint32_t mask = __ballot_sync(0xffffffffu, has);
+  if (mask == 0) return;
+  if (has) sts128(Q.base + (Q.n + __popc(mask & ((1u << lane) - 1u))) * 16u, item);
+  Q.n += __popc(mask);
+  if (Q.n >= 32u) {
+    __syncwarp();
+    Q.n -= 32u;
+    const uint4 mine = lds128(Q.base + (Q.n + lane) * 16u);
+    __syncwarp();
+    staged_read<ERRORS>(S, T, F, M, depth, alt, mine);
+  }
+}
+
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 __global__ void __launch_bounds__(kStagedThreads, MIN_CTAS)
 sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
@@ -337,10 +403,11 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
                            unsigned long long* __restrict__ n_reads) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
-  uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_rec + D.max_loci);
+  uint4* s_queue = s_rec + D.max_loci;
+  uint4* s_ent = s_queue + (kStagedThreads / 32) * kQueueSlots;
+  uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_ent + 2 * kMaxStagedEntries);
   uint32_t* s_alt = s_depth + D.max_loci;
   uint16_t* s_dir = reinterpret_cast<uint16_t*>(s_alt + D.max_rows);
-  __shared__ Entry s_ent[kMaxStagedEntries];
 
   const Tile T = tiles[blockIdx.x];
   const uint32_t n = T.l1 - T.l0;
@@ -362,7 +429,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     s_depth[i] = 0;
   }
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
-  if (threadIdx.x < T.n_entries) s_ent[threadIdx.x] = entries[T.entry_off + threadIdx.x];
+  if (threadIdx.x < 2 * T.n_entries)
+    s_ent[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(entries + T.entry_off) + threadIdx.x);
   __syncthreads();
   // directory: first staged locus at or after the start of each bucket
   for (uint32_t b = threadIdx.x; b < n_buckets; b += kStagedThreads) {
@@ -376,43 +444,55 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   }
   __syncthreads();
 
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   StagedTile S;
-  S.SV = SharedView{static_cast<uint32_t>(__cvta_generic_to_shared(s_rec)),
-                    static_cast<uint32_t>(__cvta_generic_to_shared(s_depth)),
-                    static_cast<uint32_t>(__cvta_generic_to_shared(s_alt)), F.inst, T.r0};
-  S.dir = static_cast<uint32_t>(__cvta_generic_to_shared(s_dir));
+  S.SV = SharedView{opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_rec))),
+                    opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_depth))),
+                    opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_alt))), F.inst, T.r0};
+  S.dir = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_dir)));
+  S.ent = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_ent)));
   S.n = n;
   S.shift = shift;
   S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
   S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
+  HitQueue Q{opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_queue + warp * kQueueSlots))), 0u};
   const uint32_t R = M.read_size;
   uint32_t placed = 0;
 
-  if (PAIRED) {
-    for (uint32_t t = threadIdx.x; t < T.n_templates; t += kStagedThreads) {
-      const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, M.seed));
-      const uint32_t ins = draw_insert(M, u.z);
-      Template tp;
-      if (!place(T, s_ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
-      staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * t, tp.x, tp.h, tp.frag_end);
-      staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * t + 1u, tp.x + R + ins, tp.h, tp.frag_end);
-      placed += 2;
+  // Philox block j: two single-end templates (2j, 2j+1) or one paired template (mates 2j, 2j+1)
+  const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
+  for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
+    const uint32_t j = j0 + lane;
+    const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+    uint32_t x = 0, h = 0, e = 0, fe = 0, ins = 0;
+    bool ok = false;
+    if (PAIRED) {
+      ins = draw_insert(M, u.z);
+      ok = j < n_blocks && place_staged(S, T, F, u.x, u.y, 2u * R + ins, x, h, e, fe);
+      if (ok) placed += 2;
     }
-  } else {
-    const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
-    for (uint32_t j = threadIdx.x; j < n_blocks; j += kStagedThreads) {
-      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
-      const uint32_t n_here = 2u * j + 1u < T.n_templates ? 2u : 1u;
 #pragma unroll 1
-      for (uint32_t k = 0; k < n_here; ++k) {
-        Template tp;
-        if (place(T, s_ent, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) {
-          staged_read<ERRORS>(S, T, F, M, depth, alt, 2u * j + k, tp.x, tp.h, tp.frag_end);
-          ++placed;
-        }
+    for (uint32_t k = 0; k < 2u; ++k) {
+      uint32_t xs;
+      if (PAIRED) {
+        xs = x + k * (R + ins);
+      } else {
+        ok = 2u * j + k < T.n_templates && place_staged(S, T, F, k ? u.z : u.x, k ? u.w : u.y, R, x, h, e, fe);
+        if (ok) ++placed;
+        xs = x;
       }
+      // probe: does the first staged locus at or after the read's bucket lie before the read's end?
+      bool has = false;
+      uint32_t i = 0;
+      if (ok) {
+        i = S.first_locus((xs - T.begin) >> shift);
+        has = i < n && lds32(S.SV.rec + i * 16u) < min(xs + R, fe + 1u);
+      }
+      queue_push<ERRORS>(Q, S, T, F, M, depth, alt, has, make_uint4(xs, h, 2u * j + k, i | (e << 16)), lane);
     }
   }
+  __syncwarp();
+  if (lane < Q.n) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
   __syncthreads();
 
   // ---- flush: one reduction per touched counter, coalesced over consecutive loci / rows
@@ -542,6 +622,7 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
 // ----------------------------------------------------------------- launchers
 size_t staged_smem_bytes(const StageDims& D) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
+  b += (static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + 2 * kMaxStagedEntries) * sizeof(uint4);
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint16_t);
   return (b + 15) & ~static_cast<size_t>(15);
