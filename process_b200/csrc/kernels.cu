@@ -220,9 +220,9 @@ __device__ __forceinline__ bool walk_global(const GlobalView& V, uint32_t i, uin
 template <class Err>
 __device__ __forceinline__ bool walk_shared(const SharedView& V, uint32_t i, uint32_t end, uint32_t h, uint32_t R,
                                             uint32_t frag_end, Walk& w, const Err& err) {
-  for (; i < end; ++i) {
-    const uint4 r = V.record(i);
-    if (r.x >= w.stop) return true;
+  for (;; ++i) {
+    const uint4 r = V.record(i);  // record `end` is a sentinel at position 0xffffffff
+    if (r.x >= w.stop) return i < end;
     if (r.x < w.q) continue;
     V.add_depth(i);
     if (r.z != 0) {
@@ -234,7 +234,6 @@ __device__ __forceinline__ bool walk_shared(const SharedView& V, uint32_t i, uin
       }
     }
   }
-  return false;
 }
 
 __device__ __forceinline__ uint32_t lower_bound_pos(const uint32_t* pos, uint32_t lo, uint32_t hi, uint32_t x) {
@@ -288,7 +287,7 @@ __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* ds
 
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
-constexpr int kDefaultMinCtas = 4;
+constexpr int kDefaultMinCtas = 3;
 constexpr uint32_t kQueueSlots = 64;  // per warp: < 32 waiting + <= 32 pushed in one go
 
 // hide where a shared-window address came from, so the compiler keeps it in a register
@@ -337,7 +336,7 @@ __device__ __forceinline__ bool place_staged(const StagedTile& S, const Tile& T,
     ++e;
     a = lds128(S.ent + e * 32u);
   }
-  h = __ldg(F.hap_list + a.w + __umulhi(u_hap - a.y, a.z));
+  h = __ldg(F.hap_list + (a.w + __umulhi(u_hap - a.y, a.z)));
   frag_end = lds32(S.ent + e * 32u + 16u);
   return x + (tlen - 1u) <= frag_end;  // else the template falls off its molecule
 }
@@ -382,10 +381,9 @@ struct HitQueue {
 template <bool ERRORS>
 __device__ __forceinline__ void queue_push(HitQueue& Q, const StagedTile& S, const Tile& T, const DevForest& F,
                                            const SeqModel& M, uint32_t* depth, uint32_t* alt, bool has, uint4 item,
-                                           uint32_t lane) {
+                                           uint32_t lane, uint32_t lanes_below) {
   const uint32_t mask = __ballot_sync(0xffffffffu, has);
-  if (mask == 0) return;
-  if (has) sts128(Q.base + (Q.n + __popc(mask & ((1u << lane) - 1u))) * 16u, item);
+  if (has) sts128(Q.base + (Q.n + __popc(mask & lanes_below)) * 16u, item);
   Q.n += __popc(mask);
   if (Q.n >= 32u) {
     __syncwarp();
@@ -403,7 +401,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
                            unsigned long long* __restrict__ n_reads) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
-  uint4* s_queue = s_rec + D.max_loci;
+  uint4* s_queue = s_rec + D.max_loci + 1;
   uint4* s_ent = s_queue + (kStagedThreads / 32) * kQueueSlots;
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_ent + 2 * kMaxStagedEntries);
   uint32_t* s_alt = s_depth + D.max_loci;
@@ -428,6 +426,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     s_rec[i] = r;
     s_depth[i] = 0;
   }
+  if (threadIdx.x == 0) s_rec[n] = make_uint4(0xffffffffu, 0u, 0u, 0u);  // sentinel: past every read
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
   if (threadIdx.x < 2 * T.n_entries)
     s_ent[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(entries + T.entry_off) + threadIdx.x);
@@ -459,36 +458,35 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   const uint32_t R = M.read_size;
   uint32_t placed = 0;
 
+  uint32_t lanes_below;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
+  // probe: does the first staged locus at or after the read's bucket lie before the read's end?
+  // (the sentinel record makes the load safe when the bucket is past the last locus)
+  auto probe_and_push = [&](bool ok, uint32_t xs, uint32_t h, uint32_t e, uint32_t fe, uint32_t read_id) {
+    const uint32_t i = ok ? S.first_locus((xs - T.begin) >> shift) : n;
+    const bool has = lds32(S.SV.rec + i * 16u) < min(xs + R, fe + 1u);
+    queue_push<ERRORS>(Q, S, T, F, M, depth, alt, ok && has, make_uint4(xs, h, read_id, i | (e << 16)), lane, lanes_below);
+  };
+
   // Philox block j: two single-end templates (2j, 2j+1) or one paired template (mates 2j, 2j+1)
   const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
   for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
     const uint32_t j = j0 + lane;
     const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
-    uint32_t x = 0, h = 0, e = 0, fe = 0, ins = 0;
-    bool ok = false;
+    uint32_t x, h, e, fe;
     if (PAIRED) {
-      ins = draw_insert(M, u.z);
-      ok = j < n_blocks && place_staged(S, T, F, u.x, u.y, 2u * R + ins, x, h, e, fe);
-      if (ok) placed += 2;
-    }
-#pragma unroll 1
-    for (uint32_t k = 0; k < 2u; ++k) {
-      uint32_t xs;
-      if (PAIRED) {
-        xs = x + k * (R + ins);
-      } else {
-        ok = 2u * j + k < T.n_templates && place_staged(S, T, F, k ? u.z : u.x, k ? u.w : u.y, R, x, h, e, fe);
-        if (ok) ++placed;
-        xs = x;
-      }
-      // probe: does the first staged locus at or after the read's bucket lie before the read's end?
-      bool has = false;
-      uint32_t i = 0;
-      if (ok) {
-        i = S.first_locus((xs - T.begin) >> shift);
-        has = i < n && lds32(S.SV.rec + i * 16u) < min(xs + R, fe + 1u);
-      }
-      queue_push<ERRORS>(Q, S, T, F, M, depth, alt, has, make_uint4(xs, h, 2u * j + k, i | (e << 16)), lane);
+      const uint32_t ins = draw_insert(M, u.z);
+      const bool ok = place_staged(S, T, F, u.x, u.y, 2u * R + ins, x, h, e, fe) && j < n_blocks;
+      placed += ok ? 2u : 0u;
+      probe_and_push(ok, x, h, e, fe, 2u * j);
+      probe_and_push(ok, x + R + ins, h, e, fe, 2u * j + 1u);
+    } else {
+      const bool ok0 = place_staged(S, T, F, u.x, u.y, R, x, h, e, fe) && 2u * j < T.n_templates;
+      placed += ok0 ? 1u : 0u;
+      probe_and_push(ok0, x, h, e, fe, 2u * j);
+      const bool ok1 = place_staged(S, T, F, u.z, u.w, R, x, h, e, fe) && 2u * j + 1u < T.n_templates;
+      placed += ok1 ? 1u : 0u;
+      probe_and_push(ok1, x, h, e, fe, 2u * j + 1u);
     }
   }
   __syncwarp();
@@ -622,7 +620,7 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
 // ----------------------------------------------------------------- launchers
 size_t staged_smem_bytes(const StageDims& D) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
-  b += (static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + 2 * kMaxStagedEntries) * sizeof(uint4);
+  b += (1 + static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + 2 * kMaxStagedEntries) * sizeof(uint4);
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint16_t);
   return (b + 15) & ~static_cast<size_t>(15);
