@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <map>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -16,6 +17,27 @@
 #include "../../include/pcs_seq.h"
 
 namespace pcs {
+
+// allocator that default-initialises: vector::resize() of the multi-megabyte tables below
+// must not spend time (and page faults on one thread) zeroing what is overwritten right away
+template <class T, class A = std::allocator<T>>
+struct default_init_allocator : A {
+  using A::A;
+  template <class U>
+  struct rebind {
+    using other = default_init_allocator<U, typename std::allocator_traits<A>::template rebind_alloc<U>>;
+  };
+  template <class U>
+  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
+    ::new (static_cast<void*>(p)) U;
+  }
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    std::allocator_traits<A>::construct(static_cast<A&>(*this), p, std::forward<Args>(args)...);
+  }
+};
+template <class T>
+using BigVec = std::vector<T, default_init_allocator<T>>;
 
 struct Inst {          // one placement of a SID on a haplotype subtree (device layout: uint4)
   uint32_t lo;         // first haplotype index carrying it
@@ -44,12 +66,12 @@ struct FlatForest {
   std::vector<uint32_t> leaf_sample;
 
   // loci: distinct (chr, pos) of the mutation table
-  std::vector<uint32_t> locus_pos;       // [L]
+  BigVec<uint32_t> locus_pos;            // [L]
   std::vector<uint32_t> chr_locus_off;   // [n_chr+1]
-  std::vector<uint32_t> locus_inst_off;  // [L+1]
-  std::vector<uint32_t> row_locus;       // [n_mut]
-  std::vector<uint32_t> locus_first_row; // [L+1]
-  std::vector<Inst> inst;                // sorted by row
+  BigVec<uint32_t> locus_inst_off;       // [L+1]
+  BigVec<uint32_t> row_locus;            // [n_mut]
+  BigVec<uint32_t> locus_first_row;      // [L+1]
+  BigVec<Inst> inst;                     // sorted by row
 
   // haplotype leaves, per chromosome (index inside a chromosome = haplotype index)
   std::vector<std::vector<HapRec>> chr_haps;

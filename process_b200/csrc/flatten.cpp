@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <stdexcept>
@@ -244,7 +245,22 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
       w.inst.push_back({germ_lo[g], germ_hi[g] - germ_lo[g], row, meta});
     }
   }
-  std::stable_sort(w.inst.begin(), w.inst.end(), [](const Inst& a, const Inst& b) { return a.row < b.row; });
+  // a SID no sampled haplotype inherited has an empty interval: drop it
+  w.inst.erase(std::remove_if(w.inst.begin(), w.inst.end(), [](const Inst& in) { return in.span == 0; }), w.inst.end());
+  // stable counting sort by row (rows of a chromosome are a contiguous range)
+  if (!w.inst.empty()) {
+    uint32_t lo = w.inst[0].row, hi = w.inst[0].row;
+    for (const auto& in : w.inst) {
+      lo = std::min(lo, in.row);
+      hi = std::max(hi, in.row);
+    }
+    std::vector<uint32_t> cnt(static_cast<size_t>(hi - lo) + 2, 0);
+    for (const auto& in : w.inst) ++cnt[in.row - lo + 1];
+    for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+    std::vector<Inst> sorted(w.inst.size());
+    for (const auto& in : w.inst) sorted[cnt[in.row - lo]++] = in;
+    w.inst.swap(sorted);
+  }
 }
 
 }  // namespace
@@ -305,29 +321,85 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   }
 
   timer.lap("cell tree");
-  // ---- mutation table -> loci
-  out.chr_locus_off.assign(d.n_chr + 1, 0);
+  n_threads = std::max(1u, n_threads);
+  // run fn(task) for task in [0, n_tasks) on up to n_threads threads; the first exception is rethrown
+  auto parallel_for = [&](uint32_t n_tasks, const std::function<void(uint32_t)>& fn) {
+    std::atomic<uint32_t> next_task{0};
+    std::vector<std::string> errors(n_tasks);
+    auto body = [&]() {
+      for (;;) {
+        uint32_t k = next_task.fetch_add(1);
+        if (k >= n_tasks) return;
+        try {
+          fn(k);
+        } catch (const std::exception& e) {
+          errors[k] = e.what();
+          if (errors[k].empty()) errors[k] = "flatten failed";
+        }
+      }
+    };
+    const unsigned nt = std::min<unsigned>(n_threads, n_tasks);
+    if (nt <= 1) {
+      body();
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned i = 0; i < nt; ++i) th.emplace_back(body);
+      for (auto& x : th) x.join();
+    }
+    for (const auto& e : errors)
+      if (!e.empty()) throw std::domain_error(e);
+  };
+
+  // ---- mutation table -> loci (validated and numbered in row chunks)
+  const uint32_t n_chunks = d.n_mut ? std::min<uint32_t>(4 * n_threads, (d.n_mut + 65535) / 65536) : 0;
+  auto chunk_lo = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(d.n_mut) * k / n_chunks); };
+  auto new_locus = [&](uint32_t m) {
+    return m == 0 || d.mut_chr[m - 1] != d.mut_chr[m] || d.mut_pos[m - 1] != d.mut_pos[m];
+  };
+  std::vector<uint32_t> chunk_loci(n_chunks + 1, 0);
+  parallel_for(n_chunks, [&](uint32_t k) {
+    uint32_t cnt = 0;
+    for (uint32_t m = chunk_lo(k); m < chunk_lo(k + 1); ++m) {
+      check(d.mut_chr[m] < d.n_chr, "mut_chr out of range");
+      check(d.mut_pos[m] >= 1 && d.mut_pos[m] <= d.chr_len[d.mut_chr[m]], "mutation position outside the chromosome");
+      check(d.mut_ref_len[m] >= 1 && d.mut_alt_len[m] >= 1, "ref/alt must be non-empty");
+      if (m > 0) {
+        bool ordered = d.mut_chr[m - 1] < d.mut_chr[m] ||
+                       (d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] <= d.mut_pos[m]);
+        check(ordered, "mutation table must be sorted by (chr, pos)");
+      }
+      cnt += new_locus(m) ? 1u : 0u;
+    }
+    chunk_loci[k + 1] = cnt;
+  });
+  for (uint32_t k = 0; k < n_chunks; ++k) chunk_loci[k + 1] += chunk_loci[k];
+  const uint32_t n_loci = n_chunks ? chunk_loci[n_chunks] : 0;
+  out.locus_pos.resize(n_loci);
   out.row_locus.resize(d.n_mut);
-  for (uint32_t m = 0; m < d.n_mut; ++m) {
-    check(d.mut_chr[m] < d.n_chr, "mut_chr out of range");
-    check(d.mut_pos[m] >= 1 && d.mut_pos[m] <= d.chr_len[d.mut_chr[m]], "mutation position outside the chromosome");
-    check(d.mut_ref_len[m] >= 1 && d.mut_alt_len[m] >= 1, "ref/alt must be non-empty");
-    bool same = false;
-    if (m > 0) {
-      bool ordered = d.mut_chr[m - 1] < d.mut_chr[m] ||
-                     (d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] <= d.mut_pos[m]);
-      check(ordered, "mutation table must be sorted by (chr, pos)");
-      same = d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] == d.mut_pos[m];
+  out.locus_first_row.resize(static_cast<size_t>(n_loci) + 1);
+  out.locus_first_row[n_loci] = d.n_mut;
+  out.locus_inst_off.resize(static_cast<size_t>(n_loci) + 1);
+  out.locus_inst_off[0] = 0;
+  parallel_for(n_chunks, [&](uint32_t k) {
+    uint32_t l = chunk_loci[k];  // loci before this chunk
+    for (uint32_t m = chunk_lo(k); m < chunk_lo(k + 1); ++m) {
+      if (new_locus(m)) {
+        out.locus_pos[l] = d.mut_pos[m];
+        out.locus_first_row[l] = m;
+        out.locus_inst_off[l + 1] = 0;
+        ++l;
+      }
+      out.row_locus[m] = l - 1;
     }
-    if (!same) {
-      out.locus_pos.push_back(d.mut_pos[m]);
-      out.chr_locus_off[d.mut_chr[m] + 1] = static_cast<uint32_t>(out.locus_pos.size());
-    }
-    out.row_locus[m] = static_cast<uint32_t>(out.locus_pos.size() - 1);
-  }
-  for (uint32_t c = 1; c <= d.n_chr; ++c) out.chr_locus_off[c] = std::max(out.chr_locus_off[c], out.chr_locus_off[c - 1]);
-  out.locus_first_row.assign(out.locus_pos.size() + 1, d.n_mut);
-  for (uint32_t m = d.n_mut; m-- > 0;) out.locus_first_row[out.row_locus[m]] = m;
+  });
+  // rows and loci of every chromosome (the table is sorted by chromosome)
+  std::vector<uint32_t> chr_row_off(d.n_chr + 1, d.n_mut);
+  for (uint32_t c = 0; c <= d.n_chr; ++c)
+    chr_row_off[c] = static_cast<uint32_t>(std::lower_bound(d.mut_chr, d.mut_chr + d.n_mut, static_cast<uint16_t>(c)) - d.mut_chr);
+  chr_row_off[d.n_chr] = d.n_mut;
+  out.chr_locus_off.assign(d.n_chr + 1, n_loci);
+  for (uint32_t c = 0; c < d.n_chr; ++c)
+    out.chr_locus_off[c] = chr_row_off[c] < d.n_mut ? out.row_locus[chr_row_off[c]] : n_loci;
 
   timer.lap("loci");
   // ---- events by chromosome (node-major order is preserved)
@@ -353,63 +425,68 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     }
     for (auto& w : work) w.node_ev_off[v + 1] = static_cast<uint32_t>(w.ev.size());
   }
-  std::vector<std::vector<std::pair<uint32_t, uint8_t>>> germ(d.n_chr);
-  for (uint64_t i = 0; i < d.n_germline; ++i) {
-    check(d.germ_mut[i] < d.n_mut, "germ_mut out of range");
-    germ[d.mut_chr[d.germ_mut[i]]].emplace_back(d.germ_mut[i], d.germ_allele_mask[i]);
-  }
 
   timer.lap("events by chromosome");
-  // ---- per-chromosome haplotype numbering, chromosomes in parallel
-  std::atomic<uint32_t> next{0};
-  auto run = [&]() {
-    for (;;) {
-      uint32_t c = next.fetch_add(1);
-      if (c >= d.n_chr) return;
-      try {
-        flatten_chr(d, t, work[c], germ[c]);
-      } catch (const std::exception& e) {
-        work[c].error = e.what();
-        if (work[c].error.empty()) work[c].error = "flatten failed";
-      }
+  // ---- germline SIDs by chromosome: chunks of the caller's list are bucketed in parallel
+  const uint32_t g_chunks = d.n_germline ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (d.n_germline + 65535) / 65536)) : 0;
+  std::vector<std::vector<std::vector<std::pair<uint32_t, uint8_t>>>> germ_part(g_chunks);
+  parallel_for(g_chunks, [&](uint32_t k) {
+    auto& part = germ_part[k];
+    part.resize(d.n_chr);
+    const uint64_t lo = d.n_germline * k / g_chunks, hi = d.n_germline * (k + 1) / g_chunks;
+    for (auto& v : part) v.reserve((hi - lo) / d.n_chr + 16);
+    for (uint64_t i = lo; i < hi; ++i) {
+      const uint32_t m = d.germ_mut[i];
+      check(m < d.n_mut, "germ_mut out of range");
+      part[d.mut_chr[m]].emplace_back(m, d.germ_allele_mask[i]);
     }
-  };
-  n_threads = std::max(1u, std::min<unsigned>(n_threads, d.n_chr));
-  if (n_threads == 1) {
-    run();
-  } else {
-    std::vector<std::thread> th;
-    for (unsigned i = 0; i < n_threads; ++i) th.emplace_back(run);
-    for (auto& x : th) x.join();
-  }
-  for (auto& w : work)
-    if (!w.error.empty()) throw std::domain_error(w.error);
+  });
+  timer.lap("germline by chromosome");
+  // ---- per-chromosome haplotype numbering, chromosomes in parallel (largest first)
+  std::vector<uint32_t> chr_order(d.n_chr);
+  for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
+  std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
+    return chr_row_off[a + 1] - chr_row_off[a] > chr_row_off[b + 1] - chr_row_off[b];
+  });
+  parallel_for(d.n_chr, [&](uint32_t k) {
+    const uint32_t c = chr_order[k];
+    std::vector<std::pair<uint32_t, uint8_t>> germ;
+    germ.reserve(chr_row_off[c + 1] - chr_row_off[c]);
+    for (const auto& part : germ_part) germ.insert(germ.end(), part[c].begin(), part[c].end());
+    flatten_chr(d, t, work[c], germ);
+  });
 
   timer.lap("haplotype numbering");
   // ---- merge
   out.chr_haps.resize(d.n_chr);
   out.full_fragset.resize(d.n_chr);
   out.chr_piece_off.assign(d.n_chr + 1, 0);
-  size_t n_inst = 0;
-  for (auto& w : work) n_inst += w.inst.size();
-  out.inst.reserve(n_inst);
+  std::vector<size_t> inst_off(d.n_chr + 1, 0);
+  for (uint32_t c = 0; c < d.n_chr; ++c) inst_off[c + 1] = inst_off[c] + work[c].inst.size();
+  out.inst.resize(inst_off[d.n_chr]);
+  std::vector<uint32_t> fs_base(d.n_chr + 1, 0);
+  for (uint32_t c = 0; c < d.n_chr; ++c) fs_base[c + 1] = fs_base[c] + static_cast<uint32_t>(work[c].fragsets.size());
+  parallel_for(d.n_chr, [&](uint32_t c) {
+    ChrWork& w = work[c];
+    std::copy(w.inst.begin(), w.inst.end(), out.inst.begin() + inst_off[c]);
+    // instances per locus (loci of different chromosomes are disjoint)
+    for (const auto& in : w.inst) ++out.locus_inst_off[out.row_locus[in.row] + 1];
+    for (auto& h : w.haps) h.fragset += fs_base[c];
+    out.chr_haps[c] = std::move(w.haps);
+  });
   for (uint32_t c = 0; c < d.n_chr; ++c) {
     ChrWork& w = work[c];
-    const uint32_t fs_base = static_cast<uint32_t>(out.fragsets.size());
+    const uint32_t base = fs_base[c];
     for (const auto& k : w.fragsets) {
       std::vector<Frag> fr;
       for (const auto& p : k) fr.push_back({p.first, p.second});
       out.fragsets.push_back(std::move(fr));
     }
-    out.full_fragset[c] = fs_base;  // interned first in flatten_chr
-    for (auto& h : w.haps) h.fragset += fs_base;
-    out.chr_haps[c] = std::move(w.haps);
-    for (const auto& in : w.inst)
-      if (in.span > 0) out.inst.push_back(in);  // a SID no sampled haplotype inherited
+    out.full_fragset[c] = base;  // interned first in flatten_chr
 
     // pieces: maximal intervals on which the set of covering fragments is constant
     std::vector<uint8_t> used(w.fragsets.size(), 0);
-    for (const auto& h : out.chr_haps[c]) used[h.fragset - fs_base] = 1;
+    for (const auto& h : out.chr_haps[c]) used[h.fragset - base] = 1;
     std::vector<uint32_t> bp{1u, d.chr_len[c] + 1};
     for (size_t k = 0; k < w.fragsets.size(); ++k)
       if (used[k])
@@ -425,7 +502,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
         if (!used[k]) continue;
         for (const auto& p : w.fragsets[k])
           if (p.first <= pc.begin && pc.end <= p.second) {
-            out.covers.push_back({fs_base + static_cast<uint32_t>(k), p.second});
+            out.covers.push_back({base + static_cast<uint32_t>(k), p.second});
             ++pc.cover_n;
             break;
           }
@@ -434,13 +511,9 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     }
     out.chr_piece_off[c + 1] = static_cast<uint32_t>(out.pieces.size());
   }
-
   timer.lap("merge + pieces");
   // ---- instances are sorted by row inside a chromosome and rows are chromosome-major
-  const uint32_t L = static_cast<uint32_t>(out.locus_pos.size());
-  out.locus_inst_off.assign(L + 1, 0);
-  for (const auto& in : out.inst) ++out.locus_inst_off[out.row_locus[in.row] + 1];
-  for (uint32_t l = 0; l < L; ++l) out.locus_inst_off[l + 1] += out.locus_inst_off[l];
+  for (uint32_t l = 0; l < n_loci; ++l) out.locus_inst_off[l + 1] += out.locus_inst_off[l];
   timer.lap("instance offsets");
 }
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -42,31 +43,36 @@ void require(bool ok, const char* msg) {
   if (!ok) throw std::domain_error(msg);
 }
 
+// device buffer from the device's stream-ordered memory pool (cudaMallocAsync): repeated
+// upload / plan / free cycles reuse pooled memory instead of paying cudaMalloc each time
 template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t n = 0;
+  cudaStream_t st = nullptr;
   DevBuf() = default;
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) cudaFreeAsync(p, st);
     p = nullptr;
     n = 0;
   }
-  void alloc(size_t count) {
+  void alloc(size_t count, cudaStream_t stream) {
     release();
+    st = stream;
     n = count;
-    if (count) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T)));
+    if (count) CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
   }
   size_t bytes() const { return n * sizeof(T); }
   // synchronous w.r.t. the host buffer (pageable memory): safe to free `v` afterwards
-  size_t upload(const std::vector<T>& v, cudaStream_t st) {
-    alloc(v.size());
+  template <class Vec>
+  size_t upload(const Vec& v, cudaStream_t stream) {
+    alloc(v.size(), stream);
     if (!v.empty()) {
-      CUDA_OK(cudaMemcpyAsync(p, v.data(), bytes(), cudaMemcpyHostToDevice, st));
-      CUDA_OK(cudaStreamSynchronize(st));
+      CUDA_OK(cudaMemcpyAsync(p, v.data(), bytes(), cudaMemcpyHostToDevice, stream));
+      CUDA_OK(cudaStreamSynchronize(stream));
     }
     return bytes();
   }
@@ -76,6 +82,18 @@ double now_ms() {
   using namespace std::chrono;
   return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
+
+// PCS_TIMING=1: host-side phase times on stderr
+struct Lap {
+  bool on = std::getenv("PCS_TIMING") != nullptr;
+  double t = now_ms();
+  void operator()(const char* what) {
+    if (!on) return;
+    double n = now_ms();
+    std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", what, n - t);
+    t = n;
+  }
+};
 
 }  // namespace
 
@@ -477,10 +495,10 @@ void upload_plan(pcs_plan& pl) {
   pl.h2d_bytes += pl.d_insert_cdf.upload(pl.host.insert_cdf, st);
   pl.host.model.insert_cdf = pl.d_insert_cdf.p;
   const size_t S = pl.host.info.n_out_samples;
-  pl.d_depth.alloc(S * pl.host.info.n_loci);
-  pl.d_occ.alloc(S * pl.host.info.n_mut);
-  pl.d_cov.alloc(S * pl.host.info.n_mut);
-  pl.d_counters.alloc(4);
+  pl.d_depth.alloc(S * pl.host.info.n_loci, st);
+  pl.d_occ.alloc(S * pl.host.info.n_mut, st);
+  pl.d_cov.alloc(S * pl.host.info.n_mut, st);
+  pl.d_counters.alloc(4, st);
 }
 
 void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
@@ -524,6 +542,7 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   d2h += sizeof(counters);
+  if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "run (kernels + D2H)", now_ms() - t0);
   if (stats) {
     float ms = 0;
     CUDA_OK(cudaEventElapsedTime(&ms, cx.ev[1], cx.ev[2]));
@@ -591,6 +610,10 @@ int pcs_create(pcs_ctx** out, int device_id, void* stream) {
       cx->own_stream = true;
     }
     for (auto& ev : cx->ev) CUDA_OK(cudaEventCreate(&ev));
+    cudaMemPool_t pool;
+    CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, device_id));
+    uint64_t keep = ~0ull;  // do not hand pooled memory back to the driver at every synchronisation
+    CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = cx.release();
   });
 }
@@ -622,7 +645,9 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     auto fo = std::make_unique<pcs_forest>();
     fo->ctx = cx;
     unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    Lap lap;
     pcs::flatten_forest(*desc, fo->host.flat, nt);
+    lap("flatten_forest");
     cx->bind();
     cudaStream_t st = cx->stream;
     fo->h2d_bytes += fo->d_locus_pos.upload(fo->host.flat.locus_pos, st);
@@ -630,7 +655,9 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     fo->h2d_bytes += fo->d_locus_inst_off.upload(fo->host.flat.locus_inst_off, st);
     fo->h2d_bytes += fo->d_row_locus.upload(fo->host.flat.row_locus, st);
     fo->h2d_bytes += fo->d_inst.upload(fo->host.flat.inst, st);
+    lap("upload flat arrays");
     fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
+    lap("groups + upload");
     *out = fo.release();
   });
 }
@@ -674,8 +701,11 @@ int pcs_plan_create(pcs_forest* fo, const pcs_seq_params* params, pcs_plan** out
     validate(*params);
     auto pl = std::make_unique<pcs_plan>();
     pl->forest = fo;
+    Lap lap;
     pl->host = make_host_plan(fo->host, *params);
+    lap("make_host_plan");
     upload_plan(*pl);
+    lap("upload plan + alloc tables");
     *out = pl.release();
   });
 }
@@ -711,8 +741,8 @@ int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint6
     cudaStream_t st = cx.stream;
     DevBuf<pcs::DevPlacement> d_rec;
     DevBuf<uint32_t> d_masks;
-    d_rec.alloc(cap);
-    if (masks) d_masks.alloc(cap * PCS_ERRMASK_WORDS);
+    d_rec.alloc(cap, st);
+    if (masks) d_masks.alloc(cap * PCS_ERRMASK_WORDS, st);
     CUDA_OK(cudaMemsetAsync(pl->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
     CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
                                     fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p, cap,
@@ -792,14 +822,14 @@ int pcs_count_injected(pcs_forest* fo, uint32_t n_out_samples, uint32_t read_siz
     DevBuf<unsigned long long> d_cnt;
     uint64_t h2d = d_rec.upload(h, st);
     if (masks) {
-      d_masks.alloc(n * PCS_ERRMASK_WORDS);
+      d_masks.alloc(n * PCS_ERRMASK_WORDS, st);
       if (n) CUDA_OK(cudaMemcpyAsync(d_masks.p, masks, d_masks.bytes(), cudaMemcpyHostToDevice, st));
       h2d += d_masks.bytes();
     }
-    d_depth.alloc(S * L);
-    d_occ.alloc(S * M);
-    d_cov.alloc(S * M);
-    d_cnt.alloc(4);
+    d_depth.alloc(S * L, st);
+    d_occ.alloc(S * M, st);
+    d_cov.alloc(S * M, st);
+    d_cnt.alloc(4, st);
     if (S * L != 0) CUDA_OK(cudaMemsetAsync(d_depth.p, 0, d_depth.bytes(), st));
     if (S * M != 0) CUDA_OK(cudaMemsetAsync(d_occ.p, 0, d_occ.bytes(), st));
     CUDA_OK(cudaMemsetAsync(d_cnt.p, 0, d_cnt.bytes(), st));

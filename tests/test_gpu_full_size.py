@@ -134,3 +134,79 @@ def test_config3_wgs_80x_full_size(ctx):
     assert np.array_equal(acc_o, occ) and np.array_equal(acc_c, cov)
     plan.close()
     dev.close()
+
+
+def test_config4_eight_samples_200x_sharded_eight_ways(ctx):
+    """configs[3]: 8 samples x 5000 cells, 200x WGS (37 G reads), as its 8 shards on one GPU: the shards must
+    add up to the unsharded tables, and one traced shard of one chromosome must survive the oracle's recount."""
+    f = synth_forest(config_spec("C4"))
+    dev = L.Forest(ctx, f)
+    kw = dict(coverage=200.0, purity=0.9, seed=4)
+    occ, cov, st = dev.simulate(make_params(**kw))
+    assert occ.shape[0] == 9
+    want = sum(round(200.0 * int(n) / 150) for n in f.chr_len) * 9
+    assert abs(st.n_reads - want) < 1e-5 * want
+    assert abs(cov.mean() / 200.0 - 1) < 5e-3
+    acc_o, acc_c, reads = np.zeros_like(occ), np.zeros_like(cov), 0
+    for r in range(8):
+        o, c, s = dev.simulate(make_params(shard_rank=r, shard_count=8, **kw))
+        acc_o += o
+        acc_c += c
+        reads += s.n_reads
+        assert abs(s.n_reads / (st.n_reads / 8) - 1) < 0.01  # LPT balance: near-linear scaling is possible
+    assert reads == st.n_reads
+    assert np.array_equal(acc_o, occ) and np.array_equal(acc_c, cov)
+    het, hom = germline_sets(f)
+    assert abs(occ[-1, het].sum() / cov[-1, het].sum() - 0.5) < 5e-4
+    # chromosome 21 only, shard 5 of 64, traced and recounted on explicit genomes of all 40 000 cells
+    mask = np.zeros(f.n_chr, np.uint8)
+    mask[f.chr_names.index("21")] = 1
+    Pr = make_params(chr_mask=mask, shard_rank=5, shard_count=64, **kw)
+    plan = L.Plan(dev, Pr)
+    o, c, s = plan.run()
+    rec, _ = plan.trace(cap=int(s.n_reads) + 8)
+    assert len(rec) == s.n_reads > 1_000_000
+    o2, c2 = oracle.count_injected(f, 9, 150, rec)
+    assert np.array_equal(o, o2) and np.array_equal(c, c2)
+    plan.close()
+    dev.close()
+
+
+def test_config5_stress_1e5_cells_wgd_300x(ctx):
+    """configs[4]: 100 000 cells, WGD in every clone, 200 CNAs, ~1e6 SNVs per genome, tumour + normal at 300x.
+    Explicit genomes are out of reach (1e11 SIDs); the haplotype-interval view holds it in 0.4 GB."""
+    f = synth_forest(config_spec("C5"))
+    dev = L.Forest(ctx, f)
+    info = dev.info()
+    assert info["n_haplotypes"] > 10_000_000 and info["device_bytes"] < 1 << 30
+    P = make_params(coverage=300.0, purity=0.9, seed=5, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=1e-3)
+    occ, cov, st = dev.simulate(P)
+    want = sum(round(300.0 * int(n) / 150) for n in f.chr_len) * 2
+    assert abs(st.n_reads - want) < 1e-5 * want
+    assert np.allclose(cov.mean(axis=1), 300.0, rtol=5e-3)
+    assert (occ <= cov).all()
+    het, hom = germline_sets(f)
+    snv = (f.mut_ref_len == 1) & (f.mut_alt_len == 1)
+    # normal sample: germline laws with the 1e-3 error rate
+    assert abs(occ[1, het & snv].sum() / cov[1, het & snv].sum() - 0.5 * (1 - 1e-3)) < 5e-4
+    assert abs(occ[1, hom & snv].sum() / cov[1, hom & snv].sum() - (1 - 1e-3)) < 2e-4
+    somatic = (f.mut_nature_mask & ((1 << A.PCS_NATURE_DRIVER) | (1 << A.PCS_NATURE_PASSENGER) |
+                                    (1 << A.PCS_NATURE_PRENEOPLASTIC))) != 0
+    assert occ[1, somatic].sum() == 0
+    # tumour sample: trunk passengers are clonal, heterozygous before any copy number change:
+    # VAF well inside (0.2, 0.6) at purity 0.9 whatever WGD/CNAs did afterwards
+    trunk = np.zeros(f.n_mut, bool)
+    root_events = slice(int(f.node_event_off[0]), int(f.node_event_off[1]))
+    trunk[f.ev_mut[root_events][f.ev_kind[root_events] == A.PCS_EV_SID]] = True
+    vaf = occ[0, trunk & snv].sum() / cov[0, trunk & snv].sum()
+    assert 0.2 < vaf < 0.6, vaf
+    # shards add up
+    acc_o, acc_c = np.zeros_like(occ), np.zeros_like(cov)
+    for r in range(4):
+        Pr = make_params(coverage=300.0, purity=0.9, seed=5, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=1e-3,
+                         shard_rank=r, shard_count=4)
+        o, c, _ = dev.simulate(Pr)
+        acc_o += o
+        acc_c += c
+    assert np.array_equal(acc_o, occ) and np.array_equal(acc_c, cov)
+    dev.close()
