@@ -189,6 +189,8 @@ def main():
     from process_b200 import _lib as L
 
     torch.cuda.set_device(local)
+    # the ranks share the host's cores: split them, or every rank's flattener oversubscribes the box
+    os.environ.setdefault("PCS_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -208,9 +210,9 @@ def main():
 
     def step():
         st = plan.run_device(occ.data_ptr(), cov.data_ptr())
-        if world > 1:  # the path's one exchange step: sum the per-sample count tables
-            dist.all_reduce(occ, op=dist.ReduceOp.SUM)
-            dist.all_reduce(cov, op=dist.ReduceOp.SUM)
+        if world > 1:  # the path's one exchange step: sum the per-sample count tables on rank 0
+            dist.reduce(occ, dst=0, op=dist.ReduceOp.SUM)
+            dist.reduce(cov, dst=0, op=dist.ReduceOp.SUM)
         return st
 
     def barrier():
@@ -240,7 +242,7 @@ def main():
     want = torch.tensor([float(stats[-1].sum_occurrences)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(want, op=dist.ReduceOp.SUM)
-    tables_ok = bool(int(occ.sum(dtype=torch.int64).item()) == int(want.item()))
+    tables_ok = bool(int(occ.sum(dtype=torch.int64).item()) == int(want.item())) if rank == 0 else True
     clk = clocks.stop(t0, t1) if clocks else None
     R = plan.info.read_size
     value = total_reads * R / (total_ms * 1e-3) / 1e9
@@ -277,9 +279,10 @@ def main():
             else:
                 p2 = L.Plan(d2, P)
                 s2 = p2.run_device(occ.data_ptr(), cov.data_ptr())
-                dist.all_reduce(occ, op=dist.ReduceOp.SUM)
-                dist.all_reduce(cov, op=dist.ReduceOp.SUM)
-                o, c = occ.cpu(), cov.cpu()
+                dist.reduce(occ, dst=0, op=dist.ReduceOp.SUM)
+                dist.reduce(cov, dst=0, op=dist.ReduceOp.SUM)
+                if rank == 0:
+                    o, c = occ.cpu(), cov.cpu()
                 h2d += forest.host_bytes()
                 d2h += 2 * S * M * 4
                 p2.close()

@@ -213,6 +213,16 @@ struct pcs_plan {
 
 namespace {
 
+// threads of the host flattener: PCS_HOST_THREADS, else every core
+unsigned host_threads() {
+  const char* s = std::getenv("PCS_HOST_THREADS");
+  if (s) {
+    long v = std::atol(s);
+    if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
+  }
+  return std::max(1u, std::thread::hardware_concurrency());
+}
+
 uint32_t tile_bp() {
   const char* s = std::getenv("PCS_TILE_BP");
   if (s) {
@@ -891,7 +901,7 @@ int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** out) {
   return guarded([&] {
     require(desc && out, "bad arguments");
     auto fl = std::make_unique<pcs_flat>();
-    pcs::flatten_forest(*desc, fl->host.flat, std::max(1u, std::thread::hardware_concurrency()));
+    pcs::flatten_forest(*desc, fl->host.flat, host_threads());
     fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
     *out = fl.release();
   });
