@@ -196,7 +196,7 @@ def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced):
     rows = dev.active_rows(occ, include_non_sequenced)
     ref, alt = forest.row_strings(rows)
     cols = {
-        "chr": [forest.chr_names[c] for c in forest.mut_chr[rows]],
+        "chr": np.asarray(forest.chr_names, dtype=object)[forest.mut_chr[rows]],
         "chr_pos": forest.mut_pos[rows].astype(np.int32),
         "ref": ref, "alt": alt,
         "causes": forest.row_causes(rows), "classes": forest.row_classes(rows),

@@ -126,30 +126,27 @@ class PhylogeneticForest:
         return d
 
     # ---------------------------------------------------- row annotation (host)
+    # vectorised: a WGS result has millions of rows (src/seq_simulation.cpp:52-90 builds them one by one)
     def row_strings(self, rows: np.ndarray):
         """(ref, alt) strings of the given rows.  SNV: one base each.  Deletion:
         anchor + run, alt = anchor.  Insertion: ref = anchor, alt = anchor + run."""
         rows = np.asarray(rows)
-        rc, ac = self.mut_ref_code[rows], self.mut_alt_code[rows]
-        rl, al = self.mut_ref_len[rows], self.mut_alt_len[rows]
-        ref, alt = [], []
-        for i in range(len(rows)):
-            a, b = _BASES[rc[i] & 3], _BASES[ac[i] & 3]
-            if rl[i] == 1 and al[i] == 1:
-                ref.append(a); alt.append(b)
-            else:
-                ref.append(a + b * (int(rl[i]) - 1)); alt.append(a + b * (int(al[i]) - 1))
+        rc, ac = self.mut_ref_code[rows] & 3, self.mut_alt_code[rows] & 3
+        rl, al = self.mut_ref_len[rows].astype(np.int64), self.mut_alt_len[rows].astype(np.int64)
+        ref = _BASES[rc].astype(object)
+        alt = _BASES[ac].astype(object)
+        for i in np.flatnonzero((rl != 1) | (al != 1)):  # indels are a small minority
+            a, b = _BASES[rc[i]], _BASES[ac[i]]
+            ref[i] = a + b * (int(rl[i]) - 1)
+            alt[i] = a + b * (int(al[i]) - 1)
         return ref, alt
 
     def row_causes(self, rows: np.ndarray):
-        out = []
-        for c in self.mut_cause[np.asarray(rows)]:
-            out.append(None if c < 0 else self.cause_names[int(c)])
-        return out
+        c = self.mut_cause[np.asarray(rows)]
+        table = np.asarray(list(self.cause_names) + [None], dtype=object)
+        return table[np.where(c < 0, len(self.cause_names), c)]
 
     def row_classes(self, rows: np.ndarray):
-        out = []
-        for m in self.mut_nature_mask[np.asarray(rows)]:
-            names = sorted(A.NATURE_DESCRIPTIONS[b] for b in range(4) if (int(m) >> b) & 1)
-            out.append(";".join(names))
-        return out
+        table = np.asarray([";".join(sorted(A.NATURE_DESCRIPTIONS[b] for b in range(4) if (m >> b) & 1))
+                            for m in range(16)], dtype=object)
+        return table[self.mut_nature_mask[np.asarray(rows)] & 15]
