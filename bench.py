@@ -169,6 +169,9 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: 'peer' = every rank's sampler flushes into rank 0's tables over NVLink peer memory "
+                         "(reduction fused into the kernel), 'nccl' = local tables + NCCL reduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -204,13 +207,56 @@ def main():
     dev = L.Forest(ctx, forest)
     P = make_params(shard_rank=rank, shard_count=world, **wl_params)
     plan = L.Plan(dev, P)
-    S, M = plan.info.n_out_samples, plan.info.n_mut
+    S, M, Lc = plan.info.n_out_samples, plan.info.n_mut, plan.info.n_loci
     occ = torch.zeros((S, M), dtype=torch.int32, device="cuda")
     cov = torch.zeros((S, M), dtype=torch.int32, device="cuda")
 
+    # what the shards count on their own (untimed): the reduced tables must add up to exactly this
+    st0 = plan.run_device(occ.data_ptr(), cov.data_ptr())
+    expect = torch.tensor([float(st0.sum_occurrences), float(st0.sum_depth)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+
+    exchange = args.exchange if world > 1 else "none"
+    ring = None
+    if exchange == "peer":
+        # two table sets (depth + occurrences) on rank 0, mapped by every other rank through CUDA IPC
+        words = S * Lc + S * M
+        handles = [None, None]
+        try:
+            if rank == 0:
+                owned = [ctx.shared_alloc(words) for _ in range(2)]
+                handles = [h for _, h in owned]
+            dist.broadcast_object_list(handles, src=0)
+            ring = [p for p, _ in owned] if rank == 0 else [ctx.shared_open(h) for h in handles]
+            ok = torch.ones(1, device="cuda")
+        except L.PcsError as e:  # no peer access between these GPUs
+            print(f"rank {rank}: peer tables unavailable ({e}); using NCCL reduce", file=sys.stderr)
+            ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() == 0:
+            exchange, ring = "nccl", None
+        elif rank == 0:
+            ctx.memset_u32(ring[0], words)
+            torch.cuda.synchronize()
+        dist.barrier()
+
+    step_no = [0]
+    fin_stats = [None]
+
     def step():
+        if exchange == "peer":
+            b = step_no[0] & 1
+            step_no[0] += 1
+            if rank == 0:  # zero the tables of the NEXT step; ordered before this rank's own kernel
+                ctx.memset_u32(ring[1 - b], S * Lc + S * M)
+            st = plan.accumulate(ring[b], ring[b] + 4 * S * Lc)
+            dist.barrier()  # every rank's flush has landed in rank 0's tables
+            if rank == 0:
+                fin_stats[0] = plan.finalize(ring[b], ring[b] + 4 * S * Lc, cov.data_ptr())
+            return st
         st = plan.run_device(occ.data_ptr(), cov.data_ptr())
-        if world > 1:  # the path's one exchange step: sum the per-sample count tables on rank 0
+        if world > 1:  # 'nccl': sum the per-sample count tables on rank 0
             dist.reduce(occ, dst=0, op=dist.ReduceOp.SUM)
             dist.reduce(cov, dst=0, op=dist.ReduceOp.SUM)
         return st
@@ -238,19 +284,23 @@ def main():
         dist.all_reduce(reads, op=dist.ReduceOp.SUM)
     total_ms = float(ms.item())
     total_reads = float(reads.item())
-    # the reduced tables must hold exactly what the ranks counted
-    want = torch.tensor([float(stats[-1].sum_occurrences)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(want, op=dist.ReduceOp.SUM)
-    tables_ok = bool(int(occ.sum(dtype=torch.int64).item()) == int(want.item())) if rank == 0 else True
+    # the reduced tables must hold exactly what the ranks counted on their own
+    tables_ok = True
+    if rank == 0:
+        if exchange == "peer":
+            tables_ok = (fin_stats[0].sum_occurrences == int(expect[0].item()) and
+                         fin_stats[0].sum_depth == int(expect[1].item()))
+        else:
+            tables_ok = int(occ.sum(dtype=torch.int64).item()) == int(expect[0].item())
     clk = clocks.stop(t0, t1) if clocks else None
     R = plan.info.read_size
     value = total_reads * R / (total_ms * 1e-3) / 1e9
 
     # roofline of the sampler kernel on this rank: algorithmic bytes per read
     st = stats[-1]
-    kbar = st.sum_depth / max(1, st.n_reads)
-    kalt = st.sum_occurrences / max(1, st.n_reads)
+    reads_per_step = total_reads / args.steps
+    kbar = float(expect[1].item()) / max(1.0, reads_per_step)   # job-wide: every shard sees the same mix
+    kalt = float(expect[0].item()) / max(1.0, reads_per_step)
     b_read = 24.0 + 20.0 * kbar + 8.0 * kalt
     kernel_ms = float(np.mean([s.kernel_ms for s in stats]))
     achieved = st.n_reads * b_read / (kernel_ms * 1e-3) / 1e9
@@ -278,11 +328,23 @@ def main():
                 d2h += s2.d2h_bytes
             else:
                 p2 = L.Plan(d2, P)
-                s2 = p2.run_device(occ.data_ptr(), cov.data_ptr())
-                dist.reduce(occ, dst=0, op=dist.ReduceOp.SUM)
-                dist.reduce(cov, dst=0, op=dist.ReduceOp.SUM)
-                if rank == 0:
-                    o, c = occ.cpu(), cov.cpu()
+                if exchange == "peer":
+                    b = step_no[0] & 1
+                    step_no[0] += 1
+                    if rank == 0:
+                        ctx.memset_u32(ring[1 - b], S * Lc + S * M)
+                    s2 = p2.accumulate(ring[b], ring[b] + 4 * S * Lc)
+                    dist.barrier()
+                    if rank == 0:
+                        p2.finalize(ring[b], ring[b] + 4 * S * Lc, cov.data_ptr())
+                        o = ctx.to_host(ring[b] + 4 * S * Lc, S * M)
+                        c = cov.cpu()
+                else:
+                    s2 = p2.run_device(occ.data_ptr(), cov.data_ptr())
+                    dist.reduce(occ, dst=0, op=dist.ReduceOp.SUM)
+                    dist.reduce(cov, dst=0, op=dist.ReduceOp.SUM)
+                    if rank == 0:
+                        o, c = occ.cpu(), cov.cpu()
                 h2d += forest.host_bytes()
                 d2h += 2 * S * M * 4
                 p2.close()
@@ -320,14 +382,27 @@ def main():
                        if args.workload == "C3" else args.workload,
                        "samples": S, "rows": M, "reads_per_step": total_reads / args.steps,
                        "tiles_this_rank": int(plan.info.n_tiles), "parallelism": f"tile-sharded x{world}",
+                       "exchange": {"none": "single GPU", "peer": "sampler flush adds into rank 0's tables over NVLink "
+                                    "peer memory (CUDA IPC), one barrier per step",
+                                    "nccl": "local tables + NCCL reduce to rank 0"}[exchange],
                        "l2": f"working set {(info['device_bytes'] + 3 * S * M * 4) / 1e6:.0f} MB > 126 MB L2; "
                              "count tables re-zeroed every step; no explicit flush"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(sum(s.kernel_launches for s in stats)),
+            "gpu_launches": int(sum(s.kernel_launches for s in stats) +
+                                (args.steps * fin_stats[0].kernel_launches if fin_stats[0] else 0)),
             "checks": {"reduced_tables_equal_sum_of_rank_counts": tables_ok},
             "clocks": clk,
         }
         print(json.dumps(line))
+    if ring is not None:  # mappings first, then the owner frees
+        barrier()
+        if rank != 0:
+            for p_ in ring:
+                ctx.shared_close(p_)
+        barrier()
+        if rank == 0:
+            for p_ in ring:
+                ctx.shared_free(p_)
     plan.close()
     dev.close()
     ctx.close()

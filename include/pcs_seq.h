@@ -233,6 +233,26 @@ int pcs_plan_free(pcs_plan* plan);
 int pcs_plan_run(pcs_plan* plan, int flags, uint32_t* occurrences, uint32_t* coverage,
                  pcs_run_stats* stats);
 
+/* ---- multi-GPU: accumulate every shard straight into ONE pair of tables over NVLink peer memory ----
+ * The sampler's flush is a red.global.add per touched counter, so the tables may live on another GPU:
+ * the reduction of src/seq_simulation.cpp's per-sample statistics is fused into the kernel epilogue.
+ *   owner:  pcs_shared_alloc (+ ipc handle for other processes), pcs_memset_u32, ..., pcs_plan_finalize
+ *   others: pcs_shared_open (other process) or pcs_enable_peer (other device of this process),
+ *           pcs_plan_accumulate
+ * depth is [n_out_samples][n_loci], occurrences [n_out_samples][n_mut] (pcs_plan_info). */
+int pcs_shared_alloc(pcs_ctx* ctx, size_t bytes, void** dev_ptr, unsigned char ipc_handle[64]);
+int pcs_shared_free(pcs_ctx* ctx, void* dev_ptr);
+int pcs_shared_open(pcs_ctx* ctx, const unsigned char ipc_handle[64], void** dev_ptr);
+int pcs_shared_close(pcs_ctx* ctx, void* dev_ptr);
+int pcs_enable_peer(pcs_ctx* ctx, int peer_device);
+int pcs_memset_u32(pcs_ctx* ctx, uint32_t* dev_ptr, size_t count);   /* async on the context's stream */
+int pcs_memcpy_d2h(pcs_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes); /* synchronous */
+/* run this shard's sampler adding into the given tables: no zeroing, no finalize */
+int pcs_plan_accumulate(pcs_plan* plan, uint32_t* depth, uint32_t* occurrences, pcs_run_stats* stats);
+/* coverage[s][row] = depth[s][locus(row)] (device pointers) + table checksums in stats */
+int pcs_plan_finalize(pcs_plan* plan, const uint32_t* depth, const uint32_t* occurrences, uint32_t* coverage,
+                      pcs_run_stats* stats);
+
 /* debug/parity: re-run the plan emitting every placed read as a placement
  * record (+ its error mask when the sequencer has errors) instead of counting.
  * Host buffers of capacity `cap` records; *n_out receives the number written. */

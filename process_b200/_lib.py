@@ -21,6 +21,8 @@ EXPORTS = [
     "pcs_forest_upload", "pcs_forest_free", "pcs_forest_set_groups", "pcs_forest_info",
     "pcs_plan_create", "pcs_plan_info_get", "pcs_plan_free", "pcs_plan_run", "pcs_plan_trace",
     "pcs_simulate", "pcs_count_injected", "pcs_active_rows",
+    "pcs_shared_alloc", "pcs_shared_free", "pcs_shared_open", "pcs_shared_close", "pcs_enable_peer",
+    "pcs_memset_u32", "pcs_memcpy_d2h", "pcs_plan_accumulate", "pcs_plan_finalize",
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan",
 ]
@@ -124,6 +126,37 @@ class Context:
 
     __del__ = close
 
+    # ---- tables other GPUs / processes can accumulate into over NVLink
+    def shared_alloc(self, n_words):
+        """(device pointer, 64-byte IPC handle) of n_words uint32 of plain cudaMalloc memory."""
+        ptr = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _ok(lib().pcs_shared_alloc(self._h, C.c_size_t(4 * n_words), C.byref(ptr), handle))
+        return ptr.value, bytes(handle)
+
+    def shared_free(self, ptr):
+        _ok(lib().pcs_shared_free(self._h, C.c_void_p(ptr)))
+
+    def shared_open(self, handle: bytes):
+        ptr = C.c_void_p()
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _ok(lib().pcs_shared_open(self._h, buf, C.byref(ptr)))
+        return ptr.value
+
+    def shared_close(self, ptr):
+        _ok(lib().pcs_shared_close(self._h, C.c_void_p(ptr)))
+
+    def enable_peer(self, device):
+        _ok(lib().pcs_enable_peer(self._h, C.c_int(device)))
+
+    def memset_u32(self, ptr, n_words):
+        _ok(lib().pcs_memset_u32(self._h, C.c_void_p(ptr), C.c_size_t(n_words)))
+
+    def to_host(self, ptr, n_words):
+        out = np.zeros(n_words, np.uint32)
+        _ok(lib().pcs_memcpy_d2h(self._h, C.c_void_p(out.ctypes.data), C.c_void_p(ptr), C.c_size_t(4 * n_words)))
+        return out
+
     def device_name(self):
         buf = C.create_string_buffer(256)
         _ok(lib().pcs_device_name(self._h, buf, C.c_size_t(256)))
@@ -226,6 +259,18 @@ class Plan:
         st = A.RunStats()
         _ok(lib().pcs_plan_run(self._h, C.c_int(A.PCS_RUN_DEVICE_OUTPUT), C.c_void_p(occ_ptr),
                                C.c_void_p(cov_ptr), C.byref(st)))
+        return st
+
+    def accumulate(self, depth_ptr: int, occ_ptr: int):
+        """this shard's sampler adding into depth [S, n_loci] / occ [S, n_mut] (device or peer pointers)."""
+        st = A.RunStats()
+        _ok(lib().pcs_plan_accumulate(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.byref(st)))
+        return st
+
+    def finalize(self, depth_ptr: int, occ_ptr: int, cov_ptr: int):
+        st = A.RunStats()
+        _ok(lib().pcs_plan_finalize(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.c_void_p(cov_ptr),
+                                    C.byref(st)))
         return st
 
     def trace(self, cap, with_masks=False):

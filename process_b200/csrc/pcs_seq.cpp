@@ -568,6 +568,67 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   }
 }
 
+// the sampler of this shard, adding into caller-provided tables (possibly peer memory): no zeroing, no finalize
+void accumulate_plan(pcs_plan& pl, uint32_t* d_depth, uint32_t* d_occ, pcs_run_stats* stats) {
+  pcs_forest& fo = *pl.forest;
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  const size_t S = pl.host.info.n_out_samples, M = pl.host.info.n_mut, L = pl.host.info.n_loci;
+  require(S * M == 0 || (d_depth && d_occ), "depth/occurrences table pointers are NULL");
+  (void)L;
+  const double t0 = now_ms();
+  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_OK(cudaEventRecord(cx.ev[1], st));
+  const pcs::DevForest DF = fo.dev();
+  CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
+                                          DF, pl.host.model, pl.host.dims, d_depth, d_occ, pl.d_counters.p));
+  CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
+                                          pl.d_entries.p, DF, pl.host.model, d_depth, d_occ, pl.d_counters.p));
+  CUDA_OK(cudaEventRecord(cx.ev[2], st));
+  unsigned long long counters[4] = {0, 0, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (stats) {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, cx.ev[1], cx.ev[2]));
+    *stats = pcs_run_stats{};
+    stats->kernel_ms = ms;
+    stats->total_ms = now_ms() - t0;
+    stats->kernel_launches = (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
+    stats->n_templates = pl.host.info.n_templates;
+    stats->n_reads = counters[0];
+    stats->d2h_bytes = sizeof(counters);
+  }
+}
+
+// coverage[s][row] = depth[s][locus(row)] and the table checksums, once every shard has accumulated
+void finalize_tables(pcs_plan& pl, const uint32_t* d_depth, const uint32_t* d_occ, uint32_t* d_cov, pcs_run_stats* stats) {
+  pcs_forest& fo = *pl.forest;
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  const size_t S = pl.host.info.n_out_samples, M = pl.host.info.n_mut, L = pl.host.info.n_loci;
+  require(S * M == 0 || (d_depth && d_occ && d_cov), "table pointers are NULL");
+  const double t0 = now_ms();
+  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_OK(pcs::launch_finalize(st, d_depth, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
+                               static_cast<uint32_t>(M), d_cov));
+  CUDA_OK(pcs::launch_sum_u32(st, d_depth, S * L, pl.d_counters.p + 1));
+  CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
+  unsigned long long counters[4] = {0, 0, 0, 0};
+  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (stats) {
+    *stats = pcs_run_stats{};
+    stats->total_ms = now_ms() - t0;
+    stats->kernel_launches = (S * M != 0 ? 2 : 0) + (S * L != 0 ? 1 : 0);
+    stats->sum_depth = counters[1];
+    stats->sum_occurrences = counters[2];
+    stats->d2h_bytes = sizeof(counters);
+  }
+}
+
 template <class Fn>
 int guarded(Fn&& fn) {
   try {
@@ -739,6 +800,103 @@ int pcs_plan_run(pcs_plan* pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_
   return guarded([&] {
     require(pl != nullptr, "plan is NULL");
     run_plan(*pl, flags, occ, cov, stats);
+  });
+}
+
+int pcs_plan_accumulate(pcs_plan* pl, uint32_t* depth, uint32_t* occurrences, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(pl != nullptr, "plan is NULL");
+    accumulate_plan(*pl, depth, occurrences, stats);
+  });
+}
+
+int pcs_plan_finalize(pcs_plan* pl, const uint32_t* depth, const uint32_t* occurrences, uint32_t* coverage,
+                      pcs_run_stats* stats) {
+  return guarded([&] {
+    require(pl != nullptr, "plan is NULL");
+    finalize_tables(*pl, depth, occurrences, coverage, stats);
+  });
+}
+
+int pcs_shared_alloc(pcs_ctx* cx, size_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
+  return guarded([&] {
+    require(cx && dev_ptr && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cx->bind();
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, bytes));  // plain cudaMalloc: pool memory cannot be exported this way
+    if (ipc_handle) {
+      cudaIpcMemHandle_t h;
+      cudaError_t e = cudaIpcGetMemHandle(&h, p);
+      if (e != cudaSuccess) {
+        cudaFree(p);
+        throw CudaError(std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+      }
+      std::memcpy(ipc_handle, &h, 64);
+    }
+    *dev_ptr = p;
+  });
+}
+
+int pcs_shared_free(pcs_ctx* cx, void* dev_ptr) {
+  return guarded([&] {
+    require(cx != nullptr, "ctx is NULL");
+    cx->bind();
+    if (dev_ptr) CUDA_OK(cudaFree(dev_ptr));
+  });
+}
+
+int pcs_shared_open(pcs_ctx* cx, const unsigned char ipc_handle[64], void** dev_ptr) {
+  return guarded([&] {
+    require(cx && ipc_handle && dev_ptr, "bad arguments");
+    cx->bind();
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, ipc_handle, 64);
+    CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  });
+}
+
+int pcs_shared_close(pcs_ctx* cx, void* dev_ptr) {
+  return guarded([&] {
+    require(cx != nullptr, "ctx is NULL");
+    cx->bind();
+    if (dev_ptr) CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  });
+}
+
+int pcs_enable_peer(pcs_ctx* cx, int peer_device) {
+  return guarded([&] {
+    require(cx != nullptr, "ctx is NULL");
+    cx->bind();
+    if (peer_device == cx->device) return;
+    int can = 0;
+    CUDA_OK(cudaDeviceCanAccessPeer(&can, cx->device, peer_device));
+    if (!can) throw CudaError("the devices cannot access each other's memory");
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+      cudaGetLastError();
+      return;
+    }
+    CUDA_OK(e);
+  });
+}
+
+int pcs_memset_u32(pcs_ctx* cx, uint32_t* dev_ptr, size_t count) {
+  return guarded([&] {
+    require(cx && (dev_ptr || count == 0), "bad arguments");
+    cx->bind();
+    if (count) CUDA_OK(cudaMemsetAsync(dev_ptr, 0, count * sizeof(uint32_t), cx->stream));
+  });
+}
+
+int pcs_memcpy_d2h(pcs_ctx* cx, void* host_dst, const void* dev_src, size_t bytes) {
+  return guarded([&] {
+    require(cx && (bytes == 0 || (host_dst && dev_src)), "bad arguments");
+    cx->bind();
+    if (bytes) {
+      CUDA_OK(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, cx->stream));
+      CUDA_OK(cudaStreamSynchronize(cx->stream));
+    }
   });
 }
 

@@ -1,0 +1,68 @@
+"""Multi-GPU reduction fused into the sampler's flush: shards accumulate straight into ONE pair of
+tables, which another process maps through CUDA IPC (over NVLink when it sits on another GPU).
+Runs on a single GPU too: the second shard is a child process mapping the parent's tables."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from process_b200 import _abi as A
+from process_b200 import _lib as L
+from process_b200.synth import synth_forest
+
+from conftest import make_params, small_spec
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r"""
+import sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+from process_b200 import _lib as L
+from process_b200.synth import synth_forest
+from conftest import make_params, small_spec
+handle = bytes.fromhex(sys.argv[1]); n_depth = int(sys.argv[2]); device = int(sys.argv[3])
+f = synth_forest(small_spec(1))
+ctx = L.Context(device)
+dev = L.Forest(ctx, f)
+plan = L.Plan(dev, make_params(coverage=25.0, purity=0.7, sequencer=2, error_rate=0.02, insert_size_mean=180,
+                               shard_rank=1, shard_count=2))
+base = ctx.shared_open(handle)
+st = plan.accumulate(base, base + 4 * n_depth)
+ctx.shared_close(base)
+print("child_reads", st.n_reads)
+"""
+
+
+def test_two_processes_accumulate_into_one_table(tmp_path):
+    import torch
+    f = synth_forest(small_spec(1))
+    ctx = L.Context(0)
+    dev = L.Forest(ctx, f)
+    kw = dict(coverage=25.0, purity=0.7, sequencer=A.PCS_SEQ_BASIC_RANDOM, error_rate=0.02, insert_size_mean=180)
+    want_occ, want_cov, want_st = dev.simulate(make_params(**kw))
+    plan = L.Plan(dev, make_params(shard_rank=0, shard_count=2, **kw))
+    S, M, Lc = plan.info.n_out_samples, plan.info.n_mut, plan.info.n_loci
+    base, handle = ctx.shared_alloc(S * Lc + 2 * S * M)
+    depth_p, occ_p, cov_p = base, base + 4 * S * Lc, base + 4 * (S * Lc + S * M)
+    ctx.memset_u32(base, S * Lc + 2 * S * M)
+    mine = plan.accumulate(depth_p, occ_p)  # also synchronises the memset
+    second = 1 if torch.cuda.device_count() > 1 else 0
+    script = tmp_path / "child.py"
+    script.write_text(CHILD.format(root=ROOT))
+    out = subprocess.run([sys.executable, str(script), handle.hex(), str(S * Lc), str(second)], capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    child_reads = int(out.stdout.strip().split()[-1])
+    fin = plan.finalize(depth_p, occ_p, cov_p)
+    occ = ctx.to_host(occ_p, S * M).reshape(S, M)
+    cov = ctx.to_host(cov_p, S * M).reshape(S, M)
+    assert mine.n_reads + child_reads == want_st.n_reads
+    assert np.array_equal(occ, want_occ) and np.array_equal(cov, want_cov)
+    assert fin.sum_occurrences == want_st.sum_occurrences and fin.sum_depth == want_st.sum_depth
+    ctx.shared_free(base)
+    plan.close()
+    dev.close()
+    ctx.close()
