@@ -253,6 +253,14 @@ int pcs_plan_accumulate(pcs_plan* plan, uint32_t* depth, uint32_t* occurrences, 
 int pcs_plan_finalize(pcs_plan* plan, const uint32_t* depth, const uint32_t* occurrences, uint32_t* coverage,
                       pcs_run_stats* stats);
 
+/* ---- one process, several GPUs (what the single-threaded R session needs) ----
+ * pcs_forest_replicate: a second device copy of an uploaded forest, sharing its flattened host view.
+ * pcs_simulate_multi:   forests[i] lives on device i (replicas of forests[0]); shard i of n runs on it from its
+ *                       own host thread, all samplers flush into forests[0]'s device, host tables come back. */
+int pcs_forest_replicate(pcs_forest* src, pcs_ctx* ctx, pcs_forest** replica);
+int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_params* params,
+                       uint32_t* occurrences, uint32_t* coverage, pcs_run_stats* stats);
+
 /* debug/parity: re-run the plan emitting every placed read as a placement
  * record (+ its error mask when the sequencer has errors) instead of counting.
  * Host buffers of capacity `cap` records; *n_out receives the number written. */

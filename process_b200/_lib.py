@@ -23,6 +23,7 @@ EXPORTS = [
     "pcs_simulate", "pcs_count_injected", "pcs_active_rows",
     "pcs_shared_alloc", "pcs_shared_free", "pcs_shared_open", "pcs_shared_close", "pcs_enable_peer",
     "pcs_memset_u32", "pcs_memcpy_d2h", "pcs_plan_accumulate", "pcs_plan_finalize",
+    "pcs_forest_replicate", "pcs_simulate_multi",
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan",
 ]
@@ -225,6 +226,28 @@ class Forest:
         _ok(lib().pcs_active_rows(self._h, A.ptr(occ, C.c_uint32), C.c_uint32(occ.shape[0]),
                                   C.c_int(1 if include_non_sequenced else 0), A.ptr(rows, C.c_uint32), C.byref(n)))
         return rows[:n.value].copy()
+
+
+def replicate(src: "Forest", ctx: Context) -> "Forest":
+    """a copy of an uploaded forest on another context's device, sharing the flattened host view."""
+    f = Forest.__new__(Forest)
+    f.ctx, f.forest, f.n_groups = ctx, src.forest, src.n_groups
+    f._h = C.c_void_p()
+    _ok(lib().pcs_forest_replicate(src._h, ctx._h, C.byref(f._h)))
+    return f
+
+
+def simulate_multi(forests, params: A.SeqParams):
+    """one process driving len(forests) devices: shard i runs on forests[i], tables land on forests[0]'s GPU."""
+    n_out = forests[0].n_out_samples(params)
+    n_mut = forests[0].forest.n_mut
+    occ = np.zeros((n_out, n_mut), np.uint32)
+    cov = np.zeros((n_out, n_mut), np.uint32)
+    arr = (C.c_void_p * len(forests))(*[f._h for f in forests])
+    st = A.RunStats()
+    _ok(lib().pcs_simulate_multi(arr, C.c_uint32(len(forests)), C.byref(params), A.ptr(occ, C.c_uint32),
+                                 A.ptr(cov, C.c_uint32), C.byref(st)))
+    return occ, cov, st
 
 
 class Plan:

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <random>
@@ -121,7 +122,10 @@ struct HostForest {
     return (static_cast<uint64_t>(kind) << 56) | (static_cast<uint64_t>(cell) << 16) | allele;
   }
 
+  uint64_t groups_version = 0;  // bumped by build_groups: device copies of hap_list go stale
+
   void build_groups(const uint32_t* lg, uint32_t ng) {
+    ++groups_version;
     n_groups = ng;
     leaf_group.assign(lg, lg + flat.n_leaves);
     group_cells.assign(ng, 0);
@@ -165,7 +169,8 @@ struct pcs_flat {
 
 struct pcs_forest {
   pcs_ctx* ctx = nullptr;
-  HostForest host;
+  std::shared_ptr<HostForest> host_ptr = std::make_shared<HostForest>();
+  HostForest& host = *host_ptr;  // several devices may hold one flattened forest
   DevBuf<uint32_t> d_locus_pos, d_chr_locus_off, d_locus_inst_off, d_row_locus, d_hap_list;
   DevBuf<pcs::Inst> d_inst;
   uint64_t h2d_bytes = 0;
@@ -184,9 +189,29 @@ struct pcs_forest {
 
   void set_groups(const uint32_t* lg, uint32_t ng) {
     host.build_groups(lg, ng);
+    upload_groups();
+  }
+  uint64_t uploaded_groups = 0;
+  void upload_groups() {
     ctx->bind();
     h2d_bytes += d_hap_list.upload(host.hap_list, ctx->stream);
+    uploaded_groups = host.groups_version;
   }
+  // a replica whose sibling changed the sample groups re-uploads the haplotype lists
+  void sync_groups() {
+    if (uploaded_groups != host.groups_version) upload_groups();
+  }
+  void upload_flat() {
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    h2d_bytes += d_locus_pos.upload(host.flat.locus_pos, st);
+    h2d_bytes += d_chr_locus_off.upload(host.flat.chr_locus_off, st);
+    h2d_bytes += d_locus_inst_off.upload(host.flat.locus_inst_off, st);
+    h2d_bytes += d_row_locus.upload(host.flat.row_locus, st);
+    h2d_bytes += d_inst.upload(host.flat.inst, st);
+  }
+  pcs_forest() = default;
+  explicit pcs_forest(const pcs_forest& other, pcs_ctx* cx) : ctx(cx), host_ptr(other.host_ptr), host(*host_ptr) {}
 };
 
 // host half of a plan: tile grid of this shard, sampling tables, sequencer model
@@ -719,13 +744,7 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     Lap lap;
     pcs::flatten_forest(*desc, fo->host.flat, nt);
     lap("flatten_forest");
-    cx->bind();
-    cudaStream_t st = cx->stream;
-    fo->h2d_bytes += fo->d_locus_pos.upload(fo->host.flat.locus_pos, st);
-    fo->h2d_bytes += fo->d_chr_locus_off.upload(fo->host.flat.chr_locus_off, st);
-    fo->h2d_bytes += fo->d_locus_inst_off.upload(fo->host.flat.locus_inst_off, st);
-    fo->h2d_bytes += fo->d_row_locus.upload(fo->host.flat.row_locus, st);
-    fo->h2d_bytes += fo->d_inst.upload(fo->host.flat.inst, st);
+    fo->upload_flat();
     lap("upload flat arrays");
     fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
     lap("groups + upload");
@@ -773,6 +792,7 @@ int pcs_plan_create(pcs_forest* fo, const pcs_seq_params* params, pcs_plan** out
     auto pl = std::make_unique<pcs_plan>();
     pl->forest = fo;
     Lap lap;
+    fo->sync_groups();
     pl->host = make_host_plan(fo->host, *params);
     lap("make_host_plan");
     upload_plan(*pl);
@@ -886,6 +906,111 @@ int pcs_memset_u32(pcs_ctx* cx, uint32_t* dev_ptr, size_t count) {
     require(cx && (dev_ptr || count == 0), "bad arguments");
     cx->bind();
     if (count) CUDA_OK(cudaMemsetAsync(dev_ptr, 0, count * sizeof(uint32_t), cx->stream));
+  });
+}
+
+int pcs_forest_replicate(pcs_forest* src, pcs_ctx* cx, pcs_forest** out) {
+  return guarded([&] {
+    require(src && cx && out, "bad arguments");
+    auto fo = std::make_unique<pcs_forest>(*src, cx);  // shares the flattened host view: no second flatten
+    fo->upload_flat();
+    fo->upload_groups();
+    *out = fo.release();
+  });
+}
+
+int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_params* params, uint32_t* occ,
+                       uint32_t* cov, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(forests && n >= 1 && n <= 64 && params && occ && cov, "bad arguments");
+    for (uint32_t i = 0; i < n; ++i) require(forests[i] != nullptr, "forest is NULL");
+    for (uint32_t i = 1; i < n; ++i)
+      require(forests[i]->host_ptr == forests[0]->host_ptr, "the forests must be replicas of forests[0] (pcs_forest_replicate)");
+    validate(*params);
+    const double t0 = now_ms();
+    pcs_forest& owner = *forests[0];
+    pcs_ctx& cx0 = *owner.ctx;
+    // one plan per device: shard i of n
+    std::vector<std::unique_ptr<pcs_plan>> plans(n);
+    std::vector<std::string> errors(n);
+    std::vector<pcs_run_stats> rs(n);
+    auto on_each = [&](const std::function<void(uint32_t)>& fn) {
+      std::vector<std::thread> th;
+      for (uint32_t i = 0; i < n; ++i)
+        th.emplace_back([&, i] {
+          try {
+            fn(i);
+          } catch (const std::exception& e) {
+            errors[i] = e.what();
+            if (errors[i].empty()) errors[i] = "device worker failed";
+          }
+        });
+      for (auto& t : th) t.join();
+      for (const auto& e : errors)
+        if (!e.empty()) throw CudaError(e);
+    };
+    on_each([&](uint32_t i) {
+      pcs_seq_params P = *params;
+      P.shard_rank = i;
+      P.shard_count = n;
+      auto pl = std::make_unique<pcs_plan>();
+      pl->forest = forests[i];
+      forests[i]->sync_groups();
+      pl->host = make_host_plan(forests[i]->host, P);
+      upload_plan(*pl);
+      plans[i] = std::move(pl);
+      if (forests[i]->ctx->device != cx0.device) {
+        forests[i]->ctx->bind();
+        int can = 0;
+        CUDA_OK(cudaDeviceCanAccessPeer(&can, forests[i]->ctx->device, cx0.device));
+        if (!can) throw CudaError("the devices cannot access each other's memory");
+        cudaError_t e = cudaDeviceEnablePeerAccess(cx0.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CUDA_OK(e);
+      }
+    });
+    // the tables live on the first device; every device's sampler flushes into them.  Plain cudaMalloc:
+    // peers cannot reach stream-ordered pool memory through cudaDeviceEnablePeerAccess.
+    pcs_plan& p0 = *plans[0];
+    const size_t S = p0.host.info.n_out_samples, M = p0.host.info.n_mut, L = p0.host.info.n_loci;
+    cx0.bind();
+    struct Tables {
+      uint32_t* p = nullptr;
+      ~Tables() { if (p) cudaFree(p); }
+    } tb;
+    const size_t words = S * L + 2 * S * M;
+    if (words) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tb.p), words * sizeof(uint32_t)));
+    uint32_t* t_depth = tb.p;
+    uint32_t* t_occ = tb.p + S * L;
+    uint32_t* t_cov = t_occ + S * M;
+    if (words) CUDA_OK(cudaMemsetAsync(tb.p, 0, (S * L + S * M) * sizeof(uint32_t), cx0.stream));
+    CUDA_OK(cudaStreamSynchronize(cx0.stream));
+    on_each([&](uint32_t i) { accumulate_plan(*plans[i], t_depth, t_occ, &rs[i]); });
+    pcs_run_stats fin{};
+    finalize_tables(p0, t_depth, t_occ, t_cov, &fin);
+    cx0.bind();
+    if (S * M != 0) {
+      CUDA_OK(cudaMemcpyAsync(occ, t_occ, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx0.stream));
+      CUDA_OK(cudaMemcpyAsync(cov, t_cov, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx0.stream));
+      CUDA_OK(cudaStreamSynchronize(cx0.stream));
+    }
+    for (uint32_t i = 0; i < n; ++i) {  // free each plan on its own device
+      cudaSetDevice(forests[i]->ctx->device);
+      plans[i].reset();
+    }
+    if (stats) {
+      *stats = pcs_run_stats{};
+      for (uint32_t i = 0; i < n; ++i) {
+        stats->kernel_ms = std::max(stats->kernel_ms, rs[i].kernel_ms);
+        stats->kernel_launches += rs[i].kernel_launches;
+        stats->n_templates += rs[i].n_templates;
+        stats->n_reads += rs[i].n_reads;
+      }
+      stats->kernel_launches += fin.kernel_launches;
+      stats->sum_depth = fin.sum_depth;
+      stats->sum_occurrences = fin.sum_occurrences;
+      stats->d2h_bytes = 2 * S * M * sizeof(uint32_t);
+      stats->total_ms = now_ms() - t0;
+    }
   });
 }
 

@@ -66,3 +66,30 @@ def test_two_processes_accumulate_into_one_table(tmp_path):
     plan.close()
     dev.close()
     ctx.close()
+
+
+@pytest.mark.parametrize("n_ctx", [2, 3])
+def test_one_process_several_contexts(n_ctx):
+    """pcs_simulate_multi: one host process, one context per device (or several on the one GPU there is),
+    shard i on context i, every sampler flushing into the first context's tables."""
+    import torch
+    f = synth_forest(small_spec(2))
+    n_dev = torch.cuda.device_count()
+    ctxs = [L.Context(i % n_dev) for i in range(n_ctx)]
+    first = L.Forest(ctxs[0], f)
+    forests = [first] + [L.replicate(first, c) for c in ctxs[1:]]
+    P = make_params(coverage=30.0, purity=0.6, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01)
+    want_occ, want_cov, want = first.simulate(P)
+    occ, cov, st = L.simulate_multi(forests, P)
+    assert np.array_equal(occ, want_occ) and np.array_equal(cov, want_cov)
+    assert st.n_reads == want.n_reads and st.sum_occurrences == want.sum_occurrences
+    # groups set on the first forest are what the replicas see (shared host view)
+    groups = (np.arange(f.n_leaves) % 2).astype(np.uint32)
+    first.set_groups(groups, 2)
+    want_occ, want_cov, _ = first.simulate(P)
+    occ, cov, _ = L.simulate_multi(forests, P)
+    assert occ.shape[0] == 3 and np.array_equal(occ, want_occ) and np.array_equal(cov, want_cov)
+    for fo in forests:
+        fo.close()
+    for c in ctxs:
+        c.close()
