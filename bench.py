@@ -169,6 +169,10 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sequencer", default="errorless", choices=["errorless", "constant", "random"],
+                    help="non-default sequencer models are for profiling; the headline workload is errorless")
+    ap.add_argument("--error-rate", type=float, default=1e-3)
+    ap.add_argument("--insert-size", type=int, default=0, help="paired-end reads with this mean insert (sd 10)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N>1: 'peer' = every rank's sampler flushes into rank 0's tables over NVLink peer memory "
                          "(reduction fused into the kernel), 'nccl' = local tables + NCCL reduce")
@@ -176,6 +180,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     cfg, scale, wl_params = WORKLOADS[args.workload]
+    wl_params = dict(wl_params)
+    if args.sequencer != "errorless":
+        wl_params.update(sequencer={"constant": A.PCS_SEQ_BASIC_CONSTANT, "random": A.PCS_SEQ_BASIC_RANDOM}[args.sequencer],
+                         error_rate=args.error_rate)
+    if args.insert_size:
+        wl_params.update(insert_size_mean=args.insert_size, insert_size_stddev=10)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -379,7 +389,8 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: BASELINE.json configs[2], GRCh38-length genome, 3 tumour samples x "
                                    "1000 cells + normal_sample, 80x WGS, read_size 150, ErrorlessIlluminaSequencer"
-                       if args.workload == "C3" else args.workload,
+                       if args.workload == "C3" and args.sequencer == "errorless" and not args.insert_size
+                       else f"{args.workload} sequencer={args.sequencer} error_rate={args.error_rate} insert={args.insert_size}",
                        "samples": S, "rows": M, "reads_per_step": total_reads / args.steps,
                        "tiles_this_rank": int(plan.info.n_tiles), "parallelism": f"tile-sharded x{world}",
                        "exchange": {"none": "single GPU", "peer": "sampler flush adds into rank 0's tables over NVLink "

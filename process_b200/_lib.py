@@ -121,8 +121,8 @@ class Context:
         self.device = device
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().pcs_destroy(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:  # _LIB is gone at interpreter shutdown
+            _LIB.pcs_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -176,8 +176,8 @@ class Forest:
         self.n_groups = forest.n_samples
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().pcs_forest_free(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:  # _LIB is gone at interpreter shutdown
+            _LIB.pcs_forest_free(self._h)
             self._h = None
 
     __del__ = close
@@ -262,8 +262,8 @@ class Plan:
         _ok(lib().pcs_plan_info_get(self._h, C.byref(self.info)))
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().pcs_plan_free(self._h)
+        if getattr(self, "_h", None) and _LIB is not None:  # _LIB is gone at interpreter shutdown
+            _LIB.pcs_plan_free(self._h)
             self._h = None
 
     __del__ = close

@@ -62,30 +62,38 @@ __device__ __forceinline__ float ramp(uint32_t i, uint32_t R) {
 // is any of the `n` read bases starting at `off` a sequencing error?  One Philox
 // block per tested base, counter (read, tile, (1 + hit) | base << 20, seed): the
 // outcome does not depend on scheduling.
+// Kept out of line on purpose: inlined into the walk it costs the hot kernel ~20 registers (one CTA
+// less per SM) for a branch only one read in six takes.
+__device__ __noinline__ bool draw_base_errors(uint32_t sequencer, uint32_t err_thr, float error_rate, uint32_t R,
+                                              uint32_t seed, uint32_t read, uint32_t tile, uint32_t hit, uint32_t off,
+                                              uint32_t n, uint32_t* mask) {
+  bool any = false;
+  for (uint32_t b = 0; b < n; ++b) {
+    const uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), seed));
+    bool e;
+    if (sequencer == PCS_SEQ_BASIC_CONSTANT) {
+      e = w.x < err_thr;
+    } else {
+      const float z = sqrtf(-2.0f * __logf(u01(w.x))) * cospif(2.0f * u01(w.y));
+      const float p = error_rate * ramp(off + b, R) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
+      e = u01(w.z) < fminf(p, 1.0f);
+    }
+    if (e) {
+      any = true;
+      const uint32_t i = off + b;
+      if (mask && i < 32u * PCS_ERRMASK_WORDS) mask[i >> 5] |= 1u << (i & 31);
+    }
+  }
+  return any;
+}
+
 struct ErrDraw {
   const SeqModel& M;
   uint32_t read, tile;
   uint32_t* mask;  // trace mode: error bits found, else nullptr
-  __device__ bool operator()(uint32_t hit, uint32_t off, uint32_t n) const {
+  __device__ __forceinline__ bool operator()(uint32_t hit, uint32_t off, uint32_t n) const {
     if (M.sequencer == PCS_SEQ_ERRORLESS) return false;
-    bool any = false;
-    for (uint32_t b = 0; b < n; ++b) {
-      uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), M.seed));
-      bool e;
-      if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
-        e = w.x < M.err_thr;
-      } else {
-        float z = sqrtf(-2.0f * __logf(u01(w.x))) * cospif(2.0f * u01(w.y));
-        float p = M.error_rate * ramp(off + b, M.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
-        e = u01(w.z) < fminf(p, 1.0f);
-      }
-      if (e) {
-        any = true;
-        uint32_t i = off + b;
-        if (mask && i < 32u * PCS_ERRMASK_WORDS) mask[i >> 5] |= 1u << (i & 31);
-      }
-    }
-    return any;
+    return draw_base_errors(M.sequencer, M.err_thr, M.error_rate, M.read_size, M.seed, read, tile, hit, off, n, mask);
   }
 };
 
@@ -626,13 +634,15 @@ size_t staged_smem_bytes(const StageDims& D) {
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
-static int staged_min_ctas() {
+// CTAs per SM the kernel is compiled for: PCS_MIN_CTAS overrides.  The error-model variants need ~78
+// registers uncapped; capping them at 64 (4 CTAs) spills a little and still wins on occupancy.
+static int staged_min_ctas(bool errors) {
   static const int v = [] {
     const char* s = std::getenv("PCS_MIN_CTAS");
     const int x = s ? std::atoi(s) : 0;
-    return (x >= 3 && x <= 8) ? x : kDefaultMinCtas;
+    return (x >= 3 && x <= 8) ? x : 0;
   }();
-  return v;
+  return v ? v : (errors ? 4 : kDefaultMinCtas);
 }
 
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
@@ -651,7 +661,7 @@ template <bool PAIRED, bool ERRORS>
 static cudaError_t launch_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                  const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                  uint32_t* alt, unsigned long long* n_reads) {
-  switch (staged_min_ctas()) {
+  switch (staged_min_ctas(ERRORS)) {
     case 3: return launch_staged_occ<PAIRED, ERRORS, 3>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
     case 5: return launch_staged_occ<PAIRED, ERRORS, 5>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
     case 6: return launch_staged_occ<PAIRED, ERRORS, 6>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
