@@ -261,6 +261,33 @@ int pcs_forest_replicate(pcs_forest* src, pcs_ctx* ctx, pcs_forest** replica);
 int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_params* params,
                        uint32_t* occurrences, uint32_t* coverage, pcs_run_stats* stats);
 
+/* ---- SAM output (write_SAM = TRUE; src/seq_simulation.cpp:540-564, vignettes/sequencing.Rmd:137-177, 272-309) ----
+ * Reads are materialised on the GPU (bases from the reference + carried SIDs, CIGAR, qualities, errors) with the
+ * Philox counters of the counting kernels: the tables and the SAM files of one plan describe the same reads. */
+int pcs_forest_set_reference(pcs_forest* forest, uint32_t chr, const char* bases, uint64_t len);
+int pcs_forest_load_fasta(pcs_forest* forest, const char* path, const char* const* chr_names, uint32_t* n_loaded);
+int pcs_forest_set_alt(pcs_forest* forest, const uint32_t* alt_off /*[n_mut+1]*/, const char* alt_bytes);
+
+typedef struct pcs_sam_options {
+  const char* output_dir;
+  const char* filename_prefix;        /* "chr_"  */
+  const char* template_name_prefix;   /* "r"     */
+  const char* const* chr_names;       /* [n_chr] */
+  const char* const* sample_names;    /* [n_out_samples]: read group ids */
+  uint8_t update;                     /* 0: the directory must not exist (Mode::CREATE); 1: Mode::UPDATE */
+} pcs_sam_options;
+
+/* one file <output_dir>/<filename_prefix><chr>.sam per sequenced chromosome, every sample a read group;
+ * in update mode an existing file name gets the first free suffix _<n> */
+int pcs_plan_write_sam(pcs_plan* plan, const pcs_sam_options* options, uint64_t* n_reads_written);
+
+#define PCS_MAX_CIGAR 16
+/* parity/debug: the reads of the plan as binary records.  seq/qual: [cap][read_size]; cigar: [cap][PCS_MAX_CIGAR]
+ * words (length << 4 | op, op 0 M 1 I 2 D); lengths: bases written per read */
+int pcs_plan_materialize(pcs_plan* plan, uint64_t cap, pcs_read_placement* placements, uint32_t* err_masks,
+                         uint8_t* seq, uint8_t* qual, uint32_t* cigar, uint32_t* n_cigar, uint32_t* lengths,
+                         uint64_t* n_out);
+
 /* debug/parity: re-run the plan emitting every placed read as a placement
  * record (+ its error mask when the sequencer has errors) instead of counting.
  * Host buffers of capacity `cap` records; *n_out receives the number written. */

@@ -97,3 +97,21 @@ def cell_genome(forest, which, cell, chrom, cap=1 << 16):
     frags = [(int(fa[i]), int(fo[i]), int(fb[i]), int(fe[i])) for i in range(nf.value)]
     sids = [(int(sa[i]), int(sr[i])) for i in range(ns.value)]
     return frags, sids
+
+
+def materialize(forest, ref_off, ref_bases: bytes, alt_off, alt_bytes: bytes, read_size, sequencer, error_rate,
+                placements, err_masks=None):
+    """SAM content of a placement list: (seq [n, R] uint8, qual, cigar [n, 16], n_cigar, lengths)."""
+    d = forest.as_desc()
+    placements = np.ascontiguousarray(placements, dtype=A.PLACEMENT_DTYPE)
+    n = len(placements)
+    seq = np.zeros((n, read_size), np.uint8); qual = np.zeros((n, read_size), np.uint8)
+    cigar = np.zeros((n, 16), np.uint32); nc = np.zeros(n, np.uint32); ln = np.zeros(n, np.uint32)
+    ro = np.ascontiguousarray(ref_off, dtype=np.uint64); ao = np.ascontiguousarray(alt_off, dtype=np.uint32)
+    em = None if err_masks is None else np.ascontiguousarray(err_masks, dtype=np.uint32)
+    _check(lib().oracle_materialize(
+        C.byref(d), A.ptr(ro, C.c_uint64), C.c_char_p(ref_bases), A.ptr(ao, C.c_uint32), C.c_char_p(alt_bytes),
+        C.c_uint32(read_size), C.c_uint32(sequencer), C.c_double(error_rate), C.c_void_p(placements.ctypes.data),
+        A.ptr(em, C.c_uint32), C.c_uint64(n), A.ptr(seq, C.c_uint8), A.ptr(qual, C.c_uint8), A.ptr(cigar, C.c_uint32),
+        A.ptr(nc, C.c_uint32), A.ptr(ln, C.c_uint32)))
+    return seq, qual, cigar, nc, ln

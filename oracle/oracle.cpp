@@ -658,6 +658,101 @@ int oracle_count_injected(const pcs_forest_desc* desc, uint32_t n_out_samples, u
   }
 }
 
+/* Materialise reads (SAM content) from a placement list: bases of the reference with the carried SIDs of
+ * the named allele applied, CIGAR (length << 4 | op; 0 M, 1 I, 2 D; at most 16 runs), qualities for the
+ * errorless ('I') and constant-quality (error '#', else Phred of error_rate) models; bases whose bit is set
+ * in the read's error mask are substituted by (code + 1 + offset % 3) & 3 over ACGT.
+ * ref_off[c] = offset of position 1 of chromosome c in ref_bases. */
+int oracle_materialize(const pcs_forest_desc* desc, const uint64_t* ref_off, const char* ref_bases,
+                       const uint32_t* alt_off, const char* alt_bytes, uint32_t read_size, uint32_t sequencer,
+                       double error_rate, const pcs_read_placement* rec, const uint32_t* err_masks, uint64_t n,
+                       uint8_t* seq, uint8_t* qual, uint32_t* cigar, uint32_t* n_cigar, uint32_t* lengths) {
+  try {
+    Forest f = build_forest(desc);
+    const uint32_t R = read_size;
+    std::vector<std::vector<uint64_t>> by_chr(desc->n_chr);
+    for (uint64_t i = 0; i < n; ++i) {
+      check(rec[i].chr < desc->n_chr, "placement chromosome out of range");
+      by_chr[rec[i].chr].push_back(i);
+    }
+    auto subst = [](uint8_t b, uint32_t o) -> uint8_t {
+      const char* acgt = "ACGT";
+      const char* at = std::strchr(acgt, b);
+      if (!at || !b) return b;
+      return static_cast<uint8_t>(acgt[((at - acgt) + 1 + o % 3) & 3]);
+    };
+    int qc = static_cast<int>(-10.0 * std::log10(std::max(std::min(error_rate, 1.0), 1e-5)) + 0.5);
+    qc = std::min(41, std::max(2, qc));
+    for (uint32_t c = 0; c < desc->n_chr; ++c) {
+      if (by_chr[c].empty()) continue;
+      ChrGenomes G = build_chr_genomes(f, c);
+      const char* ref = ref_bases + ref_off[c] - 1;  // ref[p]: base at 1-based position p
+      for (uint64_t i : by_chr[c]) {
+        const pcs_read_placement& r = rec[i];
+        const ChrGenome* g = r.flags == PCS_PLACE_TUMOUR ? &G.leaf.at(r.cell)
+                             : r.flags == PCS_PLACE_NORMAL_PLAIN ? &G.normal_plain : &G.normal_preneo.at(r.cell);
+        auto ai = g->alleles.find(r.allele);
+        check(ai != g->alleles.end(), "placement names a missing allele");
+        const Fragment* fr = nullptr;
+        for (const auto& [b, x] : ai->second.fragments)
+          if (r.start >= x.begin && r.start <= x.end) fr = &x;
+        check(fr != nullptr, "placement starts outside every fragment of the allele");
+        const uint32_t* mw = err_masks ? err_masks + i * PCS_ERRMASK_WORDS : nullptr;
+        uint8_t* sq = seq + i * R;
+        uint8_t* ql = qual + i * R;
+        uint32_t* cg = cigar + i * 16;
+        uint32_t nc = 0, o = 0;
+        auto push = [&](uint32_t op, uint32_t len) {
+          if (!len) return;
+          if (nc && (cg[nc - 1] & 15u) == op) cg[nc - 1] += len << 4;
+          else if (nc < 16) cg[nc++] = (len << 4) | op;
+        };
+        auto put = [&](uint8_t b) {
+          bool err = mw && o < 32 * PCS_ERRMASK_WORDS && ((mw[o >> 5] >> (o & 31)) & 1);
+          sq[o] = err ? subst(b, o) : b;
+          ql[o] = sequencer == PCS_SEQ_ERRORLESS ? 'I' : sequencer == PCS_SEQ_BASIC_CONSTANT ? (err ? '#' : static_cast<uint8_t>(33 + qc)) : 0;
+          ++o;
+        };
+        const auto& gv = f.germ[c][ai->second.origin];
+        auto gi = std::lower_bound(gv.begin(), gv.end(), std::make_pair(r.start, 0u));
+        auto si = fr->sids.lower_bound(r.start);
+        uint32_t q = r.start;
+        while (o < R && q <= fr->end) {
+          while (gi != gv.end() && gi->first < q) ++gi;
+          while (si != fr->sids.end() && si->first < q) ++si;
+          bool has = false;
+          uint32_t p = 0, m = 0;
+          if (gi != gv.end() && gi->first <= fr->end) { has = true; p = gi->first; m = gi->second; }
+          if (si != fr->sids.end() && si->first <= fr->end && (!has || si->first < p)) { has = true; p = si->first; m = si->second; }
+          if (!has || p - q >= R - o) {
+            uint32_t last = static_cast<uint32_t>(std::min<uint64_t>(static_cast<uint64_t>(q) + (R - o) - 1, fr->end));
+            push(0, last - q + 1);
+            for (uint32_t b = q; b <= last; ++b) put(static_cast<uint8_t>(ref[b]));
+            break;
+          }
+          push(0, p - q);
+          for (uint32_t b = q; b < p; ++b) put(static_cast<uint8_t>(ref[b]));
+          const uint32_t rl = desc->mut_ref_len[m], al = desc->mut_alt_len[m];
+          const uint32_t consumed = std::min(al, R - o);
+          const char* alt = alt_bytes + alt_off[m];
+          for (uint32_t b = 0; b < consumed; ++b) put(static_cast<uint8_t>(alt[b]));
+          const uint32_t mm = std::min(consumed, rl);
+          push(0, mm);
+          push(1, consumed - mm);
+          q = p + rl;
+          if (o < R && rl > al) push(2, rl - al);
+        }
+        n_cigar[i] = nc;
+        lengths[i] = o;
+      }
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 /* explicit genome of one cell on one chromosome, for hand-checked tests.
  * which: PCS_PLACE_*; cell: leaf index / root ordinal.
  * Output (capacity `cap` each, *n_frag / *n_sid receive the counts):

@@ -77,3 +77,11 @@ def ptr(arr, ctype):
         return C.cast(None, C.POINTER(ctype))
     assert arr.flags["C_CONTIGUOUS"]
     return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class SamOptions(C.Structure):
+    _fields_ = [("output_dir", C.c_char_p), ("filename_prefix", C.c_char_p), ("template_name_prefix", C.c_char_p),
+                ("chr_names", C.POINTER(C.c_char_p)), ("sample_names", C.POINTER(C.c_char_p)), ("update", C.c_uint8)]
+
+
+PCS_MAX_CIGAR = 16

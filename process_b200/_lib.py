@@ -24,6 +24,8 @@ EXPORTS = [
     "pcs_shared_alloc", "pcs_shared_free", "pcs_shared_open", "pcs_shared_close", "pcs_enable_peer",
     "pcs_memset_u32", "pcs_memcpy_d2h", "pcs_plan_accumulate", "pcs_plan_finalize",
     "pcs_forest_replicate", "pcs_simulate_multi",
+    "pcs_forest_set_reference", "pcs_forest_load_fasta", "pcs_forest_set_alt", "pcs_plan_write_sam",
+    "pcs_plan_materialize",
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan",
 ]
@@ -193,6 +195,20 @@ class Forest:
         return dict(n_loci=out[0], n_instances=out[1], n_haplotypes=out[2], n_fragment_sets=out[3],
                     n_pieces=out[4], device_bytes=out[5])
 
+    # ---- sequences (only needed to write SAM)
+    def set_reference(self, chrom, bases: bytes):
+        _ok(lib().pcs_forest_set_reference(self._h, C.c_uint32(chrom), C.c_char_p(bases), C.c_uint64(len(bases))))
+
+    def load_fasta(self, path):
+        names = (C.c_char_p * self.forest.n_chr)(*[n.encode() for n in self.forest.chr_names])
+        n = C.c_uint32(0)
+        _ok(lib().pcs_forest_load_fasta(self._h, C.c_char_p(os.fsencode(path)), names, C.byref(n)))
+        return n.value
+
+    def set_alt(self, alt_off, alt_bytes: bytes):
+        ao = _u32(alt_off)
+        _ok(lib().pcs_forest_set_alt(self._h, A.ptr(ao, C.c_uint32), C.c_char_p(alt_bytes)))
+
     def n_out_samples(self, params: A.SeqParams):
         if params.normal_only:
             return 1
@@ -295,6 +311,31 @@ class Plan:
         _ok(lib().pcs_plan_finalize(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.c_void_p(cov_ptr),
                                     C.byref(st)))
         return st
+
+    def materialize(self, cap):
+        """the plan's reads as binary records: placements, error masks, seq, qual, cigar, n_cigar, lengths."""
+        R = self.info.read_size
+        rec = np.zeros(cap, A.PLACEMENT_DTYPE)
+        masks = np.zeros((cap, A.PCS_ERRMASK_WORDS), np.uint32)
+        seq = np.zeros((cap, R), np.uint8); qual = np.zeros((cap, R), np.uint8)
+        cigar = np.zeros((cap, A.PCS_MAX_CIGAR), np.uint32)
+        nc = np.zeros(cap, np.uint32); ln = np.zeros(cap, np.uint32)
+        n = C.c_uint64(0)
+        _ok(lib().pcs_plan_materialize(self._h, C.c_uint64(cap), C.c_void_p(rec.ctypes.data), A.ptr(masks, C.c_uint32),
+                                       A.ptr(seq, C.c_uint8), A.ptr(qual, C.c_uint8), A.ptr(cigar, C.c_uint32),
+                                       A.ptr(nc, C.c_uint32), A.ptr(ln, C.c_uint32), C.byref(n)))
+        k = n.value
+        return rec[:k], masks[:k], seq[:k], qual[:k], cigar[:k], nc[:k], ln[:k]
+
+    def write_sam(self, output_dir, sample_names, filename_prefix="chr_", template_name_prefix="r", update=False):
+        f = self.forest.forest
+        chr_names = (C.c_char_p * f.n_chr)(*[n.encode() for n in f.chr_names])
+        samples = (C.c_char_p * len(sample_names))(*[n.encode() for n in sample_names])
+        opt = A.SamOptions(os.fsencode(output_dir), filename_prefix.encode(), template_name_prefix.encode(),
+                           chr_names, samples, 1 if update else 0)
+        n = C.c_uint64(0)
+        _ok(lib().pcs_plan_write_sam(self._h, C.byref(opt), C.byref(n)))
+        return n.value
 
     def trace(self, cap, with_masks=False):
         rec = np.zeros(cap, A.PLACEMENT_DTYPE)

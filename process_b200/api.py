@@ -12,7 +12,6 @@ through libpcs_seq.so; there is no CPU path.
 from __future__ import annotations
 
 import os
-import warnings
 import weakref
 from dataclasses import dataclass
 
@@ -214,16 +213,16 @@ def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced):
 
 def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
          insert_size_stddev, write_SAM, group, names, purity, with_normal_sample, preneo, normal_only,
-         include_non_sequenced, c_seed, device, cache, shard):
+         include_non_sequenced, c_seed, device, cache, shard, sam=None):
     if not isinstance(forest, PhylogeneticForest):
         raise TypeError("phylo_forest must be a PhylogeneticForest")
-    _reference_genome(forest, reference_genome)
+    ref_path = _reference_genome(forest, reference_genome)
     kind, rate = _sequencer_model(sequencer)
     mask = _chr_mask(forest, chromosomes)
     if not normal_only and not (0 <= purity <= 1):
         raise ValueError("The purity must belong to the interval [0,1].")
-    if write_SAM:
-        warnings.warn("SAM output is not built yet (SURVEY.md 8 f3): simulating counts only", stacklevel=3)
+    if write_SAM and shard[1] > 1:
+        raise NotImplementedError("write_SAM with more than one rank: every rank would write the same files")
     P = A.SeqParams(seed=c_seed, coverage=float(coverage), purity=float(purity), read_size=int(read_size),
                     insert_size_mean=int(insert_size_mean), insert_size_stddev=int(insert_size_stddev),
                     sequencer=kind, error_rate=rate, with_normal_sample=int(bool(with_normal_sample)),
@@ -236,10 +235,29 @@ def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, 
     try:
         if not normal_only:
             dev.set_groups(group, len(names) if group is not None else None)
-        occ, cov, st = dev.simulate(P)
+        out_names = [NORMAL_SAMPLE_NAME] if normal_only else list(names) + ([NORMAL_SAMPLE_NAME] if with_normal_sample else [])
+        if write_SAM:
+            # the counting kernels and the SAM records of one plan draw the same reads (same Philox counters)
+            output_dir, filename_prefix, template_name_prefix, update_SAM = sam
+            if update_SAM is False and os.path.exists(output_dir):
+                raise ValueError(f'The output directory "{output_dir}" already exists: use update_SAM=TRUE '
+                                 "to add files to it.")
+            if getattr(dev, "_fasta", None) != ref_path:
+                dev.load_fasta(ref_path)
+                dev._fasta = ref_path
+            if not getattr(dev, "_alt_set", False):
+                dev.set_alt(*forest.alt_table())
+                dev._alt_set = True
+            plan = L.Plan(dev, P)
+            try:
+                occ, cov, st = plan.run()
+                plan.write_sam(output_dir, out_names, filename_prefix, template_name_prefix, update_SAM)
+            finally:
+                plan.close()
+        else:
+            occ, cov, st = dev.simulate(P)
         if shard[1] > 1:
             occ, cov = _reduce_over_ranks(occ, cov)
-        out_names = [NORMAL_SAMPLE_NAME] if normal_only else list(names) + ([NORMAL_SAMPLE_NAME] if with_normal_sample else [])
         df = _result_dataframe(forest, dev, occ, cov, out_names, include_non_sequenced)
     finally:
         if owned:
@@ -283,7 +301,8 @@ def simulate_seq(phylo_forest, sequencer=None, reference_genome=None, chromosome
     group, names = _apply_FACS_labels(phylo_forest, cell_labelling)
     df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
                   insert_size_stddev, write_SAM, group, names, purity, with_normal_sample,
-                  preneoplastic_in_normal, False, include_non_sequenced_mutations, c_seed, device, cache, _shard())
+                  preneoplastic_in_normal, False, include_non_sequenced_mutations, c_seed, device, cache, _shard(),
+                  sam=(output_dir, filename_prefix, template_name_prefix, update_SAM))
     parameters = dict(sequencer=_sequencer_data(sequencer), reference_genome=reference_genome,
                       chromosomes=chromosomes, coverage=coverage, read_size=read_size,
                       insert_size_mean=insert_size_mean, insert_size_stddev=insert_size_stddev,
@@ -304,7 +323,8 @@ def simulate_normal_seq(phylo_forest, sequencer=None, reference_genome=None, chr
     c_seed = _resolve_seed(seed)
     df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
                   insert_size_stddev, write_SAM, None, [], 1.0, False, with_preneoplastic, True,
-                  include_non_sequenced_mutations, c_seed, device, cache, _shard())
+                  include_non_sequenced_mutations, c_seed, device, cache, _shard(),
+                  sam=(output_dir, filename_prefix, template_name_prefix, update_SAM))
     parameters = dict(sequencer=_sequencer_data(sequencer), reference_genome=reference_genome,
                       chromosomes=chromosomes, coverage=coverage, read_size=read_size,
                       insert_size_mean=insert_size_mean, insert_size_stddev=insert_size_stddev,

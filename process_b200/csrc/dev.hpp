@@ -71,6 +71,26 @@ struct StageDims {
   uint32_t max_buckets;
 };
 
+// reference bases and alt strings, needed only when reads are materialised (SAM output)
+struct SeqData {
+  const uint8_t* ref;            // ASCII bases of all loaded chromosomes, concatenated
+  const uint64_t* chr_ref_off;   // [n_chr+1] offset of position 1 of each chromosome; equal offsets = not loaded
+  const uint8_t* alt;            // alt strings of all rows, concatenated
+  const uint32_t* alt_off;       // [n_mut+1]
+};
+
+constexpr uint32_t kMaxCigar = 16;
+
+// one materialised read (device layout, 112 bytes); bases and qualities live in separate [n][R] arrays
+struct SamHeader {
+  uint32_t hap, start, frag_end, chr_sample;   // as DevPlacement
+  uint32_t read_id, tile_id, flags, mate_start; // flags: bit0 paired, bit1 second mate, bit2 CIGAR truncated
+  int32_t tlen;
+  uint32_t n_cigar, len, pad0;                  // len: bases actually written (R unless clipped by a fragment end)
+  uint32_t cigar[kMaxCigar];                    // length << 4 | op (0 M, 1 I, 2 D)
+};
+static_assert(sizeof(SamHeader) == 112, "SamHeader layout");
+
 // injected placement after host translation (cell, allele) -> haplotype index
 struct DevPlacement {
   uint32_t hap;

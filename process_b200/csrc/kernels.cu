@@ -586,6 +586,177 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   block_add_u64(placed, n_reads);
 }
 
+// ------------------------------------------------------------- SAM records
+// Materialise reads: bases from the reference + carried SIDs, CIGAR, qualities, sequencing errors.
+// Same templates, haplotypes and SID error outcomes as the counting kernels (same Philox counters),
+// so the tables and the SAM files of one call describe the same reads.  Ordinary bases draw their
+// error from block (read, tile, 0x80000000 | offset/4 [constant] or offset [random], seed).
+struct CigarBuilder {
+  uint32_t* ops;
+  uint32_t n = 0;
+  bool overflow = false;
+  __device__ void push(uint32_t op, uint32_t len) {
+    if (len == 0) return;
+    if (n > 0 && (ops[n - 1] & 15u) == op) {
+      ops[n - 1] += len << 4;
+    } else if (n < kMaxCigar) {
+      ops[n++] = (len << 4) | op;
+    } else {
+      overflow = true;
+    }
+  }
+};
+
+__device__ __forceinline__ uint8_t substitute_base(uint8_t base, uint32_t offset) {
+  const char acgt[4] = {'A', 'C', 'G', 'T'};
+  int code = base == 'A' ? 0 : base == 'C' ? 1 : base == 'G' ? 2 : base == 'T' ? 3 : -1;
+  if (code < 0) return base;  // N stays N
+  return static_cast<uint8_t>(acgt[(code + 1 + static_cast<int>(offset % 3u)) & 3]);
+}
+
+struct BaseWriter {
+  const SeqModel& M;
+  uint32_t read, tile;
+  uint8_t* seq;
+  uint8_t* qual;
+  uint32_t* mask;
+  uint32_t cached_block = 0xffffffffu;
+  uint4 cached{};
+  __device__ uint8_t phred(float e) const {
+    float q = -10.0f * log10f(fmaxf(fminf(e, 1.0f), 1e-5f));
+    int qi = static_cast<int>(q + 0.5f);
+    qi = qi < 2 ? 2 : (qi > 41 ? 41 : qi);
+    return static_cast<uint8_t>(33 + qi);
+  }
+  // base at read offset o; sid: it is base b of the hit-th carried SID (its error draw is the counting kernels')
+  __device__ void put(uint32_t o, uint8_t base, bool sid, uint32_t hit, uint32_t b) {
+    bool err = false;
+    uint8_t q = 'I';
+    if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
+      uint32_t word;
+      if (sid) {
+        const uint4 u = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), M.seed));
+        word = u.x;
+      } else {
+        const uint32_t block = 0x80000000u | (o >> 2);
+        if (block != cached_block) {
+          cached = philox4x32_10(make_uint4(read, tile, block, M.seed));
+          cached_block = block;
+        }
+        word = (o & 3u) == 0 ? cached.x : (o & 3u) == 1 ? cached.y : (o & 3u) == 2 ? cached.z : cached.w;
+      }
+      err = word < M.err_thr;
+      q = err ? '#' : phred(M.error_rate);
+    } else if (M.sequencer == PCS_SEQ_BASIC_RANDOM) {
+      const uint4 u = philox4x32_10(make_uint4(read, tile, sid ? ((1u + hit) | (b << 20)) : (0x80000000u | o), M.seed));
+      const float z = sqrtf(-2.0f * __logf(u01(u.x))) * cospif(2.0f * u01(u.y));
+      const float e = M.error_rate * ramp(o, M.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
+      err = u01(u.z) < fminf(e, 1.0f);
+      q = phred(e);
+    }
+    if (err) {
+      base = substitute_base(base, o);
+      if (mask && o < 32u * PCS_ERRMASK_WORDS) mask[o >> 5] |= 1u << (o & 31);
+    }
+    seq[o] = base;
+    qual[o] = q;
+  }
+};
+
+__device__ void materialize_read(const DevForest& F, const SeqModel& M, const SeqData& D, uint32_t chr, uint32_t l_first,
+                                 uint32_t l_end, uint32_t h, uint32_t xs, uint32_t frag_end, BaseWriter& W,
+                                 CigarBuilder& C, uint32_t& len_out) {
+  const uint32_t R = M.read_size;
+  const uint8_t* ref = D.ref + D.chr_ref_off[chr] - 1;  // ref[p] = base at 1-based position p
+  uint32_t q = xs, o = 0, hit = 0;
+  uint32_t stop = min(xs + R, frag_end + 1u);
+  for (uint32_t i = l_first; i < l_end && o < R; ++i) {
+    const uint32_t p = __ldg(F.locus_pos + i);
+    if (p >= stop) break;
+    if (p < q) continue;
+    const uint32_t k1 = __ldg(F.locus_inst_off + i + 1);
+    for (uint32_t k = __ldg(F.locus_inst_off + i); k < k1; ++k) {
+      const uint4 in = __ldg(F.inst + k);
+      if (h - in.x >= in.y) continue;
+      for (uint32_t pp = q; pp < p; ++pp) W.put(o++, ref[pp], false, 0u, 0u);
+      C.push(0u, p - q);
+      const uint32_t ref_len = in.w & 0xffu, alt_len = (in.w >> 8) & 0xffu;
+      const uint32_t consumed = min(alt_len, R - o);
+      const uint8_t* alt = D.alt + __ldg(D.alt_off + in.z);
+      for (uint32_t b = 0; b < consumed; ++b) W.put(o++, alt[b], true, hit, b);
+      const uint32_t m = min(consumed, ref_len);
+      C.push(0u, m);
+      C.push(1u, consumed - m);
+      ++hit;
+      q = p + ref_len;
+      if (o < R && ref_len > alt_len) C.push(2u, ref_len - alt_len);
+      stop = min(q + (R - o), frag_end + 1u);
+      break;  // at most one SID per position on a haplotype
+    }
+  }
+  if (o < R && q < stop) {
+    const uint32_t last = min(q + (R - o), frag_end + 1u);
+    for (uint32_t pp = q; pp < last; ++pp) W.put(o++, ref[pp], false, 0u, 0u);
+    C.push(0u, last - q);
+  }
+  len_out = o;
+}
+
+__global__ void __launch_bounds__(128)
+materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
+                         SeqData D, SamHeader* __restrict__ hdr, uint32_t* __restrict__ masks,
+                         uint8_t* __restrict__ seq, uint8_t* __restrict__ qual, unsigned long long cap,
+                         unsigned long long* __restrict__ n_out) {
+  const Tile T = tiles[blockIdx.x];
+  const uint32_t chr_l1 = F.chr_locus_off[T.chr + 1];
+  const uint32_t R = M.read_size;
+  const Entry* ent = entries + T.entry_off;
+  const uint32_t n_blocks = M.paired ? T.n_templates : (T.n_templates + 1u) >> 1;
+  for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
+    const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+    for (uint32_t k = 0; k < 2u; ++k) {
+      Template tp;
+      uint32_t ins = 0, xs, mate_start = 0;
+      int32_t tlen = 0;
+      if (M.paired) {
+        ins = draw_insert(M, u.z);
+        if (!place(T, ent, F, u.x, u.y, 2u * R + ins, tp)) break;
+        xs = tp.x + k * (R + ins);
+        mate_start = tp.x + (1u - k) * (R + ins);
+        tlen = static_cast<int32_t>(2u * R + ins) * (k == 0 ? 1 : -1);
+      } else {
+        if (2u * j + k >= T.n_templates) break;
+        if (!place(T, ent, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) continue;
+        xs = tp.x;
+      }
+      const unsigned long long idx = atomicAdd(n_out, 1ull);
+      if (idx >= cap) continue;
+      SamHeader H{};
+      H.hap = tp.h; H.start = xs; H.frag_end = tp.frag_end; H.chr_sample = T.chr | (T.sample << 16);
+      H.read_id = 2u * j + k; H.tile_id = T.id; H.flags = (M.paired ? 1u : 0u) | (M.paired && k ? 2u : 0u);
+      H.mate_start = mate_start; H.tlen = tlen;
+      uint32_t* mask = masks + idx * PCS_ERRMASK_WORDS;
+      for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) mask[i] = 0;
+      BaseWriter W{M, H.read_id, T.id, seq + idx * R, qual + idx * R, mask};
+      CigarBuilder C{H.cigar};
+      materialize_read(F, M, D, T.chr, lower_bound_pos(F.locus_pos, T.l0, chr_l1, xs), chr_l1, tp.h, xs, tp.frag_end, W, C,
+                       H.len);
+      H.n_cigar = C.n;
+      if (C.overflow) H.flags |= 4u;
+      hdr[idx] = H;
+    }
+  }
+}
+
+cudaError_t launch_materialize_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                     const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
+                                     uint32_t* masks, uint8_t* seq, uint8_t* qual, unsigned long long cap,
+                                     unsigned long long* n_out) {
+  if (n_tiles == 0) return cudaSuccess;
+  materialize_tiles_kernel<<<n_tiles, 128, 0, st>>>(tiles, entries, F, M, D, hdr, masks, seq, qual, cap, n_out);
+  return cudaGetLastError();
+}
+
 // ----------------------------------------------------------- injected reads
 __global__ void __launch_bounds__(256)
 count_injected_kernel(const DevPlacement* __restrict__ rec, const uint32_t* __restrict__ masks,

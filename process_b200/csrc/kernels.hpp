@@ -21,6 +21,10 @@ cudaError_t launch_trace_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_ti
                                const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
                                DevPlacement* trace, uint32_t* trace_masks, unsigned long long cap,
                                unsigned long long* trace_n);
+cudaError_t launch_materialize_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                     const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
+                                     uint32_t* masks, uint8_t* seq, uint8_t* qual, unsigned long long cap,
+                                     unsigned long long* n_out);
 cudaError_t launch_count_injected(cudaStream_t st, const DevPlacement* rec, const uint32_t* masks,
                                   unsigned long long n, const DevForest& F, uint32_t R, uint32_t* depth,
                                   uint32_t* alt);

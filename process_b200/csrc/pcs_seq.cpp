@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cctype>
 #include <cstring>
+#include <filesystem>
+#include <fstream>
 #include <functional>
 #include <map>
 #include <memory>
@@ -174,6 +177,38 @@ struct pcs_forest {
   DevBuf<uint32_t> d_locus_pos, d_chr_locus_off, d_locus_inst_off, d_row_locus, d_hap_list;
   DevBuf<pcs::Inst> d_inst;
   uint64_t h2d_bytes = 0;
+
+  // reference bases / alt strings: only for materialising reads (SAM output)
+  std::vector<std::string> ref_chr;     // [n_chr] ASCII bases, empty = not loaded
+  std::vector<uint32_t> alt_off;        // [n_mut+1]
+  std::string alt_bytes;
+  bool seq_dirty = true;
+  DevBuf<uint8_t> d_ref, d_alt;
+  DevBuf<uint64_t> d_chr_ref_off;
+  DevBuf<uint32_t> d_alt_off;
+
+  pcs::SeqData seq_data() {
+    const pcs::FlatForest& F = host.flat;
+    require(alt_off.size() == static_cast<size_t>(F.n_mut) + 1, "alt strings were not set (pcs_forest_set_alt)");
+    if (seq_dirty) {
+      ctx->bind();
+      std::vector<uint64_t> off(F.n_chr + 1, 0);
+      std::vector<uint8_t> all;
+      for (uint32_t c = 0; c < F.n_chr; ++c) {
+        off[c] = all.size();
+        if (c < ref_chr.size()) all.insert(all.end(), ref_chr[c].begin(), ref_chr[c].end());
+      }
+      off[F.n_chr] = all.size();
+      std::vector<uint8_t> alt(alt_bytes.begin(), alt_bytes.end());
+      h2d_bytes += d_ref.upload(all, ctx->stream);
+      h2d_bytes += d_chr_ref_off.upload(off, ctx->stream);
+      h2d_bytes += d_alt.upload(alt, ctx->stream);
+      h2d_bytes += d_alt_off.upload(alt_off, ctx->stream);
+      seq_dirty = false;
+    }
+    return pcs::SeqData{d_ref.p, d_chr_ref_off.p, d_alt.p, d_alt_off.p};
+  }
+  bool has_reference(uint32_t c) const { return c < ref_chr.size() && !ref_chr[c].empty(); }
 
   pcs::DevForest dev() const {
     pcs::DevForest F;
@@ -654,6 +689,109 @@ void finalize_tables(pcs_plan& pl, const uint32_t* d_depth, const uint32_t* d_oc
   }
 }
 
+// reads of a set of tiles as binary records (host vectors)
+struct Materialized {
+  std::vector<pcs::SamHeader> hdr;
+  std::vector<uint32_t> masks;
+  std::vector<uint8_t> seq, qual;
+};
+
+void materialize_tiles(pcs_plan& pl, const std::vector<pcs::Tile>& tiles, uint64_t cap, Materialized& out) {
+  pcs_forest& fo = *pl.forest;
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  const uint32_t R = pl.host.info.read_size;
+  for (const auto& t : tiles) require(fo.has_reference(t.chr), "the reference sequence of a sequenced chromosome is not loaded");
+  const pcs::SeqData D = fo.seq_data();
+  DevBuf<pcs::Tile> d_tiles;
+  DevBuf<pcs::SamHeader> d_hdr;
+  DevBuf<uint32_t> d_masks;
+  DevBuf<uint8_t> d_seq, d_qual;
+  d_tiles.upload(tiles, st);
+  d_hdr.alloc(cap, st);
+  d_masks.alloc(cap * PCS_ERRMASK_WORDS, st);
+  d_seq.alloc(cap * R, st);
+  d_qual.alloc(cap * R, st);
+  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  CUDA_OK(pcs::launch_materialize_tiles(st, d_tiles.p, static_cast<uint32_t>(tiles.size()), pl.d_entries.p, fo.dev(),
+                                        pl.host.model, D, d_hdr.p, d_masks.p, d_seq.p, d_qual.p, cap, pl.d_counters.p + 3));
+  unsigned long long counters[4];
+  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (counters[3] > cap) throw std::domain_error("materialize capacity too small");
+  const size_t n = counters[3];
+  out.hdr.resize(n);
+  out.masks.resize(n * PCS_ERRMASK_WORDS);
+  out.seq.resize(n * R);
+  out.qual.resize(n * R);
+  if (n) {
+    CUDA_OK(cudaMemcpyAsync(out.hdr.data(), d_hdr.p, n * sizeof(pcs::SamHeader), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(out.masks.data(), d_masks.p, out.masks.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(out.seq.data(), d_seq.p, out.seq.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(out.qual.data(), d_qual.p, out.qual.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+  }
+}
+
+void placement_of(const pcs::FlatForest& F, const pcs::SamHeader& h, pcs_read_placement& r) {
+  const uint32_t chr = h.chr_sample & 0xffffu;
+  const pcs::HapRec& hr = F.chr_haps[chr][h.hap];
+  r.cell = hr.cell;
+  r.start = h.start;
+  r.chr = static_cast<uint16_t>(chr);
+  r.allele = hr.allele;
+  r.sample = static_cast<uint16_t>(h.chr_sample >> 16);
+  r.flags = hr.kind == pcs::HAP_TUMOUR ? PCS_PLACE_TUMOUR
+            : hr.kind == pcs::HAP_NORMAL_PLAIN ? PCS_PLACE_NORMAL_PLAIN : PCS_PLACE_NORMAL_PRENEO;
+}
+
+void append_uint(std::string& s, uint64_t v) {
+  char buf[24];
+  int n = 0;
+  do { buf[n++] = static_cast<char>('0' + v % 10); v /= 10; } while (v);
+  while (n) s.push_back(buf[--n]);
+}
+
+// SAM text of one record.  Template names: <prefix><tile>_<template index> (unique per file, shared by mates).
+void append_sam_line(std::string& s, const pcs::SamHeader& h, const uint8_t* seq, const uint8_t* qual,
+                     const std::string& prefix, const std::string& chr, const std::string& sample) {
+  const bool paired = (h.flags & 1u) != 0, second = (h.flags & 2u) != 0;
+  s += prefix;
+  append_uint(s, h.tile_id);
+  s.push_back('_');
+  append_uint(s, paired ? h.read_id >> 1 : h.read_id);
+  s.push_back('\t');
+  append_uint(s, paired ? (second ? 147u : 99u) : 0u);
+  s.push_back('\t');
+  s += chr;
+  s.push_back('\t');
+  append_uint(s, h.start);
+  s += "\t60\t";
+  if (h.n_cigar == 0) s.push_back('*');
+  for (uint32_t i = 0; i < h.n_cigar; ++i) {
+    append_uint(s, h.cigar[i] >> 4);
+    s.push_back("MID"[h.cigar[i] & 3u]);
+  }
+  s.push_back('\t');
+  if (paired) {
+    s += "=\t";
+    append_uint(s, h.mate_start);
+    s.push_back('\t');
+    if (h.tlen < 0) s.push_back('-');
+    append_uint(s, static_cast<uint64_t>(h.tlen < 0 ? -static_cast<int64_t>(h.tlen) : h.tlen));
+  } else {
+    s += "*\t0\t0";
+  }
+  s.push_back('\t');
+  s.append(reinterpret_cast<const char*>(seq), h.len);
+  s.push_back('\t');
+  s.append(reinterpret_cast<const char*>(qual), h.len);
+  s += "\tRG:Z:";
+  s += sample;
+  s.push_back('\n');
+}
+
 template <class Fn>
 int guarded(Fn&& fn) {
   try {
@@ -1011,6 +1149,155 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
       stats->d2h_bytes = 2 * S * M * sizeof(uint32_t);
       stats->total_ms = now_ms() - t0;
     }
+  });
+}
+
+int pcs_forest_set_reference(pcs_forest* fo, uint32_t chr, const char* bases, uint64_t len) {
+  return guarded([&] {
+    require(fo && bases, "bad arguments");
+    const pcs::FlatForest& F = fo->host.flat;
+    require(chr < F.n_chr, "chromosome out of range");
+    require(len == F.chr_len[chr], "the reference sequence length differs from the chromosome length");
+    fo->ref_chr.resize(F.n_chr);
+    std::string& dst = fo->ref_chr[chr];
+    dst.assign(bases, len);
+    for (auto& ch : dst) ch = static_cast<char>(std::toupper(static_cast<unsigned char>(ch)));
+    fo->seq_dirty = true;
+  });
+}
+
+int pcs_forest_load_fasta(pcs_forest* fo, const char* path, const char* const* chr_names, uint32_t* n_loaded) {
+  return guarded([&] {
+    require(fo && path && chr_names, "bad arguments");
+    const pcs::FlatForest& F = fo->host.flat;
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error(std::string("The reference genome file \"") + path + "\" does not exists.");
+    std::map<std::string, uint32_t> index;
+    for (uint32_t c = 0; c < F.n_chr; ++c) index[chr_names[c]] = c;
+    fo->ref_chr.resize(F.n_chr);
+    std::string line, name, seq;
+    uint32_t loaded = 0;
+    auto flush = [&]() {
+      if (name.empty()) return;
+      std::string key = name;
+      if (!index.count(key) && key.rfind("chr", 0) == 0) key = key.substr(3);
+      auto it = index.find(key);
+      if (it != index.end()) {
+        require(seq.size() == F.chr_len[it->second], "a FASTA sequence length differs from the chromosome length");
+        for (auto& ch : seq) ch = static_cast<char>(std::toupper(static_cast<unsigned char>(ch)));
+        fo->ref_chr[it->second] = seq;
+        ++loaded;
+      }
+    };
+    while (std::getline(in, line)) {
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      if (!line.empty() && line[0] == '>') {
+        flush();
+        size_t e = line.find_first_of(" \t", 1);
+        name = line.substr(1, e == std::string::npos ? std::string::npos : e - 1);
+        seq.clear();
+      } else {
+        seq += line;
+      }
+    }
+    flush();
+    fo->seq_dirty = true;
+    if (n_loaded) *n_loaded = loaded;
+  });
+}
+
+int pcs_forest_set_alt(pcs_forest* fo, const uint32_t* alt_off, const char* alt_bytes) {
+  return guarded([&] {
+    require(fo && alt_off && alt_bytes, "bad arguments");
+    const pcs::FlatForest& F = fo->host.flat;
+    fo->alt_off.assign(alt_off, alt_off + F.n_mut + 1);
+    require(fo->alt_off[0] == 0, "alt_off must start at 0");
+    for (uint32_t m = 0; m < F.n_mut; ++m)
+      require(fo->alt_off[m + 1] >= fo->alt_off[m] + 1, "every row needs a non-empty alt string");
+    fo->alt_bytes.assign(alt_bytes, fo->alt_off[F.n_mut]);
+    fo->seq_dirty = true;
+  });
+}
+
+int pcs_plan_materialize(pcs_plan* pl, uint64_t cap, pcs_read_placement* placements, uint32_t* err_masks, uint8_t* seq,
+                         uint8_t* qual, uint32_t* cigar, uint32_t* n_cigar, uint32_t* lengths, uint64_t* n_out) {
+  return guarded([&] {
+    require(pl && placements && seq && qual && cigar && n_cigar && lengths && n_out, "bad arguments");
+    std::vector<pcs::Tile> tiles = pl->host.tiles;
+    tiles.insert(tiles.end(), pl->host.tiles_global.begin(), pl->host.tiles_global.end());
+    Materialized m;
+    materialize_tiles(*pl, tiles, cap, m);
+    const uint32_t R = pl->host.info.read_size;
+    *n_out = m.hdr.size();
+    for (size_t i = 0; i < m.hdr.size(); ++i) {
+      placement_of(pl->forest->host.flat, m.hdr[i], placements[i]);
+      n_cigar[i] = m.hdr[i].n_cigar;
+      lengths[i] = m.hdr[i].len;
+      std::memcpy(cigar + i * pcs::kMaxCigar, m.hdr[i].cigar, sizeof(uint32_t) * pcs::kMaxCigar);
+    }
+    if (err_masks && !m.masks.empty()) std::memcpy(err_masks, m.masks.data(), m.masks.size() * sizeof(uint32_t));
+    if (!m.seq.empty()) {
+      std::memcpy(seq, m.seq.data(), m.hdr.size() * R);
+      std::memcpy(qual, m.qual.data(), m.hdr.size() * R);
+    }
+  });
+}
+
+int pcs_plan_write_sam(pcs_plan* pl, const pcs_sam_options* opt, uint64_t* n_written) {
+  return guarded([&] {
+    require(pl && opt && opt->output_dir && opt->chr_names && opt->sample_names, "bad arguments");
+    namespace fs = std::filesystem;
+    const pcs::FlatForest& F = pl->forest->host.flat;
+    const fs::path dir(opt->output_dir);
+    // ReadSimulator<>::Mode::CREATE refuses an existing directory, UPDATE adds files to it
+    // (src/seq_simulation.cpp:545-549, vignettes/sequencing.Rmd:283-309)
+    if (fs::exists(dir) && !opt->update)
+      throw std::domain_error("The output directory \"" + dir.string() + "\" already exists: use update_SAM=TRUE to add files to it.");
+    fs::create_directories(dir);
+    const std::string fprefix = opt->filename_prefix ? opt->filename_prefix : "chr_";
+    const std::string tprefix = opt->template_name_prefix ? opt->template_name_prefix : "r";
+    const uint32_t R = pl->host.info.read_size, mates = pl->host.info.reads_per_template;
+    std::vector<pcs::Tile> tiles = pl->host.tiles;
+    tiles.insert(tiles.end(), pl->host.tiles_global.begin(), pl->host.tiles_global.end());
+    uint64_t written = 0;
+    const uint64_t batch_cap = 1u << 20;
+    for (uint32_t c = 0; c < F.n_chr; ++c) {
+      std::vector<pcs::Tile> mine;
+      for (const auto& t : tiles)
+        if (t.chr == c) mine.push_back(t);
+      if (mine.empty()) continue;
+      std::stable_sort(mine.begin(), mine.end(), [](const pcs::Tile& a, const pcs::Tile& b) { return a.begin < b.begin; });
+      fs::path file = dir / (fprefix + opt->chr_names[c] + ".sam");
+      for (uint32_t k = 1; fs::exists(file); ++k) file = dir / (fprefix + opt->chr_names[c] + "_" + std::to_string(k) + ".sam");
+      std::ofstream out(file, std::ios::binary);
+      if (!out) throw std::runtime_error("cannot write \"" + file.string() + "\"");
+      std::string text = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:" + std::string(opt->chr_names[c]) + "\tLN:" + std::to_string(F.chr_len[c]) + "\n";
+      for (uint32_t s = 0; s < pl->host.info.n_out_samples; ++s)
+        text += std::string("@RG\tID:") + opt->sample_names[s] + "\tSM:" + opt->sample_names[s] + "\tPL:ILLUMINA\n";
+      text += "@PG\tID:pcs_seq\tPN:pcs_seq\n";
+      size_t i = 0;
+      while (i < mine.size()) {
+        std::vector<pcs::Tile> batch;
+        uint64_t reads = 0;
+        while (i < mine.size() && (batch.empty() || reads + static_cast<uint64_t>(mine[i].n_templates) * mates <= batch_cap)) {
+          reads += static_cast<uint64_t>(mine[i].n_templates) * mates;
+          batch.push_back(mine[i++]);
+        }
+        Materialized m;
+        materialize_tiles(*pl, batch, std::max<uint64_t>(reads, 1), m);
+        for (size_t r = 0; r < m.hdr.size(); ++r) {
+          append_sam_line(text, m.hdr[r], m.seq.data() + r * R, m.qual.data() + r * R, tprefix, opt->chr_names[c],
+                          opt->sample_names[m.hdr[r].chr_sample >> 16]);
+          if (text.size() > (8u << 20)) {
+            out.write(text.data(), static_cast<std::streamsize>(text.size()));
+            text.clear();
+          }
+        }
+        written += m.hdr.size();
+      }
+      out.write(text.data(), static_cast<std::streamsize>(text.size()));
+    }
+    if (n_written) *n_written = written;
   });
 }
 

@@ -141,6 +141,13 @@ class PhylogeneticForest:
             alt[i] = a + b * (int(al[i]) - 1)
         return ref, alt
 
+    def alt_table(self):
+        """(alt_off [n_mut+1] uint32, alt_bytes) of every row, the layout pcs_forest_set_alt takes."""
+        _, alt = self.row_strings(np.arange(self.n_mut))
+        lens = self.mut_alt_len.astype(np.int64)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)
+        return off, "".join(alt).encode()
+
     def row_causes(self, rows: np.ndarray):
         c = self.mut_cause[np.asarray(rows)]
         table = np.asarray(list(self.cause_names) + [None], dtype=object)

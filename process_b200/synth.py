@@ -373,3 +373,33 @@ def config_spec(name: str, seed: int = 0, scale: float = 1.0) -> SynthSpec:
                          n_preneo_snv=1000, n_preneo_indel=500, trunk_snv=900_000, node_snv_mean=5.0,
                          n_clones=8, clone_cna=25, wgd_clones=8, cna_len=(100_000, 20_000_000), seed=seed)
     raise ValueError(f"unknown config {name}")
+
+
+def write_reference_fasta(forest: PhylogeneticForest, path: str, seed: int = 0, line: int = 60) -> str:
+    """a random reference genome with the forest's chromosome names and lengths (there is no network for the
+    real FASTA); also sets forest.reference_path."""
+    rng = np.random.default_rng(seed)
+    with open(path, "w") as fh:
+        for name, n in zip(forest.chr_names, forest.chr_len):
+            seq = np.frombuffer(b"ACGT", dtype="S1")[rng.integers(0, 4, int(n))].tobytes().decode()
+            fh.write(f">{name} synthetic\n")
+            for i in range(0, len(seq), line):
+                fh.write(seq[i:i + line] + "\n")
+    forest.reference_path = path
+    return path
+
+
+def read_fasta(path: str) -> dict:
+    out, name, parts = {}, None, []
+    with open(path) as fh:
+        for ln in fh:
+            ln = ln.strip()
+            if ln.startswith(">"):
+                if name is not None:
+                    out[name] = "".join(parts)
+                name, parts = ln[1:].split()[0], []
+            else:
+                parts.append(ln)
+    if name is not None:
+        out[name] = "".join(parts)
+    return out

@@ -276,10 +276,9 @@ def test_committed_vectors_on_gpu(ctx, name):
 def test_python_mirror_schema_and_parameters(ctx, tmp_path):
     """simulate_seq()/simulate_normal_seq() through the mirror of the Rcpp interface."""
     from process_b200 import api
+    from process_b200.synth import write_reference_fasta
     f = synth_forest(small_spec(4))
-    ref = tmp_path / "ref.fa"
-    ref.write_text(">1\nACGT\n")
-    f.reference_path = str(ref)
+    write_reference_fasta(f, str(tmp_path / "ref.fa"))
     r = api.simulate_seq(f, chromosomes=["1", "X"], coverage=20, purity=0.8, seed=5,
                          sequencer=api.BasicIlluminaSequencer(1e-3))
     df = r["mutations"]
@@ -300,8 +299,7 @@ def test_python_mirror_schema_and_parameters(ctx, tmp_path):
                                      "template_name_prefix", "include_non_sequenced_mutations", "seed"]
     allrows = api.simulate_seq(f, coverage=0.01, seed=5, include_non_sequenced_mutations=True)["mutations"]
     assert len(allrows) > len(df)
-    with pytest.warns(UserWarning):
-        n = api.simulate_normal_seq(f, coverage=20, seed=5)
+    n = api.simulate_normal_seq(f, coverage=20, seed=5, write_SAM=False)
     assert [c for c in n["mutations"].columns if "." in c] == ["normal_sample.occurrences", "normal_sample.coverage",
                                                               "normal_sample.VAF"]
     assert "with_preneoplastic" in n["parameters"]
