@@ -250,7 +250,7 @@ struct Call {
 
 inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std::vector<uint32_t>* groups,
                      const std::vector<std::string>& group_names) {
-  get_reference_genome(forest, c.reference_genome);
+  const std::string ref_genome = get_reference_genome(forest, c.reference_genome).string();
   const int c_seed = get_random_seed(c.seed);
 
   pcs_seq_params P{};
@@ -305,7 +305,37 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
   const size_t S = names.size(), M = forest.mut_pos.size();
   std::vector<uint32_t> occ(S * M), cov(S * M);
   SeqResult res;
-  pcs_check(pcs_simulate(fo, &P, occ.data(), cov.data(), &res.stats));
+  if (c.write_SAM) {
+    // Mode::CREATE / Mode::UPDATE (src/seq_simulation.cpp:545-549); reads and tables come from one plan
+    std::vector<const char*> chr_names, sample_names;
+    for (const auto& n : forest.chr_names) chr_names.push_back(n.c_str());
+    for (const auto& n : names) sample_names.push_back(n.c_str());
+    pcs_check(pcs_forest_load_fasta(fo, ref_genome.c_str(), chr_names.data(), nullptr));
+    std::vector<uint32_t> alt_off(M + 1, 0);
+    std::string alt_bytes;
+    for (size_t r = 0; r < M; ++r) {
+      alt_bytes += forest.rows[r].alt;
+      alt_off[r + 1] = static_cast<uint32_t>(alt_bytes.size());
+    }
+    pcs_check(pcs_forest_set_alt(fo, alt_off.data(), alt_bytes.c_str()));
+    pcs_plan* plan = nullptr;
+    pcs_check(pcs_plan_create(fo, &P, &plan));
+    struct PlanGuard {
+      pcs_plan* p;
+      ~PlanGuard() { pcs_plan_free(p); }
+    } guard{plan};
+    pcs_check(pcs_plan_run(plan, PCS_RUN_HOST_OUTPUT, occ.data(), cov.data(), &res.stats));
+    pcs_sam_options opt{};
+    opt.output_dir = c.output_dir.c_str();
+    opt.filename_prefix = c.filename_prefix.c_str();
+    opt.template_name_prefix = c.template_name_prefix.c_str();
+    opt.chr_names = chr_names.data();
+    opt.sample_names = sample_names.data();
+    opt.update = c.update_SAM_dir ? 1 : 0;
+    pcs_check(pcs_plan_write_sam(plan, &opt, nullptr));
+  } else {
+    pcs_check(pcs_simulate(fo, &P, occ.data(), cov.data(), &res.stats));
+  }
 
   // get_result_dataframe(): src/seq_simulation.cpp:52-181
   std::vector<uint32_t> rows(std::max<size_t>(M, 1));
@@ -398,7 +428,6 @@ inline SeqResult simulate_seq(const PhylogeneticForest& forest, const Sequencer&
                               const bool& include_non_sequenced_mutations = false,
                               const std::optional<int>& seed = std::nullopt) {
   if (!(purity >= 0 && purity <= 1)) throw std::domain_error("The purity must belong to the interval [0,1].");
-  if (write_SAM) throw std::runtime_error("SAM output is not built yet (SURVEY.md 8 f3)");
   std::vector<uint32_t> groups;
   std::vector<std::string> names;
   apply_FACS_labels(forest, FACS_labelling_function, groups, names);
@@ -409,20 +438,18 @@ inline SeqResult simulate_seq(const PhylogeneticForest& forest, const Sequencer&
   return detail::run(forest, c, FACS_labelling_function ? &groups : nullptr, names);
 }
 
-// the reference's default here is write_SAM = TRUE (src/sequencing.cpp:275-276); the SAM writer is not
-// built yet, so the mirror's default is false and true is refused
+// defaults as the reference's: output_dir "ProCESS_normal_SAM", write_SAM = TRUE (src/sequencing.cpp:268-282)
 inline SeqResult simulate_normal_seq(const PhylogeneticForest& forest, const Sequencer& sequencer = {},
                                      const std::optional<std::string>& reference_genome = std::nullopt,
                                      const std::optional<std::vector<std::string>>& chromosome_ids = std::nullopt,
                                      const double& coverage = 10, const int& read_size = 150,
                                      const int& insert_size_mean = 0, const int& insert_size_stddev = 10,
-                                     const std::string& output_dir = "ProCESS_normal_SAM", const bool& write_SAM = false,
+                                     const std::string& output_dir = "ProCESS_normal_SAM", const bool& write_SAM = true,
                                      const bool& update_SAM_dir = false, const bool& with_preneoplastic = false,
                                      const std::string& filename_prefix = "chr_",
                                      const std::string& template_name_prefix = "r",
                                      const bool& include_non_sequenced_mutations = false,
                                      const std::optional<int>& seed = std::nullopt) {
-  if (write_SAM) throw std::runtime_error("SAM output is not built yet (SURVEY.md 8 f3)");
   detail::Call c{&sequencer, reference_genome, chromosome_ids, coverage, read_size, insert_size_mean,
                  insert_size_stddev, output_dir, write_SAM, update_SAM_dir, 1.0, false, with_preneoplastic, true,
                  filename_prefix, template_name_prefix, include_non_sequenced_mutations, seed};

@@ -99,7 +99,8 @@ int main(int argc, char** argv) {
     }
     std::printf("#seed\t%d\tsequencer\t%s\treads\t%llu\n", r.parameters.seed, r.parameters.sequencer_name->c_str(),
                 static_cast<unsigned long long>(r.stats.n_reads));
-    SeqResult n = simulate_normal_seq(f, seq, std::nullopt, std::nullopt, 400.0, 20, 0, 10, "ProCESS_normal_SAM", false,
+    const std::string sam_dir = argc >= 4 ? argv[3] : "ProCESS_normal_SAM";
+    SeqResult n = simulate_normal_seq(f, seq, std::nullopt, std::nullopt, 400.0, 20, 0, 10, sam_dir, argc >= 4,
                                       false, true, "chr_", "r", true, 7);
     std::printf("#normal\t%zu\t%s\t%zu\n", n.samples.size(), n.samples[0].name.c_str(), n.chr.size());
     return 0;

@@ -100,6 +100,23 @@ EXPECTED_GENOMES = {
 }
 
 
+# Reference for the SAM content checks: "ACGT" repeated (position p holds "ACGT"[(p-1) % 4]); alt strings below.
+REF = ("ACGT" * 250)
+ALT = ["C", "G", "A", "T", "G", "ATTT", "C", "G"]   # rows 0..7 (row 2: deletion AC..->A; row 5: insertion A->ATTT)
+# read C: cell 0, allele 1, start 296 (read_size 10): ref 296..299 = "TACG", the deletion's anchor alt "A" (5M),
+#         4 deleted bases (4D), ref 305..309 = "ACGTA" (5M)
+# read E: cell 1, allele 1, start 595: ref 595..599 = "GTACG", insertion alt "ATTT" = 1M + 3I, ref 601 = "A"
+# read A: cell 0, allele 0, start 95: ref 95..99 = "GTACG", SNV alt "C" at 100, ref 101..104 = "ACGT"
+# read L: cell 0, allele 0, start 395, error at offset 4 (position 399, "G" -> "ACGT"[(2+1+4%3)&3] = "A"),
+#         SNV alt "G" at 400
+EXPECTED_SAM = {
+    0: ("GTACGCACGT", "10M"),        # read A
+    2: ("TACGAACGTA", "5M4D5M"),     # read C
+    5: ("GTACAGACGT", "10M"),        # read L
+    6: ("GTACGATTTA", "6M3I1M"),     # read E
+}
+
+
 def forest():
     from process_b200.forest import PhylogeneticForest
     kw = {k: (v if k in ("chr_names", "sample_names") else np.asarray(v)) for k, v in FOREST.items()}

@@ -28,8 +28,9 @@ def test_cpp_mirror_matches_python_mirror(driver, tmp_path):
     from golden import micro_forest as MF
     from process_b200 import api
     ref = tmp_path / "ref.fa"
-    ref.write_text(">1\nACGT\n")
-    out = subprocess.run([driver, "run", str(ref)], capture_output=True, text=True)
+    ref.write_text(">1 micro\n" + MF.REF + "\n")
+    sam_dir = tmp_path / "normal_sam"
+    out = subprocess.run([driver, "run", str(ref), str(sam_dir)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.strip().split("\n")
     header = lines[0].split("\t")
@@ -52,4 +53,9 @@ def test_cpp_mirror_matches_python_mirror(driver, tmp_path):
     assert meta[1] == "7" and meta[3] == "BasicIlluminaSequencer" and int(meta[5]) == r["_stats"]["n_reads"]
     normal = [l for l in lines if l.startswith("#normal")][0].split("\t")
     assert normal[1] == "1" and normal[2] == "normal_sample"
+    # simulate_normal_seq wrote its SAM file (write_SAM = TRUE is the reference's default for it)
+    sam = (sam_dir / "chr_1.sam").read_text().split("\n")
+    assert sam[0].startswith("@HD") and any(l.startswith("@RG\tID:normal_sample") for l in sam)
+    reads = [l.split("\t") for l in sam if l and not l.startswith("@")]
+    assert len(reads) > 10_000 and all(r[5] in ("20M",) or "D" in r[5] or "I" in r[5] for r in reads[:2000])
     api.release_device_cache()

@@ -49,6 +49,23 @@ def test_micro_forest_hand_computed_counts():
     assert occ1[1].tolist() == [0, 0, 0, 0, 0, 1, 0, 0] and cov1[1].tolist() == [0, 0, 0, 0, 0, 1, 0, 0]
 
 
+def test_micro_forest_hand_computed_sam_content():
+    f = MF.forest()
+    rec, masks = MF.placements()
+    alt_off = np.concatenate([[0], np.cumsum([len(a) for a in MF.ALT])]).astype(np.uint32)
+    seq, qual, cigar, nc, ln = oracle.materialize(f, np.asarray([0, 1000], np.uint64), MF.REF.encode(), alt_off,
+                                                  "".join(MF.ALT).encode(), MF.READ_SIZE, A.PCS_SEQ_BASIC_CONSTANT, 1e-3,
+                                                  rec, masks)
+    for i, (want_seq, want_cigar) in MF.EXPECTED_SAM.items():
+        got_cigar = "".join(f"{int(op) >> 4}{'MID'[int(op) & 3]}" for op in cigar[i, :nc[i]])
+        assert seq[i, :ln[i]].tobytes().decode() == want_seq, i
+        assert got_cigar == want_cigar, i
+    # constant-quality model: Phred 30 everywhere except the erroneous base
+    assert qual[5].tobytes().decode() == "????#?????" and qual[0].tobytes().decode() == "?" * 10
+    # reads clamped by the end of their fragment (H, J) are shorter than read_size
+    assert ln[9] == 5 and ln[11] == 3
+
+
 @pytest.mark.parametrize("name", ["errorless_single", "random_quality_paired"])
 def test_oracle_reproduces_committed_vectors(name):
     z = np.load(os.path.join(GOLD, f"injected_{name}.npz"))
