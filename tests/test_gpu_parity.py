@@ -307,3 +307,47 @@ def test_python_mirror_schema_and_parameters(ctx, tmp_path):
                            cell_labelling=lambda cell: "odd" if cell.cell_id % 2 else "")["mutations"]
     assert any(c.startswith(f.sample_names[0] + "_odd.") for c in lab.columns)
     api.release_device_cache()
+
+
+def test_degenerate_forests_and_parameters(ctx):
+    """no mutations at all, a forest without events, reads longer than a chromosome, tiny coverage, no samples"""
+    from process_b200.forest import PhylogeneticForest
+    # two cells, nothing but the germline genome: every table is empty but the reads are still placed
+    bare = PhylogeneticForest(
+        chr_names=["1", "Y"], chr_len=np.asarray([5000, 120]), chr_n_alleles=np.asarray([2, 1]),
+        node_parent=np.asarray([-1, 0, 0]), sample_names=["a"], leaf_node=np.asarray([1, 2]), leaf_sample=np.asarray([0, 0]),
+        node_event_off=np.zeros(4), ev_kind=np.zeros(0), ev_chr=np.zeros(0), ev_pos=np.zeros(0), ev_len=np.zeros(0),
+        ev_allele=np.zeros(0), ev_dest=np.zeros(0), ev_mut=np.zeros(0), ev_nature=np.zeros(0),
+        mut_chr=np.zeros(0), mut_pos=np.zeros(0), mut_ref_len=np.zeros(0), mut_alt_len=np.zeros(0),
+        germ_mut=np.zeros(0), germ_allele_mask=np.zeros(0)).normalise()
+    dev = L.Forest(ctx, bare)
+    occ, cov, st = dev.simulate(make_params(coverage=30.0))
+    assert occ.shape == (2, 0) and st.n_reads > 1500
+    # read_size 150 > chromosome Y (120 bp): every template on it falls off the molecule
+    occ, cov, st = dev.simulate(make_params(coverage=30.0, chr_mask=[0, 1]))
+    assert st.n_reads == 0
+    assert oracle.simulate(bare, make_params(coverage=30.0, chr_mask=[0, 1]))["n_reads"] == 0
+    dev.close()
+    # one germline SNV, tiny coverage, huge coverage on few positions
+    one = PhylogeneticForest(
+        chr_names=["1"], chr_len=np.asarray([400]), chr_n_alleles=np.asarray([2]), node_parent=np.asarray([-1]),
+        sample_names=["a"], leaf_node=np.asarray([0]), leaf_sample=np.asarray([0]), node_event_off=np.zeros(2),
+        ev_kind=np.zeros(0), ev_chr=np.zeros(0), ev_pos=np.zeros(0), ev_len=np.zeros(0), ev_allele=np.zeros(0),
+        ev_dest=np.zeros(0), ev_mut=np.zeros(0), ev_nature=np.zeros(0), mut_chr=np.zeros(1), mut_pos=np.asarray([200]),
+        mut_ref_len=np.ones(1), mut_alt_len=np.ones(1), germ_mut=np.zeros(1), germ_allele_mask=np.asarray([1])).normalise()
+    dev = L.Forest(ctx, one)
+    occ, cov, st = dev.simulate(make_params(coverage=0.001))
+    assert st.n_reads <= 2
+    P = make_params(coverage=30000.0, read_size=100, with_normal_sample=0)
+    plan = L.Plan(dev, P)
+    occ, cov, st = plan.run()
+    rec, _ = plan.trace(cap=int(st.n_reads) + 8)
+    o2, c2 = oracle.count_injected(one, 1, 100, rec)
+    assert np.array_equal(occ, o2) and np.array_equal(cov, c2)
+    assert abs(occ[0, 0] / cov[0, 0] - 0.5) < 0.02 and cov[0, 0] > 20000
+    plan.close()
+    # no output sample at all: no tumour groups requested and no normal sample
+    dev.set_groups(np.zeros(1, np.uint32), 1)
+    occ, cov, st = dev.simulate(make_params(coverage=5.0, with_normal_sample=0, purity=0.0))
+    assert occ.shape[0] == 1 and occ.sum() >= 0  # purity 0: the tumour sample is all normal cells
+    dev.close()
