@@ -323,12 +323,12 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 
 struct StagedTile {
   SharedView SV;
-  uint32_t dir;    // shared address of uint16 [buckets]
+  uint32_t dir;    // shared address of uint2 [buckets]: {index, position} of the first locus at/after the bucket
   uint32_t ent;    // shared address of the tile's entries (32 bytes each)
   uint32_t n, shift, stage_end, chr_l1;
-  __device__ __forceinline__ uint32_t first_locus(uint32_t bucket) const {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(dir + bucket * 2u));
+  __device__ __forceinline__ uint2 first_locus(uint32_t bucket) const {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(dir + bucket * 8u));
     return v;
   }
 };
@@ -411,9 +411,9 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
   uint4* s_queue = s_rec + D.max_loci + 1;
   uint4* s_ent = s_queue + (kStagedThreads / 32) * kQueueSlots;
-  uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_ent + 2 * kMaxStagedEntries);
+  uint2* s_dir = reinterpret_cast<uint2*>(s_ent + 2 * kMaxStagedEntries);
+  uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
-  uint16_t* s_dir = reinterpret_cast<uint16_t*>(s_alt + D.max_rows);
 
   const Tile T = tiles[blockIdx.x];
   const uint32_t n = T.l1 - T.l0;
@@ -447,7 +447,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       uint32_t mid = (lo + hi) >> 1;
       if (s_rec[mid].x < x) lo = mid + 1; else hi = mid;
     }
-    s_dir[b] = static_cast<uint16_t>(lo);
+    s_dir[b] = make_uint2(lo, s_rec[lo].x);  // s_rec[n] is the sentinel at 0xffffffff
   }
   __syncthreads();
 
@@ -471,9 +471,10 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   // probe: does the first staged locus at or after the read's bucket lie before the read's end?
   // (the sentinel record makes the load safe when the bucket is past the last locus)
   auto probe_and_push = [&](bool ok, uint32_t xs, uint32_t h, uint32_t e, uint32_t fe, uint32_t read_id) {
-    const uint32_t i = ok ? S.first_locus((xs - T.begin) >> shift) : n;
-    const bool has = lds32(S.SV.rec + i * 16u) < min(xs + R, fe + 1u);
-    queue_push<ERRORS>(Q, S, T, F, M, depth, alt, ok && has, make_uint4(xs, h, read_id, i | (e << 16)), lane, lanes_below);
+    // one load: index and position of the first locus at/after the read's bucket (bucket 0 when !ok: harmless)
+    const uint2 d = S.first_locus(ok ? (xs - T.begin) >> shift : 0u);
+    const bool has = ok && d.y < min(xs + R, fe + 1u);
+    queue_push<ERRORS>(Q, S, T, F, M, depth, alt, has, make_uint4(xs, h, read_id, d.x | (e << 16)), lane, lanes_below);
   };
 
   // Philox block j: two single-end templates (2j, 2j+1) or one paired template (mates 2j, 2j+1)
@@ -801,7 +802,7 @@ size_t staged_smem_bytes(const StageDims& D) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
   b += (1 + static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + 2 * kMaxStagedEntries) * sizeof(uint4);
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
-  b += static_cast<size_t>(D.max_buckets) * sizeof(uint16_t);
+  b += static_cast<size_t>(D.max_buckets) * sizeof(uint2);
   return (b + 15) & ~static_cast<size_t>(15);
 }
 
