@@ -9,17 +9,15 @@ namespace pcs {
 // One way of drawing a haplotype for a read that starts inside a tile: the
 // haplotype leaves of one (sample group | normal cells, fragment set) list.
 // A single 32-bit draw u picks the entry (first with u <= thr) and the leaf inside
-// it: leaf = umulhi(u - base, scale), scale = floor(list_n * 2^32 / (thr - base + 1)).
+// it: leaf = umulhi(u - base, scale), base = previous entry's thr + 1 (0 for the first),
+// scale = floor(list_n * 2^32 / (thr - base + 1)).  16 bytes: one LDS.128 per read.
 struct Entry {
   uint32_t thr;       // last draw value belonging to this entry (cumulative)
-  uint32_t base;      // first draw value belonging to this entry
   uint32_t scale;
   uint32_t list_off;  // into hap_list
   uint32_t frag_end;  // last position of the fragment the tile lies in (reads never cross it)
-  uint32_t list_n;
-  uint32_t pad0, pad1;
 };
-static_assert(sizeof(Entry) == 32, "Entry layout");
+static_assert(sizeof(Entry) == 16, "Entry layout");
 
 constexpr uint32_t kMaxStagedEntries = 16;  // tiles drawing from more lists use the global kernel
 

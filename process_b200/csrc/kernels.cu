@@ -264,10 +264,13 @@ template <class EntryPtr>
 __device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const DevForest& F, uint32_t u_start, uint32_t u_hap,
                                       uint32_t tlen, Template& out) {
   out.x = T.begin + __umulhi(u_start, T.len);
-  uint32_t e = 0;
-  while (u_hap > ent[e].thr) ++e;  // the last entry's thr is 0xffffffff
-  const uint32_t leaf = __umulhi(u_hap - ent[e].base, ent[e].scale);
-  out.h = __ldg(F.hap_list + ent[e].list_off + leaf);
+  uint32_t e = 0, base = 0;
+  while (u_hap > ent[e].thr) {  // the last entry's thr is 0xffffffff
+    base = ent[e].thr + 1u;
+    ++e;
+  }
+  const uint32_t leaf = __umulhi(u_hap - base, ent[e].scale);
+  out.h = __ldg(F.hap_list + (ent[e].list_off + leaf));
   out.frag_end = ent[e].frag_end;
   return out.x + (tlen - 1u) <= out.frag_end;  // else the template falls off its molecule
 }
@@ -339,13 +342,15 @@ __device__ __forceinline__ bool place_staged(const StagedTile& S, const Tile& T,
                                              uint32_t& frag_end) {
   x = T.begin + __umulhi(u_start, T.len);
   e = 0;
-  uint4 a = lds128(S.ent);
+  uint32_t base = 0;
+  uint4 a = lds128(S.ent);  // {thr, scale, list_off, frag_end}
   while (u_hap > a.x) {  // the last entry's thr is 0xffffffff
+    base = a.x + 1u;
     ++e;
-    a = lds128(S.ent + e * 32u);
+    a = lds128(S.ent + e * 16u);
   }
-  h = __ldg(F.hap_list + (a.w + __umulhi(u_hap - a.y, a.z)));
-  frag_end = lds32(S.ent + e * 32u + 16u);
+  h = __ldg(F.hap_list + (a.z + __umulhi(u_hap - base, a.y)));
+  frag_end = a.w;
   return x + (tlen - 1u) <= frag_end;  // else the template falls off its molecule
 }
 
@@ -355,7 +360,7 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
                                             uint32_t* depth, uint32_t* alt, uint4 item) {
   const uint32_t R = M.read_size;
   const uint32_t xs = item.x, h = item.y, read_id = item.z, i = item.w & 0xffffu;
-  const uint32_t frag_end = lds32(S.ent + (item.w >> 16) * 32u + 16u);
+  const uint32_t frag_end = lds32(S.ent + (item.w >> 16) * 16u + 12u);
   Walk w;
   w.init(xs, R, frag_end);
   bool done;
@@ -411,7 +416,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
   uint4* s_queue = s_rec + D.max_loci + 1;
   uint4* s_ent = s_queue + (kStagedThreads / 32) * kQueueSlots;
-  uint2* s_dir = reinterpret_cast<uint2*>(s_ent + 2 * kMaxStagedEntries);
+  uint2* s_dir = reinterpret_cast<uint2*>(s_ent + kMaxStagedEntries);
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
 
@@ -436,7 +441,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   }
   if (threadIdx.x == 0) s_rec[n] = make_uint4(0xffffffffu, 0u, 0u, 0u);  // sentinel: past every read
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
-  if (threadIdx.x < 2 * T.n_entries)
+  if (threadIdx.x < T.n_entries)
     s_ent[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(entries + T.entry_off) + threadIdx.x);
   __syncthreads();
   // directory: first staged locus at or after the start of each bucket
@@ -800,7 +805,7 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
 // ----------------------------------------------------------------- launchers
 size_t staged_smem_bytes(const StageDims& D) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
-  b += (1 + static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + 2 * kMaxStagedEntries) * sizeof(uint4);
+  b += (1 + static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + kMaxStagedEntries) * sizeof(uint4);
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint2);
   return (b + 15) & ~static_cast<size_t>(15);

@@ -406,18 +406,21 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
         const pcs::Piece& pc = F.pieces[pi];
         std::vector<double> w;
         std::vector<pcs::Entry> es;
+        std::vector<uint32_t> es_n;  // haplotypes in each entry's list
         for (uint32_t k = 0; k < pc.cover_n; ++k) {
           const pcs::Cover& cv = F.covers[pc.cover_off + k];
           if (purity > 0) {
             auto it = fo.list_index.find(HostForest::list_key(samples[s].group, cv.fragset));
             if (it != fo.list_index.end() && it->second.second > 0) {
               w.push_back(purity / nT * it->second.second);
-              es.push_back(pcs::Entry{0u, 0u, 0u, it->second.first, cv.frag_end, it->second.second, 0u, 0u});
+              es.push_back(pcs::Entry{0u, 0u, it->second.first, cv.frag_end});
+              es_n.push_back(it->second.second);
             }
           }
           if (purity < 1 && cv.fragset == F.full_fragset[c]) {
             w.push_back((1 - purity) / n_normal_cells * nit->second.second);
-            es.push_back(pcs::Entry{0u, 0u, 0u, nit->second.first, cv.frag_end, nit->second.second, 0u, 0u});
+            es.push_back(pcs::Entry{0u, 0u, nit->second.first, cv.frag_end});
+            es_n.push_back(nit->second.second);
           }
         }
         if (es.empty()) continue;
@@ -433,9 +436,8 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
             if (static_cast<uint64_t>(thr[i]) + 1 <= base) continue;
             const uint64_t width = static_cast<uint64_t>(thr[i]) + 1 - base;
             es[i].thr = thr[i];
-            es[i].base = static_cast<uint32_t>(base);
-            // leaf = umulhi(u - base, scale) < list_n
-            es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es[i].list_n) << 32) / width));
+            // leaf = umulhi(u - base, scale) < list_n, base = previous kept entry's thr + 1
+            es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es_n[i]) << 32) / width));
             kept.push_back(es[i]);
             base = static_cast<uint64_t>(thr[i]) + 1;
           }
