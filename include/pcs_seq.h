@@ -305,11 +305,11 @@ int pcs_count_injected(pcs_forest* forest, uint32_t n_out_samples, uint32_t read
                        uint64_t n, uint32_t* occurrences, uint32_t* coverage,
                        pcs_run_stats* stats);
 
-/* rows with occurrences > 0 in at least one sample (get_active_mutations);
- * with include_non_sequenced != 0 also the rows carried by at least one cell of
- * the sequenced samples.  rows_out has capacity n_mut; *n_rows receives the count. */
+/* rows with occurrences > 0 in at least one sample (get_active_mutations, src/seq_simulation.cpp:142-167);
+ * with include_non_sequenced != 0 also the rows some sequenced cell carries (params says which cells were
+ * sequenced; NULL = all).  rows_out has capacity n_mut; *n_rows receives the count. */
 int pcs_active_rows(pcs_forest* forest, const uint32_t* occurrences, uint32_t n_out_samples,
-                    int include_non_sequenced, uint32_t* rows_out, uint32_t* n_rows);
+                    int include_non_sequenced, const pcs_seq_params* params, uint32_t* rows_out, uint32_t* n_rows);
 
 /* ---- host-only introspection of the flattened view (no GPU needed).  Used by the
  * CPU test-suite to check the haplotype-interval view against explicit per-cell

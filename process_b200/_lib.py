@@ -235,12 +235,13 @@ class Forest:
                                      C.byref(st)))
         return occ, cov, st
 
-    def active_rows(self, occ, include_non_sequenced=False):
+    def active_rows(self, occ, include_non_sequenced=False, params=None):
         occ = np.ascontiguousarray(occ, dtype=np.uint32)
         rows = np.zeros(max(1, self.forest.n_mut), np.uint32)
         n = C.c_uint32(0)
         _ok(lib().pcs_active_rows(self._h, A.ptr(occ, C.c_uint32), C.c_uint32(occ.shape[0]),
-                                  C.c_int(1 if include_non_sequenced else 0), A.ptr(rows, C.c_uint32), C.byref(n)))
+                                  C.c_int(1 if include_non_sequenced else 0),
+                                  C.byref(params) if params is not None else None, A.ptr(rows, C.c_uint32), C.byref(n)))
         return rows[:n.value].copy()
 
 

@@ -188,11 +188,11 @@ def release_device_cache():
     _ctx_cache.clear()
 
 
-def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced):
+def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, params=None):
     """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181.
     Sample columns in name order (std::map iteration), rows in SID order."""
     import pandas as pd
-    rows = dev.active_rows(occ, include_non_sequenced)
+    rows = dev.active_rows(occ, include_non_sequenced, params)
     ref, alt = forest.row_strings(rows)
     cols = {
         "chr": np.asarray(forest.chr_names, dtype=object)[forest.mut_chr[rows]],
@@ -258,7 +258,7 @@ def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, 
             occ, cov, st = dev.simulate(P)
         if shard[1] > 1:
             occ, cov = _reduce_over_ranks(occ, cov)
-        df = _result_dataframe(forest, dev, occ, cov, out_names, include_non_sequenced)
+        df = _result_dataframe(forest, dev, occ, cov, out_names, include_non_sequenced, P)
     finally:
         if owned:
             dev.close()

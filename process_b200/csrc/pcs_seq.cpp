@@ -1446,14 +1446,33 @@ int pcs_count_injected(pcs_forest* fo, uint32_t n_out_samples, uint32_t read_siz
 }
 
 int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples, int include_non_sequenced,
-                    uint32_t* rows_out, uint32_t* n_rows) {
+                    const pcs_seq_params* params, uint32_t* rows_out, uint32_t* n_rows) {
   return guarded([&] {
     require(fo && occ && rows_out && n_rows, "bad arguments");
     const pcs::FlatForest& F = fo->host.flat;
     std::vector<uint8_t> carried;
     if (include_non_sequenced) {
+      // rows some SEQUENCED cell inherits: an instance whose haplotype interval holds a haplotype of a
+      // sequenced kind (tumour cells unless normal_only; the normal cells that are in the mix)
+      const bool normal_only = params && params->normal_only;
+      const bool preneo = params && params->preneoplastic_in_normal;
+      const bool normals = !params || normal_only || params->with_normal_sample || params->purity < 1.0;
       carried.assign(F.n_mut, 0);
-      for (const auto& in : F.inst) carried[in.row] = 1;  // inherited by at least one sampled haplotype
+      for (uint32_t c = 0; c < F.n_chr; ++c) {
+        std::vector<uint32_t> seq_haps;  // sorted haplotype indices of the sequenced cells
+        const auto& haps = F.chr_haps[c];
+        for (uint32_t h = 0; h < haps.size(); ++h) {
+          const bool on = haps[h].kind == pcs::HAP_TUMOUR ? !normal_only
+                          : normals && (haps[h].kind == (preneo ? pcs::HAP_NORMAL_PRENEO : pcs::HAP_NORMAL_PLAIN));
+          if (on) seq_haps.push_back(h);
+        }
+        for (uint32_t l = F.chr_locus_off[c]; l < F.chr_locus_off[c + 1]; ++l)
+          for (uint32_t i = F.locus_inst_off[l]; i < F.locus_inst_off[l + 1]; ++i) {
+            const pcs::Inst& in = F.inst[i];
+            auto it = std::lower_bound(seq_haps.begin(), seq_haps.end(), in.lo);
+            if (it != seq_haps.end() && *it - in.lo < in.span) carried[in.row] = 1;
+          }
+      }
     }
     uint32_t k = 0;
     for (uint32_t m = 0; m < F.n_mut; ++m) {

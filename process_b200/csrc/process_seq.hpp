@@ -340,7 +340,7 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
   // get_result_dataframe(): src/seq_simulation.cpp:52-181
   std::vector<uint32_t> rows(std::max<size_t>(M, 1));
   uint32_t n = 0;
-  pcs_check(pcs_active_rows(fo, occ.data(), static_cast<uint32_t>(S), c.include_non_sequenced_mutations, rows.data(), &n));
+  pcs_check(pcs_active_rows(fo, occ.data(), static_cast<uint32_t>(S), c.include_non_sequenced_mutations, &P, rows.data(), &n));
   rows.resize(n);
   for (uint32_t r : rows) {
     res.chr.push_back(forest.chr_names[forest.mut_chr[r]]);

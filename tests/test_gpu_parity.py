@@ -303,6 +303,12 @@ def test_python_mirror_schema_and_parameters(ctx, tmp_path):
     assert [c for c in n["mutations"].columns if "." in c] == ["normal_sample.occurrences", "normal_sample.coverage",
                                                               "normal_sample.VAF"]
     assert "with_preneoplastic" in n["parameters"]
+    # include_non_sequenced_mutations: every row a SEQUENCED cell carries, and only those
+    nn = api.simulate_normal_seq(f, coverage=0.01, seed=5, write_SAM=False, include_non_sequenced_mutations=True)
+    assert set(nn["mutations"]["classes"]) == {"germinal"} and len(nn["mutations"]) == len(f.germ_mut)
+    np_ = api.simulate_normal_seq(f, coverage=0.01, seed=5, write_SAM=False, include_non_sequenced_mutations=True,
+                                  with_preneoplastic=True)
+    assert set(np_["mutations"]["classes"]) == {"germinal", "preneoplastic"}
     lab = api.simulate_seq(f, coverage=5, seed=5, with_normal_sample=False,
                            cell_labelling=lambda cell: "odd" if cell.cell_id % 2 else "")["mutations"]
     assert any(c.startswith(f.sample_names[0] + "_odd.") for c in lab.columns)
