@@ -24,7 +24,20 @@ CASES = {
                                                       error_rate=0.03, preneoplastic_in_normal=1)),
 }
 
+def distribution_fixture():
+    """oracle free-run depth / occurrence tables of one fixed forest: the GPU sampler's
+    tables must be statistically indistinguishable from these (KS on depth and VAF)."""
+    f = synth_forest(small_spec(7, chr_names=["1"], chr_len=[2_000_000], chr_n_alleles=[2], sample_cells=[30, 50],
+                                germline_density=1.5e-3, cna_len=(50_000, 300_000)))
+    P = make_params(coverage=100.0, purity=0.8, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01, seed=21)
+    r = oracle.simulate(f, P, n_threads=8)
+    np.savez_compressed(os.path.join(HERE, "distribution_oracle.npz"), occ=r["occ"].astype(np.uint16),
+                        cov=r["cov"].astype(np.uint16), n_reads=r["n_reads"], forest_seed=7)
+    print("distribution fixture", r["n_reads"], "reads", r["cov"].mean())
+
+
 if __name__ == "__main__":
+    distribution_fixture()
     for name, case in CASES.items():
         f = synth_forest(small_spec(case["seed"]))
         P = make_params(**case["params"])

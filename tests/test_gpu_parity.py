@@ -357,3 +357,45 @@ def test_degenerate_forests_and_parameters(ctx):
     occ, cov, st = dev.simulate(make_params(coverage=5.0, with_normal_sample=0, purity=0.0))
     assert occ.shape[0] == 1 and occ.sum() >= 0  # purity 0: the tumour sample is all normal cells
     dev.close()
+
+
+def test_distributions_match_committed_oracle_fixture(ctx):
+    """the same comparison against tables the oracle produced once and that are committed under tests/golden/"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "distribution_oracle.npz"))
+    f = synth_forest(small_spec(int(z["forest_seed"]), chr_names=["1"], chr_len=[2_000_000], chr_n_alleles=[2],
+                                sample_cells=[30, 50], germline_density=1.5e-3, cna_len=(50_000, 300_000)))
+    P = make_params(coverage=100.0, purity=0.8, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01, seed=2)
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.simulate(P)
+    dev.close()
+    ref = dict(occ=z["occ"].astype(np.uint32), cov=z["cov"].astype(np.uint32))
+    assert abs(st.n_reads / int(z["n_reads"]) - 1) < 5e-3
+    for s in range(occ.shape[0]):
+        assert abs(cov[s].mean() / ref["cov"][s].mean() - 1) < 5e-3
+    p = _ks_pvalues(f, P, occ, cov, ref)
+    assert p.min() > 0.01, p
+
+
+def test_config1_free_running_matches_oracle_at_full_size(ctx):
+    """configs[0] itself -- the reference's own CPU-runnable case: chr22-sized genome, 4 samples of 100/100/560/560
+    cells + normal sample, errorless, 50x, 85.5 M reads -- GPU sampler against the oracle run in full."""
+    from process_b200.synth import config_spec
+    f = synth_forest(config_spec("C1"))
+    P = make_params(coverage=50.0, purity=1.0, seed=12)
+    ref = oracle.simulate(f, P, n_threads=8)
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.simulate(P)
+    dev.close()
+    assert abs(st.n_reads / ref["n_reads"] - 1) < 1e-3
+    for s in range(occ.shape[0]):
+        assert abs(cov[s].mean() / ref["cov"][s].mean() - 1) < 5e-3, s
+    p = _ks_pvalues(f, P, occ, cov, ref)
+    assert p.min() > 0.01, p
+    # sample-level VAF spectrum of the somatic rows: same clonal / subclonal structure
+    somatic = (f.mut_nature_mask & ((1 << A.PCS_NATURE_DRIVER) | (1 << A.PCS_NATURE_PASSENGER) |
+                                    (1 << A.PCS_NATURE_PRENEOPLASTIC))) != 0
+    for s in range(4):
+        vg = occ[s, somatic].sum() / cov[s, somatic].sum()
+        vo = ref["occ"][s, somatic].sum() / ref["cov"][s, somatic].sum()
+        assert abs(vg / vo - 1) < 0.02, (s, vg, vo)
