@@ -283,13 +283,18 @@ unsigned host_threads() {
   return std::max(1u, std::thread::hardware_concurrency());
 }
 
-uint32_t tile_bp() {
+// Tile width.  PCS_TILE_BP overrides; otherwise 2^18 bp, narrowed for small jobs so that the grid still has
+// a few thousand CTAs (148 SMs x 4 resident CTAs x several waves).  A function of the forest and the call's
+// parameters only -- never of the number of GPUs -- so tile ids and results do not depend on sharding.
+uint32_t tile_bp(uint64_t sequenced_bp_all_samples) {
   const char* s = std::getenv("PCS_TILE_BP");
   if (s) {
     long v = std::atol(s);
     if (v >= 1024) return static_cast<uint32_t>(v);
   }
-  return 1u << 18;
+  uint32_t w = 1u << 18;
+  while (w > (1u << 13) && sequenced_bp_all_samples / w < 148ull * 32ull) w >>= 1;
+  return w;
 }
 
 uint32_t stage_loci_cap() {
@@ -381,7 +386,10 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   if (P.normal_only || P.with_normal_sample) samples.push_back({true, 0});
 
   const uint32_t normal_group = fo.n_groups + (P.preneoplastic_in_normal ? 1u : 0u);
-  const uint32_t W = tile_bp();
+  uint64_t sequenced_bp = 0;
+  for (uint32_t c = 0; c < F.n_chr; ++c)
+    if (chr_mask.empty() || chr_mask[c]) sequenced_bp += F.chr_len[c];
+  const uint32_t W = tile_bp(sequenced_bp * samples.size());
   const uint32_t lcap = stage_loci_cap();
   const uint32_t shards = P.shard_count ? P.shard_count : 1;
 
