@@ -54,9 +54,9 @@ struct SeqModel {
   uint32_t sequencer;       // PCS_SEQ_*
   uint32_t err_thr;         // floor(error_rate * 2^32), constant-quality model
   float error_rate;         // random-quality model
-  uint32_t insert_n;        // entries of the insert-size CDF (paired)
+  uint32_t insert_n;        // columns of the insert-size alias table (paired)
   uint32_t insert_min;      // smallest insert with non-zero probability
-  const uint32_t* insert_cdf;  // [insert_n] cumulative thresholds over the u32 range
+  const uint32_t* insert_alias;  // [insert_n][2] {keep threshold over the u32 range, alias column}
   uint32_t seed;
   uint32_t reach;           // bases past a tile's last start position a template can span (without deletions)
   uint32_t dir_shift;       // staged kernel: log2 of the bucket size of the in-tile locus directory

@@ -275,13 +275,13 @@ __device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const DevFore
   return out.x + (tlen - 1u) <= out.frag_end;  // else the template falls off its molecule
 }
 
+// insert size ~ Binomial(t, p) (get_bin_dist, src/seq_simulation.cpp:431-451) by Walker's alias method:
+// the high part of u * n picks a column, the low part is the coin -- one 8-byte load, no search
 __device__ __forceinline__ uint32_t draw_insert(const SeqModel& M, uint32_t u) {
-  uint32_t lo = 0, hi = M.insert_n - 1;
-  while (lo < hi) {
-    uint32_t mid = (lo + hi) >> 1;
-    if (u > __ldg(M.insert_cdf + mid)) lo = mid + 1; else hi = mid;
-  }
-  return M.insert_min + lo;
+  const uint64_t prod = static_cast<uint64_t>(u) * M.insert_n;
+  const uint32_t col = static_cast<uint32_t>(prod >> 32), coin = static_cast<uint32_t>(prod);
+  const uint2 a = __ldg(reinterpret_cast<const uint2*>(M.insert_alias) + col);  // {keep threshold, alias}
+  return M.insert_min + (coin < a.x ? col : a.y);
 }
 
 __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* dst) {

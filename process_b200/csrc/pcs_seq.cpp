@@ -255,7 +255,7 @@ struct HostPlan {
   std::vector<pcs::Tile> tiles_global;  // this shard, too dense to stage
   pcs::StageDims dims{};
   std::vector<pcs::Entry> entries;
-  std::vector<uint32_t> insert_cdf;
+  std::vector<uint32_t> insert_alias;  // [n][2] {keep threshold, alias column}
   pcs::SeqModel model{};
   pcs_plan_info info{};
 };
@@ -265,7 +265,7 @@ struct pcs_plan {
   HostPlan host;
   DevBuf<pcs::Tile> d_tiles, d_tiles_global;
   DevBuf<pcs::Entry> d_entries;
-  DevBuf<uint32_t> d_insert_cdf;
+  DevBuf<uint32_t> d_insert_alias;
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
   DevBuf<unsigned long long> d_counters;  // [0] reads placed [1] sum depth [2] sum occ [3] trace count
   uint64_t h2d_bytes = 0;
@@ -341,7 +341,7 @@ void validate(const pcs_seq_params& P) {
 }
 
 // Binomial(t, p) as selection thresholds over its support
-void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& cdf, uint32_t& kmin, uint32_t& kmax) {
+void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& alias, uint32_t& kmin, uint32_t& kmax) {
   double q = static_cast<double>(sd) * sd / mean;
   double p = 1 - q;
   uint32_t t = static_cast<uint32_t>(mean / p);
@@ -358,8 +358,31 @@ void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& cdf, uint32
   kmax = t;
   while (kmin < kmax && pmf[kmin] < 1e-18) ++kmin;
   while (kmax > kmin && pmf[kmax] < 1e-18) --kmax;
-  std::vector<double> w(pmf.begin() + kmin, pmf.begin() + kmax + 1);
-  cdf = thresholds(w);
+  // Walker / Vose alias table over the support [kmin, kmax]
+  const uint32_t n = kmax - kmin + 1;
+  std::vector<double> scaled(n);
+  double total = 0;
+  for (uint32_t i = 0; i < n; ++i) total += pmf[kmin + i];
+  for (uint32_t i = 0; i < n; ++i) scaled[i] = pmf[kmin + i] / total * n;
+  std::vector<uint32_t> small, large;
+  for (uint32_t i = 0; i < n; ++i) (scaled[i] < 1.0 ? small : large).push_back(i);
+  alias.assign(2 * static_cast<size_t>(n), 0);
+  auto set = [&](uint32_t col, double keep, uint32_t other) {
+    alias[2 * col] = static_cast<uint32_t>(std::min(4294967295.0, std::floor(keep * 4294967296.0)));
+    alias[2 * col + 1] = other;
+  };
+  while (!small.empty() && !large.empty()) {
+    const uint32_t s_ = small.back(), l_ = large.back();
+    small.pop_back();
+    set(s_, scaled[s_], l_);
+    scaled[l_] -= 1.0 - scaled[s_];
+    if (scaled[l_] < 1.0) {
+      large.pop_back();
+      small.push_back(l_);
+    }
+  }
+  for (uint32_t i : large) set(i, 1.0, i);
+  for (uint32_t i : small) set(i, 1.0, i);
 }
 
 struct OutSample {
@@ -377,7 +400,7 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   const uint32_t mates = paired ? 2 : 1;
 
   uint32_t kmin = 0, kmax = 0;
-  if (paired) insert_table(P.insert_size_mean, P.insert_size_stddev, pl.insert_cdf, kmin, kmax);
+  if (paired) insert_table(P.insert_size_mean, P.insert_size_stddev, pl.insert_alias, kmin, kmax);
   const uint64_t reach = paired ? 2ull * R + kmax : R;
 
   std::vector<OutSample> samples;
@@ -394,7 +417,6 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   const uint32_t shards = P.shard_count ? P.shard_count : 1;
 
   std::vector<pcs::Entry>& entries = pl.entries;
-  std::vector<uint32_t>& cdf = pl.insert_cdf;
   std::vector<pcs::Tile> all;
   std::vector<double> tile_w;
   uint64_t total_templates = 0;
@@ -541,13 +563,13 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   pl.dims.max_buckets = (pl.dims.max_buckets + 63) & ~63u;
 
   pcs::SeqModel& M = pl.model;
-  M.insert_cdf = nullptr;
+  M.insert_alias = nullptr;
   M.read_size = R;
   M.paired = paired ? 1 : 0;
   M.sequencer = P.sequencer;
   M.err_thr = static_cast<uint32_t>(std::min(4294967295.0, std::floor(P.error_rate * 4294967296.0)));
   M.error_rate = static_cast<float>(P.error_rate);
-  M.insert_n = static_cast<uint32_t>(cdf.size());
+  M.insert_n = static_cast<uint32_t>(pl.insert_alias.size() / 2);
   M.insert_min = kmin;
   M.seed = static_cast<uint32_t>(P.seed);
   M.reach = static_cast<uint32_t>(reach);
@@ -572,8 +594,8 @@ void upload_plan(pcs_plan& pl) {
   pl.h2d_bytes += pl.d_tiles.upload(pl.host.tiles, st);
   pl.h2d_bytes += pl.d_tiles_global.upload(pl.host.tiles_global, st);
   pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
-  pl.h2d_bytes += pl.d_insert_cdf.upload(pl.host.insert_cdf, st);
-  pl.host.model.insert_cdf = pl.d_insert_cdf.p;
+  pl.h2d_bytes += pl.d_insert_alias.upload(pl.host.insert_alias, st);
+  pl.host.model.insert_alias = pl.d_insert_alias.p;
   const size_t S = pl.host.info.n_out_samples;
   pl.d_depth.alloc(S * pl.host.info.n_loci, st);
   pl.d_occ.alloc(S * pl.host.info.n_mut, st);

@@ -115,7 +115,7 @@ def test_write_sam_files_and_directory_modes(tmp_path):
     assert "chr_1_1.sam" in os.listdir(out)
     # paired reads: flags, mates, template length
     out2 = str(tmp_path / "paired")
-    api.simulate_seq(f, coverage=2.0, write_SAM=True, output_dir=out2, seed=5, insert_size_mean=200, insert_size_stddev=10,
+    api.simulate_seq(f, coverage=30.0, write_SAM=True, output_dir=out2, seed=5, insert_size_mean=200, insert_size_stddev=10,
                      chromosomes=["2"], with_normal_sample=False, filename_prefix="x_", template_name_prefix="tpl")
     _, reads = parse_sam(os.path.join(out2, "x_2.sam"))
     by_name = {}
@@ -127,6 +127,16 @@ def test_write_sam_files_and_directory_modes(tmp_path):
         assert first[1] == "99" and second[1] == "147" and first[6] == "="
         assert first[7] == second[3] and second[7] == first[3]
         assert int(first[8]) == -int(second[8]) == int(second[3]) - int(first[3]) + 150
+    # insert sizes follow get_bin_dist(200, 10): Binomial(t = 200/p, p = 1 - 100/200)  (src/seq_simulation.cpp:431-451)
+    from scipy import stats
+    ins = np.asarray([int(a[8] if a[1] == "99" else b[8]) - 300 for a, b in by_name.values()])
+    t, pr = int(200 / 0.5), 0.5
+    assert len(ins) > 15_000 and abs(ins.mean() - t * pr) < 0.35 and abs(ins.std() - 10.0) < 0.3
+    obs = np.bincount(ins, minlength=t + 1)[150:251]
+    exp = stats.binom(t, pr).pmf(np.arange(150, 251)) * len(ins)
+    keep = exp > 5
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    assert stats.chi2(keep.sum() - 1).sf(chi2) > 1e-3
     # simulate_normal_seq writes SAM by default (src/sequencing.cpp:275-276)
     n = api.simulate_normal_seq(f, coverage=2.0, seed=6, output_dir=str(tmp_path / "normal"))
     assert sorted(os.listdir(str(tmp_path / "normal"))) == sorted(f"chr_{x}.sam" for x in f.chr_names)
