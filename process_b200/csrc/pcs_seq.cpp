@@ -967,6 +967,9 @@ int pcs_plan_create(pcs_forest* fo, const pcs_seq_params* params, pcs_plan** out
     lap("make_host_plan");
     upload_plan(*pl);
     lap("upload plan + alloc tables");
+    if (lap.on)
+      std::fprintf(stderr, "[pcs host]    tiles: %zu staged, %zu global; staged smem %zu B\n", pl->host.tiles.size(),
+                   pl->host.tiles_global.size(), pcs::staged_smem_bytes(pl->host.dims));
     *out = pl.release();
   });
 }
