@@ -399,3 +399,22 @@ def test_config1_free_running_matches_oracle_at_full_size(ctx):
         vg = occ[s, somatic].sum() / cov[s, somatic].sum()
         vo = ref["occ"][s, somatic].sum() / ref["cov"][s, somatic].sum()
         assert abs(vg / vo - 1) < 0.02, (s, vg, vo)
+
+
+@pytest.mark.parametrize("cap", ["0", "48"])
+def test_global_memory_kernel_for_tiles_too_dense_to_stage(ctx, forests, cap, monkeypatch):
+    """PCS_STAGE_LOCI=0 sends every tile through sample_tiles_global_kernel (no shared-memory staging);
+    48 mixes tiny staged tiles with global ones.  Both must count what the oracle recounts."""
+    monkeypatch.setenv("PCS_STAGE_LOCI", cap)
+    f = forests[1]
+    dev = L.Forest(ctx, f)
+    for kw in (dict(), dict(sequencer=A.PCS_SEQ_BASIC_RANDOM, error_rate=0.03, insert_size_mean=160)):
+        P = make_params(coverage=10.0, purity=0.7, seed=9, **kw)
+        plan = L.Plan(dev, P)
+        occ, cov, st = plan.run()
+        rec, masks = plan.trace(cap=int(st.n_reads) + 8, with_masks=True)
+        occ2, cov2 = oracle.count_injected(f, plan.info.n_out_samples, P.read_size, rec, masks)
+        assert len(rec) == st.n_reads > 10_000
+        assert np.array_equal(occ, occ2) and np.array_equal(cov, cov2)
+        plan.close()
+    dev.close()
