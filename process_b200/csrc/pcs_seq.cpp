@@ -107,7 +107,46 @@ struct pcs_ctx {
   bool own_stream = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   void bind() const { CUDA_OK(cudaSetDevice(device)); }
+  // pinned staging buffer for the result tables: D2H into pinned memory runs at link speed, the copy
+  // into the caller's (pageable) buffers is spread over host threads
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  void* staging(size_t bytes) {
+    if (bytes > pinned_bytes) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_bytes = 0;
+      CUDA_OK(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
+      pinned_bytes = bytes;
+    }
+    return pinned;
+  }
 };
+
+namespace {
+// threads of the host flattener: PCS_HOST_THREADS, else every core
+unsigned host_threads() {
+  const char* s = std::getenv("PCS_HOST_THREADS");
+  if (s) {
+    long v = std::atol(s);
+    if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
+  }
+  return std::max(1u, std::thread::hardware_concurrency());
+}
+
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+  const unsigned nt = std::max(1u, std::min(8u, host_threads()));
+  if (bytes < (8u << 20) || nt == 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
+  for (size_t off = 0; off < bytes; off += chunk)
+    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off)); });
+  for (auto& t : th) t.join();
+}
+}  // namespace
 
 // host half of an uploaded forest: flattened view + output sample groups
 struct HostForest {
@@ -273,16 +312,6 @@ struct pcs_plan {
 
 namespace {
 
-// threads of the host flattener: PCS_HOST_THREADS, else every core
-unsigned host_threads() {
-  const char* s = std::getenv("PCS_HOST_THREADS");
-  if (s) {
-    long v = std::atol(s);
-    if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
-  }
-  return std::max(1u, std::thread::hardware_concurrency());
-}
-
 // Tile width.  PCS_TILE_BP overrides; otherwise 2^18 bp, narrowed for small jobs so that the grid still has
 // a few thousand CTAs (148 SMs x 4 resident CTAs x several waves).  A function of the forest and the call's
 // parameters only -- never of the number of GPUs -- so tile ids and results do not depend on sharding.
@@ -416,12 +445,20 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   const uint32_t lcap = stage_loci_cap();
   const uint32_t shards = P.shard_count ? P.shard_count : 1;
 
-  std::vector<pcs::Entry>& entries = pl.entries;
-  std::vector<pcs::Tile> all;
-  std::vector<double> tile_w;
-  uint64_t total_templates = 0;
-
-  for (uint32_t s = 0; s < samples.size(); ++s) {
+  // every output sample plans its own tiles (independent RNG streams), on its own host thread
+  struct PerSample {
+    std::vector<pcs::Entry> entries;
+    std::vector<pcs::Tile> all;
+    std::vector<double> tile_w;
+    uint64_t total_templates = 0;
+    std::string error;
+  };
+  std::vector<PerSample> per(samples.size());
+  auto plan_sample = [&](uint32_t s) {
+    std::vector<pcs::Entry>& entries = per[s].entries;
+    std::vector<pcs::Tile>& all = per[s].all;
+    std::vector<double>& tile_w = per[s].tile_w;
+    uint64_t& total_templates = per[s].total_templates;
     double purity = samples[s].is_normal ? 0.0 : P.purity;
     uint32_t nT = samples[s].is_normal ? 0 : fo.group_cells[samples[s].group];
     if (nT == 0) purity = 0.0;
@@ -517,6 +554,33 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
         total_templates += k;
       }
     }
+  };
+  {
+    std::vector<std::thread> th;
+    for (uint32_t s = 0; s < samples.size(); ++s)
+      th.emplace_back([&, s] {
+        try {
+          plan_sample(s);
+        } catch (const std::exception& e) {
+          per[s].error = e.what();
+          if (per[s].error.empty()) per[s].error = "planning failed";
+        }
+      });
+    for (auto& t : th) t.join();
+    for (const auto& ps : per)
+      if (!ps.error.empty()) throw std::domain_error(ps.error);
+  }
+  std::vector<pcs::Entry>& entries = pl.entries;
+  std::vector<pcs::Tile> all;
+  uint64_t total_templates = 0;
+  for (auto& ps : per) {
+    const uint32_t base = static_cast<uint32_t>(entries.size());
+    entries.insert(entries.end(), ps.entries.begin(), ps.entries.end());
+    for (auto& t : ps.all) {
+      t.entry_off += base;
+      all.push_back(t);
+    }
+    total_templates += ps.total_templates;
   }
   for (size_t i = 0; i < all.size(); ++i) all[i].id = static_cast<uint32_t>(i);
 
@@ -635,14 +699,21 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   launches += (S * M != 0 ? 2 : 0) + (S * L != 0 ? 1 : 0);
   CUDA_OK(cudaEventRecord(cx.ev[3], st));
   uint64_t d2h = 0;
-  if (!dev_out && S * M != 0) {
-    CUDA_OK(cudaMemcpyAsync(occ, d_occ, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(cov, d_cov, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    d2h += 2 * S * M * sizeof(uint32_t);
+  const size_t table_bytes = S * M * sizeof(uint32_t);
+  char* stage = nullptr;
+  if (!dev_out && table_bytes != 0) {
+    stage = static_cast<char*>(cx.staging(2 * table_bytes));
+    CUDA_OK(cudaMemcpyAsync(stage, d_occ, table_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(stage + table_bytes, d_cov, table_bytes, cudaMemcpyDeviceToHost, st));
+    d2h += 2 * table_bytes;
   }
   unsigned long long counters[4] = {0, 0, 0, 0};
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
+  if (stage) {
+    parallel_copy(occ, stage, table_bytes);
+    parallel_copy(cov, stage + table_bytes, table_bytes);
+  }
   d2h += sizeof(counters);
   if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "run (kernels + D2H)", now_ms() - t0);
   if (stats) {
@@ -891,6 +962,7 @@ int pcs_destroy(pcs_ctx* cx) {
     for (auto& ev : cx->ev)
       if (ev) cudaEventDestroy(ev);
     if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
+    if (cx->pinned) cudaFreeHost(cx->pinned);
     delete cx;
   });
 }
