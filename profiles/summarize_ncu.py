@@ -47,7 +47,10 @@ def main():
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
         return float(v.replace(",", "")) * scale
     traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
-    json.dump({"kernel": name, "dram_bytes_per_launch": traffic, "source": f"profiles/{tag}_sampler_ncu_raw.csv",
+    inst = float(m["smsp__inst_executed.sum"][0].replace(",", ""))
+    json.dump({"kernel": name, "dram_bytes_per_launch": traffic, "warp_instructions_per_launch": inst,
+               "issue_active_pct": float(m["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+               "source": f"profiles/{tag}_sampler_ncu_raw.csv",
                "command": "ncu --set full --clock-control none --import-source on -k regex:sample_tiles_staged "
                           "-s 3 -c 1 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e"},
               open(os.path.join(HERE, "sampler_traffic.json"), "w"), indent=1)
