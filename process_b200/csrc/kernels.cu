@@ -128,7 +128,7 @@ struct Walk {
 
 // a locus as the walk sees it: one SID instance inline (the common case) or a list
 struct Locus {
-  uint32_t p, lo, span, lens, row, k0, n_multi;
+  uint32_t lo, span, lens, row, k0, n_multi;
 };
 
 struct GlobalView {
@@ -138,8 +138,7 @@ struct GlobalView {
   uint32_t* depth;           // [L] of the sample (nullptr: trace mode)
   uint32_t* alt;             // [M] of the sample
   __device__ __forceinline__ uint32_t position(uint32_t i) const { return __ldg(pos + i); }
-  __device__ __forceinline__ void load(uint32_t i, uint32_t p, Locus& L) const {
-    L.p = p;
+  __device__ __forceinline__ void load(uint32_t i, Locus& L) const {
     L.k0 = __ldg(ioff + i);
     const uint32_t n = __ldg(ioff + i + 1) - L.k0;
     L.span = 0;
@@ -212,7 +211,7 @@ __device__ __forceinline__ bool walk_global(const GlobalView& V, uint32_t i, uin
     if (p < w.q) continue;  // inside the reference bases a carried SID replaced
     V.add_depth(i);
     Locus L;
-    V.load(i, p, L);
+    V.load(i, L);
     if (L.span != 0) {
       if (h - L.lo < L.span && !carried_sid(V, p, L.lens, L.row, false, R, frag_end, w, err)) return true;
     } else {
@@ -257,7 +256,7 @@ __device__ __forceinline__ uint32_t lower_bound_pos(const uint32_t* pos, uint32_
 // each: start, haplotype).  Paired-end: block j yields template j (start,
 // haplotype, insert).
 struct Template {
-  uint32_t x, h, ins, frag_end;
+  uint32_t x, h, frag_end;
 };
 
 template <class EntryPtr>
