@@ -295,10 +295,23 @@ __device__ __forceinline__ void block_add_u64(uint32_t v, unsigned long long* ds
   }
 }
 
+// *dst += total - (sum of `minus` over the block)
+__device__ __forceinline__ void block_sub_u64(unsigned long long total, uint32_t minus, unsigned long long* dst) {
+  for (int o = 16; o > 0; o >>= 1) minus += __shfl_xor_sync(0xffffffffu, minus, o);
+  __shared__ uint32_t s_minus[32];
+  if ((threadIdx.x & 31) == 0) s_minus[threadIdx.x >> 5] = minus;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long m = 0;
+    for (uint32_t i = 0; i < (blockDim.x + 31) / 32; ++i) m += s_minus[i];
+    if (total > m) atomicAdd(dst, total - m);
+  }
+}
+
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
 constexpr int kDefaultMinCtas = 3;
-constexpr uint32_t kQueueSlots = 64;  // per warp: < 32 waiting + <= 32 pushed in one go
+constexpr uint32_t kQueueSlots = 96;  // per warp: < 32 waiting + <= 64 pushed by one Philox block per lane
 
 // hide where a shared-window address came from, so the compiler keeps it in a register
 // instead of rebuilding it from SR_CgaCtaId inside every loop
@@ -317,49 +330,41 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t r;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr));
-  return r;
-}
-
 struct StagedTile {
   SharedView SV;
   uint32_t dir;    // shared address of uint2 [buckets]: {index, position} of the first locus at/after the bucket
-  uint32_t ent;    // shared address of the tile's entries (32 bytes each)
-  uint32_t n, shift, stage_end, chr_l1;
+  uint32_t ent;    // shared address of the tile's entries (16 bytes each)
+  uint32_t n, stage_end, chr_l1;
   __device__ __forceinline__ uint2 first_locus(uint32_t bucket) const {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(dir + bucket * 8u));
     return v;
   }
+  // the sampling entry a haplotype draw falls in: {thr, scale, list_off, frag_end}; base = first draw value of the entry
+  __device__ __forceinline__ uint4 entry_of(uint32_t u_hap, uint32_t& base) const {
+    uint32_t addr = ent;
+    base = 0;
+    uint4 a = lds128(addr);
+    while (u_hap > a.x) {  // the last entry's thr is 0xffffffff
+      base = a.x + 1u;
+      addr += 16u;
+      a = lds128(addr);
+    }
+    return a;
+  }
 };
 
-// start and haplotype of one template from two 32-bit draws; entries read from shared memory
-__device__ __forceinline__ bool place_staged(const StagedTile& S, const Tile& T, const DevForest& F, uint32_t u_start,
-                                             uint32_t u_hap, uint32_t tlen, uint32_t& x, uint32_t& h, uint32_t& e,
-                                             uint32_t& frag_end) {
-  x = T.begin + __umulhi(u_start, T.len);
-  e = 0;
-  uint32_t base = 0;
-  uint4 a = lds128(S.ent);  // {thr, scale, list_off, frag_end}
-  while (u_hap > a.x) {  // the last entry's thr is 0xffffffff
-    base = a.x + 1u;
-    ++e;
-    a = lds128(S.ent + e * 16u);
-  }
-  h = __ldg(F.hap_list + (a.z + __umulhi(u_hap - base, a.y)));
-  frag_end = a.w;
-  return x + (tlen - 1u) <= frag_end;  // else the template falls off its molecule
-}
-
-// one queued read through the staged loci (and past them, if a carried deletion stretches it that far)
+// one queued read {start offset in the tile, haplotype draw, read id, first staged locus to look at} through the
+// staged loci (and past them, if a carried deletion stretches it that far).  The haplotype is resolved here, not
+// where the read was drawn: three reads out of four never get this far and never need it.
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
                                             uint32_t* depth, uint32_t* alt, uint4 item) {
   const uint32_t R = M.read_size;
-  const uint32_t xs = item.x, h = item.y, read_id = item.z, i = item.w & 0xffffu;
-  const uint32_t frag_end = lds32(S.ent + (item.w >> 16) * 16u + 12u);
+  uint32_t base;
+  const uint4 a = S.entry_of(item.y, base);
+  const uint32_t h = __ldg(F.hap_list + (a.z + __umulhi(item.y - base, a.y)));
+  const uint32_t xs = T.begin + item.x, read_id = item.z, i = item.w, frag_end = a.w;
   Walk w;
   w.init(xs, R, frag_end);
   bool done;
@@ -383,28 +388,17 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
 }
 
 // Per-warp queue of reads that may span a locus.  Drawing and probing stay converged
-// (every lane works on its own read); the divergent part -- the walk, which four reads
-// out of five never need -- runs only when 32 reads are waiting, one per lane.
+// (every lane works on its own reads); the divergent part -- the walk, which three reads
+// out of four never need -- runs only when 32 reads are waiting, one per lane.
 struct HitQueue {
   uint32_t base;  // shared address of this warp's kQueueSlots uint4 slots
-  uint32_t n;     // reads waiting (warp-uniform)
-};
-
-template <bool ERRORS>
-__device__ __forceinline__ void queue_push(HitQueue& Q, const StagedTile& S, const Tile& T, const DevForest& F,
-                                           const SeqModel& M, uint32_t* depth, uint32_t* alt, bool has, uint4 item,
-                                           uint32_t lane, uint32_t lanes_below) {
-  const uint32_t mask = __ballot_sync(0xffffffffu, has);
-  if (has) sts128(Q.base + (Q.n + __popc(mask & lanes_below)) * 16u, item);
-  Q.n += __popc(mask);
-  if (Q.n >= 32u) {
-    __syncwarp();
-    Q.n -= 32u;
-    const uint4 mine = lds128(Q.base + (Q.n + lane) * 16u);
-    __syncwarp();
-    staged_read<ERRORS>(S, T, F, M, depth, alt, mine);
+  uint32_t tail;  // shared address one past the last waiting read (warp-uniform)
+  __device__ __forceinline__ void push(bool has, uint4 item, uint32_t lanes_below) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, has);
+    if (has) sts128(tail + __popc(mask & lanes_below) * 16u, item);
+    tail += __popc(mask) * 16u;
   }
-}
+};
 
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 __global__ void __launch_bounds__(kStagedThreads, MIN_CTAS)
@@ -418,6 +412,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   uint2* s_dir = reinterpret_cast<uint2*>(s_ent + kMaxStagedEntries);
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
+  __shared__ uint32_t s_safe;
 
   const Tile T = tiles[blockIdx.x];
   const uint32_t n = T.l1 - T.l0;
@@ -442,6 +437,14 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
   if (threadIdx.x < T.n_entries)
     s_ent[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(entries + T.entry_off) + threadIdx.x);
+  if (threadIdx.x == 32) {
+    // start offsets below s_safe fit their molecule whatever haplotype is drawn: the longest template
+    // (M.reach bases) ends at or before the nearest fragment end of any entry
+    uint32_t min_fe = 0xffffffffu;
+    for (uint32_t e = 0; e < T.n_entries; ++e) min_fe = min(min_fe, __ldg(&entries[T.entry_off + e].frag_end));
+    const long long lim = static_cast<long long>(min_fe) + 2 - static_cast<long long>(M.reach) - T.begin;
+    s_safe = lim <= 0 ? 0u : (lim >= static_cast<long long>(T.len) ? T.len : static_cast<uint32_t>(lim));
+  }
   __syncthreads();
   // directory: first staged locus at or after the start of each bucket
   for (uint32_t b = threadIdx.x; b < n_buckets; b += kStagedThreads) {
@@ -451,7 +454,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       uint32_t mid = (lo + hi) >> 1;
       if (s_rec[mid].x < x) lo = mid + 1; else hi = mid;
     }
-    s_dir[b] = make_uint2(lo, s_rec[lo].x);  // s_rec[n] is the sentinel at 0xffffffff
+    s_dir[b] = make_uint2(lo, s_rec[lo].x - T.begin);  // s_rec[n] is the sentinel at 0xffffffff; offsets from T.begin
   }
   __syncthreads();
 
@@ -463,47 +466,71 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   S.dir = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_dir)));
   S.ent = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_ent)));
   S.n = n;
-  S.shift = shift;
   S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
   S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
-  HitQueue Q{opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_queue + warp * kQueueSlots))), 0u};
+  HitQueue Q;
+  Q.base = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_queue + warp * kQueueSlots)));
+  Q.tail = Q.base;
   const uint32_t R = M.read_size;
-  uint32_t placed = 0;
+  const uint32_t safe = s_safe, len = T.len;
+  uint32_t dropped = 0;  // templates that fell off their molecule
 
   uint32_t lanes_below;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
-  // probe: does the first staged locus at or after the read's bucket lie before the read's end?
-  // (the sentinel record makes the load safe when the bucket is past the last locus)
-  auto probe_and_push = [&](bool ok, uint32_t xs, uint32_t h, uint32_t e, uint32_t fe, uint32_t read_id) {
-    // one load: index and position of the first locus at/after the read's bucket (bucket 0 when !ok: harmless)
-    const uint2 d = S.first_locus(ok ? (xs - T.begin) >> shift : 0u);
-    const bool has = ok && d.y < min(xs + R, fe + 1u);
-    queue_push<ERRORS>(Q, S, T, F, M, depth, alt, has, make_uint4(xs, h, read_id, d.x | (e << 16)), lane, lanes_below);
+  // does a template of tlen bases starting at offset off fit the fragment its haplotype draw selects?
+  auto fits = [&](uint32_t u_hap, uint32_t off, uint32_t tlen) {
+    uint32_t base;
+    return T.begin + off + (tlen - 1u) <= S.entry_of(u_hap, base).w;
+  };
+  // probe: the directory gives index and offset of the first staged locus at or after the read's bucket in one
+  // load; the read goes to the queue if that locus lies before its end (the sentinel covers empty buckets)
+  auto drain = [&]() {
+    while (Q.tail >= Q.base + 32u * 16u) {
+      __syncwarp();
+      Q.tail -= 32u * 16u;
+      const uint4 mine = lds128(Q.tail + lane * 16u);
+      __syncwarp();
+      staged_read<ERRORS>(S, T, F, M, depth, alt, mine);
+    }
   };
 
   // Philox block j: two single-end templates (2j, 2j+1) or one paired template (mates 2j, 2j+1)
   const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
+  const uint32_t n_second = PAIRED ? T.n_templates : T.n_templates >> 1;  // blocks whose second read exists
   for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
     const uint32_t j = j0 + lane;
     const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
-    uint32_t x, h, e, fe;
     if (PAIRED) {
-      const uint32_t ins = draw_insert(M, u.z);
-      const bool ok = place_staged(S, T, F, u.x, u.y, 2u * R + ins, x, h, e, fe) && j < n_blocks;
-      placed += ok ? 2u : 0u;
-      probe_and_push(ok, x, h, e, fe, 2u * j);
-      probe_and_push(ok, x + R + ins, h, e, fe, 2u * j + 1u);
+      const uint32_t off = __umulhi(u.x, len), off2 = off + R + draw_insert(M, u.z);
+      bool ok = j < n_blocks;
+      if (off >= safe && ok && !fits(u.y, off, off2 - off + R)) {
+        ok = false;
+        ++dropped;
+      }
+      const uint2 d0 = S.first_locus(off >> shift), d1 = S.first_locus(off2 >> shift);
+      Q.push(ok && d0.y < off + R, make_uint4(off, u.y, 2u * j, d0.x), lanes_below);
+      Q.push(ok && d1.y < off2 + R, make_uint4(off2, u.y, 2u * j + 1u, d1.x), lanes_below);
     } else {
-      const bool ok0 = place_staged(S, T, F, u.x, u.y, R, x, h, e, fe) && 2u * j < T.n_templates;
-      placed += ok0 ? 1u : 0u;
-      probe_and_push(ok0, x, h, e, fe, 2u * j);
-      const bool ok1 = place_staged(S, T, F, u.z, u.w, R, x, h, e, fe) && 2u * j + 1u < T.n_templates;
-      placed += ok1 ? 1u : 0u;
-      probe_and_push(ok1, x, h, e, fe, 2u * j + 1u);
+      const uint32_t off0 = __umulhi(u.x, len), off1 = __umulhi(u.z, len);
+      bool ok0 = j < n_blocks, ok1 = j < n_second;
+      if (max(off0, off1) >= safe) {  // last tile of a fragment only
+        if (ok0 && !fits(u.y, off0, R)) {
+          ok0 = false;
+          ++dropped;
+        }
+        if (ok1 && !fits(u.w, off1, R)) {
+          ok1 = false;
+          ++dropped;
+        }
+      }
+      const uint2 d0 = S.first_locus(off0 >> shift), d1 = S.first_locus(off1 >> shift);
+      Q.push(ok0 && d0.y < off0 + R, make_uint4(off0, u.y, 2u * j, d0.x), lanes_below);
+      Q.push(ok1 && d1.y < off1 + R, make_uint4(off1, u.w, 2u * j + 1u, d1.x), lanes_below);
     }
+    drain();
   }
   __syncwarp();
-  if (lane < Q.n) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
+  if (lane < (Q.tail - Q.base) / 16u) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
   __syncthreads();
 
   // ---- flush: one reduction per touched counter, coalesced over consecutive loci / rows
@@ -517,7 +544,9 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     const uint32_t v = s_alt[r];
     if (v) atomicAdd(alt_s + r, v);
   }
-  block_add_u64(placed, n_reads);
+  // reads placed = every template of the tile but the dropped ones
+  const uint32_t mates = PAIRED ? 2u : 1u;
+  block_sub_u64(static_cast<unsigned long long>(T.n_templates) * mates, dropped * mates, n_reads);
 }
 
 // ------------------------------------------- global-memory sampler (fallback, trace)
