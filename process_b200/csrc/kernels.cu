@@ -87,27 +87,42 @@ __device__ __noinline__ bool draw_base_errors(uint32_t sequencer, uint32_t err_t
   return any;
 }
 
+// Error policies of the locus walk.  count(V, row, abs_row, hit, off, n): the read carries the SID of `row`
+// as its hit-th carried SID on read bases [off, off+n); add the occurrence unless a sequencing error hides it.
+template <class View>
+__device__ __forceinline__ void add_alt_row(const View& V, uint32_t row, bool abs_row) {
+  if (abs_row) V.add_alt_abs(row); else V.add_alt(row);
+}
+
 struct ErrDraw {
   const SeqModel& M;
   uint32_t read, tile;
   uint32_t* mask;  // trace mode: error bits found, else nullptr
-  __device__ __forceinline__ bool operator()(uint32_t hit, uint32_t off, uint32_t n) const {
-    if (M.sequencer == PCS_SEQ_ERRORLESS) return false;
-    return draw_base_errors(M.sequencer, M.err_thr, M.error_rate, M.read_size, M.seed, read, tile, hit, off, n, mask);
+  template <class View>
+  __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
+                                        uint32_t n) const {
+    if (M.sequencer != PCS_SEQ_ERRORLESS &&
+        draw_base_errors(M.sequencer, M.err_thr, M.error_rate, M.read_size, M.seed, read, tile, hit, off, n, mask))
+      return;
+    add_alt_row(V, row, abs_row);
   }
 };
 
 struct NoErr {
-  __device__ __forceinline__ bool operator()(uint32_t, uint32_t, uint32_t) const { return false; }
+  template <class View>
+  __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t, uint32_t, uint32_t) const {
+    add_alt_row(V, row, abs_row);
+  }
 };
 
 struct ErrMaskLookup {
   const uint32_t* mask;  // nullptr: no errors
-  __device__ bool operator()(uint32_t, uint32_t off, uint32_t n) const {
-    if (!mask) return false;
-    for (uint32_t i = off; i < off + n; ++i)
-      if (i < 32u * PCS_ERRMASK_WORDS && ((mask[i >> 5] >> (i & 31)) & 1u)) return true;
-    return false;
+  template <class View>
+  __device__ void count(const View& V, uint32_t row, bool abs_row, uint32_t, uint32_t off, uint32_t n) const {
+    if (mask)
+      for (uint32_t i = off; i < off + n; ++i)
+        if (i < 32u * PCS_ERRMASK_WORDS && ((mask[i >> 5] >> (i & 31)) & 1u)) return;
+    add_alt_row(V, row, abs_row);
   }
 };
 
@@ -179,6 +194,69 @@ struct SharedView {
   __device__ __forceinline__ uint4 instance(uint32_t k) const { return __ldg(inst + k); }
 };
 
+// what the error draw needs of the sequencer model, by value (registers, also across a call)
+struct ErrModel {
+  uint32_t sequencer, err_thr, read_size, seed;
+  float error_rate;
+};
+__device__ __forceinline__ ErrModel err_model(const SeqModel& M) {
+  return ErrModel{M.sequencer, M.err_thr, M.read_size, M.seed, M.error_rate};
+}
+
+// is read base `o`, base b of the read's hit-th carried SID, a sequencing error?  The draw of
+// draw_base_errors for that base: block (read, tile, (1 + hit) | b << 20, seed).
+__device__ __forceinline__ bool sid_base_error(const ErrModel& E, uint32_t read, uint32_t tile, uint32_t hit,
+                                               uint32_t b, uint32_t o) {
+  const uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), E.seed));
+  if (E.sequencer == PCS_SEQ_BASIC_CONSTANT) return w.x < E.err_thr;
+  const float z = sqrtf(-2.0f * __logf(u01(w.x))) * cospif(2.0f * u01(w.y));
+  const float p = E.error_rate * ramp(o, E.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
+  return u01(w.z) < fminf(p, 1.0f);
+}
+
+// Staged kernel, error models: the error draw of a carried SID costs a Philox block per SID base, and inside
+// the walk it would run with the few lanes that carry a SID at that moment (and as long as the longest
+// insertion among them).  So the walk counts the occurrence at once and queues the carried SID
+// {read, row, hit, read offset | base << 16 | bases left << 24}; the warp settles 32 queued bases at a time,
+// one per lane (settle_carried): a lane draws for the base of its item, puts the item back for the next base
+// if there is one, and the FIRST erroneous base of a SID takes the occurrence back.  Same Philox counters as
+// the immediate draw: an occurrence survives iff none of its bases is an error, whatever the order.
+constexpr uint32_t kCarriedSlots = 96;  // per warp; a SID that finds the queue full is settled on the spot
+
+// out of line: the queue-full path inside the walk is cold and must not cost the walk registers
+__device__ __noinline__ void settle_sid_cold(ErrModel E, uint32_t alt_addr, uint32_t read, uint32_t tile, uint32_t row,
+                                             uint32_t hit, uint32_t off, uint32_t n) {
+  for (uint32_t b = 0; b < n; ++b)
+    if (sid_base_error(E, read, tile, hit, b, off + b)) return;
+  asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(alt_addr + row * 4u) : "memory");
+}
+
+struct ErrDefer {
+  const SeqModel& M;
+  uint32_t read, tile;
+  uint32_t slots;       // shared address of this warp's kCarriedSlots uint4 slots
+  uint32_t count_addr;  // shared address of the number of waiting items
+  template <class View>
+  __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
+                                        uint32_t n) const {
+    ErrDraw{M, read, tile, nullptr}.count(V, row, abs_row, hit, off, n);
+  }
+  __device__ __forceinline__ void count(const SharedView& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
+                                        uint32_t n) const {
+    const uint32_t rel = abs_row ? row - V.r0 : row;
+    uint32_t slot;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
+    if (slot < kCarriedSlots) {
+      V.add_alt(rel);
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slots + slot * 16u), "r"(read), "r"(rel),
+                   "r"(hit), "r"(off | ((n - 1u) << 24))
+                   : "memory");
+    } else {
+      settle_sid_cold(err_model(M), V.alt, read, tile, rel, hit, off, n);
+    }
+  }
+};
+
 // a carried SID at position p: count it unless a sequencing error hides it, then let an
 // indel move the read's frame.  Returns false when the read is used up.
 template <class View, class Err>
@@ -187,9 +265,7 @@ __device__ __forceinline__ bool carried_sid(const View& V, uint32_t p, uint32_t 
   const uint32_t ref_len = lens & 0xffu, alt_len = (lens >> 8) & 0xffu;
   const uint32_t rem_p = w.rem - (p - w.q);  // bases left when the read reaches p (>= 1)
   const uint32_t consumed = min(alt_len, rem_p);
-  if (!err(w.hit, R - rem_p, consumed)) {
-    if (abs_row) V.add_alt_abs(row); else V.add_alt(row);
-  }
+  err.count(V, row, abs_row, w.hit, R - rem_p, consumed);
   ++w.hit;
   if ((lens & 0xffffu) != 0x0101u) {
     w.rem = rem_p - consumed;
@@ -330,10 +406,21 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(addr) : "memory");
+  return r;
+}
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 struct StagedTile {
   SharedView SV;
   uint32_t dir;    // shared address of uint2 [buckets]: {index, position} of the first locus at/after the bucket
   uint32_t ent;    // shared address of the tile's entries (16 bytes each)
+  uint32_t carried, carried_n;  // error models: shared addresses of this warp's carried-SID queue and its count
   uint32_t n, stage_end, chr_l1;
   __device__ __forceinline__ uint2 first_locus(uint32_t bucket) const {
     uint2 v;
@@ -369,7 +456,7 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   w.init(xs, R, frag_end);
   bool done;
   if (ERRORS) {
-    const ErrDraw err{M, read_id, T.id, nullptr};
+    const ErrDefer err{M, read_id, T.id, S.carried, S.carried_n};
     done = walk_shared(S.SV, i, S.n, h, R, frag_end, w, err);
     if (!done && w.stop > S.stage_end && T.l1 < S.chr_l1) {
       const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
@@ -400,6 +487,41 @@ struct HitQueue {
   }
 };
 
+// Error models: settle the SID bases the walks of this warp queued, 32 at a time (all of them when `all`).
+// Called converged.  Out of line, so that its registers (a Philox block and the quality model's float math)
+// are not the sampling loop's.
+__device__ __noinline__ void settle_carried(ErrModel E, uint32_t slots, uint32_t count_addr, uint32_t alt_addr,
+                                            uint32_t tile, bool all) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t lanes_below;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
+  __syncwarp();
+  uint32_t waiting = min(lds32(count_addr), kCarriedSlots);
+  const uint32_t before = waiting;
+  while (waiting >= 32u || (all && waiting != 0u)) {
+    const uint32_t take = min(waiting, 32u);
+    waiting -= take;
+    const uint32_t first = slots + waiting * 16u;
+    const bool have = lane < take;
+    uint4 c = make_uint4(0u, 0u, 0u, 0u);  // {read, row, hit, read offset | base << 16 | bases left << 24}
+    if (have) c = lds128(first + lane * 16u);
+    const uint32_t o = c.w & 0xffffu, b = (c.w >> 16) & 0xffu;
+    if (have && sid_base_error(E, c.x, tile, c.z, b, o)) {
+      bool first_error = true;  // rare: was an earlier base of this SID already an error?
+      for (uint32_t e = 0; e < b && first_error; ++e) first_error = !sid_base_error(E, c.x, tile, c.z, e, o - b + e);
+      if (first_error) asm volatile("red.shared.add.u32 [%0], 0xffffffff;" ::"r"(alt_addr + c.y * 4u) : "memory");
+    }
+    // insertions: the item goes back for its next base (every lane has read its item: the ballot is the fence)
+    const bool more = (c.w >> 24) != 0u;
+    const uint32_t mask = __ballot_sync(0xffffffffu, more);
+    if (more) sts128(first + __popc(mask & lanes_below) * 16u, make_uint4(c.x, c.y, c.z, c.w + 0x00010001u - 0x01000000u));
+    waiting += __popc(mask);
+    __syncwarp();
+  }
+  if (lane == 0 && waiting != before) sts32(count_addr, waiting);
+  __syncwarp();
+}
+
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 __global__ void __launch_bounds__(kStagedThreads, MIN_CTAS)
 sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
@@ -408,11 +530,14 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   extern __shared__ __align__(16) unsigned char smem[];
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
   uint4* s_queue = s_rec + D.max_loci + 1;
-  uint4* s_ent = s_queue + (kStagedThreads / 32) * kQueueSlots;
+  uint4* s_carried = s_queue + (kStagedThreads / 32) * kQueueSlots;
+  uint4* s_ent = s_carried + (ERRORS ? (kStagedThreads / 32) * kCarriedSlots : 0u);
   uint2* s_dir = reinterpret_cast<uint2*>(s_ent + kMaxStagedEntries);
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
   __shared__ uint32_t s_safe;
+  __shared__ uint32_t s_carried_n[kStagedThreads / 32];
+  if (threadIdx.x < kStagedThreads / 32) s_carried_n[threadIdx.x] = 0;
 
   const Tile T = tiles[blockIdx.x];
   const uint32_t n = T.l1 - T.l0;
@@ -465,6 +590,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
                     opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_alt))), F.inst, T.r0};
   S.dir = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_dir)));
   S.ent = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_ent)));
+  S.carried = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried + (ERRORS ? warp * kCarriedSlots : 0u))));
+  S.carried_n = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried_n + warp)));
   S.n = n;
   S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
   S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
@@ -484,6 +611,9 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   };
   // probe: the directory gives index and offset of the first staged locus at or after the read's bucket in one
   // load; the read goes to the queue if that locus lies before its end (the sentinel covers empty buckets)
+  auto flush_carried = [&](bool all) {
+    if (ERRORS) settle_carried(err_model(M), S.carried, S.carried_n, S.SV.alt, T.id, all);
+  };
   auto drain = [&]() {
     while (Q.tail >= Q.base + 32u * 16u) {
       __syncwarp();
@@ -491,6 +621,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       const uint4 mine = lds128(Q.tail + lane * 16u);
       __syncwarp();
       staged_read<ERRORS>(S, T, F, M, depth, alt, mine);
+      flush_carried(false);
     }
   };
 
@@ -531,6 +662,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   }
   __syncwarp();
   if (lane < (Q.tail - Q.base) / 16u) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
+  flush_carried(true);
   __syncthreads();
 
   // ---- flush: one reduction per touched counter, coalesced over consecutive loci / rows
@@ -831,9 +963,10 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
 }
 
 // ----------------------------------------------------------------- launchers
-size_t staged_smem_bytes(const StageDims& D) {
+size_t staged_smem_bytes(const StageDims& D, bool errors) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
-  b += (1 + static_cast<size_t>(kStagedThreads / 32) * kQueueSlots + kMaxStagedEntries) * sizeof(uint4);
+  b += (1 + static_cast<size_t>(kStagedThreads / 32) * (kQueueSlots + (errors ? kCarriedSlots : 0u)) + kMaxStagedEntries) *
+       sizeof(uint4);
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint2);
   return (b + 15) & ~static_cast<size_t>(15);
@@ -854,7 +987,7 @@ template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 static cudaError_t launch_staged_occ(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                      const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                      uint32_t* alt, unsigned long long* n_reads) {
-  const size_t smem = staged_smem_bytes(D);
+  const size_t smem = staged_smem_bytes(D, ERRORS);
   auto kern = sample_tiles_staged_kernel<PAIRED, ERRORS, MIN_CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;

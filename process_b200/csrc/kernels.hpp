@@ -10,7 +10,7 @@
 
 namespace pcs {
 
-size_t staged_smem_bytes(const StageDims& D);
+size_t staged_smem_bytes(const StageDims& D, bool errors);
 cudaError_t launch_sample_tiles_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                        const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                        uint32_t* alt, unsigned long long* n_reads);

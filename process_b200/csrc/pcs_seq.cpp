@@ -1041,7 +1041,7 @@ int pcs_plan_create(pcs_forest* fo, const pcs_seq_params* params, pcs_plan** out
     lap("upload plan + alloc tables");
     if (lap.on)
       std::fprintf(stderr, "[pcs host]    tiles: %zu staged, %zu global; staged smem %zu B\n", pl->host.tiles.size(),
-                   pl->host.tiles_global.size(), pcs::staged_smem_bytes(pl->host.dims));
+                   pl->host.tiles_global.size(), pcs::staged_smem_bytes(pl->host.dims, pl->host.model.sequencer != PCS_SEQ_ERRORLESS));
     *out = pl.release();
   });
 }
