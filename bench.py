@@ -335,10 +335,13 @@ def main():
     if not args.no_e2e:
         e2e_steps = max(1, min(args.steps, 3))
         h2d = d2h = 0
-        barrier()
-        t_e = time.perf_counter()
         e2e_reads = 0
-        for _ in range(e2e_steps):
+        for it in range(1 + e2e_steps):  # one untimed pass first: it pins the library's staging memory
+            if it == 1:
+                barrier()
+                t_e = time.perf_counter()
+                h2d = d2h = 0
+                e2e_reads = 0
             d2 = L.Forest(ctx, forest)
             if world == 1:
                 o, c, s2 = d2.simulate(make_params(**wl_params))

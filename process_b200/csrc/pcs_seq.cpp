@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -47,6 +48,29 @@ void require(bool ok, const char* msg) {
   if (!ok) throw std::domain_error(msg);
 }
 
+// threads of the host flattener: PCS_HOST_THREADS, else every core
+unsigned host_threads() {
+  const char* s = std::getenv("PCS_HOST_THREADS");
+  if (s) {
+    long v = std::atol(s);
+    if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
+  }
+  return std::max(1u, std::thread::hardware_concurrency());
+}
+
+void parallel_copy(void* dst, const void* src, size_t bytes) {
+  const unsigned nt = std::max(1u, std::min(16u, host_threads()));
+  if (bytes < (4u << 20) || nt == 1) {
+    std::memcpy(dst, src, bytes);
+    return;
+  }
+  std::vector<std::thread> th;
+  const size_t chunk = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
+  for (size_t off = 0; off < bytes; off += chunk)
+    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off)); });
+  for (auto& t : th) t.join();
+}
+
 // device buffer from the device's stream-ordered memory pool (cudaMallocAsync): repeated
 // upload / plan / free cycles reuse pooled memory instead of paying cudaMalloc each time
 template <class T>
@@ -70,6 +94,18 @@ struct DevBuf {
     if (count) CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&p), count * sizeof(T), stream));
   }
   size_t bytes() const { return n * sizeof(T); }
+  // through a pinned staging area: host threads copy `v` there (safe to free `v` afterwards), the DMA runs at
+  // link speed and is left in flight; the caller synchronises before the staging area is written again
+  template <class Vec>
+  size_t upload_staged(const Vec& v, cudaStream_t stream, char* stage, size_t& stage_off) {
+    alloc(v.size(), stream);
+    if (!v.empty()) {
+      parallel_copy(stage + stage_off, v.data(), bytes());
+      CUDA_OK(cudaMemcpyAsync(p, stage + stage_off, bytes(), cudaMemcpyHostToDevice, stream));
+      stage_off += (bytes() + 255) & ~static_cast<size_t>(255);
+    }
+    return bytes();
+  }
   // synchronous w.r.t. the host buffer (pageable memory): safe to free `v` afterwards
   template <class Vec>
   size_t upload(const Vec& v, cudaStream_t stream) {
@@ -116,37 +152,30 @@ struct pcs_ctx {
       if (pinned) cudaFreeHost(pinned);
       pinned = nullptr;
       pinned_bytes = 0;
+      bytes += bytes / 8;  // forests of one study differ a little: do not re-pin for every one of them
       CUDA_OK(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
       pinned_bytes = bytes;
     }
     return pinned;
   }
+  // second stream: the tables of one sample travel to the host while the next sample is being sampled
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t copier() {
+    if (!copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    return copy_stream;
+  }
+  // events that mark the chunks of a pipelined device-to-host copy (created on first use)
+  std::vector<cudaEvent_t> chunk_ev;
+  cudaEvent_t chunk_event(size_t i) {
+    while (chunk_ev.size() <= i) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      chunk_ev.push_back(e);
+    }
+    return chunk_ev[i];
+  }
 };
 
-namespace {
-// threads of the host flattener: PCS_HOST_THREADS, else every core
-unsigned host_threads() {
-  const char* s = std::getenv("PCS_HOST_THREADS");
-  if (s) {
-    long v = std::atol(s);
-    if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
-  }
-  return std::max(1u, std::thread::hardware_concurrency());
-}
-
-void parallel_copy(void* dst, const void* src, size_t bytes) {
-  const unsigned nt = std::max(1u, std::min(8u, host_threads()));
-  if (bytes < (8u << 20) || nt == 1) {
-    std::memcpy(dst, src, bytes);
-    return;
-  }
-  std::vector<std::thread> th;
-  const size_t chunk = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
-  for (size_t off = 0; off < bytes; off += chunk)
-    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off)); });
-  for (auto& t : th) t.join();
-}
-}  // namespace
 
 // host half of an uploaded forest: flattened view + output sample groups
 struct HostForest {
@@ -278,11 +307,20 @@ struct pcs_forest {
   void upload_flat() {
     ctx->bind();
     cudaStream_t st = ctx->stream;
-    h2d_bytes += d_locus_pos.upload(host.flat.locus_pos, st);
-    h2d_bytes += d_chr_locus_off.upload(host.flat.chr_locus_off, st);
-    h2d_bytes += d_locus_inst_off.upload(host.flat.locus_inst_off, st);
-    h2d_bytes += d_row_locus.upload(host.flat.row_locus, st);
-    h2d_bytes += d_inst.upload(host.flat.inst, st);
+    const pcs::FlatForest& F = host.flat;
+    auto padded = [](size_t n, size_t elem) { return (n * elem + 255) & ~static_cast<size_t>(255); };
+    const size_t total = padded(F.locus_pos.size(), 4) + padded(F.chr_locus_off.size(), 4) +
+                         padded(F.locus_inst_off.size(), 4) + padded(F.row_locus.size(), 4) +
+                         padded(F.inst.size(), sizeof(pcs::Inst));
+    CUDA_OK(cudaStreamSynchronize(st));  // nothing in flight may still use the staging area
+    char* stage = static_cast<char*>(ctx->staging(total));
+    size_t off = 0;
+    h2d_bytes += d_locus_pos.upload_staged(F.locus_pos, st, stage, off);
+    h2d_bytes += d_chr_locus_off.upload_staged(F.chr_locus_off, st, stage, off);
+    h2d_bytes += d_locus_inst_off.upload_staged(F.locus_inst_off, st, stage, off);
+    h2d_bytes += d_row_locus.upload_staged(F.row_locus, st, stage, off);
+    h2d_bytes += d_inst.upload_staged(F.inst, st, stage, off);
+    CUDA_OK(cudaStreamSynchronize(st));
   }
   pcs_forest() = default;
   explicit pcs_forest(const pcs_forest& other, pcs_ctx* cx) : ctx(cx), host_ptr(other.host_ptr), host(*host_ptr) {}
@@ -303,6 +341,9 @@ struct pcs_plan {
   pcs_forest* forest = nullptr;
   HostPlan host;
   DevBuf<pcs::Tile> d_tiles, d_tiles_global;
+  // the staged tiles once more, grouped by output sample (host-output runs launch sample by sample)
+  DevBuf<pcs::Tile> d_tiles_by_sample;
+  std::vector<uint32_t> sample_tile_off;
   DevBuf<pcs::Entry> d_entries;
   DevBuf<uint32_t> d_insert_alias;
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
@@ -445,25 +486,27 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   const uint32_t lcap = stage_loci_cap();
   const uint32_t shards = P.shard_count ? P.shard_count : 1;
 
-  // every output sample plans its own tiles (independent RNG streams), on its own host thread
-  struct PerSample {
+  // every (output sample, chromosome) plans its own tiles with its own RNG stream: independent tasks for
+  // the host threads, merged in (sample, chromosome) order afterwards
+  struct PerTask {
     std::vector<pcs::Entry> entries;
     std::vector<pcs::Tile> all;
     std::vector<double> tile_w;
     uint64_t total_templates = 0;
     std::string error;
   };
-  std::vector<PerSample> per(samples.size());
-  auto plan_sample = [&](uint32_t s) {
-    std::vector<pcs::Entry>& entries = per[s].entries;
-    std::vector<pcs::Tile>& all = per[s].all;
-    std::vector<double>& tile_w = per[s].tile_w;
-    uint64_t& total_templates = per[s].total_templates;
+  std::vector<PerTask> per(samples.size() * static_cast<size_t>(F.n_chr));
+  auto plan_task = [&](uint32_t s, uint32_t c) {
+    PerTask& task = per[static_cast<size_t>(s) * F.n_chr + c];
+    std::vector<pcs::Entry>& entries = task.entries;
+    std::vector<pcs::Tile>& all = task.all;
+    std::vector<double>& tile_w = task.tile_w;
+    uint64_t& total_templates = task.total_templates;
     double purity = samples[s].is_normal ? 0.0 : P.purity;
     uint32_t nT = samples[s].is_normal ? 0 : fo.group_cells[samples[s].group];
     if (nT == 0) purity = 0.0;
-    for (uint32_t c = 0; c < F.n_chr; ++c) {
-      if (!chr_mask.empty() && !chr_mask[c]) continue;
+    {
+      if (!chr_mask.empty() && !chr_mask[c]) return;
       const size_t first_tile = all.size();
       // normal cells: every one carries each germline allele whole
       auto nit = fo.list_index.find(HostForest::list_key(normal_group, F.full_fragset[c]));
@@ -556,16 +599,21 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     }
   };
   {
-    std::vector<std::thread> th;
-    for (uint32_t s = 0; s < samples.size(); ++s)
-      th.emplace_back([&, s] {
+    std::atomic<size_t> next{0};
+    auto worker = [&] {
+      for (size_t k = next.fetch_add(1); k < per.size(); k = next.fetch_add(1)) {
         try {
-          plan_sample(s);
+          plan_task(static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr));
         } catch (const std::exception& e) {
-          per[s].error = e.what();
-          if (per[s].error.empty()) per[s].error = "planning failed";
+          per[k].error = e.what();
+          if (per[k].error.empty()) per[k].error = "planning failed";
         }
-      });
+      }
+    };
+    const size_t nt = std::min<size_t>(per.size(), std::max(1u, host_threads()));
+    std::vector<std::thread> th;
+    for (size_t w = 1; w < nt; ++w) th.emplace_back(worker);
+    worker();
     for (auto& t : th) t.join();
     for (const auto& ps : per)
       if (!ps.error.empty()) throw std::domain_error(ps.error);
@@ -657,6 +705,8 @@ void upload_plan(pcs_plan& pl) {
   cudaStream_t st = fo.ctx->stream;
   pl.h2d_bytes += pl.d_tiles.upload(pl.host.tiles, st);
   pl.h2d_bytes += pl.d_tiles_global.upload(pl.host.tiles_global, st);
+  pl.d_tiles_by_sample.release();
+  pl.sample_tile_off.clear();
   pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
   pl.h2d_bytes += pl.d_insert_alias.upload(pl.host.insert_alias, st);
   pl.host.model.insert_alias = pl.d_insert_alias.p;
@@ -686,34 +736,109 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
   CUDA_OK(cudaEventRecord(cx.ev[1], st));
   const pcs::DevForest DF = fo.dev();
-  CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
-                                          DF, pl.host.model, pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
-  CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
-                                          pl.d_entries.p, DF, pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
-  launches += (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
-  CUDA_OK(cudaEventRecord(cx.ev[2], st));
-  CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
-                               static_cast<uint32_t>(M), d_cov));
-  CUDA_OK(pcs::launch_sum_u32(st, pl.d_depth.p, S * L, pl.d_counters.p + 1));
-  CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
-  launches += (S * M != 0 ? 2 : 0) + (S * L != 0 ? 1 : 0);
-  CUDA_OK(cudaEventRecord(cx.ev[3], st));
   uint64_t d2h = 0;
   const size_t table_bytes = S * M * sizeof(uint32_t);
-  char* stage = nullptr;
-  if (!dev_out && table_bytes != 0) {
-    stage = static_cast<char*>(cx.staging(2 * table_bytes));
-    CUDA_OK(cudaMemcpyAsync(stage, d_occ, table_bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_OK(cudaMemcpyAsync(stage + table_bytes, d_cov, table_bytes, cudaMemcpyDeviceToHost, st));
+  // tables back to the caller's (pageable) buffers: the DMA lands in pinned memory chunk by chunk, and host
+  // threads copy chunk k out while chunk k+1 is still on the link
+  struct Chunk {
+    char* dst;
+    const char* src;
+    size_t bytes;
+  };
+  std::vector<Chunk> chunks;
+  // host output, several samples, everything staged: sample by sample, so that the tables of sample s cross
+  // the link (second stream) while sample s+1 is being sampled.  Same tiles, same counters, same tables.
+  const bool by_sample = !dev_out && S > 1 && M != 0 && pl.host.tiles_global.empty() && !pl.host.tiles.empty() &&
+                         std::getenv("PCS_NO_SPLIT") == nullptr;
+  if (by_sample) {
+    if (pl.sample_tile_off.empty()) {
+      std::vector<pcs::Tile> sorted = pl.host.tiles;
+      std::stable_sort(sorted.begin(), sorted.end(), [](const pcs::Tile& a, const pcs::Tile& b) { return a.sample < b.sample; });
+      pl.sample_tile_off.assign(S + 1, 0);
+      for (const auto& t : sorted) ++pl.sample_tile_off[t.sample + 1];
+      for (size_t i = 0; i < S; ++i) pl.sample_tile_off[i + 1] += pl.sample_tile_off[i];
+      pl.h2d_bytes += pl.d_tiles_by_sample.upload(sorted, st);
+      CUDA_OK(cudaEventRecord(cx.ev[1], st));  // the upload above is not kernel time
+    }
+    cudaStream_t cs = cx.copier();
+    char* stage = static_cast<char*>(cx.staging(2 * table_bytes));
+    const size_t row_bytes = M * sizeof(uint32_t);
+    for (size_t smp = 0; smp < S; ++smp) {
+      const uint32_t t0 = pl.sample_tile_off[smp], t1 = pl.sample_tile_off[smp + 1];
+      CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles_by_sample.p + t0, t1 - t0, pl.d_entries.p, DF, pl.host.model,
+                                              pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
+      CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p + smp * L, fo.d_row_locus.p, 1u, static_cast<uint32_t>(L),
+                                   static_cast<uint32_t>(M), d_cov + smp * M));
+      launches += (t1 > t0 ? 1 : 0) + 1;
+      cudaEvent_t done = cx.chunk_event(2 * S + smp);
+      CUDA_OK(cudaEventRecord(done, st));
+      CUDA_OK(cudaStreamWaitEvent(cs, done, 0));
+      const char* dev_tbl[2] = {reinterpret_cast<const char*>(d_occ + smp * M), reinterpret_cast<const char*>(d_cov + smp * M)};
+      char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M), reinterpret_cast<char*>(cov + smp * M)};
+      for (int t = 0; t < 2; ++t) {
+        char* sp = stage + (2 * smp + t) * row_bytes;
+        CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], row_bytes, cudaMemcpyDeviceToHost, cs));
+        CUDA_OK(cudaEventRecord(cx.chunk_event(chunks.size()), cs));
+        chunks.push_back({host_tbl[t], sp, row_bytes});
+      }
+    }
+    d2h += 2 * table_bytes;
+    CUDA_OK(cudaEventRecord(cx.ev[2], st));
+  } else {
+    CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
+                                            DF, pl.host.model, pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
+    CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
+                                            pl.d_entries.p, DF, pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
+    launches += (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
+    CUDA_OK(cudaEventRecord(cx.ev[2], st));
+    CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
+                                 static_cast<uint32_t>(M), d_cov));
+    launches += S * M != 0 ? 1 : 0;
+  }
+  CUDA_OK(pcs::launch_sum_u32(st, pl.d_depth.p, S * L, pl.d_counters.p + 1));
+  CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
+  launches += (S * M != 0 ? 1 : 0) + (S * L != 0 ? 1 : 0);
+  CUDA_OK(cudaEventRecord(cx.ev[3], st));
+  if (!by_sample && !dev_out && table_bytes != 0) {
+    char* stage = static_cast<char*>(cx.staging(2 * table_bytes));
+    const size_t cb = std::max<size_t>(4u << 20, ((2 * table_bytes / 16) + 4095) & ~static_cast<size_t>(4095));
+    const char* dev_tbl[2] = {reinterpret_cast<const char*>(d_occ), reinterpret_cast<const char*>(d_cov)};
+    char* host_tbl[2] = {reinterpret_cast<char*>(occ), reinterpret_cast<char*>(cov)};
+    for (int t = 0; t < 2; ++t)
+      for (size_t off = 0; off < table_bytes; off += cb) {
+        const size_t nb = std::min(cb, table_bytes - off);
+        char* sp = stage + t * table_bytes + off;
+        CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t] + off, nb, cudaMemcpyDeviceToHost, st));
+        CUDA_OK(cudaEventRecord(cx.chunk_event(chunks.size()), st));
+        chunks.push_back({host_tbl[t] + off, sp, nb});
+      }
     d2h += 2 * table_bytes;
   }
   unsigned long long counters[4] = {0, 0, 0, 0};
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
-  CUDA_OK(cudaStreamSynchronize(st));
-  if (stage) {
-    parallel_copy(occ, stage, table_bytes);
-    parallel_copy(cov, stage + table_bytes, table_bytes);
+  if (!chunks.empty()) {
+    const unsigned nt = std::max(1u, std::min(16u, host_threads()));
+    std::vector<cudaError_t> werr(nt, cudaSuccess);
+    std::vector<std::thread> th;
+    for (unsigned w = 0; w < nt; ++w)
+      th.emplace_back([&, w] {
+        cudaSetDevice(cx.device);
+        for (size_t k = 0; k < chunks.size(); ++k) {
+          const cudaError_t e = cudaEventSynchronize(cx.chunk_ev[k]);
+          if (e != cudaSuccess) {
+            werr[w] = e;
+            return;
+          }
+          const size_t lo = (chunks[k].bytes * w / nt) & ~static_cast<size_t>(63);
+          const size_t hi = w + 1 == nt ? chunks[k].bytes : (chunks[k].bytes * (w + 1) / nt) & ~static_cast<size_t>(63);
+          if (hi > lo) std::memcpy(chunks[k].dst + lo, chunks[k].src + lo, hi - lo);
+        }
+      });
+    for (auto& t : th) t.join();
+    for (cudaError_t e : werr) CUDA_OK(e);
   }
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (by_sample) CUDA_OK(cudaStreamSynchronize(cx.copy_stream));
   d2h += sizeof(counters);
   if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "run (kernels + D2H)", now_ms() - t0);
   if (stats) {
@@ -963,6 +1088,8 @@ int pcs_destroy(pcs_ctx* cx) {
       if (ev) cudaEventDestroy(ev);
     if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
     if (cx->pinned) cudaFreeHost(cx->pinned);
+    for (auto& ev : cx->chunk_ev) cudaEventDestroy(ev);
+    if (cx->copy_stream) cudaStreamDestroy(cx->copy_stream);
     delete cx;
   });
 }
