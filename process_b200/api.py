@@ -16,6 +16,7 @@ import weakref
 from dataclasses import dataclass
 
 import numpy as np
+import pandas as pd
 
 from . import _abi as A
 from . import _lib as L
@@ -86,12 +87,51 @@ class SampledCell:
     birth_time: float = 0.0
 
 
+class VectorisedLabelling:
+    """A cell_labelling evaluated ONCE over all sampled cells instead of once per cell
+    (the reference calls an R closure per cell, src/seq_simulation.cpp:196-201; at 1e5 sampled
+    cells that loop is the host bottleneck -- SURVEY.md 8 f4).  `fn` receives a dict of
+    equal-length columns (cell_id, sample and the forest's per-leaf attributes: epistate,
+    mutant, species, birth_time when present) and returns one string label per cell.
+    Same sample names, same order of first appearance as the per-cell form."""
+
+    def __init__(self, fn):
+        if not callable(fn):
+            raise ValueError("The FACs_labelling_function must be a function.")
+        self.fn = fn
+
+
+def _vectorised_labels(forest: PhylogeneticForest, labelling: VectorisedLabelling):
+    attrs = getattr(forest, "leaf_attrs", None) or {}
+    sample_names = np.asarray(forest.sample_names, dtype=object)
+    cols = {"cell_id": np.asarray(forest.leaf_node).astype(np.int64), "sample": sample_names[forest.leaf_sample]}
+    cols.update({k: np.asarray(v) for k, v in attrs.items()})
+    labels = np.asarray(labelling.fn(cols), dtype=object)
+    if labels.shape != (forest.n_leaves,):
+        raise ValueError("The vectorised labelling function must return one label per sampled cell.")
+    if not all(isinstance(x, str) for x in labels):
+        raise ValueError("The labelling function must return a string.")
+    # order of first appearance when cells are visited sample by sample, leaves in order within a sample
+    visit = np.argsort(forest.leaf_sample, kind="stable")
+    key = np.char.add(np.char.add(forest.leaf_sample[visit].astype(str), "\x1f"), labels[visit].astype(str))
+    code, uniq = pd.factorize(key)
+    group = np.zeros(forest.n_leaves, np.uint32)
+    group[visit] = code.astype(np.uint32)
+    names = []
+    for u in uniq:
+        s, label = u.split("\x1f", 1)
+        names.append(forest.sample_names[int(s)] + ("_" + label if label != "" else ""))
+    return group, names
+
+
 def _apply_FACS_labels(forest: PhylogeneticForest, labelling):
     """apply_FACS_labels()/split_by_labels(), src/seq_simulation.cpp:183-243: one
     callback per sampled cell; cells of sample S labelled L go to sample "S_L"
     (or "S" for the empty label), new samples in order of first appearance."""
     if labelling is None:
         return None, list(forest.sample_names)
+    if isinstance(labelling, VectorisedLabelling):
+        return _vectorised_labels(forest, labelling)
     if not callable(labelling):
         raise ValueError("The FACs_labelling_function must be a function.")
     attrs = getattr(forest, "leaf_attrs", None) or {}

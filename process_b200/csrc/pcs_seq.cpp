@@ -462,6 +462,7 @@ struct OutSample {
 
 HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   HostPlan pl;
+  Lap lap;
   const pcs::FlatForest& F = fo.flat;
   std::vector<uint8_t> chr_mask;
   if (P.chr_mask) chr_mask.assign(P.chr_mask, P.chr_mask + F.n_chr);
@@ -618,6 +619,7 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     for (const auto& ps : per)
       if (!ps.error.empty()) throw std::domain_error(ps.error);
   }
+  lap("  plan: tiles + templates");
   std::vector<pcs::Entry>& entries = pl.entries;
   std::vector<pcs::Tile> all;
   uint64_t total_templates = 0;
@@ -632,10 +634,16 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   }
   for (size_t i = 0; i < all.size(); ++i) all[i].id = static_cast<uint32_t>(i);
 
+  lap("  plan: merge");
   // shard: longest-processing-time greedy on templates; ties by tile id => deterministic
   std::vector<uint32_t> order(all.size());
-  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return all[a].n_templates > all[b].n_templates; });
+  {
+    // one 64-bit key per tile (templates descending, then tile id): a plain sort of integers
+    std::vector<uint64_t> key(all.size());
+    for (size_t i = 0; i < all.size(); ++i) key[i] = (static_cast<uint64_t>(~all[i].n_templates) << 32) | i;
+    std::sort(key.begin(), key.end());
+    for (size_t i = 0; i < all.size(); ++i) order[i] = static_cast<uint32_t>(key[i]);
+  }
   // tiles whose loci / instances / rows fit the staging capacity go to the staged kernel
   uint32_t dir_shift = 5;
   while ((((static_cast<uint64_t>(W) + reach) >> dir_shift) + 1) > 4096) ++dir_shift;
@@ -652,6 +660,7 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
       pl.tiles_global.push_back(t);
     }
   };
+  pl.tiles.reserve(all.size() / shards + 16);
   uint64_t mine = 0;
   if (shards == 1) {
     for (uint32_t i : order)
@@ -669,6 +678,7 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     }
     mine = load[P.shard_rank];
   }
+  lap("  plan: order + shard");
   // round the capacities so that plans of similar forests share one shared-memory footprint
   pl.dims.max_loci = (pl.dims.max_loci + 63) & ~63u;
   pl.dims.max_rows = (pl.dims.max_rows + 63) & ~63u;

@@ -62,3 +62,27 @@ def test_seed_resolution():
     assert -2**31 <= api._resolve_seed(None) < 2**31
     with pytest.raises(ValueError):
         api._resolve_seed("x")
+
+
+def test_vectorised_labelling_equals_per_cell_labelling():
+    """one evaluation over all sampled cells gives the samples (names, order of first
+    appearance, membership) of the per-cell callback of src/seq_simulation.cpp:183-243."""
+    import numpy as np
+    from conftest import small_spec
+    from process_b200.synth import synth_forest
+    f = synth_forest(small_spec(2, sample_cells=[40, 35, 50]))
+    rng = np.random.default_rng(0)
+    f.leaf_attrs = {"epistate": rng.choice(np.array(["+", "-", ""], dtype=object), f.n_leaves),
+                    "mutant": rng.choice(np.array(["A", "B"], dtype=object), f.n_leaves)}
+    per_cell = lambda c: c.epistate if c.mutant == "A" else ""
+    g0, n0 = api._apply_FACS_labels(f, per_cell)
+    vec = api.VectorisedLabelling(lambda cols: np.where(cols["mutant"] == "A", cols["epistate"], ""))
+    g1, n1 = api._apply_FACS_labels(f, vec)
+    assert n0 == n1 and len(n0) > f.n_samples
+    assert np.array_equal(g0, g1)
+    with pytest.raises(ValueError, match="one label per sampled cell"):
+        api._apply_FACS_labels(f, api.VectorisedLabelling(lambda cols: ["x"]))
+    with pytest.raises(ValueError, match="must return a string"):
+        api._apply_FACS_labels(f, api.VectorisedLabelling(lambda cols: np.arange(f.n_leaves)))
+    with pytest.raises(ValueError, match="must be a function"):
+        api.VectorisedLabelling(3)

@@ -418,3 +418,44 @@ def test_global_memory_kernel_for_tiles_too_dense_to_stage(ctx, forests, cap, mo
         assert np.array_equal(occ, occ2) and np.array_equal(cov, cov2)
         plan.close()
     dev.close()
+
+
+@pytest.mark.parametrize("seqm,rate", SEQ[1:])
+@pytest.mark.parametrize("insert", [0, 180])
+def test_dense_sids_and_insertions_with_error_models(ctx, seqm, rate, insert):
+    """A read here carries three or four SIDs, a third of them indels: the per-warp queue of carried SIDs
+    overflows (bases settled on the spot), insertions are settled base by base over several rounds,
+    and reads stretched by deletions leave the staged window.  Tables must still equal the oracle's
+    recount of the very reads the GPU placed, error bits included."""
+    f = synth_forest(small_spec(9, chr_names=["1", "2"], chr_len=[60_000, 40_000], chr_n_alleles=[2, 2],
+                                sample_cells=[5, 6], germline_density=2.5e-2, germline_hom_frac=0.7,
+                                germline_indel_frac=0.35, indel_frac=0.35, n_preneo_snv=50, n_preneo_indel=50,
+                                cna_len=(2000, 15000)))
+    P = make_params(coverage=60.0, purity=0.8, sequencer=seqm, error_rate=rate, insert_size_mean=insert, seed=3)
+    dev = L.Forest(ctx, f)
+    plan = L.Plan(dev, P)
+    occ, cov, st = plan.run()
+    rec, masks = plan.trace(cap=int(st.n_reads) + 16, with_masks=True)
+    assert len(rec) == st.n_reads > 20_000
+    occ2, cov2 = oracle.count_injected(f, plan.info.n_out_samples, P.read_size, rec, masks)
+    assert occ.sum() > 2 * st.n_reads  # several carried SIDs per read
+    assert np.array_equal(occ, occ2)
+    assert np.array_equal(cov, cov2)
+    plan.close()
+    dev.close()
+
+
+@pytest.mark.parametrize("seqm,rate", [SEQ[0], SEQ[2]])
+def test_sample_by_sample_launches_equal_one_launch(ctx, forests, seqm, rate, monkeypatch):
+    """Host-output runs launch the sampler sample by sample (tables of sample s cross the link while
+    s+1 is sampled); PCS_NO_SPLIT keeps the single launch.  Same tiles, same counters: same tables."""
+    f = forests[0]
+    P = make_params(coverage=25.0, purity=0.7, sequencer=seqm, error_rate=rate, seed=5)
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.simulate(P)
+    monkeypatch.setenv("PCS_NO_SPLIT", "1")
+    occ1, cov1, st1 = dev.simulate(P)
+    monkeypatch.delenv("PCS_NO_SPLIT")
+    assert st.n_reads == st1.n_reads and st.kernel_launches > st1.kernel_launches
+    assert np.array_equal(occ, occ1) and np.array_equal(cov, cov1)
+    dev.close()
