@@ -612,7 +612,10 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   // probe: the directory gives index and offset of the first staged locus at or after the read's bucket in one
   // load; the read goes to the queue if that locus lies before its end (the sentinel covers empty buckets)
   auto flush_carried = [&](bool all) {
-    if (ERRORS) settle_carried(err_model(M), S.carried, S.carried_n, S.SV.alt, T.id, all);
+    if (!ERRORS) return;
+    __syncwarp();  // the walks' pushes (shared atomics of other lanes) are visible
+    const uint32_t waiting = lds32(S.carried_n);
+    if (waiting >= 32u || (all && waiting != 0u)) settle_carried(err_model(M), S.carried, S.carried_n, S.SV.alt, T.id, all);
   };
   auto drain = [&]() {
     while (Q.tail >= Q.base + 32u * 16u) {

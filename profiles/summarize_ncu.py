@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turn an ncu report of the sampler kernel into the small files kept under profiles/:
-   python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep r01_v4
-writes profiles/<tag>_sampler_ncu_raw.csv, <tag>_sampler_summary.md and sampler_traffic.json."""
+   python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep r01_v4 [--no-traffic]
+writes profiles/<tag>_sampler_ncu_raw.csv, <tag>_sampler_summary.md and (unless --no-traffic: captures of
+other sequencer models than the headline one) sampler_traffic.json, which bench.py reads."""
 import csv
 import io
 import json
@@ -46,6 +47,9 @@ def main():
         v, u = m[key]
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[u]
         return float(v.replace(",", "")) * scale
+    if "--no-traffic" in sys.argv:
+        print("\n".join(lines[:14]))
+        return
     traffic = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
     inst = float(m["smsp__inst_executed.sum"][0].replace(",", ""))
     json.dump({"kernel": name, "dram_bytes_per_launch": traffic, "warp_instructions_per_launch": inst,
