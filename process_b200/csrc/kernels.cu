@@ -3,10 +3,13 @@
 //   sample_tiles_staged_kernel  the hot kernel.  One CTA per tile: the tile's sorted loci
 //                         are staged in shared memory as 16-byte records {position,
 //                         carrier interval, SID lengths, row} next to a bucket directory;
-//                         every thread draws templates with Philox4x32-10 (one block =
-//                         two single-end reads), walks the loci its reads span and counts
-//                         depth / occurrences with shared-memory atomics; one coalesced
-//                         red.global per touched counter at the end.
+//                         every thread draws template starts with Philox4x32-10 (one block =
+//                         two single-end reads) and probes the directory; reads that may span
+//                         a locus wait in a per-warp queue and are walked 32 at a time
+//                         (haplotype resolved there), counting depth / occurrences with
+//                         shared-memory atomics; the error models settle the carried SIDs
+//                         32 bases at a time from a second queue; one coalesced red.global
+//                         per touched counter at the end.
 //   sample_tiles_global_kernel  same walk straight from global memory (tiles too dense
 //                         to stage) and the read-tracing debug mode.
 //   count_injected_kernel the same locus walk over a caller-supplied placement list
