@@ -7,6 +7,8 @@
 // DFS order, so the carriers of a SID are one contiguous interval [lo, lo+span) of
 // haplotype indices and "does this read carry the SID" is one unsigned compare.
 #pragma once
+#include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <map>
 #include <memory>
@@ -18,26 +20,52 @@
 
 namespace pcs {
 
-// allocator that default-initialises: vector::resize() of the multi-megabyte tables below
-// must not spend time (and page faults on one thread) zeroing what is overwritten right away
-template <class T, class A = std::allocator<T>>
-struct default_init_allocator : A {
-  using A::A;
-  template <class U>
-  struct rebind {
-    using other = default_init_allocator<U, typename std::allocator_traits<A>::template rebind_alloc<U>>;
-  };
-  template <class U>
-  void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) {
-    ::new (static_cast<void*>(p)) U;
+// A big table of the flattened view: a typed window into memory owned by the forest's FlatStore.
+template <class T>
+struct Table {
+  T* p = nullptr;
+  size_t n = 0;
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  T* begin() { return p; }
+  T* end() { return p + n; }
+  const T* begin() const { return p; }
+  const T* end() const { return p + n; }
+};
+
+// Where the big tables live.  Either one block the caller lends for the forest's lifetime -- pinned host
+// memory, so that the H2D DMA reads the tables where the flattener wrote them, no staging copy and no page
+// faults on fresh heap pages -- or the heap (also the fallback once the block is used up).  Memory comes
+// back uninitialised: every table is written in full by flatten_forest.
+struct FlatStore {
+  char* base = nullptr;
+  size_t capacity = 0, used = 0;
+  std::vector<std::unique_ptr<char[]>> heap;
+
+  void* take(size_t bytes) {
+    bytes = (std::max<size_t>(bytes, 1) + 255) & ~static_cast<size_t>(255);
+    if (base && used + bytes <= capacity) {
+      void* q = base + used;
+      used += bytes;
+      return q;
+    }
+    heap.emplace_back(new char[bytes]);
+    return heap.back().get();
   }
-  template <class U, class... Args>
-  void construct(U* p, Args&&... args) {
-    std::allocator_traits<A>::construct(static_cast<A&>(*this), p, std::forward<Args>(args)...);
+  template <class T>
+  Table<T> table(size_t count) {
+    return Table<T>{static_cast<T*>(take(count * sizeof(T))), count};
+  }
+  // is [q, q + bytes) inside the lent block?
+  bool lent(const void* q, size_t bytes) const {
+    const char* c = static_cast<const char*>(q);
+    return base && c >= base && c + bytes <= base + used;
   }
 };
-template <class T>
-using BigVec = std::vector<T, default_init_allocator<T>>;
 
 struct Inst {          // one placement of a SID on a haplotype subtree (device layout: uint4)
   uint32_t lo;         // first haplotype index carrying it
@@ -66,12 +94,13 @@ struct FlatForest {
   std::vector<uint32_t> leaf_sample;
 
   // loci: distinct (chr, pos) of the mutation table
-  BigVec<uint32_t> locus_pos;            // [L]
+  FlatStore store;                       // backing memory of the five tables below
+  Table<uint32_t> locus_pos;             // [L]
   std::vector<uint32_t> chr_locus_off;   // [n_chr+1]
-  BigVec<uint32_t> locus_inst_off;       // [L+1]
-  BigVec<uint32_t> row_locus;            // [n_mut]
-  BigVec<uint32_t> locus_first_row;      // [L+1]
-  BigVec<Inst> inst;                     // sorted by row
+  Table<uint32_t> locus_inst_off;        // [L+1]
+  Table<uint32_t> row_locus;             // [n_mut]
+  Table<uint32_t> locus_first_row;       // [L+1]
+  Table<Inst> inst;                      // sorted by row; inside a row: somatic placements in DFS order, then germline
 
   // haplotype leaves, per chromosome (index inside a chromosome = haplotype index)
   std::vector<std::vector<HapRec>> chr_haps;
@@ -84,7 +113,9 @@ struct FlatForest {
   std::vector<Cover> covers;
 };
 
-// throws std::domain_error on malformed input
+// throws std::domain_error on malformed input.  A block lent through out.store before the call is kept and used.
 void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads);
+// bytes of lent memory that are always enough for the tables of `d` (FlatStore::capacity)
+size_t flat_store_bytes(const pcs_forest_desc& d);
 
 }  // namespace pcs

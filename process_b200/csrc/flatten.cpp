@@ -67,7 +67,9 @@ struct ChrWork {
   std::vector<FragKey> fragsets;
   std::map<FragKey, uint32_t> intern;
   std::unordered_map<uint64_t, std::vector<std::pair<uint16_t, uint16_t>>> wgd_map;
-  std::string error;
+  uint32_t germ_lo[2] = {0, 0}, germ_hi[2] = {0, 0};  // haplotype interval below each germline allele
+  std::vector<Piece> pieces;          // cover_off is LOCAL until merge
+  std::vector<Cover> covers;          // fragset is LOCAL until merge
 
   uint32_t intern_set(const FragKey& k) {
     auto it = intern.find(k);
@@ -132,8 +134,9 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   }
 }
 
-void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
-                 const std::vector<std::pair<uint32_t, uint8_t>>& germ /* (row, mask) of this chr */) {
+// haplotype numbering of one chromosome: leaves (w.haps), the SOMATIC placements sorted by row (w.inst),
+// the interval below each germline allele, the pieces its fragment sets cut the chromosome into
+void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   const uint32_t chr = w.chr;
   const uint32_t clen = d.chr_len[chr];
   const uint8_t n0 = d.chr_n_alleles[chr];
@@ -142,7 +145,8 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
 
   const uint32_t full = w.intern_set(FragKey{{1u, clen}});
   uint32_t counter = 0;
-  uint32_t germ_lo[2] = {0, 0}, germ_hi[2] = {0, 0};
+  uint32_t* germ_lo = w.germ_lo;
+  uint32_t* germ_hi = w.germ_hi;
 
   struct Frame {
     uint32_t node, fragset, ev_i, child_i, open_base;
@@ -235,31 +239,35 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w,
     germ_hi[g] = counter;
   }
 
-  for (const auto& [row, mask] : germ) {
-    check(mask != 0 && (mask >> n0) == 0, "germ_allele_mask names a missing allele");
-    uint32_t meta = static_cast<uint32_t>(d.mut_ref_len[row]) | (static_cast<uint32_t>(d.mut_alt_len[row]) << 8);
-    if (mask == 3) {
-      w.inst.push_back({germ_lo[0], germ_hi[1] - germ_lo[0], row, meta});
-    } else {
-      uint32_t g = mask == 1 ? 0 : 1;
-      w.inst.push_back({germ_lo[g], germ_hi[g] - germ_lo[g], row, meta});
-    }
-  }
   // a SID no sampled haplotype inherited has an empty interval: drop it
   w.inst.erase(std::remove_if(w.inst.begin(), w.inst.end(), [](const Inst& in) { return in.span == 0; }), w.inst.end());
-  // stable counting sort by row (rows of a chromosome are a contiguous range)
-  if (!w.inst.empty()) {
-    uint32_t lo = w.inst[0].row, hi = w.inst[0].row;
-    for (const auto& in : w.inst) {
-      lo = std::min(lo, in.row);
-      hi = std::max(hi, in.row);
+  // by row, placements of one row in DFS order
+  std::stable_sort(w.inst.begin(), w.inst.end(), [](const Inst& x, const Inst& y) { return x.row < y.row; });
+
+  // pieces: maximal intervals on which the set of covering fragments is constant
+  std::vector<uint8_t> used(w.fragsets.size(), 0);
+  for (const auto& h : w.haps) used[h.fragset] = 1;
+  std::vector<uint32_t> bp{1u, clen + 1};
+  for (size_t k = 0; k < w.fragsets.size(); ++k)
+    if (used[k])
+      for (const auto& p : w.fragsets[k]) {
+        bp.push_back(p.first);
+        bp.push_back(p.second + 1);
+      }
+  std::sort(bp.begin(), bp.end());
+  bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
+  for (size_t i = 0; i + 1 < bp.size(); ++i) {
+    Piece pc{chr, bp[i], bp[i + 1] - 1, static_cast<uint32_t>(w.covers.size()), 0};
+    for (size_t k = 0; k < w.fragsets.size(); ++k) {
+      if (!used[k]) continue;
+      for (const auto& p : w.fragsets[k])
+        if (p.first <= pc.begin && pc.end <= p.second) {
+          w.covers.push_back({static_cast<uint32_t>(k), p.second});
+          ++pc.cover_n;
+          break;
+        }
     }
-    std::vector<uint32_t> cnt(static_cast<size_t>(hi - lo) + 2, 0);
-    for (const auto& in : w.inst) ++cnt[in.row - lo + 1];
-    for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
-    std::vector<Inst> sorted(w.inst.size());
-    for (const auto& in : w.inst) sorted[cnt[in.row - lo]++] = in;
-    w.inst.swap(sorted);
+    if (pc.cover_n) w.pieces.push_back(pc);
   }
 }
 
@@ -282,7 +290,13 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   PhaseTimer timer;
   check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
   check(d.n_nodes >= 1, "the forest has no nodes");
-  out = FlatForest{};
+  {
+    FlatStore keep = std::move(out.store);  // a block lent by the caller survives the reset
+    keep.used = 0;
+    keep.heap.clear();
+    out = FlatForest{};
+    out.store = std::move(keep);
+  }
   out.n_chr = d.n_chr;
   out.n_mut = d.n_mut;
   out.n_leaves = d.n_leaves;
@@ -374,19 +388,17 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   });
   for (uint32_t k = 0; k < n_chunks; ++k) chunk_loci[k + 1] += chunk_loci[k];
   const uint32_t n_loci = n_chunks ? chunk_loci[n_chunks] : 0;
-  out.locus_pos.resize(n_loci);
-  out.row_locus.resize(d.n_mut);
-  out.locus_first_row.resize(static_cast<size_t>(n_loci) + 1);
+  out.locus_pos = out.store.table<uint32_t>(n_loci);
+  out.row_locus = out.store.table<uint32_t>(d.n_mut);
+  out.locus_first_row = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
   out.locus_first_row[n_loci] = d.n_mut;
-  out.locus_inst_off.resize(static_cast<size_t>(n_loci) + 1);
-  out.locus_inst_off[0] = 0;
+  out.locus_inst_off = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
   parallel_for(n_chunks, [&](uint32_t k) {
     uint32_t l = chunk_loci[k];  // loci before this chunk
     for (uint32_t m = chunk_lo(k); m < chunk_lo(k + 1); ++m) {
       if (new_locus(m)) {
         out.locus_pos[l] = d.mut_pos[m];
         out.locus_first_row[l] = m;
-        out.locus_inst_off[l + 1] = 0;
         ++l;
       }
       out.row_locus[m] = l - 1;
@@ -427,94 +439,152 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   }
 
   timer.lap("events by chromosome");
-  // ---- germline SIDs by chromosome: chunks of the caller's list are bucketed in parallel
-  const uint32_t g_chunks = d.n_germline ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (d.n_germline + 65535) / 65536)) : 0;
-  std::vector<std::vector<std::vector<std::pair<uint32_t, uint8_t>>>> germ_part(g_chunks);
-  parallel_for(g_chunks, [&](uint32_t k) {
-    auto& part = germ_part[k];
-    part.resize(d.n_chr);
-    const uint64_t lo = d.n_germline * k / g_chunks, hi = d.n_germline * (k + 1) / g_chunks;
-    for (auto& v : part) v.reserve((hi - lo) / d.n_chr + 16);
-    for (uint64_t i = lo; i < hi; ++i) {
-      const uint32_t m = d.germ_mut[i];
-      check(m < d.n_mut, "germ_mut out of range");
-      part[d.mut_chr[m]].emplace_back(m, d.germ_allele_mask[i]);
-    }
-  });
-  timer.lap("germline by chromosome");
-  // ---- per-chromosome haplotype numbering, chromosomes in parallel (largest first)
+  // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
   std::vector<uint32_t> chr_order(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
   std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
-    return chr_row_off[a + 1] - chr_row_off[a] > chr_row_off[b + 1] - chr_row_off[b];
+    return work[a].ev.size() != work[b].ev.size() ? work[a].ev.size() > work[b].ev.size() : a < b;
   });
-  parallel_for(d.n_chr, [&](uint32_t k) {
-    const uint32_t c = chr_order[k];
-    std::vector<std::pair<uint32_t, uint8_t>> germ;
-    germ.reserve(chr_row_off[c + 1] - chr_row_off[c]);
-    for (const auto& part : germ_part) germ.insert(germ.end(), part[c].begin(), part[c].end());
-    flatten_chr(d, t, work[c], germ);
-  });
-
+  parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]]); });
   timer.lap("haplotype numbering");
-  // ---- merge
+
+  // ---- germline SIDs by row.  The caller's list comes in any order; a SID is normally listed once, so the
+  // list is scattered into one allele-mask byte per row (0 = not germline).  Should a row be listed twice, a
+  // stably sorted copy of the list is walked instead (same result, slower).
+  const uint64_t G = d.n_germline;
+  check(G <= 0xffffffffull, "too many germline SIDs");
+  const uint32_t g_chunks = G ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (G + 65535) / 65536)) : 0;
+  std::unique_ptr<std::atomic<uint8_t>[]> row_mask(new std::atomic<uint8_t>[static_cast<size_t>(d.n_mut) + 1]());
+  parallel_for(g_chunks, [&](uint32_t k) {
+    const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
+    for (uint64_t i = lo; i < hi; ++i) {
+      check(d.germ_mut[i] < d.n_mut, "germ_mut out of range");
+      check(d.germ_allele_mask[i] != 0, "germ_allele_mask names a missing allele");
+      row_mask[d.germ_mut[i]].store(d.germ_allele_mask[i], std::memory_order_relaxed);
+    }
+  });
+  // chunks of loci (a locus never straddles two chunks); germline rows per chunk
+  const uint32_t m_chunks = n_loci ? std::min<uint32_t>(4 * n_threads, (n_loci + 65535) / 65536) : 0;
+  auto chunk_locus = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n_loci) * k / m_chunks); };
+  std::vector<uint64_t> germ_before(m_chunks + 1, 0);
+  parallel_for(m_chunks, [&](uint32_t k) {
+    uint64_t cnt = 0;
+    for (uint32_t m = out.locus_first_row[chunk_locus(k)]; m < out.locus_first_row[chunk_locus(k + 1)]; ++m)
+      cnt += row_mask[m].load(std::memory_order_relaxed) != 0;
+    germ_before[k + 1] = cnt;
+  });
+  for (uint32_t k = 0; k < m_chunks; ++k) germ_before[k + 1] += germ_before[k];
+  const bool listed_once = germ_before[m_chunks] == G;
+  std::vector<uint32_t> g_mut;   // only when a row is listed more than once
+  std::vector<uint8_t> g_mask;
+  if (!listed_once) {
+    std::vector<uint64_t> key(G);  // (row, list index): a plain sort keeps the list order inside a row
+    for (uint64_t i = 0; i < G; ++i) key[i] = (static_cast<uint64_t>(d.germ_mut[i]) << 32) | i;
+    std::sort(key.begin(), key.end());
+    g_mut.resize(G);
+    g_mask.resize(G);
+    for (uint64_t i = 0; i < G; ++i) {
+      g_mut[i] = static_cast<uint32_t>(key[i] >> 32);
+      g_mask[i] = d.germ_allele_mask[key[i] & 0xffffffffull];
+    }
+    for (uint32_t k = 0; k <= m_chunks; ++k)
+      germ_before[k] = std::lower_bound(g_mut.begin(), g_mut.end(), out.locus_first_row[chunk_locus(k)]) - g_mut.begin();
+  }
+  timer.lap("germline by row");
+
+  // ---- instances: somatic placements (few, already sorted by row inside each chromosome) merged with the
+  // germline, written once, in place, by chunks of loci; every chunk knows where its output starts
+  std::vector<Inst> som;
+  {
+    size_t n_som = 0;
+    for (const auto& w : work) n_som += w.inst.size();
+    som.reserve(n_som);
+    for (const auto& w : work) som.insert(som.end(), w.inst.begin(), w.inst.end());  // chromosome-major = row-major
+  }
+  check(som.size() + G <= 0xffffffffull, "too many SID placements");
+  const size_t n_inst = som.size() + G;
+  out.inst = out.store.table<Inst>(n_inst);
+  out.locus_inst_off[n_loci] = static_cast<uint32_t>(n_inst);
+  auto row_less = [](const Inst& in, uint32_t row) { return in.row < row; };
+  parallel_for(m_chunks, [&](uint32_t k) {
+    const uint32_t l0 = chunk_locus(k), l1 = chunk_locus(k + 1);
+    size_t si = std::lower_bound(som.begin(), som.end(), out.locus_first_row[l0], row_less) - som.begin();
+    const size_t s1 = std::lower_bound(som.begin(), som.end(), out.locus_first_row[l1], row_less) - som.begin();
+    size_t gi = germ_before[k];
+    const size_t g1 = germ_before[k + 1];
+    size_t pos = gi + si;  // the instances of every row before this chunk
+    Inst* inst = out.inst.data();
+    auto germline = [&](uint32_t m, uint8_t mask) {
+      const ChrWork& w = work[d.mut_chr[m]];
+      check((mask >> d.chr_n_alleles[w.chr]) == 0, "germ_allele_mask names a missing allele");
+      const uint32_t meta = static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8);
+      if (mask == 3) {
+        inst[pos++] = {w.germ_lo[0], w.germ_hi[1] - w.germ_lo[0], m, meta};
+      } else {
+        const uint32_t g = mask == 1 ? 0 : 1;
+        inst[pos++] = {w.germ_lo[g], w.germ_hi[g] - w.germ_lo[g], m, meta};
+      }
+    };
+    for (uint32_t l = l0; l < l1; ++l) {
+      out.locus_inst_off[l] = static_cast<uint32_t>(pos);
+      const uint32_t row_end = out.locus_first_row[l + 1];
+      for (uint32_t m = out.locus_first_row[l]; m < row_end; ++m) {
+        while (si < s1 && som[si].row == m) inst[pos++] = som[si++];
+        if (listed_once) {
+          const uint8_t mask = row_mask[m].load(std::memory_order_relaxed);
+          if (mask) {
+            germline(m, mask);
+            ++gi;
+          }
+        } else {
+          while (gi < g1 && g_mut[gi] == m) germline(m, g_mask[gi++]);
+        }
+      }
+    }
+    check(gi == g1 && si == s1 && pos == g1 + s1, "internal: instance merge out of step");
+  });
+  timer.lap("instances");
+
+  // ---- merge the per-chromosome haplotypes, fragment sets and pieces
   out.chr_haps.resize(d.n_chr);
   out.full_fragset.resize(d.n_chr);
   out.chr_piece_off.assign(d.n_chr + 1, 0);
-  std::vector<size_t> inst_off(d.n_chr + 1, 0);
-  for (uint32_t c = 0; c < d.n_chr; ++c) inst_off[c + 1] = inst_off[c] + work[c].inst.size();
-  out.inst.resize(inst_off[d.n_chr]);
-  std::vector<uint32_t> fs_base(d.n_chr + 1, 0);
-  for (uint32_t c = 0; c < d.n_chr; ++c) fs_base[c + 1] = fs_base[c] + static_cast<uint32_t>(work[c].fragsets.size());
+  std::vector<uint32_t> fs_base(d.n_chr + 1, 0), cover_base(d.n_chr + 1, 0);
+  for (uint32_t c = 0; c < d.n_chr; ++c) {
+    fs_base[c + 1] = fs_base[c] + static_cast<uint32_t>(work[c].fragsets.size());
+    cover_base[c + 1] = cover_base[c] + static_cast<uint32_t>(work[c].covers.size());
+    out.chr_piece_off[c + 1] = out.chr_piece_off[c] + static_cast<uint32_t>(work[c].pieces.size());
+  }
+  out.fragsets.resize(fs_base[d.n_chr]);
+  out.covers.resize(cover_base[d.n_chr]);
+  out.pieces.resize(out.chr_piece_off[d.n_chr]);
   parallel_for(d.n_chr, [&](uint32_t c) {
     ChrWork& w = work[c];
-    std::copy(w.inst.begin(), w.inst.end(), out.inst.begin() + inst_off[c]);
-    // instances per locus (loci of different chromosomes are disjoint)
-    for (const auto& in : w.inst) ++out.locus_inst_off[out.row_locus[in.row] + 1];
-    for (auto& h : w.haps) h.fragset += fs_base[c];
-    out.chr_haps[c] = std::move(w.haps);
-  });
-  for (uint32_t c = 0; c < d.n_chr; ++c) {
-    ChrWork& w = work[c];
     const uint32_t base = fs_base[c];
-    for (const auto& k : w.fragsets) {
-      std::vector<Frag> fr;
-      for (const auto& p : k) fr.push_back({p.first, p.second});
-      out.fragsets.push_back(std::move(fr));
+    for (auto& h : w.haps) h.fragset += base;
+    out.chr_haps[c] = std::move(w.haps);
+    for (size_t k = 0; k < w.fragsets.size(); ++k) {
+      std::vector<Frag>& fr = out.fragsets[base + k];
+      fr.reserve(w.fragsets[k].size());
+      for (const auto& p : w.fragsets[k]) fr.push_back({p.first, p.second});
     }
     out.full_fragset[c] = base;  // interned first in flatten_chr
-
-    // pieces: maximal intervals on which the set of covering fragments is constant
-    std::vector<uint8_t> used(w.fragsets.size(), 0);
-    for (const auto& h : out.chr_haps[c]) used[h.fragset - base] = 1;
-    std::vector<uint32_t> bp{1u, d.chr_len[c] + 1};
-    for (size_t k = 0; k < w.fragsets.size(); ++k)
-      if (used[k])
-        for (const auto& p : w.fragsets[k]) {
-          bp.push_back(p.first);
-          bp.push_back(p.second + 1);
-        }
-    std::sort(bp.begin(), bp.end());
-    bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
-    for (size_t i = 0; i + 1 < bp.size(); ++i) {
-      Piece pc{c, bp[i], bp[i + 1] - 1, static_cast<uint32_t>(out.covers.size()), 0};
-      for (size_t k = 0; k < w.fragsets.size(); ++k) {
-        if (!used[k]) continue;
-        for (const auto& p : w.fragsets[k])
-          if (p.first <= pc.begin && pc.end <= p.second) {
-            out.covers.push_back({base + static_cast<uint32_t>(k), p.second});
-            ++pc.cover_n;
-            break;
-          }
-      }
-      if (pc.cover_n) out.pieces.push_back(pc);
+    for (size_t k = 0; k < w.covers.size(); ++k)
+      out.covers[cover_base[c] + k] = {w.covers[k].fragset + base, w.covers[k].frag_end};
+    for (size_t k = 0; k < w.pieces.size(); ++k) {
+      Piece pc = w.pieces[k];
+      pc.cover_off += cover_base[c];
+      out.pieces[out.chr_piece_off[c] + k] = pc;
     }
-    out.chr_piece_off[c + 1] = static_cast<uint32_t>(out.pieces.size());
-  }
-  timer.lap("merge + pieces");
-  // ---- instances are sorted by row inside a chromosome and rows are chromosome-major
-  for (uint32_t l = 0; l < n_loci; ++l) out.locus_inst_off[l + 1] += out.locus_inst_off[l];
-  timer.lap("instance offsets");
+  });
+  timer.lap("merge");
+}
+
+size_t flat_store_bytes(const pcs_forest_desc& d) {
+  auto padded = [](size_t n, size_t elem) { return (std::max<size_t>(n * elem, 1) + 255) & ~static_cast<size_t>(255); };
+  // loci <= rows; a SID event or a germline entry places at most one instance
+  return 2 * padded(d.n_mut, 4) + 2 * padded(static_cast<size_t>(d.n_mut) + 1, 4) +
+         padded(static_cast<size_t>(d.n_events + d.n_germline), sizeof(Inst));
 }
 
 }  // namespace pcs

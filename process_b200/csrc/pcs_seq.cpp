@@ -17,6 +17,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -158,6 +159,49 @@ struct pcs_ctx {
     }
     return pinned;
   }
+  // Pinned blocks lent to forests for their flat tables (pcs::FlatStore): the flattener writes the tables
+  // where the H2D DMA reads them.  A freed forest hands its block back; the next upload takes it again, so a
+  // session that uploads forest after forest pins memory once.
+  struct PinnedBlock {
+    void* p = nullptr;
+    size_t bytes = 0;
+  };
+  std::mutex pool_mutex;
+  std::vector<PinnedBlock> pool;
+  PinnedBlock lend(size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lock(pool_mutex);
+      size_t best = pool.size();
+      for (size_t i = 0; i < pool.size(); ++i)
+        if (pool[i].bytes >= bytes && (best == pool.size() || pool[i].bytes < pool[best].bytes)) best = i;
+      if (best != pool.size()) {
+        PinnedBlock b = pool[best];
+        pool.erase(pool.begin() + static_cast<std::ptrdiff_t>(best));
+        return b;
+      }
+      if (!pool.empty()) {  // too small for this forest: do not keep it pinned next to the new one
+        cudaFreeHost(pool.back().p);
+        pool.pop_back();
+      }
+    }
+    PinnedBlock b;
+    b.bytes = bytes + bytes / 8;  // forests of one study differ a little: do not re-pin for every one of them
+    bind();
+    CUDA_OK(cudaHostAlloc(&b.p, b.bytes, cudaHostAllocPortable));
+    return b;
+  }
+  void give_back(PinnedBlock b) {
+    if (!b.p) return;
+    std::lock_guard<std::mutex> lock(pool_mutex);
+    pool.push_back(b);
+    while (pool.size() > 2) {  // keep the two largest
+      size_t smallest = 0;
+      for (size_t i = 1; i < pool.size(); ++i)
+        if (pool[i].bytes < pool[smallest].bytes) smallest = i;
+      cudaFreeHost(pool[smallest].p);
+      pool.erase(pool.begin() + static_cast<std::ptrdiff_t>(smallest));
+    }
+  }
   // second stream: the tables of one sample travel to the host while the next sample is being sampled
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copier() {
@@ -180,6 +224,21 @@ struct pcs_ctx {
 // host half of an uploaded forest: flattened view + output sample groups
 struct HostForest {
   pcs::FlatForest flat;
+  // pinned block lent by a context for flat.store; handed back when the last device copy of the forest dies
+  pcs_ctx* lender = nullptr;
+  pcs_ctx::PinnedBlock block;
+  HostForest() = default;
+  HostForest(const HostForest&) = delete;
+  HostForest& operator=(const HostForest&) = delete;
+  ~HostForest() {
+    if (lender) lender->give_back(block);
+  }
+  void borrow(pcs_ctx* cx, size_t bytes) {
+    block = cx->lend(bytes);
+    lender = cx;
+    flat.store.base = static_cast<char*>(block.p);
+    flat.store.capacity = block.bytes;
+  }
   uint32_t n_groups = 0;
   std::vector<uint32_t> leaf_group;
   std::vector<uint32_t> group_cells;  // tumour cells per group
@@ -304,22 +363,40 @@ struct pcs_forest {
   void sync_groups() {
     if (uploaded_groups != host.groups_version) upload_groups();
   }
+  // a table in the lent (pinned) block is DMA'd from where the flattener wrote it and left in flight; anything
+  // else goes through the context's pinned staging area
+  template <class T>
+  void upload_table(DevBuf<T>& dst, const pcs::Table<T>& src, std::vector<std::pair<DevBuf<T>*, const pcs::Table<T>*>>& staged) {
+    cudaStream_t st = ctx->stream;
+    if (src.empty() || host.flat.store.lent(src.data(), src.size() * sizeof(T))) {
+      dst.alloc(src.size(), st);
+      if (!src.empty()) CUDA_OK(cudaMemcpyAsync(dst.p, src.data(), dst.bytes(), cudaMemcpyHostToDevice, st));
+      h2d_bytes += dst.bytes();
+    } else {
+      staged.emplace_back(&dst, &src);
+    }
+  }
   void upload_flat() {
     ctx->bind();
     cudaStream_t st = ctx->stream;
     const pcs::FlatForest& F = host.flat;
-    auto padded = [](size_t n, size_t elem) { return (n * elem + 255) & ~static_cast<size_t>(255); };
-    const size_t total = padded(F.locus_pos.size(), 4) + padded(F.chr_locus_off.size(), 4) +
-                         padded(F.locus_inst_off.size(), 4) + padded(F.row_locus.size(), 4) +
-                         padded(F.inst.size(), sizeof(pcs::Inst));
+    std::vector<std::pair<DevBuf<uint32_t>*, const pcs::Table<uint32_t>*>> staged32;
+    std::vector<std::pair<DevBuf<pcs::Inst>*, const pcs::Table<pcs::Inst>*>> staged_inst;
+    h2d_bytes += d_chr_locus_off.upload(F.chr_locus_off, st);  // tiny, pageable, synchronous: before the big ones
+    upload_table(d_locus_pos, F.locus_pos, staged32);
+    upload_table(d_locus_inst_off, F.locus_inst_off, staged32);
+    upload_table(d_row_locus, F.row_locus, staged32);
+    upload_table(d_inst, F.inst, staged_inst);
+    if (staged32.empty() && staged_inst.empty()) return;
+    auto padded = [](size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); };
+    size_t total = 0;
+    for (const auto& [dst, src] : staged32) total += padded(src->size() * 4);
+    for (const auto& [dst, src] : staged_inst) total += padded(src->size() * sizeof(pcs::Inst));
     CUDA_OK(cudaStreamSynchronize(st));  // nothing in flight may still use the staging area
     char* stage = static_cast<char*>(ctx->staging(total));
     size_t off = 0;
-    h2d_bytes += d_locus_pos.upload_staged(F.locus_pos, st, stage, off);
-    h2d_bytes += d_chr_locus_off.upload_staged(F.chr_locus_off, st, stage, off);
-    h2d_bytes += d_locus_inst_off.upload_staged(F.locus_inst_off, st, stage, off);
-    h2d_bytes += d_row_locus.upload_staged(F.row_locus, st, stage, off);
-    h2d_bytes += d_inst.upload_staged(F.inst, st, stage, off);
+    for (const auto& [dst, src] : staged32) h2d_bytes += dst->upload_staged(*src, st, stage, off);
+    for (const auto& [dst, src] : staged_inst) h2d_bytes += dst->upload_staged(*src, st, stage, off);
     CUDA_OK(cudaStreamSynchronize(st));
   }
   pcs_forest() = default;
@@ -1098,6 +1175,7 @@ int pcs_destroy(pcs_ctx* cx) {
       if (ev) cudaEventDestroy(ev);
     if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
     if (cx->pinned) cudaFreeHost(cx->pinned);
+    for (auto& b : cx->pool) cudaFreeHost(b.p);
     for (auto& ev : cx->chunk_ev) cudaEventDestroy(ev);
     if (cx->copy_stream) cudaStreamDestroy(cx->copy_stream);
     delete cx;
@@ -1119,9 +1197,10 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     require(cx && desc && out, "bad arguments");
     auto fo = std::make_unique<pcs_forest>();
     fo->ctx = cx;
-    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
     Lap lap;
-    pcs::flatten_forest(*desc, fo->host.flat, nt);
+    fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
+    lap("pinned block");
+    pcs::flatten_forest(*desc, fo->host.flat, host_threads());
     lap("flatten_forest");
     fo->upload_flat();
     lap("upload flat arrays");
@@ -1135,6 +1214,7 @@ int pcs_forest_free(pcs_forest* fo) {
   return guarded([&] {
     if (!fo) return;
     cudaSetDevice(fo->ctx->device);
+    cudaStreamSynchronize(fo->ctx->stream);  // an upload may still be reading the forest's pinned block
     delete fo;
   });
 }
