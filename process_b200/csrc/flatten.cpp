@@ -367,25 +367,35 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   // ---- mutation table -> loci (validated and numbered in row chunks)
   const uint32_t n_chunks = d.n_mut ? std::min<uint32_t>(4 * n_threads, (d.n_mut + 65535) / 65536) : 0;
   auto chunk_lo = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(d.n_mut) * k / n_chunks); };
-  auto new_locus = [&](uint32_t m) {
-    return m == 0 || d.mut_chr[m - 1] != d.mut_chr[m] || d.mut_pos[m - 1] != d.mut_pos[m];
-  };
   std::vector<uint32_t> chunk_loci(n_chunks + 1, 0);
-  parallel_for(n_chunks, [&](uint32_t k) {
-    uint32_t cnt = 0;
-    for (uint32_t m = chunk_lo(k); m < chunk_lo(k + 1); ++m) {
-      check(d.mut_chr[m] < d.n_chr, "mut_chr out of range");
-      check(d.mut_pos[m] >= 1 && d.mut_pos[m] <= d.chr_len[d.mut_chr[m]], "mutation position outside the chromosome");
-      check(d.mut_ref_len[m] >= 1 && d.mut_alt_len[m] >= 1, "ref/alt must be non-empty");
-      if (m > 0) {
-        bool ordered = d.mut_chr[m - 1] < d.mut_chr[m] ||
-                       (d.mut_chr[m - 1] == d.mut_chr[m] && d.mut_pos[m - 1] <= d.mut_pos[m]);
-        check(ordered, "mutation table must be sorted by (chr, pos)");
+  {
+    const uint16_t* mc = d.mut_chr;
+    const uint32_t* mp = d.mut_pos;
+    const uint32_t* clen = d.chr_len;
+    const uint32_t n_chr = d.n_chr;
+    parallel_for(n_chunks, [&, mc, mp, clen, n_chr](uint32_t k) {
+      const uint32_t lo = chunk_lo(k), hi = chunk_lo(k + 1);
+      uint32_t cnt = 0;
+      bool ok_chr = true, ok_pos = true, ok_len = true, ok_order = true;
+      // row lo is compared with its predecessor too (chunk edges are ordinary rows)
+      uint32_t pc = lo ? mc[lo - 1] : 0, pp = lo ? mp[lo - 1] : 0;
+      for (uint32_t m = lo; m < hi; ++m) {
+        const uint32_t c = mc[m], p = mp[m];
+        ok_chr &= c < n_chr;
+        ok_pos &= p >= 1 && p <= clen[c < n_chr ? c : 0];
+        ok_len &= d.mut_ref_len[m] >= 1 && d.mut_alt_len[m] >= 1;
+        ok_order &= m == 0 || pc < c || (pc == c && pp <= p);
+        cnt += (m == 0 || pc != c || pp != p) ? 1u : 0u;
+        pc = c;
+        pp = p;
       }
-      cnt += new_locus(m) ? 1u : 0u;
-    }
-    chunk_loci[k + 1] = cnt;
-  });
+      check(ok_chr, "mut_chr out of range");
+      check(ok_pos, "mutation position outside the chromosome");
+      check(ok_len, "ref/alt must be non-empty");
+      check(ok_order, "mutation table must be sorted by (chr, pos)");
+      chunk_loci[k + 1] = cnt;
+    });
+  }
   for (uint32_t k = 0; k < n_chunks; ++k) chunk_loci[k + 1] += chunk_loci[k];
   const uint32_t n_loci = n_chunks ? chunk_loci[n_chunks] : 0;
   out.locus_pos = out.store.table<uint32_t>(n_loci);
@@ -393,17 +403,29 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   out.locus_first_row = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
   out.locus_first_row[n_loci] = d.n_mut;
   out.locus_inst_off = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
-  parallel_for(n_chunks, [&](uint32_t k) {
-    uint32_t l = chunk_loci[k];  // loci before this chunk
-    for (uint32_t m = chunk_lo(k); m < chunk_lo(k + 1); ++m) {
-      if (new_locus(m)) {
-        out.locus_pos[l] = d.mut_pos[m];
-        out.locus_first_row[l] = m;
-        ++l;
+  {
+    const uint16_t* mc = d.mut_chr;
+    const uint32_t* mp = d.mut_pos;
+    uint32_t* locus_pos = out.locus_pos.data();
+    uint32_t* first_row = out.locus_first_row.data();
+    uint32_t* row_locus = out.row_locus.data();
+    parallel_for(n_chunks, [&, mc, mp, locus_pos, first_row, row_locus](uint32_t k) {
+      const uint32_t lo = chunk_lo(k), hi = chunk_lo(k + 1);
+      uint32_t l = chunk_loci[k];  // loci before this chunk
+      uint32_t pc = lo ? mc[lo - 1] : 0, pp = lo ? mp[lo - 1] : 0;
+      for (uint32_t m = lo; m < hi; ++m) {
+        const uint32_t c = mc[m], p = mp[m];
+        if (m == 0 || pc != c || pp != p) {
+          locus_pos[l] = p;
+          first_row[l] = m;
+          ++l;
+        }
+        row_locus[m] = l - 1;
+        pc = c;
+        pp = p;
       }
-      out.row_locus[m] = l - 1;
-    }
-  });
+    });
+  }
   // rows and loci of every chromosome (the table is sorted by chromosome)
   std::vector<uint32_t> chr_row_off(d.n_chr + 1, d.n_mut);
   for (uint32_t c = 0; c <= d.n_chr; ++c)
@@ -454,23 +476,81 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   const uint64_t G = d.n_germline;
   check(G <= 0xffffffffull, "too many germline SIDs");
   const uint32_t g_chunks = G ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (G + 65535) / 65536)) : 0;
+  // relaxed atomics (plain byte moves): a row listed twice may be written by two threads
   std::unique_ptr<std::atomic<uint8_t>[]> row_mask(new std::atomic<uint8_t>[static_cast<size_t>(d.n_mut) + 1]());
-  parallel_for(g_chunks, [&](uint32_t k) {
-    const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
-    for (uint64_t i = lo; i < hi; ++i) {
-      check(d.germ_mut[i] < d.n_mut, "germ_mut out of range");
-      check(d.germ_allele_mask[i] != 0, "germ_allele_mask names a missing allele");
-      row_mask[d.germ_mut[i]].store(d.germ_allele_mask[i], std::memory_order_relaxed);
+  {
+    // Threads must not write mask bytes of the same cache line, or the line bounces between cores for every
+    // entry.  A list sorted by row is scattered chunk by chunk as it lies; any other order is first partitioned
+    // by row range (bucket = row >> shift, at most 64 of them), then every bucket is scattered by one thread.
+    uint32_t shift = 6;
+    while ((d.n_mut >> shift) >= 64) ++shift;
+    const uint32_t n_buckets = (d.n_mut >> shift) + 1;
+    std::vector<uint32_t> hist(static_cast<size_t>(g_chunks) * n_buckets, 0);
+    std::vector<uint8_t> chunk_sorted(g_chunks, 1);
+    parallel_for(g_chunks, [&](uint32_t k) {
+      const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
+      uint32_t h[64] = {0};  // on the stack: neighbouring rows of `hist` share cache lines
+      uint32_t prev = lo ? d.germ_mut[lo - 1] : 0;
+      bool sorted = true;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t m = d.germ_mut[i];
+        check(m < d.n_mut, "germ_mut out of range");
+        check(d.germ_allele_mask[i] != 0, "germ_allele_mask names a missing allele");
+        sorted &= prev <= m;
+        prev = m;
+        ++h[m >> shift];
+      }
+      chunk_sorted[k] = sorted;
+      std::copy(h, h + n_buckets, hist.data() + static_cast<size_t>(k) * n_buckets);
+    });
+    if (std::find(chunk_sorted.begin(), chunk_sorted.end(), 0) == chunk_sorted.end()) {
+      // chunk k writes rows [germ_mut[lo], germ_mut[hi-1]]: only the two edge bytes can share a line
+      parallel_for(g_chunks, [&](uint32_t k) {
+        const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
+        for (uint64_t i = lo; i < hi; ++i) row_mask[d.germ_mut[i]].store(d.germ_allele_mask[i], std::memory_order_relaxed);
+      });
+    } else {
+      // hist -> where chunk k writes its entries of bucket b: buckets in order, chunks in order inside a bucket
+      std::vector<uint64_t> bucket_off(n_buckets + 1, 0);
+      {
+        uint64_t run = 0;
+        for (uint32_t b = 0; b < n_buckets; ++b) {
+          bucket_off[b] = run;
+          for (uint32_t k = 0; k < g_chunks; ++k) {
+            uint32_t& h = hist[static_cast<size_t>(k) * n_buckets + b];
+            const uint32_t cnt = h;
+            h = static_cast<uint32_t>(run);
+            run += cnt;
+          }
+        }
+        bucket_off[n_buckets] = run;
+      }
+      check(d.n_mut <= (1u << 30), "too many rows for an unsorted germline list: sort it by row");
+      std::unique_ptr<uint32_t[]> part(new uint32_t[G]);  // row | mask << 30
+      parallel_for(g_chunks, [&](uint32_t k) {
+        const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
+        uint32_t at[64];
+        std::copy(hist.data() + static_cast<size_t>(k) * n_buckets, hist.data() + static_cast<size_t>(k + 1) * n_buckets, at);
+        for (uint64_t i = lo; i < hi; ++i) {
+          const uint32_t m = d.germ_mut[i];
+          const uint32_t q = at[m >> shift]++;
+          part[q] = m | static_cast<uint32_t>(d.germ_allele_mask[i]) << 30;
+        }
+      });
+      parallel_for(n_buckets, [&](uint32_t b) {  // bucket = 2^shift rows, shift >= 6: whole cache lines
+        for (uint64_t i = bucket_off[b]; i < bucket_off[b + 1]; ++i)
+          row_mask[part[i] & 0x3fffffffu].store(static_cast<uint8_t>(part[i] >> 30), std::memory_order_relaxed);
+      });
     }
-  });
+  }
   // chunks of loci (a locus never straddles two chunks); germline rows per chunk
   const uint32_t m_chunks = n_loci ? std::min<uint32_t>(4 * n_threads, (n_loci + 65535) / 65536) : 0;
   auto chunk_locus = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n_loci) * k / m_chunks); };
   std::vector<uint64_t> germ_before(m_chunks + 1, 0);
   parallel_for(m_chunks, [&](uint32_t k) {
     uint64_t cnt = 0;
-    for (uint32_t m = out.locus_first_row[chunk_locus(k)]; m < out.locus_first_row[chunk_locus(k + 1)]; ++m)
-      cnt += row_mask[m].load(std::memory_order_relaxed) != 0;
+    const uint32_t r0 = out.locus_first_row[chunk_locus(k)], r1 = out.locus_first_row[chunk_locus(k + 1)];
+    for (uint32_t m = r0; m < r1; ++m) cnt += row_mask[m].load(std::memory_order_relaxed) != 0;
     germ_before[k + 1] = cnt;
   });
   for (uint32_t k = 0; k < m_chunks; ++k) germ_before[k + 1] += germ_before[k];

@@ -295,6 +295,7 @@ struct HostForest {
 
 struct pcs_flat {
   HostForest host;
+  std::unique_ptr<char[]> block;  // lent to host.flat.store like the pinned block of an uploaded forest
 };
 
 struct pcs_forest {
@@ -1814,7 +1815,13 @@ int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** out) {
   return guarded([&] {
     require(desc && out, "bad arguments");
     auto fl = std::make_unique<pcs_flat>();
+    // same code path as pcs_forest_upload: the tables are written into a lent block (plain memory here)
+    const size_t bytes = pcs::flat_store_bytes(*desc);
+    fl->block.reset(new char[bytes]);
+    fl->host.flat.store.base = fl->block.get();
+    fl->host.flat.store.capacity = bytes;
     pcs::flatten_forest(*desc, fl->host.flat, host_threads());
+    require(fl->host.flat.store.heap.empty(), "internal: the lent block was too small for the flat tables");
     fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
     *out = fl.release();
   });

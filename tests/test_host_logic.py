@@ -88,6 +88,46 @@ def test_flat_view_with_two_roots_and_nested_copies():
     assert check_flat_against_explicit_genomes(f) >= 10
 
 
+def _all_hap_rows(f):
+    fl = L.Flat(f)
+    out = []
+    n_roots = int((f.node_parent < 0).sum())
+    cells = [(A.PCS_PLACE_TUMOUR, l) for l in range(f.n_leaves)] + [(A.PCS_PLACE_NORMAL_PLAIN, 0)] + \
+            [(A.PCS_PLACE_NORMAL_PRENEO, r) for r in range(n_roots)]
+    for c in range(f.n_chr):
+        for kind, cell in cells:
+            for a, h, fs in fl.cell_haps(kind, cell, c):
+                out.append((c, kind, cell, a, h, fs, fl.hap_rows(c, h).tolist()))
+    return fl.info(), out
+
+
+def test_germline_list_order_does_not_matter():
+    """the germline list is taken in any order: sorted by row (scattered where it lies), shuffled (partitioned by
+    row range first), and with a row listed twice (sorted copy): same view"""
+    f = synth_forest(small_spec(3))
+    rng = np.random.default_rng(5)
+    order = np.argsort(f.germ_mut, kind="stable")
+    base_mut, base_mask = f.germ_mut.copy(), f.germ_allele_mask.copy()
+    f.germ_mut, f.germ_allele_mask = base_mut[order].copy(), base_mask[order].copy()
+    info_sorted, rows_sorted = _all_hap_rows(f)
+    p = rng.permutation(len(base_mut))
+    f.germ_mut, f.germ_allele_mask = base_mut[p].copy(), base_mask[p].copy()
+    info_shuffled, rows_shuffled = _all_hap_rows(f)
+    assert info_sorted == info_shuffled and rows_sorted == rows_shuffled
+    assert check_flat_against_explicit_genomes(f) > 100
+    # a heterozygous SID listed once per allele instead of once with both bits: two instances, same carriers
+    het = np.flatnonzero(base_mask == 3)[:5]
+    assert len(het) == 5
+    mut = np.concatenate([base_mut, base_mut[het]])
+    mask = np.concatenate([base_mask, np.full(5, 2, np.uint8)])
+    mask[het] = 1
+    p = rng.permutation(len(mut))
+    f.germ_mut, f.germ_allele_mask = mut[p].astype(np.uint32), mask[p].astype(np.uint8)
+    info_dup, rows_dup = _all_hap_rows(f)
+    assert info_dup["n_instances"] == info_sorted["n_instances"] + 5
+    assert [(r[:6], sorted(set(r[6]))) for r in rows_dup] == [(r[:6], sorted(set(r[6]))) for r in rows_sorted]
+
+
 def test_malformed_forests_are_refused():
     f = MF.forest()
     f.mut_pos = f.mut_pos[::-1].copy()
