@@ -408,6 +408,8 @@ struct pcs_forest {
 struct HostPlan {
   std::vector<pcs::Tile> tiles;         // this shard, staged in shared memory, heaviest first
   std::vector<pcs::Tile> tiles_global;  // this shard, too dense to stage
+  std::vector<pcs::Tile> tiles_by_sample;   // `tiles` grouped by output sample (same order inside a sample)
+  std::vector<uint32_t> sample_tile_off;    // [n_out_samples + 1]
   pcs::StageDims dims{};
   std::vector<pcs::Entry> entries;
   std::vector<uint32_t> insert_alias;  // [n][2] {keep threshold, alias column}
@@ -420,8 +422,7 @@ struct pcs_plan {
   HostPlan host;
   DevBuf<pcs::Tile> d_tiles, d_tiles_global;
   // the staged tiles once more, grouped by output sample (host-output runs launch sample by sample)
-  DevBuf<pcs::Tile> d_tiles_by_sample;
-  std::vector<uint32_t> sample_tile_off;
+  DevBuf<pcs::Tile> d_tiles_by_sample;  // uploaded by the first run that needs it
   DevBuf<pcs::Entry> d_entries;
   DevBuf<uint32_t> d_insert_alias;
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
@@ -538,193 +539,291 @@ struct OutSample {
   uint32_t group;
 };
 
+// run fn(k) for k in [0, n) on the host threads; the first failure is rethrown as std::domain_error
+template <class Fn>
+void host_tasks(size_t n, Fn&& fn) {
+  std::vector<std::string> errors(n);
+  std::atomic<size_t> next{0};
+  auto worker = [&] {
+    for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) {
+      try {
+        fn(k);
+      } catch (const std::exception& e) {
+        errors[k] = e.what();
+        if (errors[k].empty()) errors[k] = "planning failed";
+      }
+    }
+  };
+  const size_t nt = std::min<size_t>(n, std::max(1u, host_threads()));
+  std::vector<std::thread> th;
+  for (size_t w = 1; w < nt; ++w) th.emplace_back(worker);
+  worker();
+  for (auto& t : th) t.join();
+  for (const auto& e : errors)
+    if (!e.empty()) throw std::domain_error(e);
+}
+
+// first element >= key of the sorted range [first, last), expected near `first`
+const uint32_t* gallop(const uint32_t* first, const uint32_t* last, uint32_t key) {
+  size_t step = 1;
+  const uint32_t* lo = first;  // everything before lo is < key
+  while (static_cast<size_t>(last - lo) > step && lo[step - 1] < key) {
+    lo += step;
+    step <<= 1;
+  }
+  return std::lower_bound(lo, std::min(lo + step, last), key);
+}
+
+// The part of a plan no output sample changes: parameters resolved, and per chromosome the tile GEOMETRY
+// (window, staged loci, rows) -- pieces cut into windows of <= W bp and <= lcap staged loci.
+struct PlanSetup {
+  const HostForest* fo = nullptr;
+  pcs_seq_params P{};
+  std::vector<uint8_t> chr_mask;
+  std::vector<OutSample> samples;
+  uint32_t R = 0, mates = 1, kmin = 0, kmax = 0, W = 0, lcap = 0, shards = 1, normal_group = 0, dir_shift = 5;
+  uint64_t reach = 0;
+  bool paired = false;
+  std::vector<uint32_t> insert_alias;
+  struct ChrGrid {
+    std::vector<pcs::Tile> tiles;         // chr, begin, len, l0, l1, r0, n_rows
+    std::vector<uint32_t> piece_tile_off; // [pieces of the chromosome + 1]
+  };
+  std::vector<ChrGrid> grid;
+  bool sequenced(uint32_t c) const { return chr_mask.empty() || chr_mask[c]; }
+};
+
+PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
+  PlanSetup ps;
+  ps.fo = &fo;
+  ps.P = P;
+  const pcs::FlatForest& F = fo.flat;
+  if (P.chr_mask) ps.chr_mask.assign(P.chr_mask, P.chr_mask + F.n_chr);
+  ps.P.chr_mask = nullptr;  // the caller's pointer is not kept
+  ps.R = P.read_size;
+  ps.paired = P.insert_size_mean > 0;
+  ps.mates = ps.paired ? 2 : 1;
+  if (ps.paired) insert_table(P.insert_size_mean, P.insert_size_stddev, ps.insert_alias, ps.kmin, ps.kmax);
+  ps.reach = ps.paired ? 2ull * ps.R + ps.kmax : ps.R;
+  if (!P.normal_only)
+    for (uint32_t g = 0; g < fo.n_groups; ++g) ps.samples.push_back({false, g});
+  if (P.normal_only || P.with_normal_sample) ps.samples.push_back({true, 0});
+  ps.normal_group = fo.n_groups + (P.preneoplastic_in_normal ? 1u : 0u);
+  uint64_t sequenced_bp = 0;
+  for (uint32_t c = 0; c < F.n_chr; ++c)
+    if (ps.sequenced(c)) sequenced_bp += F.chr_len[c];
+  ps.W = tile_bp(sequenced_bp * ps.samples.size());
+  ps.lcap = stage_loci_cap();
+  ps.shards = P.shard_count ? P.shard_count : 1;
+  while ((((static_cast<uint64_t>(ps.W) + ps.reach) >> ps.dir_shift) + 1) > 4096) ++ps.dir_shift;
+
+  ps.grid.resize(F.n_chr);
+  host_tasks(F.n_chr, [&](size_t ci) {
+    const uint32_t c = static_cast<uint32_t>(ci);
+    PlanSetup::ChrGrid& g = ps.grid[c];
+    g.piece_tile_off.assign(F.chr_piece_off[c + 1] - F.chr_piece_off[c] + 1, 0);
+    if (!ps.sequenced(c)) return;
+    const uint32_t* lp = F.locus_pos.data();
+    const uint32_t* c_lo = lp + F.chr_locus_off[c];
+    const uint32_t* c_hi = lp + F.chr_locus_off[c + 1];
+    const uint32_t* near = c_lo;  // pieces and windows come in increasing position: searches resume here
+    for (uint32_t pi = F.chr_piece_off[c]; pi < F.chr_piece_off[c + 1]; ++pi) {
+      const pcs::Piece& pc = F.pieces[pi];
+      for (uint64_t b = pc.begin; b <= pc.end;) {
+        pcs::Tile t{};
+        t.chr = c;
+        t.begin = static_cast<uint32_t>(b);
+        near = gallop(near, c_hi, t.begin);
+        t.l0 = static_cast<uint32_t>(near - lp);
+        uint64_t len = std::min<uint64_t>(ps.W, pc.end - b + 1);
+        for (;;) {  // shrink the window until its loci fit the staging capacity
+          uint64_t last = std::min<uint64_t>(b + len + ps.reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
+          t.l1 = static_cast<uint32_t>(gallop(near, c_hi, static_cast<uint32_t>(last)) - lp);
+          if (t.l1 - t.l0 <= ps.lcap || len <= 2048) break;
+          len = std::max<uint64_t>(2048, len / 2);
+        }
+        t.len = static_cast<uint32_t>(len);
+        t.r0 = F.locus_first_row[t.l0];
+        t.n_rows = F.locus_first_row[t.l1] - t.r0;
+        g.tiles.push_back(t);
+        b += len;
+      }
+      g.piece_tile_off[pi - F.chr_piece_off[c] + 1] = static_cast<uint32_t>(g.tiles.size());
+    }
+  });
+  return ps;
+}
+
+// tiles of one (output sample, chromosome): sampling entries per piece, template counts (multinomial over
+// the tiles with the RNG stream of (seed, sample, chromosome)); entry_off is relative to `entries`
+struct SampleChrPlan {
+  std::vector<pcs::Entry> entries;
+  std::vector<pcs::Tile> tiles;
+  uint64_t total_templates = 0;
+};
+
+void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan& task) {
+  const HostForest& fo = *ps.fo;
+  const pcs::FlatForest& F = fo.flat;
+  const pcs_seq_params& P = ps.P;
+  if (!ps.sequenced(c)) return;
+  double purity = ps.samples[s].is_normal ? 0.0 : P.purity;
+  const uint32_t nT = ps.samples[s].is_normal ? 0 : fo.group_cells[ps.samples[s].group];
+  if (nT == 0) purity = 0.0;
+  std::vector<pcs::Entry>& entries = task.entries;
+  std::vector<pcs::Tile>& all = task.tiles;
+  std::vector<double> tile_w;
+  const PlanSetup::ChrGrid& g = ps.grid[c];
+  all.reserve(g.tiles.size());
+  tile_w.reserve(g.tiles.size());
+  // normal cells: every one carries each germline allele whole
+  auto nit = fo.list_index.find(HostForest::list_key(ps.normal_group, F.full_fragset[c]));
+  require(nit != fo.list_index.end(), "internal: normal haplotype list missing");
+  const uint32_t n_normal_cells = P.preneoplastic_in_normal ? F.n_roots : 1;
+  std::vector<double> w;
+  std::vector<pcs::Entry> es;
+  std::vector<uint32_t> es_n;  // haplotypes in each entry's list
+  for (uint32_t pi = F.chr_piece_off[c]; pi < F.chr_piece_off[c + 1]; ++pi) {
+    const pcs::Piece& pc = F.pieces[pi];
+    w.clear();
+    es.clear();
+    es_n.clear();
+    for (uint32_t k = 0; k < pc.cover_n; ++k) {
+      const pcs::Cover& cv = F.covers[pc.cover_off + k];
+      if (purity > 0) {
+        auto it = fo.list_index.find(HostForest::list_key(ps.samples[s].group, cv.fragset));
+        if (it != fo.list_index.end() && it->second.second > 0) {
+          w.push_back(purity / nT * it->second.second);
+          es.push_back(pcs::Entry{0u, 0u, it->second.first, cv.frag_end});
+          es_n.push_back(it->second.second);
+        }
+      }
+      if (purity < 1 && cv.fragset == F.full_fragset[c]) {
+        w.push_back((1 - purity) / n_normal_cells * nit->second.second);
+        es.push_back(pcs::Entry{0u, 0u, nit->second.first, cv.frag_end});
+        es_n.push_back(nit->second.second);
+      }
+    }
+    if (es.empty()) continue;
+    double wsum = 0;
+    for (double x : w) wsum += x;
+    const std::vector<uint32_t> thr = thresholds(w);
+    const uint32_t entry_off = static_cast<uint32_t>(entries.size());
+    uint32_t n_kept = 0;
+    {
+      // entries whose share of the draw range is empty can never be picked: drop them
+      uint64_t base = 0;
+      for (size_t i = 0; i < es.size(); ++i) {
+        if (static_cast<uint64_t>(thr[i]) + 1 <= base) continue;
+        const uint64_t width = static_cast<uint64_t>(thr[i]) + 1 - base;
+        es[i].thr = thr[i];
+        // leaf = umulhi(u - base, scale) < list_n, base = previous kept entry's thr + 1
+        es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es_n[i]) << 32) / width));
+        entries.push_back(es[i]);
+        ++n_kept;
+        base = static_cast<uint64_t>(thr[i]) + 1;
+      }
+    }
+    const uint32_t lp = pi - F.chr_piece_off[c];
+    for (uint32_t ti = g.piece_tile_off[lp]; ti < g.piece_tile_off[lp + 1]; ++ti) {
+      pcs::Tile t = g.tiles[ti];
+      t.entry_off = entry_off;
+      t.n_entries = n_kept;
+      t.sample = s;
+      all.push_back(t);
+      tile_w.push_back(wsum * t.len);
+    }
+  }
+  // templates of this (sample, chromosome), multinomial over its tiles
+  const uint64_t N = static_cast<uint64_t>(std::llround(P.coverage * F.chr_len[c] / (static_cast<double>(ps.R) * ps.mates)));
+  std::seed_seq sq{static_cast<uint32_t>(P.seed), s, c, 0x7115u};
+  std::mt19937_64 rng(sq);
+  double wleft = 0;
+  for (double x : tile_w) wleft += x;
+  uint64_t left = all.empty() ? 0 : N;
+  for (size_t i = 0; i < all.size() && left > 0; ++i) {
+    double p = (i + 1 == all.size()) ? 1.0 : std::min(1.0, std::max(0.0, tile_w[i] / wleft));
+    uint64_t k = p >= 1.0 ? left : static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(left), p)(rng));
+    require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
+    all[i].n_templates = static_cast<uint32_t>(k);
+    left -= k;
+    wleft -= tile_w[i];
+    task.total_templates += k;
+  }
+}
+
+// tile indices by descending template count, ties by index: LSD radix sort of the counts (stable)
+std::vector<uint32_t> heaviest_first(const std::vector<pcs::Tile>& all) {
+  const size_t n = all.size();
+  std::vector<uint32_t> order(n), tmp(n);
+  for (size_t i = 0; i < n; ++i) order[i] = static_cast<uint32_t>(i);
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = 11 * pass;
+    uint32_t cnt[2049] = {0};
+    for (size_t i = 0; i < n; ++i) ++cnt[((~all[order[i]].n_templates >> shift) & 2047u) + 1];
+    for (int d = 0; d < 2048; ++d) cnt[d + 1] += cnt[d];
+    for (size_t i = 0; i < n; ++i) tmp[cnt[(~all[order[i]].n_templates >> shift) & 2047u]++] = order[i];
+    order.swap(tmp);
+  }
+  return order;
+}
+
+void set_model(HostPlan& pl, const PlanSetup& ps) {
+  pcs::SeqModel& M = pl.model;
+  M.insert_alias = nullptr;
+  M.read_size = ps.R;
+  M.paired = ps.paired ? 1 : 0;
+  M.sequencer = ps.P.sequencer;
+  M.err_thr = static_cast<uint32_t>(std::min(4294967295.0, std::floor(ps.P.error_rate * 4294967296.0)));
+  M.error_rate = static_cast<float>(ps.P.error_rate);
+  M.insert_n = static_cast<uint32_t>(ps.insert_alias.size() / 2);
+  M.insert_min = ps.kmin;
+  M.seed = static_cast<uint32_t>(ps.P.seed);
+  M.reach = static_cast<uint32_t>(ps.reach);
+  M.dir_shift = ps.dir_shift;
+}
+
 HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   HostPlan pl;
   Lap lap;
   const pcs::FlatForest& F = fo.flat;
-  std::vector<uint8_t> chr_mask;
-  if (P.chr_mask) chr_mask.assign(P.chr_mask, P.chr_mask + F.n_chr);
-  const uint32_t R = P.read_size;
-  const bool paired = P.insert_size_mean > 0;
-  const uint32_t mates = paired ? 2 : 1;
-
-  uint32_t kmin = 0, kmax = 0;
-  if (paired) insert_table(P.insert_size_mean, P.insert_size_stddev, pl.insert_alias, kmin, kmax);
-  const uint64_t reach = paired ? 2ull * R + kmax : R;
-
-  std::vector<OutSample> samples;
-  if (!P.normal_only)
-    for (uint32_t g = 0; g < fo.n_groups; ++g) samples.push_back({false, g});
-  if (P.normal_only || P.with_normal_sample) samples.push_back({true, 0});
-
-  const uint32_t normal_group = fo.n_groups + (P.preneoplastic_in_normal ? 1u : 0u);
-  uint64_t sequenced_bp = 0;
-  for (uint32_t c = 0; c < F.n_chr; ++c)
-    if (chr_mask.empty() || chr_mask[c]) sequenced_bp += F.chr_len[c];
-  const uint32_t W = tile_bp(sequenced_bp * samples.size());
-  const uint32_t lcap = stage_loci_cap();
-  const uint32_t shards = P.shard_count ? P.shard_count : 1;
-
-  // every (output sample, chromosome) plans its own tiles with its own RNG stream: independent tasks for
-  // the host threads, merged in (sample, chromosome) order afterwards
-  struct PerTask {
-    std::vector<pcs::Entry> entries;
-    std::vector<pcs::Tile> all;
-    std::vector<double> tile_w;
-    uint64_t total_templates = 0;
-    std::string error;
-  };
-  std::vector<PerTask> per(samples.size() * static_cast<size_t>(F.n_chr));
-  auto plan_task = [&](uint32_t s, uint32_t c) {
-    PerTask& task = per[static_cast<size_t>(s) * F.n_chr + c];
-    std::vector<pcs::Entry>& entries = task.entries;
-    std::vector<pcs::Tile>& all = task.all;
-    std::vector<double>& tile_w = task.tile_w;
-    uint64_t& total_templates = task.total_templates;
-    double purity = samples[s].is_normal ? 0.0 : P.purity;
-    uint32_t nT = samples[s].is_normal ? 0 : fo.group_cells[samples[s].group];
-    if (nT == 0) purity = 0.0;
-    {
-      if (!chr_mask.empty() && !chr_mask[c]) return;
-      const size_t first_tile = all.size();
-      // normal cells: every one carries each germline allele whole
-      auto nit = fo.list_index.find(HostForest::list_key(normal_group, F.full_fragset[c]));
-      require(nit != fo.list_index.end(), "internal: normal haplotype list missing");
-      const uint32_t n_normal_cells = P.preneoplastic_in_normal ? F.n_roots : 1;
-      for (uint32_t pi = F.chr_piece_off[c]; pi < F.chr_piece_off[c + 1]; ++pi) {
-        const pcs::Piece& pc = F.pieces[pi];
-        std::vector<double> w;
-        std::vector<pcs::Entry> es;
-        std::vector<uint32_t> es_n;  // haplotypes in each entry's list
-        for (uint32_t k = 0; k < pc.cover_n; ++k) {
-          const pcs::Cover& cv = F.covers[pc.cover_off + k];
-          if (purity > 0) {
-            auto it = fo.list_index.find(HostForest::list_key(samples[s].group, cv.fragset));
-            if (it != fo.list_index.end() && it->second.second > 0) {
-              w.push_back(purity / nT * it->second.second);
-              es.push_back(pcs::Entry{0u, 0u, it->second.first, cv.frag_end});
-              es_n.push_back(it->second.second);
-            }
-          }
-          if (purity < 1 && cv.fragset == F.full_fragset[c]) {
-            w.push_back((1 - purity) / n_normal_cells * nit->second.second);
-            es.push_back(pcs::Entry{0u, 0u, nit->second.first, cv.frag_end});
-            es_n.push_back(nit->second.second);
-          }
-        }
-        if (es.empty()) continue;
-        double wsum = 0;
-        for (double x : w) wsum += x;
-        std::vector<uint32_t> thr = thresholds(w);
-        const uint32_t entry_off = static_cast<uint32_t>(entries.size());
-        {
-          // entries whose share of the draw range is empty can never be picked: drop them
-          std::vector<pcs::Entry> kept;
-          uint64_t base = 0;
-          for (size_t i = 0; i < es.size(); ++i) {
-            if (static_cast<uint64_t>(thr[i]) + 1 <= base) continue;
-            const uint64_t width = static_cast<uint64_t>(thr[i]) + 1 - base;
-            es[i].thr = thr[i];
-            // leaf = umulhi(u - base, scale) < list_n, base = previous kept entry's thr + 1
-            es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es_n[i]) << 32) / width));
-            kept.push_back(es[i]);
-            base = static_cast<uint64_t>(thr[i]) + 1;
-          }
-          es.swap(kept);
-          for (const auto& e : es) entries.push_back(e);
-        }
-        const uint32_t* lp = F.locus_pos.data();
-        const uint32_t* c_lo = lp + F.chr_locus_off[c];
-        const uint32_t* c_hi = lp + F.chr_locus_off[c + 1];
-        for (uint64_t b = pc.begin; b <= pc.end;) {
-          pcs::Tile t{};
-          t.chr = c;
-          t.begin = static_cast<uint32_t>(b);
-          t.entry_off = entry_off;
-          t.n_entries = static_cast<uint32_t>(es.size());
-          t.sample = s;
-          t.l0 = static_cast<uint32_t>(std::lower_bound(c_lo, c_hi, t.begin) - lp);
-          uint64_t len = std::min<uint64_t>(W, pc.end - b + 1);
-          for (;;) {  // shrink the window until its loci fit the staging capacity
-            uint64_t last = std::min<uint64_t>(b + len + reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
-            t.l1 = static_cast<uint32_t>(std::lower_bound(c_lo, c_hi, static_cast<uint32_t>(last)) - lp);
-            if (t.l1 - t.l0 <= lcap || len <= 2048) break;
-            len = std::max<uint64_t>(2048, len / 2);
-          }
-          t.len = static_cast<uint32_t>(len);
-          t.r0 = F.locus_first_row[t.l0];
-          t.n_rows = F.locus_first_row[t.l1] - t.r0;
-          all.push_back(t);
-          tile_w.push_back(wsum * t.len);
-          b += len;
-        }
-      }
-      // templates of this (sample, chromosome), multinomial over its tiles
-      uint64_t N = static_cast<uint64_t>(std::llround(P.coverage * F.chr_len[c] / (static_cast<double>(R) * mates)));
-      std::seed_seq sq{static_cast<uint32_t>(P.seed), s, c, 0x7115u};
-      std::mt19937_64 rng(sq);
-      double wleft = 0;
-      for (size_t i = first_tile; i < all.size(); ++i) wleft += tile_w[i];
-      uint64_t left = all.size() > first_tile ? N : 0;
-      for (size_t i = first_tile; i < all.size() && left > 0; ++i) {
-        double p = (i + 1 == all.size()) ? 1.0 : std::min(1.0, std::max(0.0, tile_w[i] / wleft));
-        uint64_t k = p >= 1.0 ? left : static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(left), p)(rng));
-        require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
-        all[i].n_templates = static_cast<uint32_t>(k);
-        left -= k;
-        wleft -= tile_w[i];
-        total_templates += k;
-      }
-    }
-  };
-  {
-    std::atomic<size_t> next{0};
-    auto worker = [&] {
-      for (size_t k = next.fetch_add(1); k < per.size(); k = next.fetch_add(1)) {
-        try {
-          plan_task(static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr));
-        } catch (const std::exception& e) {
-          per[k].error = e.what();
-          if (per[k].error.empty()) per[k].error = "planning failed";
-        }
-      }
-    };
-    const size_t nt = std::min<size_t>(per.size(), std::max(1u, host_threads()));
-    std::vector<std::thread> th;
-    for (size_t w = 1; w < nt; ++w) th.emplace_back(worker);
-    worker();
-    for (auto& t : th) t.join();
-    for (const auto& ps : per)
-      if (!ps.error.empty()) throw std::domain_error(ps.error);
-  }
-  lap("  plan: tiles + templates");
+  PlanSetup ps = plan_setup(fo, P);
+  lap("  plan: tile geometry");
+  // every (output sample, chromosome) is an independent task with its own RNG stream
+  std::vector<SampleChrPlan> per(ps.samples.size() * static_cast<size_t>(F.n_chr));
+  host_tasks(per.size(), [&](size_t k) {
+    plan_sample_chr(ps, static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr), per[k]);
+  });
+  lap("  plan: entries + templates");
+  // merged in (sample, chromosome) order: the position in this order is the tile id
   std::vector<pcs::Entry>& entries = pl.entries;
   std::vector<pcs::Tile> all;
+  {
+    size_t n_tiles = 0, n_entries = 0;
+    for (const auto& t : per) {
+      n_tiles += t.tiles.size();
+      n_entries += t.entries.size();
+    }
+    all.reserve(n_tiles);
+    entries.reserve(n_entries);
+  }
   uint64_t total_templates = 0;
-  for (auto& ps : per) {
+  for (auto& task : per) {
     const uint32_t base = static_cast<uint32_t>(entries.size());
-    entries.insert(entries.end(), ps.entries.begin(), ps.entries.end());
-    for (auto& t : ps.all) {
+    entries.insert(entries.end(), task.entries.begin(), task.entries.end());
+    for (auto& t : task.tiles) {
       t.entry_off += base;
+      t.id = static_cast<uint32_t>(all.size());
       all.push_back(t);
     }
-    total_templates += ps.total_templates;
+    total_templates += task.total_templates;
   }
-  for (size_t i = 0; i < all.size(); ++i) all[i].id = static_cast<uint32_t>(i);
-
   lap("  plan: merge");
   // shard: longest-processing-time greedy on templates; ties by tile id => deterministic
-  std::vector<uint32_t> order(all.size());
-  {
-    // one 64-bit key per tile (templates descending, then tile id): a plain sort of integers
-    std::vector<uint64_t> key(all.size());
-    for (size_t i = 0; i < all.size(); ++i) key[i] = (static_cast<uint64_t>(~all[i].n_templates) << 32) | i;
-    std::sort(key.begin(), key.end());
-    for (size_t i = 0; i < all.size(); ++i) order[i] = static_cast<uint32_t>(key[i]);
-  }
+  const std::vector<uint32_t> order = heaviest_first(all);
   // tiles whose loci / instances / rows fit the staging capacity go to the staged kernel
-  uint32_t dir_shift = 5;
-  while ((((static_cast<uint64_t>(W) + reach) >> dir_shift) + 1) > 4096) ++dir_shift;
+  const uint32_t lcap = ps.lcap, dir_shift = ps.dir_shift, shards = ps.shards;
+  const uint64_t reach = ps.reach;
   auto stageable = [&](const pcs::Tile& t) {
     return lcap > 0 && t.l1 - t.l0 <= lcap && t.n_rows <= 2 * lcap && t.n_entries <= pcs::kMaxStagedEntries;
   };
@@ -756,34 +855,35 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     }
     mine = load[P.shard_rank];
   }
+  // the staged tiles once more, grouped by output sample, heaviest first inside a sample: host-output runs
+  // launch sample by sample
+  const size_t S = ps.samples.size();
+  pl.sample_tile_off.assign(S + 1, 0);
+  for (const auto& t : pl.tiles) ++pl.sample_tile_off[t.sample + 1];
+  for (size_t i = 0; i < S; ++i) pl.sample_tile_off[i + 1] += pl.sample_tile_off[i];
+  {
+    std::vector<uint32_t> at(pl.sample_tile_off.begin(), pl.sample_tile_off.end() - 1);
+    pl.tiles_by_sample.resize(pl.tiles.size());
+    for (const auto& t : pl.tiles) pl.tiles_by_sample[at[t.sample]++] = t;
+  }
   lap("  plan: order + shard");
   // round the capacities so that plans of similar forests share one shared-memory footprint
   pl.dims.max_loci = (pl.dims.max_loci + 63) & ~63u;
   pl.dims.max_rows = (pl.dims.max_rows + 63) & ~63u;
   pl.dims.max_buckets = (pl.dims.max_buckets + 63) & ~63u;
 
-  pcs::SeqModel& M = pl.model;
-  M.insert_alias = nullptr;
-  M.read_size = R;
-  M.paired = paired ? 1 : 0;
-  M.sequencer = P.sequencer;
-  M.err_thr = static_cast<uint32_t>(std::min(4294967295.0, std::floor(P.error_rate * 4294967296.0)));
-  M.error_rate = static_cast<float>(P.error_rate);
-  M.insert_n = static_cast<uint32_t>(pl.insert_alias.size() / 2);
-  M.insert_min = kmin;
-  M.seed = static_cast<uint32_t>(P.seed);
-  M.reach = static_cast<uint32_t>(reach);
-  M.dir_shift = dir_shift;
+  pl.insert_alias = ps.insert_alias;
+  set_model(pl, ps);
 
-  pl.info.n_out_samples = static_cast<uint32_t>(samples.size());
+  pl.info.n_out_samples = static_cast<uint32_t>(ps.samples.size());
   pl.info.n_mut = F.n_mut;
   pl.info.n_loci = static_cast<uint32_t>(F.locus_pos.size());
   pl.info.n_tiles = pl.tiles.size() + pl.tiles_global.size();
   pl.info.n_tiles_total = all.size();
   pl.info.n_templates = mine;
   pl.info.n_templates_total = total_templates;
-  pl.info.reads_per_template = mates;
-  pl.info.read_size = R;
+  pl.info.reads_per_template = ps.mates;
+  pl.info.read_size = ps.R;
   return pl;
 }
 
@@ -794,7 +894,6 @@ void upload_plan(pcs_plan& pl) {
   pl.h2d_bytes += pl.d_tiles.upload(pl.host.tiles, st);
   pl.h2d_bytes += pl.d_tiles_global.upload(pl.host.tiles_global, st);
   pl.d_tiles_by_sample.release();
-  pl.sample_tile_off.clear();
   pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
   pl.h2d_bytes += pl.d_insert_alias.upload(pl.host.insert_alias, st);
   pl.host.model.insert_alias = pl.d_insert_alias.p;
@@ -839,20 +938,15 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   const bool by_sample = !dev_out && S > 1 && M != 0 && pl.host.tiles_global.empty() && !pl.host.tiles.empty() &&
                          std::getenv("PCS_NO_SPLIT") == nullptr;
   if (by_sample) {
-    if (pl.sample_tile_off.empty()) {
-      std::vector<pcs::Tile> sorted = pl.host.tiles;
-      std::stable_sort(sorted.begin(), sorted.end(), [](const pcs::Tile& a, const pcs::Tile& b) { return a.sample < b.sample; });
-      pl.sample_tile_off.assign(S + 1, 0);
-      for (const auto& t : sorted) ++pl.sample_tile_off[t.sample + 1];
-      for (size_t i = 0; i < S; ++i) pl.sample_tile_off[i + 1] += pl.sample_tile_off[i];
-      pl.h2d_bytes += pl.d_tiles_by_sample.upload(sorted, st);
+    if (pl.d_tiles_by_sample.p == nullptr) {
+      pl.h2d_bytes += pl.d_tiles_by_sample.upload(pl.host.tiles_by_sample, st);
       CUDA_OK(cudaEventRecord(cx.ev[1], st));  // the upload above is not kernel time
     }
     cudaStream_t cs = cx.copier();
     char* stage = static_cast<char*>(cx.staging(2 * table_bytes));
     const size_t row_bytes = M * sizeof(uint32_t);
     for (size_t smp = 0; smp < S; ++smp) {
-      const uint32_t t0 = pl.sample_tile_off[smp], t1 = pl.sample_tile_off[smp + 1];
+      const uint32_t t0 = pl.host.sample_tile_off[smp], t1 = pl.host.sample_tile_off[smp + 1];
       CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles_by_sample.p + t0, t1 - t0, pl.d_entries.p, DF, pl.host.model,
                                               pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
       CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p + smp * L, fo.d_row_locus.p, 1u, static_cast<uint32_t>(L),
