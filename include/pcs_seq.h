@@ -327,6 +327,12 @@ int pcs_flat_fragset(const pcs_flat* flat, uint32_t fragset, uint32_t cap, uint3
 /* mutation rows carried by haplotype `hap` of chromosome `chr` (germline included) */
 int pcs_flat_hap_rows(const pcs_flat* flat, uint32_t chr, uint32_t hap, uint32_t cap, uint32_t* rows,
                       uint32_t* n);
+/* the haplotypes of chromosome(fragset) the sampler draws from for output group `group` and fragment set
+ * `fragset`: group < n_groups = tumour cells of that group, n_groups = normal cells (germline only),
+ * n_groups + 1 = normal cells with the pre-neoplastic SIDs.  *offset: position of the list in the device's
+ * hap_list.  Lists are in increasing haplotype order and tile hap_list in (group, fragset) order. */
+int pcs_flat_group_list(const pcs_flat* flat, uint32_t group, uint32_t fragset, uint32_t cap, uint32_t* haps,
+                        uint32_t* offset, uint32_t* n);
 /* host half of pcs_plan_create: tile grid of the shard named in params */
 int pcs_flat_plan(const pcs_flat* flat, const pcs_seq_params* params, pcs_plan_info* info, uint64_t cap,
                   uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,

@@ -27,7 +27,7 @@ EXPORTS = [
     "pcs_forest_set_reference", "pcs_forest_load_fasta", "pcs_forest_set_alt", "pcs_plan_write_sam",
     "pcs_plan_materialize",
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
-    "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan",
+    "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan", "pcs_flat_group_list",
 ]
 
 
@@ -104,6 +104,14 @@ class Flat:
         _ok(lib().pcs_flat_hap_rows(self._h, C.c_uint32(chrom), C.c_uint32(hap), C.c_uint32(cap),
                                     A.ptr(rows, C.c_uint32), C.byref(n)))
         return rows[:n.value].copy()
+
+    def group_list(self, group, fragset, cap=1 << 16):
+        """(offset in hap_list, haplotype indices) of the sampling list of (group, fragment set)"""
+        h = np.zeros(cap, np.uint32); off = C.c_uint32(0); n = C.c_uint32(0)
+        _ok(lib().pcs_flat_group_list(self._h, C.c_uint32(group), C.c_uint32(fragset), C.c_uint32(cap),
+                                      A.ptr(h, C.c_uint32), C.byref(off), C.byref(n)))
+        assert n.value <= cap
+        return int(off.value), h[:n.value].copy()
 
     def plan(self, params: A.SeqParams, cap=1 << 22):
         info = A.PlanInfo()

@@ -263,21 +263,40 @@ struct HostForest {
       require(leaf_group[l] < ng, "leaf group out of range");
       ++group_cells[leaf_group[l]];
     }
-    std::map<uint64_t, std::vector<uint32_t>> lists;
-    for (uint32_t c = 0; c < flat.n_chr; ++c) {
-      const auto& haps = flat.chr_haps[c];
-      for (uint32_t h = 0; h < haps.size(); ++h) {
-        const pcs::HapRec& r = haps[h];
-        uint32_t g = r.kind == pcs::HAP_TUMOUR ? leaf_group[r.cell] : ng + (r.kind == pcs::HAP_NORMAL_PRENEO ? 1u : 0u);
-        lists[list_key(g, r.fragset)].push_back(h);
-      }
-    }
+    // haplotype lists per (group | normal kind, fragment set), concatenated in key order.  A fragment set
+    // belongs to one chromosome, so a list holds haplotype indices of that chromosome in increasing order:
+    // count, offsets in key order, fill -- the two passes over the haplotypes run per chromosome in parallel.
+    const size_t n_fs = flat.fragsets.size(), n_keys = (static_cast<size_t>(ng) + 2) * n_fs;
+    auto group_of = [&](const pcs::HapRec& r) {
+      return r.kind == pcs::HAP_TUMOUR ? leaf_group[r.cell] : ng + (r.kind == pcs::HAP_NORMAL_PRENEO ? 1u : 0u);
+    };
+    std::vector<uint32_t> count(n_keys + 1, 0);  // key = group * n_fs + fragset: the order of list_key()
+    auto per_chr = [&](const std::function<void(uint32_t)>& fn) {
+      std::atomic<uint32_t> next{0};
+      auto worker = [&] {
+        for (uint32_t c = next.fetch_add(1); c < flat.n_chr; c = next.fetch_add(1)) fn(c);
+      };
+      const unsigned nt = std::min<unsigned>(flat.n_chr, host_threads());
+      std::vector<std::thread> th;
+      for (unsigned w = 1; w < nt; ++w) th.emplace_back(worker);
+      worker();
+      for (auto& t : th) t.join();
+    };
+    per_chr([&](uint32_t c) {
+      for (const pcs::HapRec& r : flat.chr_haps[c]) ++count[static_cast<size_t>(group_of(r)) * n_fs + r.fragset + 1];
+    });
     hap_list.clear();
     list_index.clear();
-    for (auto& [k, v] : lists) {
-      list_index[k] = {static_cast<uint32_t>(hap_list.size()), static_cast<uint32_t>(v.size())};
-      hap_list.insert(hap_list.end(), v.begin(), v.end());
+    for (size_t k = 0; k < n_keys; ++k) {
+      if (count[k + 1])
+        list_index[list_key(static_cast<uint32_t>(k / n_fs), static_cast<uint32_t>(k % n_fs))] = {count[k], count[k + 1]};
+      count[k + 1] += count[k];
     }
+    hap_list.resize(count[n_keys]);
+    per_chr([&](uint32_t c) {  // count[key] = where the next haplotype of the list goes
+      const auto& haps = flat.chr_haps[c];
+      for (uint32_t h = 0; h < haps.size(); ++h) hap_list[count[static_cast<size_t>(group_of(haps[h])) * n_fs + haps[h].fragset]++] = h;
+    });
   }
 
   void build_lookup() {
@@ -2003,6 +2022,23 @@ int pcs_flat_hap_rows(const pcs_flat* fl, uint32_t chr, uint32_t hap, uint32_t c
           ++k;
         }
     *n = k;
+  });
+}
+
+int pcs_flat_group_list(const pcs_flat* fl, uint32_t group, uint32_t fragset, uint32_t cap, uint32_t* haps,
+                        uint32_t* offset, uint32_t* n) {
+  return guarded([&] {
+    require(fl && n, "bad arguments");
+    const HostForest& H = fl->host;
+    require(group < H.n_groups + 2 && fragset < H.flat.fragsets.size(), "group or fragment set out of range");
+    auto it = H.list_index.find(HostForest::list_key(group, fragset));
+    *n = 0;
+    if (offset) *offset = 0;
+    if (it == H.list_index.end()) return;
+    *n = it->second.second;
+    if (offset) *offset = it->second.first;
+    require(static_cast<size_t>(it->second.first) + it->second.second <= H.hap_list.size(), "internal: list outside hap_list");
+    for (uint32_t i = 0; i < it->second.second && i < cap; ++i) haps[i] = H.hap_list[it->second.first + i];
   });
 }
 

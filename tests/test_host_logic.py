@@ -128,6 +128,40 @@ def test_germline_list_order_does_not_matter():
     assert [(r[:6], sorted(set(r[6]))) for r in rows_dup] == [(r[:6], sorted(set(r[6]))) for r in rows_sorted]
 
 
+@pytest.mark.parametrize("regroup", [False, True])
+def test_sampling_lists_partition_the_haplotypes(regroup):
+    """every haplotype is in exactly the list of (its output group | normal kind, its fragment set); lists are in
+    increasing haplotype order and tile the device's hap_list in (group, fragment set) order, no gaps"""
+    f = synth_forest(small_spec(4))
+    fl = L.Flat(f)
+    n_groups = f.n_samples
+    leaf_group = np.asarray(f.leaf_sample, np.uint32)
+    if regroup:
+        n_groups = 4
+        leaf_group = (np.arange(f.n_leaves) % 4).astype(np.uint32)
+        fl.set_groups(leaf_group, n_groups)
+    info = fl.info()
+    n_roots = int((f.node_parent < 0).sum())
+    want = {}
+    cells = [(A.PCS_PLACE_TUMOUR, l) for l in range(f.n_leaves)] + [(A.PCS_PLACE_NORMAL_PLAIN, 0)] + \
+            [(A.PCS_PLACE_NORMAL_PRENEO, r) for r in range(n_roots)]
+    for c in range(f.n_chr):
+        for kind, cell in cells:
+            g = int(leaf_group[cell]) if kind == A.PCS_PLACE_TUMOUR else n_groups + (kind == A.PCS_PLACE_NORMAL_PRENEO)
+            for a, h, fs in fl.cell_haps(kind, cell, c):
+                want.setdefault((g, fs), []).append(h)
+    assert sum(len(v) for v in want.values()) == info["n_haplotypes"]
+    at = 0
+    for g in range(n_groups + 2):
+        for fs in range(info["n_fragment_sets"]):
+            off, haps = fl.group_list(g, fs)
+            assert haps.tolist() == sorted(want.get((g, fs), []))
+            if len(haps):
+                assert off == at
+                at += len(haps)
+    assert at == info["n_haplotypes"]
+
+
 def test_malformed_forests_are_refused():
     f = MF.forest()
     f.mut_pos = f.mut_pos[::-1].copy()
