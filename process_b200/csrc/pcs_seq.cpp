@@ -202,6 +202,13 @@ struct pcs_ctx {
       pool.erase(pool.begin() + static_cast<std::ptrdiff_t>(smallest));
     }
   }
+  // run counters come back into pinned memory: a D2H copy into pageable memory would block the calling
+  // thread until the stream has drained, and with it the host threads that copy finished tables out
+  unsigned long long* pinned_counters = nullptr;  // [4]
+  unsigned long long* counters_home() {
+    if (!pinned_counters) CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned_counters), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    return pinned_counters;
+  }
   // second stream: the tables of one sample travel to the host while the next sample is being sampled
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copier() {
@@ -1015,8 +1022,10 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
       }
     d2h += 2 * table_bytes;
   }
-  unsigned long long counters[4] = {0, 0, 0, 0};
-  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  // asynchronous (pinned destination): the host threads below start copying finished chunks out while the
+  // sampler is still running
+  unsigned long long* counters = cx.counters_home();
+  CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
   if (!chunks.empty()) {
     const unsigned nt = std::max(1u, std::min(16u, host_threads()));
     std::vector<cudaError_t> werr(nt, cudaSuccess);
@@ -1040,7 +1049,7 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   }
   CUDA_OK(cudaStreamSynchronize(st));
   if (by_sample) CUDA_OK(cudaStreamSynchronize(cx.copy_stream));
-  d2h += sizeof(counters);
+  d2h += 4 * sizeof(unsigned long long);
   if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "run (kernels + D2H)", now_ms() - t0);
   if (stats) {
     float ms = 0;
@@ -1289,6 +1298,7 @@ int pcs_destroy(pcs_ctx* cx) {
       if (ev) cudaEventDestroy(ev);
     if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
     if (cx->pinned) cudaFreeHost(cx->pinned);
+    if (cx->pinned_counters) cudaFreeHost(cx->pinned_counters);
     for (auto& b : cx->pool) cudaFreeHost(b.p);
     for (auto& ev : cx->chunk_ev) cudaEventDestroy(ev);
     if (cx->copy_stream) cudaStreamDestroy(cx->copy_stream);
