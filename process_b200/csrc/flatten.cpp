@@ -55,16 +55,32 @@ bool holds(const FragKey& s, uint32_t pos) {
 struct Tree {
   std::vector<uint32_t> child_off, child_idx, roots;
   std::vector<int64_t> node_leaf;
+  // The same tree in DFS PREORDER (roots in order, children by increasing node index): position i holds node
+  // pre_node[i], its subtree is the range [i, pre_end[i]), its first child is i + 1 and the sibling after a
+  // child c is pre_end[c].  The haplotype numbering walks the tree once per allele copy: laid out like this
+  // every walk reads memory front to back instead of chasing node indices.
+  std::vector<uint32_t> pre_node, pre_end, root_pos;
+  std::vector<int64_t> pre_leaf;
+};
+
+// one event of a chromosome, gathered next to its neighbours in walk order
+struct Ev {
+  uint32_t x;      // SID: mutation row; CNA: first position; WGD: index of the event in the caller's arrays
+  uint32_t y;      // SID: position of the row; CNA: length
+  uint32_t meta;   // SID: ref_len | alt_len << 8
+  uint16_t allele, dest;
+  uint8_t kind, nature;
 };
 
 struct ChrWork {
   uint32_t chr = 0;
-  std::vector<uint64_t> ev;           // events of this chromosome (+ WGD), node-major
-  std::vector<uint32_t> node_ev_off;  // [n_nodes+1]
+  std::vector<Ev> ev;                 // events of this chromosome (+ WGD), by preorder position
+  std::vector<uint32_t> ev_off;       // [n_nodes+1], indexed by preorder position
   bool has_wgd = false;
   std::vector<Inst> inst;
   std::vector<HapRec> haps;           // fragset is a LOCAL id until merge
   std::vector<FragKey> fragsets;
+  std::vector<uint8_t> fs_empty;      // fragment set has no DNA left
   std::map<FragKey, uint32_t> intern;
   std::unordered_map<uint64_t, std::vector<std::pair<uint16_t, uint16_t>>> wgd_map;
   uint32_t germ_lo[2] = {0, 0}, germ_hi[2] = {0, 0};  // haplotype interval below each germline allele
@@ -76,10 +92,38 @@ struct ChrWork {
     if (it != intern.end()) return it->second;
     uint32_t id = static_cast<uint32_t>(fragsets.size());
     fragsets.push_back(k);
+    fs_empty.push_back(k.empty() ? 1 : 0);
     intern.emplace(k, id);
     return id;
   }
 };
+
+// events of chromosome w.chr (and every WGD) in walk order, with what the walk needs of the rows they name
+void gather_events(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
+  const uint32_t n = d.n_nodes, chr = w.chr;
+  w.ev_off.assign(static_cast<size_t>(n) + 1, 0);
+  for (uint32_t i = 0; i < n; ++i) {
+    const uint32_t v = t.pre_node[i];
+    for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+      const uint8_t kind = d.ev_kind[e];
+      if (kind == PCS_EV_WGD) {
+        w.has_wgd = true;
+        w.ev.push_back({static_cast<uint32_t>(e), 0u, 0u, 0, 0, kind, d.ev_nature[e]});
+      } else if (d.ev_chr[e] == chr) {
+        if (kind == PCS_EV_SID) {
+          const uint32_t m = d.ev_mut[e];
+          check(m < d.n_mut && d.mut_chr[m] == chr, "SID event names a row of another chromosome");
+          w.ev.push_back({m, d.mut_pos[m], static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8),
+                          d.ev_allele[e], 0, kind, d.ev_nature[e]});
+        } else {
+          check(d.ev_len[e] >= 1, "CNA length must be positive");
+          w.ev.push_back({d.ev_pos[e], d.ev_len[e], 0u, d.ev_allele[e], d.ev_dest[e], kind, d.ev_nature[e]});
+        }
+      }
+    }
+    w.ev_off[i + 1] = static_cast<uint32_t>(w.ev.size());
+  }
+}
 
 // which allele ids exist where: only needed to give WGD copies their ids
 void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
@@ -92,12 +136,10 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   for (uint16_t a = 0; a < d.chr_n_alleles[w.chr]; ++a) base.ids.push_back(a);
   base.next = d.chr_n_alleles[w.chr];
   pool.push_back(base);
-  std::vector<std::pair<uint32_t, uint32_t>> stack;
-  for (uint32_t r : t.roots) stack.emplace_back(r, 0u);
-  while (!stack.empty()) {
-    auto [v, si] = stack.back();
-    stack.pop_back();
-    uint32_t cur = si;
+  std::vector<std::pair<uint32_t, uint32_t>> stack;  // (end of the subtree, allele state below it)
+  for (uint32_t i = 0; i < d.n_nodes; ++i) {
+    while (!stack.empty() && stack.back().first <= i) stack.pop_back();
+    uint32_t cur = stack.empty() ? 0u : stack.back().second;
     bool own = false;
     auto make_own = [&]() {
       if (!own) {
@@ -106,21 +148,20 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
         own = true;
       }
     };
-    for (uint32_t i = w.node_ev_off[v]; i < w.node_ev_off[v + 1]; ++i) {
-      uint64_t e = w.ev[i];
-      if (d.ev_kind[e] == PCS_EV_CNA_AMP) {
+    for (uint32_t k = w.ev_off[i]; k < w.ev_off[i + 1]; ++k) {
+      const Ev& e = w.ev[k];
+      if (e.kind == PCS_EV_CNA_AMP) {
         const auto& ids = pool[cur].ids;
-        if (!std::binary_search(ids.begin(), ids.end(), d.ev_allele[e])) continue;
-        uint16_t dest = d.ev_dest[e];
-        check(!std::binary_search(ids.begin(), ids.end(), dest), "amplification destination allele exists");
+        if (!std::binary_search(ids.begin(), ids.end(), e.allele)) continue;
+        check(!std::binary_search(ids.begin(), ids.end(), e.dest), "amplification destination allele exists");
         make_own();
         auto& mid = pool[cur].ids;
-        mid.insert(std::upper_bound(mid.begin(), mid.end(), dest), dest);
-        pool[cur].next = std::max<uint32_t>(pool[cur].next, dest + 1u);
-      } else if (d.ev_kind[e] == PCS_EV_WGD) {
+        mid.insert(std::upper_bound(mid.begin(), mid.end(), e.dest), e.dest);
+        pool[cur].next = std::max<uint32_t>(pool[cur].next, e.dest + 1u);
+      } else if (e.kind == PCS_EV_WGD) {
         make_own();
         std::vector<uint16_t> snapshot = pool[cur].ids;
-        auto& m = w.wgd_map[e];
+        auto& m = w.wgd_map[e.x];
         for (uint16_t a : snapshot) {
           check(pool[cur].next < 65535, "allele id overflow");
           uint16_t nd = static_cast<uint16_t>(pool[cur].next++);
@@ -130,7 +171,7 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
         }
       }
     }
-    for (uint32_t c = t.child_off[v]; c < t.child_off[v + 1]; ++c) stack.emplace_back(t.child_idx[c], cur);
+    if (t.pre_end[i] > i + 1) stack.emplace_back(t.pre_end[i], cur);
   }
 }
 
@@ -141,15 +182,22 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   const uint32_t clen = d.chr_len[chr];
   const uint8_t n0 = d.chr_n_alleles[chr];
   check(n0 >= 1 && n0 <= 2, "chr_n_alleles must be 1 or 2");
+  gather_events(d, t, w);
   if (w.has_wgd) wgd_prepass(d, t, w);
 
   const uint32_t full = w.intern_set(FragKey{{1u, clen}});
   uint32_t counter = 0;
   uint32_t* germ_lo = w.germ_lo;
   uint32_t* germ_hi = w.germ_hi;
+  const uint32_t* ev_off = w.ev_off.data();
+  const uint32_t* pre_end = t.pre_end.data();
+  const int64_t* pre_leaf = t.pre_leaf.data();
 
   struct Frame {
-    uint32_t node, fragset, ev_i, child_i, open_base;
+    uint32_t node;        // preorder position
+    uint32_t fragset, ev_i;
+    uint32_t next_child;  // preorder position of the next child to walk; == pre_end[node]: none left
+    uint32_t open_base;
     uint16_t allele;
     bool root_base, preneo_done, leaf_done;
   };
@@ -160,9 +208,9 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
     germ_lo[g] = counter;
     w.haps.push_back({0u, full, g, HAP_NORMAL_PLAIN});
     ++counter;
-    for (uint32_t ri = 0; ri < t.roots.size(); ++ri) {
-      uint32_t r = t.roots[ri];
-      stack.push_back({r, full, w.node_ev_off[r], 0u, static_cast<uint32_t>(open.size()), g, true, false, false});
+    for (uint32_t ri = 0; ri < t.root_pos.size(); ++ri) {
+      const uint32_t r = t.root_pos[ri];
+      stack.push_back({r, full, ev_off[r], r + 1, static_cast<uint32_t>(open.size()), g, true, false, false});
       while (!stack.empty()) {
         Frame& f = stack.back();
         const uint32_t v = f.node;
@@ -171,40 +219,32 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
           w.haps.push_back({ri, f.fragset, f.allele, HAP_NORMAL_PRENEO});
           ++counter;
         };
-        if (f.ev_i < w.node_ev_off[v + 1]) {
-          uint64_t e = w.ev[f.ev_i++];
-          uint8_t kind = d.ev_kind[e];
-          if (f.root_base && !f.preneo_done &&
-              !(kind == PCS_EV_SID && d.ev_nature[e] == PCS_NATURE_PRENEOPLASTIC))
+        if (f.ev_i < ev_off[v + 1]) {
+          const Ev e = w.ev[f.ev_i++];
+          if (f.root_base && !f.preneo_done && !(e.kind == PCS_EV_SID && e.nature == PCS_NATURE_PRENEOPLASTIC))
             preneo_leaf();
-          if (kind == PCS_EV_WGD) {
-            auto it = w.wgd_map.find(e);
+          if (e.kind == PCS_EV_WGD) {
+            auto it = w.wgd_map.find(e.x);
             if (it == w.wgd_map.end()) continue;
             for (const auto& [a, nd] : it->second)
               if (a == f.allele) {
-                Frame nf{v, f.fragset, f.ev_i, 0u, static_cast<uint32_t>(open.size()), nd, false, true, false};
+                Frame nf{v, f.fragset, f.ev_i, v + 1, static_cast<uint32_t>(open.size()), nd, false, true, false};
                 stack.push_back(nf);  // invalidates f; loop re-reads the top
                 break;
               }
             continue;
           }
-          if (d.ev_allele[e] != f.allele) continue;
-          if (kind == PCS_EV_SID) {
-            uint32_t m = d.ev_mut[e];
-            check(m < d.n_mut && d.mut_chr[m] == chr, "SID event names a row of another chromosome");
-            if (holds(w.fragsets[f.fragset], d.mut_pos[m])) {
+          if (e.allele != f.allele) continue;
+          if (e.kind == PCS_EV_SID) {
+            if (holds(w.fragsets[f.fragset], e.y)) {
               open.push_back(static_cast<uint32_t>(w.inst.size()));
-              w.inst.push_back({counter, 0u, m,
-                                static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8)});
+              w.inst.push_back({counter, 0u, e.x, e.meta});
             }
-          } else if (kind == PCS_EV_CNA_DEL) {
-            check(d.ev_len[e] >= 1, "CNA length must be positive");
-            f.fragset = w.intern_set(remove_range(w.fragsets[f.fragset], d.ev_pos[e],
-                                                  d.ev_pos[e] + d.ev_len[e] - 1, clen));
-          } else if (kind == PCS_EV_CNA_AMP) {
-            check(d.ev_len[e] >= 1, "CNA length must be positive");
-            uint32_t fs = w.intern_set(clip(w.fragsets[f.fragset], d.ev_pos[e], d.ev_pos[e] + d.ev_len[e] - 1));
-            Frame nf{v, fs, f.ev_i, 0u, static_cast<uint32_t>(open.size()), d.ev_dest[e], false, true, false};
+          } else if (e.kind == PCS_EV_CNA_DEL) {
+            f.fragset = w.intern_set(remove_range(w.fragsets[f.fragset], e.x, e.x + e.y - 1, clen));
+          } else if (e.kind == PCS_EV_CNA_AMP) {
+            uint32_t fs = w.intern_set(clip(w.fragsets[f.fragset], e.x, e.x + e.y - 1));
+            Frame nf{v, fs, f.ev_i, v + 1, static_cast<uint32_t>(open.size()), e.dest, false, true, false};
             stack.push_back(nf);
           } else {
             throw std::domain_error("unknown event kind");
@@ -212,18 +252,19 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
           continue;
         }
         if (f.root_base && !f.preneo_done) preneo_leaf();
-        const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
-        const bool dead = w.fragsets[f.fragset].empty();  // no DNA left: nothing below can be read
-        if (nc == 0 && !f.leaf_done) {
+        const uint32_t end = pre_end[v];
+        const bool dead = w.fs_empty[f.fragset] != 0;  // no DNA left: nothing below can be read
+        if (end == v + 1 && !f.leaf_done) {
           f.leaf_done = true;
-          if (t.node_leaf[v] >= 0 && !dead) {
-            w.haps.push_back({static_cast<uint32_t>(t.node_leaf[v]), f.fragset, f.allele, HAP_TUMOUR});
+          if (pre_leaf[v] >= 0 && !dead) {
+            w.haps.push_back({static_cast<uint32_t>(pre_leaf[v]), f.fragset, f.allele, HAP_TUMOUR});
             ++counter;
           }
         }
-        if (!dead && f.child_i < nc) {
-          uint32_t c = t.child_idx[t.child_off[v] + f.child_i++];
-          Frame nf{c, f.fragset, w.node_ev_off[c], 0u, static_cast<uint32_t>(open.size()), f.allele, false, true, false};
+        if (!dead && f.next_child < end) {
+          const uint32_t c = f.next_child;
+          f.next_child = pre_end[c];
+          Frame nf{c, f.fragset, ev_off[c], c + 1, static_cast<uint32_t>(open.size()), f.allele, false, true, false};
           stack.push_back(nf);
           continue;
         }
@@ -334,6 +375,36 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     t.node_leaf[d.leaf_node[l]] = l;
   }
 
+  // preorder layout
+  {
+    const uint32_t n = d.n_nodes;
+    t.pre_node.resize(n);
+    t.pre_end.resize(n);
+    t.pre_leaf.resize(n);
+    std::vector<uint32_t> pos_of(n);
+    std::vector<uint32_t> stack;
+    uint32_t next = 0;
+    for (uint32_t r : t.roots) {
+      t.root_pos.push_back(next);
+      stack.push_back(r);
+      while (!stack.empty()) {
+        const uint32_t v = stack.back();
+        stack.pop_back();
+        pos_of[v] = next;
+        t.pre_node[next] = v;
+        t.pre_leaf[next] = t.node_leaf[v];
+        ++next;
+        for (uint32_t c = t.child_off[v + 1]; c > t.child_off[v]; --c) stack.push_back(t.child_idx[c - 1]);  // smallest on top
+      }
+    }
+    check(next == n, "internal: preorder does not cover the tree");
+    // subtree ends: a node's subtree ends where its last child's does; children come after their parent
+    for (uint32_t i = n; i-- > 0;) {
+      const uint32_t v = t.pre_node[i];
+      const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
+      t.pre_end[i] = nc ? t.pre_end[pos_of[t.child_idx[t.child_off[v + 1] - 1]]] : i + 1;
+    }
+  }
   timer.lap("cell tree");
   n_threads = std::max(1u, n_threads);
   // run fn(task) for task in [0, n_tasks) on up to n_threads threads; the first exception is rethrown
@@ -436,36 +507,36 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     out.chr_locus_off[c] = chr_row_off[c] < d.n_mut ? out.row_locus[chr_row_off[c]] : n_loci;
 
   timer.lap("loci");
-  // ---- events by chromosome (node-major order is preserved)
+  // ---- events: validated here in chunks; every chromosome gathers its own in walk order (flatten_chr)
   std::vector<ChrWork> work(d.n_chr);
-  for (uint32_t c = 0; c < d.n_chr; ++c) {
-    work[c].chr = c;
-    work[c].node_ev_off.assign(d.n_nodes + 1, 0);
-  }
+  for (uint32_t c = 0; c < d.n_chr; ++c) work[c].chr = c;
   check(d.node_event_off[0] == 0 && d.node_event_off[d.n_nodes] == d.n_events, "node_event_off is not a CSR of the events");
-  for (uint32_t v = 0; v < d.n_nodes; ++v) {
+  check(d.n_events <= 0xffffffffull, "too many events");
+  for (uint32_t v = 0; v < d.n_nodes; ++v)
     check(d.node_event_off[v] <= d.node_event_off[v + 1], "node_event_off must be non-decreasing");
-    for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
-      if (d.ev_kind[e] == PCS_EV_WGD) {
-        for (auto& w : work) {
-          w.ev.push_back(e);
-          w.has_wgd = true;
-        }
-      } else {
-        check(d.ev_kind[e] <= PCS_EV_CNA_DEL, "unknown event kind");
+  const uint32_t e_chunks = d.n_events ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (d.n_events + 65535) / 65536)) : 0;
+  std::vector<uint64_t> chr_events(static_cast<size_t>(d.n_chr) * std::max(1u, e_chunks), 0);
+  parallel_for(e_chunks, [&](uint32_t k) {
+    const uint64_t lo = d.n_events * k / e_chunks, hi = d.n_events * (k + 1) / e_chunks;
+    std::vector<uint64_t> cnt(d.n_chr, 0);
+    for (uint64_t e = lo; e < hi; ++e) {
+      check(d.ev_kind[e] <= PCS_EV_WGD, "unknown event kind");
+      if (d.ev_kind[e] != PCS_EV_WGD) {
         check(d.ev_chr[e] < d.n_chr, "event chromosome out of range");
-        work[d.ev_chr[e]].ev.push_back(e);
+        ++cnt[d.ev_chr[e]];
       }
     }
-    for (auto& w : work) w.node_ev_off[v + 1] = static_cast<uint32_t>(w.ev.size());
-  }
-
-  timer.lap("events by chromosome");
+    std::copy(cnt.begin(), cnt.end(), chr_events.begin() + static_cast<size_t>(k) * d.n_chr);
+  });
+  std::vector<uint64_t> chr_load(d.n_chr, 0);
+  for (uint32_t k = 0; k < e_chunks; ++k)
+    for (uint32_t c = 0; c < d.n_chr; ++c) chr_load[c] += chr_events[static_cast<size_t>(k) * d.n_chr + c];
+  timer.lap("events checked");
   // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
   std::vector<uint32_t> chr_order(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
   std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
-    return work[a].ev.size() != work[b].ev.size() ? work[a].ev.size() > work[b].ev.size() : a < b;
+    return chr_load[a] != chr_load[b] ? chr_load[a] > chr_load[b] : a < b;
   });
   parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]]); });
   timer.lap("haplotype numbering");
