@@ -234,3 +234,42 @@ def test_parameter_validation_messages():
         fl.plan(make_params(sequencer=9))
     info, _ = fl.plan(make_params(normal_only=1, purity=7.0))  # purity is ignored for the normal sample
     assert info.n_out_samples == 1
+
+
+_THREAD_PROBE = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from conftest import make_params, small_spec
+from process_b200 import _abi as A, _lib as L
+from process_b200.synth import synth_forest
+# > 65 536 rows: the row passes of the flattener run in several chunks
+f = synth_forest(small_spec(2, chr_len=[30_000_000, 20_000_000, 12_000_000], germline_density=3e-3, sample_cells=[10, 12, 9],
+                            node_snv_mean=40, cna_len=(100000, 5000000)))
+fl = L.Flat(f)
+h = hashlib.sha256(repr(sorted(fl.info().items())).encode())
+rng = np.random.default_rng(0)
+for c in range(f.n_chr):
+    for l in rng.choice(f.n_leaves, 4, replace=False):
+        for a, hp, fs in fl.cell_haps(A.PCS_PLACE_TUMOUR, int(l), c):
+            h.update(np.asarray(fl.hap_rows(c, hp)).tobytes())
+            h.update(repr((a, hp, fs, fl.fragset(fs))).encode())
+info, tiles = fl.plan(make_params(coverage=20.0), cap=1 << 22)
+for k in sorted(tiles):
+    h.update(tiles[k].tobytes())
+print(f.n_mut, info.n_tiles_total, info.n_templates_total, h.hexdigest())
+"""
+
+
+def test_flat_view_and_plan_do_not_depend_on_the_number_of_host_threads():
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, PCS_HOST_THREADS=nt)
+        r = subprocess.run([sys.executable, "-c", _THREAD_PROBE, root], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert int(outs[0].split()[0]) > 130_000 and outs[0] == outs[1] == outs[2], outs
