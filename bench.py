@@ -131,6 +131,14 @@ def cpu_sample_params(forest, workload_params, budget_reads):
     return make_params(chr_mask=mask, **kw), desc
 
 
+def workload_name(args):
+    """config.workload of the JSON line: the same words in both arms"""
+    if args.workload == "C3" and args.sequencer == "errorless" and not args.insert_size:
+        return (f"{args.workload}: BASELINE.json configs[2], GRCh38-length genome, 3 tumour samples x "
+                "1000 cells + normal_sample, 80x WGS, read_size 150, ErrorlessIlluminaSequencer")
+    return f"{args.workload} sequencer={args.sequencer} error_rate={args.error_rate} insert={args.insert_size}"
+
+
 def run_reference(args, forest, wl_params):
     import oracle
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +160,7 @@ def run_reference(args, forest, wl_params):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": args.workload, "note": "CPU oracle (port of the RACES@1142937 semantics; the reference "
+        "config": {"workload": workload_name(args), "note": "CPU oracle (port of the RACES@1142937 semantics; the reference "
                    "itself cannot be built here), bounded sample"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -412,10 +420,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE.json configs[2], GRCh38-length genome, 3 tumour samples x "
-                                   "1000 cells + normal_sample, 80x WGS, read_size 150, ErrorlessIlluminaSequencer"
-                       if args.workload == "C3" and args.sequencer == "errorless" and not args.insert_size
-                       else f"{args.workload} sequencer={args.sequencer} error_rate={args.error_rate} insert={args.insert_size}",
+            "config": {"workload": workload_name(args),
                        "samples": S, "rows": M, "reads_per_step": total_reads / args.steps,
                        "tiles_this_rank": int(plan.info.n_tiles), "parallelism": f"tile-sharded x{world}",
                        "exchange": {"none": "single GPU", "peer": "sampler flush adds into rank 0's tables over NVLink "
