@@ -373,3 +373,86 @@ def simulate_normal_seq(phylo_forest, sequencer=None, reference_genome=None, chr
                       template_name_prefix=template_name_prefix,
                       include_non_sequenced_mutations=include_non_sequenced_mutations, seed=c_seed)
     return {"mutations": df, "parameters": parameters, "_stats": st.as_dict()}
+
+
+# --------------------------------------------------------------------------- downstream data formats
+# The R helpers that take simulate_seq()'s result apart.  They never touch the sampler: they are
+# here so that the column contract of the result ("<sample>.occurrences/.coverage/.VAF", row identity
+# (chr, chr_pos, ref, alt)) is exercised by the same code a user of the reference would run next.
+
+def _mutations_frame(seq_results):
+    """a result list is reduced to its "mutations" field (R/seq_to_long.R:34-41)"""
+    if isinstance(seq_results, dict) and "mutations" in seq_results:
+        return seq_results["mutations"]
+    return seq_results
+
+
+def seq_to_long(seq_results):
+    """Wide result -> long format, one block of rows per sample in column order (R/seq_to_long.R:31-67).
+
+    Samples are the columns ending in ".VAF"; per sample the three columns "<sample>.occurrences",
+    "<sample>.coverage", "<sample>.VAF" become NV, DP, VAF.  Columns of the result: chr, from, ref, alt, causes,
+    classes, NV, DP, VAF, sample_name, to (to == from)."""
+    import pandas as pd
+    df = _mutations_frame(seq_results)
+    samples = [c[:-len(".VAF")] for c in df.columns if c.endswith(".VAF")]
+    fixed = ["chr", "chr_pos", "ref", "alt", "causes", "classes"]
+    blocks = []
+    for sn in samples:
+        cols = [f"{sn}.occurrences", f"{sn}.coverage", f"{sn}.VAF"]
+        missing = [c for c in fixed + cols if c not in df.columns]
+        if missing:
+            raise ValueError(f"seq_to_long: column(s) {', '.join(missing)} missing from the sequencing result")
+        b = df[fixed + cols].copy()
+        b.columns = ["chr", "from", "ref", "alt", "causes", "classes", "NV", "DP", "VAF"]
+        b["sample_name"] = sn
+        blocks.append(b)
+    if not blocks:
+        out = pd.DataFrame({k: [] for k in ["chr", "from", "ref", "alt", "causes", "classes", "NV", "DP", "VAF", "sample_name"]})
+    else:
+        out = pd.concat(blocks, ignore_index=True)
+    out["to"] = out["from"]
+    return out
+
+
+def _validate_chromosomes(df, chromosomes):
+    """R/ggplot_config.R:75-94"""
+    present = list(dict.fromkeys(df["chr"].tolist()))
+    if chromosomes is None:
+        return present
+    chromosomes = [chromosomes] if isinstance(chromosomes, str) else list(chromosomes)
+    unknown = [c for c in chromosomes if c not in present]
+    if unknown:
+        names = ", ".join(map(str, unknown))
+        msg = f"The chromosomes {names} are" if len(unknown) > 1 else f"The chromosome {names} is"
+        raise ValueError(msg + " not present in the sequence reference data.")
+    return chromosomes
+
+
+def get_seq_data(seq_res, sample, chromosomes=None):
+    """{"tumour": long rows of `sample`, "normal": long rows of "normal_sample"}, restricted to `chromosomes`
+    (R/plot_genome_wide_mutations.R:3-19)."""
+    df = _mutations_frame(seq_res)
+    chromosomes = _validate_chromosomes(df, chromosomes)
+    data = seq_to_long(df)
+    data = data[data["chr"].isin(chromosomes)]
+    available = list(dict.fromkeys(data["sample_name"].tolist()))
+    if sample not in available:
+        raise ValueError("Inserted 'sample' is not available, available samples are: " + ", ".join(available))
+    return {"tumour": data[data["sample_name"] == sample].reset_index(drop=True),
+            "normal": data[data["sample_name"] == "normal_sample"].reset_index(drop=True)}
+
+
+def depth_ratio(seq_result, sample, chromosomes=None):
+    """The table behind plot_DR(): tumour rows joined with the normal sample on (chr, from, ref, alt),
+    DR = DP.tumour / DP.normal (R/plot_genome_wide_mutations.R:75-108; the subsampling to N points and the
+    plot itself are not rebuilt)."""
+    df = _mutations_frame(seq_result)
+    need = ["normal_sample.occurrences", "normal_sample.coverage", "normal_sample.VAF"]
+    if not all(c in df.columns for c in need):
+        raise ValueError('The parameter "seq_result" does not contain the mandatory normal sample "normal_sample".')
+    data = get_seq_data(df, sample, chromosomes)
+    d = data["tumour"].merge(data["normal"], on=["chr", "from", "ref", "alt"], how="left", suffixes=(".tumour", ".normal"))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        d["DR"] = d["DP.tumour"].to_numpy(np.float64) / d["DP.normal"].to_numpy(np.float64)
+    return d

@@ -86,3 +86,52 @@ def test_vectorised_labelling_equals_per_cell_labelling():
         api._apply_FACS_labels(f, api.VectorisedLabelling(lambda cols: np.arange(f.n_leaves)))
     with pytest.raises(ValueError, match="must be a function"):
         api.VectorisedLabelling(3)
+
+
+def _wide_example():
+    """the data frame of the reference's own example, R/seq_to_long.R:14-26"""
+    import pandas as pd
+    return pd.DataFrame({
+        "chr": ["chr1", "chr2"], "chr_pos": [100, 200], "ref": ["A", "C"], "alt": ["T", "G"],
+        "causes": ["SBS5", "SBS1"], "classes": ["germinal", "passneger"],
+        "Sample.A.occurrences": [10, 90], "Sample.A.coverage": [100, 100], "Sample.A.VAF": [0.1, 0.9],
+        "normal_sample.occurrences": [45, 52], "normal_sample.coverage": [100, 100], "normal_sample.VAF": [0.45, 0.52]})
+
+
+def test_seq_to_long_on_the_reference_example():
+    """wide -> long as R/seq_to_long.R:31-67 does it: samples found by the ".VAF" suffix, one block per sample in
+    column order, occurrences/coverage renamed NV/DP, chr_pos renamed from, to == from"""
+    wide = _wide_example()
+    long = api.seq_to_long(wide)
+    assert list(long.columns) == ["chr", "from", "ref", "alt", "causes", "classes", "NV", "DP", "VAF", "sample_name", "to"]
+    assert long["sample_name"].tolist() == ["Sample.A", "Sample.A", "normal_sample", "normal_sample"]
+    assert long["NV"].tolist() == [10, 90, 45, 52] and long["DP"].tolist() == [100] * 4
+    assert long["VAF"].tolist() == [0.1, 0.9, 0.45, 0.52]
+    assert long["from"].tolist() == [100, 200, 100, 200] == long["to"].tolist()
+    assert long["chr"].tolist() == ["chr1", "chr2"] * 2 and long["classes"].tolist() == ["germinal", "passneger"] * 2
+    # a result list is reduced to its "mutations" field
+    assert api.seq_to_long({"mutations": wide, "parameters": {}}).equals(long)
+    with pytest.raises(ValueError, match="Sample.A.coverage"):
+        api.seq_to_long(wide.drop(columns=["Sample.A.coverage"]))
+    assert len(api.seq_to_long(wide[["chr", "chr_pos", "ref", "alt", "causes", "classes"]])) == 0
+
+
+def test_get_seq_data_and_depth_ratio_follow_the_plot_helpers():
+    """R/plot_genome_wide_mutations.R:3-19, 90-108 and R/ggplot_config.R:75-94"""
+    wide = _wide_example()
+    d = api.get_seq_data(wide, "Sample.A")
+    assert d["tumour"]["NV"].tolist() == [10, 90] and d["normal"]["NV"].tolist() == [45, 52]
+    d = api.get_seq_data(wide, "Sample.A", chromosomes=["chr2"])
+    assert d["tumour"]["from"].tolist() == [200] and d["normal"]["from"].tolist() == [200]
+    with pytest.raises(ValueError, match="The chromosome chr9 is not present in the sequence reference data."):
+        api.get_seq_data(wide, "Sample.A", chromosomes=["chr1", "chr9"])
+    with pytest.raises(ValueError, match="The chromosomes chr8, chr9 are not present"):
+        api.get_seq_data(wide, "Sample.A", chromosomes=["chr8", "chr9"])
+    with pytest.raises(ValueError, match="available samples are: Sample.A, normal_sample"):
+        api.get_seq_data(wide, "Sample.B")
+    wide["Sample.A.coverage"] = [150, 50]
+    dr = api.depth_ratio({"mutations": wide}, "Sample.A")
+    assert dr["DR"].tolist() == [1.5, 0.5]
+    assert {"DP.tumour", "DP.normal", "VAF.tumour", "VAF.normal", "NV.tumour", "NV.normal"} <= set(dr.columns)
+    with pytest.raises(ValueError, match='mandatory normal sample "normal_sample"'):
+        api.depth_ratio(wide.drop(columns=["normal_sample.VAF"]), "Sample.A")
