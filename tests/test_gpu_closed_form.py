@@ -1,0 +1,37 @@
+"""The GPU sampler against CLOSED-FORM expectations (tests/closed_form.py) instead of against the oracle's
+Monte Carlo: E[depth] and E[occurrences] of every (sample, row) from the explicit genomes.
+
+Written in round 1 after the GPU budget was spent, so it has never run on a B200: it is skipped unless
+PCS_EXTRA_GPU_TESTS=1 until one run has confirmed it (its CPU twin, on the oracle, is
+test_oracle_golden.py::test_oracle_matches_closed_form_expectations)."""
+import os
+
+import numpy as np
+import pytest
+
+from process_b200 import _lib as L
+from process_b200.synth import synth_forest
+
+from conftest import make_params
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PCS_EXTRA_GPU_TESTS") != "1", reason="not yet confirmed on a B200 (set PCS_EXTRA_GPU_TESTS=1)")]
+
+
+@pytest.mark.parametrize("purity", [0.7, 1.0])
+def test_sampler_matches_closed_form_expectations(purity):
+    import closed_form as CF
+    f = synth_forest(CF.snv_only_spec())
+    coverage, R = 3000.0, 100
+    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R)
+    ctx = L.Context(0)
+    dev = L.Forest(ctx, f)
+    occ, cov, st = dev.simulate(make_params(coverage=coverage, purity=purity, read_size=R, seed=11))
+    dev.close()
+    ctx.close()
+    assert st.n_reads > 1_000_000
+    for obs, exp in ((cov, e_cov), (occ, e_occ)):
+        z, impossible = CF.z_scores(obs, exp)
+        assert impossible == 0
+        assert len(z) > 1500 and abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.5
+        assert abs(obs.sum() / exp.sum() - 1) < 2e-3

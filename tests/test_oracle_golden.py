@@ -128,3 +128,23 @@ def test_oracle_rejects_malformed_input():
         oracle.count_injected(f, 1, 10, bad)
     with pytest.raises(oracle.OracleError):
         oracle.simulate(f, make_params(insert_size_mean=10, insert_size_stddev=10))  # sd^2 > mean
+
+
+@pytest.mark.parametrize("purity", [0.7, 1.0])
+def test_oracle_matches_closed_form_expectations(purity):
+    """E[depth] and E[occurrences] of every (sample, row), written down in closed form from the explicit genomes
+    (tests/closed_form.py: amplified, deleted and WGD-doubled alleles, purity, the normal sample, reads that fall
+    off a fragment end), against a 3000x oracle run: Poisson z-scores centred, unit variance, no outlier, and
+    nothing counted where the expectation is exactly zero"""
+    import closed_form as CF
+    f = synth_forest(CF.snv_only_spec())
+    assert (f.ev_kind == A.PCS_EV_WGD).sum() >= 1 and (f.ev_kind == A.PCS_EV_CNA_AMP).sum() >= 1 and \
+        (f.ev_kind == A.PCS_EV_CNA_DEL).sum() >= 1
+    coverage, R = 3000.0, 100
+    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R)
+    r = oracle.simulate(f, make_params(coverage=coverage, purity=purity, read_size=R, seed=11), n_threads=4)
+    for obs, exp in ((r["cov"], e_cov), (r["occ"], e_occ)):
+        z, impossible = CF.z_scores(obs, exp)
+        assert impossible == 0
+        assert len(z) > 1500 and abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.0
+        assert abs(obs.sum() / exp.sum() - 1) < 2e-3
