@@ -130,11 +130,11 @@ def test_oracle_rejects_malformed_input():
         oracle.simulate(f, make_params(insert_size_mean=10, insert_size_stddev=10))  # sd^2 > mean
 
 
-@pytest.mark.parametrize("purity", [0.7, 1.0])
-def test_oracle_matches_closed_form_expectations(purity):
+@pytest.mark.parametrize("purity,error_rate", [(0.7, 0.0), (1.0, 0.0), (0.7, 0.1)])
+def test_oracle_matches_closed_form_expectations(purity, error_rate):
     """E[depth] and E[occurrences] of every (sample, row), written down in closed form from the explicit genomes
     (tests/closed_form.py: amplified, deleted and WGD-doubled alleles, purity, the normal sample, reads that fall
-    off a fragment end), against a 3000x oracle run: Poisson z-scores centred, unit variance, no outlier, and
+    off a fragment end, constant-quality sequencing errors), against a 3000x oracle run: Poisson z-scores centred, unit variance, no outlier, and
     nothing counted where the expectation is exactly zero"""
     import closed_form as CF
     f = synth_forest(CF.snv_only_spec())
@@ -142,8 +142,10 @@ def test_oracle_matches_closed_form_expectations(purity):
         (f.ev_kind == A.PCS_EV_CNA_DEL).sum() >= 1
     coverage, R = 3000.0, 100
     e_cov, e_occ = CF.expected_tables(f, coverage, purity, R)
-    r = oracle.simulate(f, make_params(coverage=coverage, purity=purity, read_size=R, seed=11), n_threads=4)
-    for obs, exp in ((r["cov"], e_cov), (r["occ"], e_occ)):
+    kw = dict(sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=error_rate) if error_rate else {}
+    r = oracle.simulate(f, make_params(coverage=coverage, purity=purity, read_size=R, seed=11, **kw), n_threads=4)
+    # constant-quality errors: an SNV occurrence survives with probability 1 - error_rate; depth is unaffected
+    for obs, exp in ((r["cov"], e_cov), (r["occ"], e_occ * (1 - error_rate))):
         z, impossible = CF.z_scores(obs, exp)
         assert impossible == 0
         assert len(z) > 1500 and abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.0
