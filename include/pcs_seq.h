@@ -208,7 +208,9 @@ enum {
 int pcs_abi_version(void);
 const char* pcs_last_error(void);
 
-/* one context per GPU; `stream` is a cudaStream_t (NULL = a stream owned by the context) */
+/* one context per GPU; `stream` is a cudaStream_t (NULL = a stream owned by the context).
+ * Lifetime: free every forest (pcs_forest_free) and plan (pcs_plan_free) made on a context before
+ * pcs_destroy; a forest hands the pinned block its tables were built in back to its context. */
 int pcs_create(pcs_ctx** ctx, int device_id, void* stream);
 int pcs_destroy(pcs_ctx* ctx);
 int pcs_device_name(pcs_ctx* ctx, char* buf, size_t buf_len);
