@@ -12,6 +12,7 @@ through libpcs_seq.so; there is no CPU path.
 from __future__ import annotations
 
 import os
+import atexit
 import weakref
 from dataclasses import dataclass
 
@@ -226,6 +227,11 @@ def release_device_cache():
     for c in _ctx_cache.values():
         c.close()
     _ctx_cache.clear()
+
+
+# forests before their contexts, also when the interpreter exits with the cache still populated
+# (include/pcs_seq.h: lifetime rule of pcs_destroy)
+atexit.register(release_device_cache)
 
 
 def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, params=None):
