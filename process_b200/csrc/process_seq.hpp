@@ -18,6 +18,7 @@
 #include <map>
 #include <memory>
 #include <optional>
+#include <ostream>
 #include <random>
 #include <set>
 #include <stdexcept>
@@ -33,6 +34,8 @@ namespace process_b200 {
 class ErrorlessIlluminaSequencer {
  public:
   double get_error_rate() const { return 0; }
+  // show(): src/sequencers.cpp:25-31 (model and platform names are RACES'; "[UNVERIFIED-RACES]" wording)
+  void show(std::ostream& os) const { os << "Errorless Illumina (platform: \"ILLUMINA\")" << std::endl; }
 };
 
 class BasicIlluminaSequencer {
@@ -50,6 +53,11 @@ class BasicIlluminaSequencer {
   void set_error_rate(const double& e) { error_rate = e; }
   const bool& producing_random_scores() const { return random_quality_scores; }
   void set_random_scores(const bool& r) { random_quality_scores = r; }
+  // show(): src/sequencers.cpp:44-78
+  void show(std::ostream& os) const {
+    os << "Basic Illumina (platform: \"ILLUMINA\" error rate: " << std::to_string(error_rate)
+       << (random_quality_scores ? " random quality scores" : " constant quality scores") << ")" << std::endl;
+  }
 };
 
 // sequencer = NULL | ErrorlessIlluminaSequencer | BasicIlluminaSequencer (src/seq_simulation.cpp:386-428)

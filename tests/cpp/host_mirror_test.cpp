@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <sstream>
 
 #include "../../process_b200/csrc/process_seq.hpp"
 
@@ -75,6 +76,13 @@ int main(int argc, char** argv) {
     ok &= b.get_error_rate() == 4e-3 && b.producing_random_scores();
     b.set_random_scores(false);
     ok &= !b.producing_random_scores() && ErrorlessIlluminaSequencer().get_error_rate() == 0;
+    {
+      std::ostringstream os;
+      b.show(os);
+      ErrorlessIlluminaSequencer().show(os);
+      ok &= os.str() == "Basic Illumina (platform: \"ILLUMINA\" error rate: 0.004000 constant quality scores)\n"
+                        "Errorless Illumina (platform: \"ILLUMINA\")\n";
+    }
     std::vector<uint32_t> groups;
     std::vector<std::string> names;
     LabellingFunction lab = [](const SampledCell& c) { return c.cell_id == 1 ? std::string("") : std::string("B"); };
