@@ -98,33 +98,6 @@ struct ChrWork {
   }
 };
 
-// events of chromosome w.chr (and every WGD) in walk order, with what the walk needs of the rows they name
-void gather_events(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
-  const uint32_t n = d.n_nodes, chr = w.chr;
-  w.ev_off.assign(static_cast<size_t>(n) + 1, 0);
-  for (uint32_t i = 0; i < n; ++i) {
-    const uint32_t v = t.pre_node[i];
-    for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
-      const uint8_t kind = d.ev_kind[e];
-      if (kind == PCS_EV_WGD) {
-        w.has_wgd = true;
-        w.ev.push_back({static_cast<uint32_t>(e), 0u, 0u, 0, 0, kind, d.ev_nature[e]});
-      } else if (d.ev_chr[e] == chr) {
-        if (kind == PCS_EV_SID) {
-          const uint32_t m = d.ev_mut[e];
-          check(m < d.n_mut && d.mut_chr[m] == chr, "SID event names a row of another chromosome");
-          w.ev.push_back({m, d.mut_pos[m], static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8),
-                          d.ev_allele[e], 0, kind, d.ev_nature[e]});
-        } else {
-          check(d.ev_len[e] >= 1, "CNA length must be positive");
-          w.ev.push_back({d.ev_pos[e], d.ev_len[e], 0u, d.ev_allele[e], d.ev_dest[e], kind, d.ev_nature[e]});
-        }
-      }
-    }
-    w.ev_off[i + 1] = static_cast<uint32_t>(w.ev.size());
-  }
-}
-
 // which allele ids exist where: only needed to give WGD copies their ids
 void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   struct AState {
@@ -182,7 +155,15 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   const uint32_t clen = d.chr_len[chr];
   const uint8_t n0 = d.chr_n_alleles[chr];
   check(n0 >= 1 && n0 <= 2, "chr_n_alleles must be 1 or 2");
-  gather_events(d, t, w);
+  // what the walk needs of the rows the SID events name; here and not where the events were dealt out, because
+  // the rows of one chromosome are a few MB of the mutation table, and those of all of them are not
+  for (Ev& e : w.ev)
+    if (e.kind == PCS_EV_SID) {
+      const uint32_t m = e.x;
+      check(m < d.n_mut && d.mut_chr[m] == chr, "SID event names a row of another chromosome");
+      e.y = d.mut_pos[m];
+      e.meta = static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8);
+    }
   if (w.has_wgd) wgd_prepass(d, t, w);
 
   const uint32_t full = w.intern_set(FragKey{{1u, clen}});
@@ -507,31 +488,75 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     out.chr_locus_off[c] = chr_row_off[c] < d.n_mut ? out.row_locus[chr_row_off[c]] : n_loci;
 
   timer.lap("loci");
-  // ---- events: validated here in chunks; every chromosome gathers its own in walk order (flatten_chr)
+  // ---- events: validated and dealt to their chromosomes in WALK order (by preorder position of the node, then
+  // in the node's own order), with what the walk needs of the rows they name.  One counting pass and one filling
+  // pass over chunks of preorder positions: every event is read twice, whatever the number of chromosomes; a
+  // WGD goes to every chromosome.
   std::vector<ChrWork> work(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) work[c].chr = c;
   check(d.node_event_off[0] == 0 && d.node_event_off[d.n_nodes] == d.n_events, "node_event_off is not a CSR of the events");
   check(d.n_events <= 0xffffffffull, "too many events");
   for (uint32_t v = 0; v < d.n_nodes; ++v)
     check(d.node_event_off[v] <= d.node_event_off[v + 1], "node_event_off must be non-decreasing");
-  const uint32_t e_chunks = d.n_events ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (d.n_events + 65535) / 65536)) : 0;
-  std::vector<uint64_t> chr_events(static_cast<size_t>(d.n_chr) * std::max(1u, e_chunks), 0);
-  parallel_for(e_chunks, [&](uint32_t k) {
-    const uint64_t lo = d.n_events * k / e_chunks, hi = d.n_events * (k + 1) / e_chunks;
-    std::vector<uint64_t> cnt(d.n_chr, 0);
-    for (uint64_t e = lo; e < hi; ++e) {
-      check(d.ev_kind[e] <= PCS_EV_WGD, "unknown event kind");
-      if (d.ev_kind[e] != PCS_EV_WGD) {
-        check(d.ev_chr[e] < d.n_chr, "event chromosome out of range");
-        ++cnt[d.ev_chr[e]];
-      }
-    }
-    std::copy(cnt.begin(), cnt.end(), chr_events.begin() + static_cast<size_t>(k) * d.n_chr);
-  });
   std::vector<uint64_t> chr_load(d.n_chr, 0);
-  for (uint32_t k = 0; k < e_chunks; ++k)
-    for (uint32_t c = 0; c < d.n_chr; ++c) chr_load[c] += chr_events[static_cast<size_t>(k) * d.n_chr + c];
-  timer.lap("events checked");
+  {
+    const uint32_t n = d.n_nodes, n_chr = d.n_chr;
+    const uint32_t p_chunks = std::max(1u, std::min<uint32_t>(4 * n_threads, (n + 4095) / 4096));
+    auto pos_lo = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n) * k / p_chunks); };
+    parallel_for(n_chr, [&](uint32_t c) { work[c].ev_off.assign(static_cast<size_t>(n) + 1, 0); });
+    std::atomic<bool> any_wgd{false};
+    parallel_for(p_chunks, [&](uint32_t k) {  // ev_off[c][i + 1] = events of chromosome c in the node at position i
+      bool wgd = false;
+      for (uint32_t i = pos_lo(k); i < pos_lo(k + 1); ++i) {
+        const uint32_t v = t.pre_node[i];
+        for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+          const uint8_t kind = d.ev_kind[e];
+          check(kind <= PCS_EV_WGD, "unknown event kind");
+          if (kind == PCS_EV_WGD) {
+            wgd = true;
+            for (uint32_t c = 0; c < n_chr; ++c) ++work[c].ev_off[i + 1];
+          } else {
+            check(d.ev_chr[e] < n_chr, "event chromosome out of range");
+            ++work[d.ev_chr[e]].ev_off[i + 1];
+          }
+        }
+      }
+      if (wgd) any_wgd.store(true, std::memory_order_relaxed);
+    });
+    parallel_for(n_chr, [&](uint32_t c) {
+      ChrWork& w = work[c];
+      for (uint32_t i = 0; i < n; ++i) w.ev_off[i + 1] += w.ev_off[i];
+      w.ev.resize(w.ev_off[n]);
+      w.has_wgd = any_wgd.load(std::memory_order_relaxed);
+      chr_load[c] = w.ev_off[n];
+    });
+    parallel_for(p_chunks, [&](uint32_t k) {
+      const uint32_t i0 = pos_lo(k), i1 = pos_lo(k + 1);
+      std::vector<uint32_t> at(n_chr);  // where the next event of each chromosome goes
+      for (uint32_t c = 0; c < n_chr; ++c) at[c] = work[c].ev_off[i0];
+      for (uint32_t i = i0; i < i1; ++i) {
+        const uint32_t v = t.pre_node[i];
+        for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+          const uint8_t kind = d.ev_kind[e];
+          if (kind == PCS_EV_WGD) {
+            for (uint32_t c = 0; c < n_chr; ++c)
+              work[c].ev[at[c]++] = Ev{static_cast<uint32_t>(e), 0u, 0u, 0, 0, kind, d.ev_nature[e]};
+            continue;
+          }
+          const uint32_t c = d.ev_chr[e];
+          if (kind == PCS_EV_SID) {  // position and lengths of the row: looked up per chromosome (flatten_chr)
+            work[c].ev[at[c]++] = Ev{d.ev_mut[e], 0u, 0u, d.ev_allele[e], 0, kind, d.ev_nature[e]};
+          } else {
+            check(d.ev_len[e] >= 1, "CNA length must be positive");
+            work[c].ev[at[c]++] = Ev{d.ev_pos[e], d.ev_len[e], 0u, d.ev_allele[e], d.ev_dest[e], kind, d.ev_nature[e]};
+          }
+        }
+      }
+      for (uint32_t c = 0; c < n_chr; ++c)
+        check(at[c] == work[c].ev_off[i1], "internal: events dealt out of step");
+    });
+  }
+  timer.lap("events by chromosome");
   // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
   std::vector<uint32_t> chr_order(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
