@@ -61,6 +61,7 @@ struct Tree {
   // every walk reads memory front to back instead of chasing node indices.
   std::vector<uint32_t> pre_node, pre_end, root_pos;
   std::vector<int64_t> pre_leaf;
+  std::vector<uint32_t> leaf_pos, leaf_id;  // the sampled cells by increasing preorder position, and their leaf index
 };
 
 // one event of a chromosome, gathered next to its neighbours in walk order
@@ -76,6 +77,7 @@ struct ChrWork {
   uint32_t chr = 0;
   std::vector<Ev> ev;                 // events of this chromosome (+ WGD), by preorder position
   std::vector<uint32_t> ev_off;       // [n_nodes+1], indexed by preorder position
+  std::vector<uint32_t> ev_nodes;     // the preorder positions that have events of this chromosome, increasing
   bool has_wgd = false;
   std::vector<Inst> inst;
   std::vector<HapRec> haps;           // fragset is a LOCAL id until merge
@@ -172,90 +174,166 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   uint32_t* germ_hi = w.germ_hi;
   const uint32_t* ev_off = w.ev_off.data();
   const uint32_t* pre_end = t.pre_end.data();
-  const int64_t* pre_leaf = t.pre_leaf.data();
 
-  struct Frame {
-    uint32_t node;        // preorder position
-    uint32_t fragset, ev_i;
-    uint32_t next_child;  // preorder position of the next child to walk; == pre_end[node]: none left
-    uint32_t open_base;
+  // The numbering is a recursion over (subtree, allele copy):
+  //   walk(node, first event, fragment set, allele): the node's events from `first event` on -- a SID the allele
+  //   still holds opens an instance, a deletion changes the fragment set, an amplification or a WGD walks the
+  //   SAME subtree for the new copy from the next event on, before anything else happens -- then the node's leaf,
+  //   then its children; every instance opened in a node is carried by the haplotypes numbered until its subtree
+  //   ends.
+  // In preorder a subtree is the range [i, pre_end[i]), so one walk is a scan over consecutive positions.  What a
+  // node changed (fragment set, opened instances) is put on `undo` and taken back when the scan reaches the end
+  // of its subtree.  Nothing happens at a node without events of this chromosome but its leaf, so the scan goes
+  // from one node with events to the next (ev_nodes) and numbers the sampled cells in between (leaf_pos) in one
+  // tight loop: the cost is O(events + haplotypes), not O(nodes) per allele copy.  Only copies (rare) start a
+  // nested scan.
+  struct Scan {
+    uint32_t p, end;        // next position to look at, end of the subtree this scan covers
+    uint32_t k;             // kNodeStart, or the next event of node p (the scan was interrupted by a copy)
+    uint32_t fs;            // fragment set of the allele at p
+    uint32_t undo_base;     // undo entries below this one belong to enclosing scans
+    uint32_t node_fs, node_open;  // state when the events of node p began
+    uint32_t li, ei;        // first sampled cell / first node with events at or after p
+    uint32_t root;          // ordinal of the root this scan started at, if it is the root's own scan
     uint16_t allele;
-    bool root_base, preneo_done, leaf_done;
+    bool root_base, preneo_done;
   };
-  std::vector<Frame> stack;
+  struct Undo {
+    uint32_t end, fs, open_size;
+  };
+  constexpr uint32_t kNodeStart = 0xffffffffu, kNever = 0xffffffffu;
+  std::vector<Scan> scans;
+  std::vector<Undo> undo;
   std::vector<uint32_t> open;  // instances whose interval is still growing
+  const uint32_t* leaf_pos = t.leaf_pos.data();
+  const uint32_t* leaf_id = t.leaf_id.data();
+  const uint32_t n_leaf_pos = static_cast<uint32_t>(t.leaf_pos.size());
+  const uint32_t* ev_nodes = w.ev_nodes.data();
+  const uint32_t n_ev_nodes = static_cast<uint32_t>(w.ev_nodes.size());
+  auto close_to = [&](uint32_t open_size) {  // instances opened since are carried by [lo, counter)
+    for (size_t k = open_size; k < open.size(); ++k) {
+      Inst& in = w.inst[open[k]];
+      in.span = counter - in.lo;
+    }
+    open.resize(open_size);
+  };
 
+  w.inst.reserve(w.ev.size());
   for (uint16_t g = 0; g < n0; ++g) {
     germ_lo[g] = counter;
     w.haps.push_back({0u, full, g, HAP_NORMAL_PLAIN});
     ++counter;
     for (uint32_t ri = 0; ri < t.root_pos.size(); ++ri) {
       const uint32_t r = t.root_pos[ri];
-      stack.push_back({r, full, ev_off[r], r + 1, static_cast<uint32_t>(open.size()), g, true, false, false});
-      while (!stack.empty()) {
-        Frame& f = stack.back();
-        const uint32_t v = f.node;
+      scans.push_back({r, pre_end[r], kNodeStart, full, static_cast<uint32_t>(undo.size()), full,
+                       static_cast<uint32_t>(open.size()),
+                       static_cast<uint32_t>(std::lower_bound(leaf_pos, leaf_pos + n_leaf_pos, r) - leaf_pos),
+                       static_cast<uint32_t>(std::lower_bound(ev_nodes, ev_nodes + n_ev_nodes, r) - ev_nodes), ri, g, true,
+                       false});
+      while (!scans.empty()) {
+        Scan& sc = scans.back();
+        uint32_t k = sc.k;
+        if (k == kNodeStart) {
+          while (undo.size() > sc.undo_base && undo.back().end <= sc.p) {  // subtrees that ended at or before p
+            close_to(undo.back().open_size);
+            sc.fs = undo.back().fs;
+            undo.pop_back();
+          }
+          if (sc.p >= sc.end) {  // this subtree is done (its undo entries all ended at or before sc.end)
+            scans.pop_back();
+            continue;
+          }
+          const uint32_t next_ev = sc.ei < n_ev_nodes ? ev_nodes[sc.ei] : kNever;
+          if (next_ev != sc.p && !(sc.root_base && sc.p == r)) {
+            // nodes without events: number their sampled cells up to the next stop
+            uint32_t stop = std::min(sc.end, next_ev);
+            if (undo.size() > sc.undo_base) stop = std::min(stop, undo.back().end);
+            uint32_t li = sc.li;
+            const uint32_t fs = sc.fs;
+            const uint16_t allele = sc.allele;
+            for (; li < n_leaf_pos && leaf_pos[li] < stop; ++li) w.haps.push_back({leaf_id[li], fs, allele, HAP_TUMOUR});
+            counter += li - sc.li;
+            sc.li = li;
+            sc.p = stop;
+            continue;
+          }
+          k = ev_off[sc.p];
+          sc.node_fs = sc.fs;
+          sc.node_open = static_cast<uint32_t>(open.size());
+        } else {
+          sc.k = kNodeStart;
+        }
+        const uint32_t p = sc.p;
+        const bool root_node = sc.root_base && p == r;
         auto preneo_leaf = [&]() {
-          f.preneo_done = true;
-          w.haps.push_back({ri, f.fragset, f.allele, HAP_NORMAL_PRENEO});
+          sc.preneo_done = true;
+          w.haps.push_back({sc.root, sc.fs, sc.allele, HAP_NORMAL_PRENEO});
           ++counter;
         };
-        if (f.ev_i < ev_off[v + 1]) {
-          const Ev e = w.ev[f.ev_i++];
-          if (f.root_base && !f.preneo_done && !(e.kind == PCS_EV_SID && e.nature == PCS_NATURE_PRENEOPLASTIC))
+        bool copied = false;
+        for (const uint32_t k_end = ev_off[p + 1]; k < k_end;) {
+          const Ev e = w.ev[k++];
+          if (root_node && !sc.preneo_done && !(e.kind == PCS_EV_SID && e.nature == PCS_NATURE_PRENEOPLASTIC))
             preneo_leaf();
+          uint32_t copy_fs = 0;
+          uint16_t copy_allele = 0;
           if (e.kind == PCS_EV_WGD) {
             auto it = w.wgd_map.find(e.x);
             if (it == w.wgd_map.end()) continue;
+            bool mine = false;
             for (const auto& [a, nd] : it->second)
-              if (a == f.allele) {
-                Frame nf{v, f.fragset, f.ev_i, v + 1, static_cast<uint32_t>(open.size()), nd, false, true, false};
-                stack.push_back(nf);  // invalidates f; loop re-reads the top
+              if (a == sc.allele) {
+                mine = true;
+                copy_fs = sc.fs;
+                copy_allele = nd;
                 break;
               }
-            continue;
-          }
-          if (e.allele != f.allele) continue;
-          if (e.kind == PCS_EV_SID) {
-            if (holds(w.fragsets[f.fragset], e.y)) {
-              open.push_back(static_cast<uint32_t>(w.inst.size()));
-              w.inst.push_back({counter, 0u, e.x, e.meta});
-            }
-          } else if (e.kind == PCS_EV_CNA_DEL) {
-            f.fragset = w.intern_set(remove_range(w.fragsets[f.fragset], e.x, e.x + e.y - 1, clen));
-          } else if (e.kind == PCS_EV_CNA_AMP) {
-            uint32_t fs = w.intern_set(clip(w.fragsets[f.fragset], e.x, e.x + e.y - 1));
-            Frame nf{v, fs, f.ev_i, v + 1, static_cast<uint32_t>(open.size()), e.dest, false, true, false};
-            stack.push_back(nf);
+            if (!mine) continue;
           } else {
-            throw std::domain_error("unknown event kind");
+            if (e.allele != sc.allele) continue;
+            if (e.kind == PCS_EV_SID) {
+              if (holds(w.fragsets[sc.fs], e.y)) {
+                open.push_back(static_cast<uint32_t>(w.inst.size()));
+                w.inst.push_back({counter, 0u, e.x, e.meta});
+              }
+              continue;
+            }
+            if (e.kind == PCS_EV_CNA_DEL) {
+              sc.fs = w.intern_set(remove_range(w.fragsets[sc.fs], e.x, e.x + e.y - 1, clen));
+              continue;
+            }
+            if (e.kind != PCS_EV_CNA_AMP) throw std::domain_error("unknown event kind");
+            copy_fs = w.intern_set(clip(w.fragsets[sc.fs], e.x, e.x + e.y - 1));
+            copy_allele = e.dest;
           }
-          continue;
+          // the copy: this subtree once more, from the next event on, before this scan goes on
+          sc.k = k;
+          const Scan copy{p, pre_end[p], k, copy_fs, static_cast<uint32_t>(undo.size()), copy_fs,
+                          static_cast<uint32_t>(open.size()), sc.li, sc.ei, 0u, copy_allele, false, true};
+          scans.push_back(copy);  // invalidates sc
+          copied = true;
+          break;
         }
-        if (f.root_base && !f.preneo_done) preneo_leaf();
-        const uint32_t end = pre_end[v];
-        const bool dead = w.fs_empty[f.fragset] != 0;  // no DNA left: nothing below can be read
-        if (end == v + 1 && !f.leaf_done) {
-          f.leaf_done = true;
-          if (pre_leaf[v] >= 0 && !dead) {
-            w.haps.push_back({static_cast<uint32_t>(pre_leaf[v]), f.fragset, f.allele, HAP_TUMOUR});
+        if (copied) continue;
+        if (root_node && !sc.preneo_done) preneo_leaf();
+        if (sc.fs != sc.node_fs || open.size() != sc.node_open)
+          undo.push_back({pre_end[p], sc.node_fs, sc.node_open});
+        const bool dead = w.fs_empty[sc.fs] != 0;  // no DNA left: nothing below can be read
+        if (sc.ei < n_ev_nodes && ev_nodes[sc.ei] == p) ++sc.ei;
+        if (sc.li < n_leaf_pos && leaf_pos[sc.li] == p) {  // a sampled cell (always a leaf of the tree)
+          if (!dead) {
+            w.haps.push_back({leaf_id[sc.li], sc.fs, sc.allele, HAP_TUMOUR});
             ++counter;
           }
+          ++sc.li;
         }
-        if (!dead && f.next_child < end) {
-          const uint32_t c = f.next_child;
-          f.next_child = pre_end[c];
-          Frame nf{c, f.fragset, ev_off[c], c + 1, static_cast<uint32_t>(open.size()), f.allele, false, true, false};
-          stack.push_back(nf);
-          continue;
+        if (dead && pre_end[p] != p + 1) {  // skip the subtree
+          sc.p = pre_end[p];
+          sc.li = static_cast<uint32_t>(std::lower_bound(leaf_pos + sc.li, leaf_pos + n_leaf_pos, sc.p) - leaf_pos);
+          sc.ei = static_cast<uint32_t>(std::lower_bound(ev_nodes + sc.ei, ev_nodes + n_ev_nodes, sc.p) - ev_nodes);
+        } else {
+          sc.p = p + 1;
         }
-        // frame done: every instance opened in it is carried by [lo, counter)
-        for (size_t k = f.open_base; k < open.size(); ++k) {
-          Inst& in = w.inst[open[k]];
-          in.span = counter - in.lo;
-        }
-        open.resize(f.open_base);
-        stack.pop_back();
       }
     }
     germ_hi[g] = counter;
@@ -263,8 +341,26 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
 
   // a SID no sampled haplotype inherited has an empty interval: drop it
   w.inst.erase(std::remove_if(w.inst.begin(), w.inst.end(), [](const Inst& in) { return in.span == 0; }), w.inst.end());
-  // by row, placements of one row in DFS order
-  std::stable_sort(w.inst.begin(), w.inst.end(), [](const Inst& x, const Inst& y) { return x.row < y.row; });
+  // by row, placements of one row in DFS order: stable LSD radix sort on (row - smallest row), 11 bits a pass
+  if (w.inst.size() > 1) {
+    uint32_t row_min = 0xffffffffu, row_max = 0;
+    for (const Inst& in : w.inst) {
+      row_min = std::min(row_min, in.row);
+      row_max = std::max(row_max, in.row);
+    }
+    std::vector<Inst> tmp(w.inst.size());
+    Inst* src = w.inst.data();
+    Inst* dst = tmp.data();
+    const size_t n_inst = w.inst.size();
+    for (uint32_t shift = 0; shift < 32 && ((row_max - row_min) >> shift) != 0; shift += 11) {
+      uint32_t cnt[2049] = {0};
+      for (size_t i = 0; i < n_inst; ++i) ++cnt[(((src[i].row - row_min) >> shift) & 2047u) + 1];
+      for (uint32_t b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
+      for (size_t i = 0; i < n_inst; ++i) dst[cnt[((src[i].row - row_min) >> shift) & 2047u]++] = src[i];
+      std::swap(src, dst);
+    }
+    if (src != w.inst.data()) w.inst.swap(tmp);
+  }
 
   // pieces: maximal intervals on which the set of covering fragments is constant
   std::vector<uint8_t> used(w.fragsets.size(), 0);
@@ -385,6 +481,13 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
       const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
       t.pre_end[i] = nc ? t.pre_end[pos_of[t.child_idx[t.child_off[v + 1] - 1]]] : i + 1;
     }
+    t.leaf_pos.reserve(d.n_leaves);
+    t.leaf_id.reserve(d.n_leaves);
+    for (uint32_t i = 0; i < n; ++i)
+      if (t.pre_leaf[i] >= 0) {
+        t.leaf_pos.push_back(i);
+        t.leaf_id.push_back(static_cast<uint32_t>(t.pre_leaf[i]));
+      }
   }
   timer.lap("cell tree");
   n_threads = std::max(1u, n_threads);
@@ -525,7 +628,10 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     });
     parallel_for(n_chr, [&](uint32_t c) {
       ChrWork& w = work[c];
-      for (uint32_t i = 0; i < n; ++i) w.ev_off[i + 1] += w.ev_off[i];
+      for (uint32_t i = 0; i < n; ++i) {
+        if (w.ev_off[i + 1]) w.ev_nodes.push_back(i);
+        w.ev_off[i + 1] += w.ev_off[i];
+      }
       w.ev.resize(w.ev_off[n]);
       w.has_wgd = any_wgd.load(std::memory_order_relaxed);
       chr_load[c] = w.ev_off[n];
