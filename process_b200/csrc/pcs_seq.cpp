@@ -1943,9 +1943,12 @@ int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** out) {
     fl->block.reset(new char[bytes]);
     fl->host.flat.store.base = fl->block.get();
     fl->host.flat.store.capacity = bytes;
+    Lap lap;
     pcs::flatten_forest(*desc, fl->host.flat, host_threads());
+    lap("flatten_forest");
     require(fl->host.flat.store.heap.empty(), "internal: the lent block was too small for the flat tables");
     fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
+    lap("sample groups");
     *out = fl.release();
   });
 }
