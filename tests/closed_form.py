@@ -9,7 +9,9 @@ c and a locus at position x:
     E[occ(m)]   = the same sum over the molecules that carry row m
 
 with one molecule per (cell, allele, fragment [b, e]); w = purity / n_tumour_cells for a tumour cell of the sample
-and (1 - purity) for the normal cell (germline alleles, whole).  Nothing here shares code with the oracle's
+and (1 - purity) for the normal cell (germline alleles, whole).  Paired reads (A4, A16): N = round(coverage *
+chr_len / (2 R)) templates of 2 R + k bases, k ~ Binomial(t = floor(mean / p), p = 1 - sd^2 / mean); the second mate
+starts R + k bases after the first, both mates count, and the template must fit the fragment.  Nothing here shares code with the oracle's
 sampler or the product: it uses only oracle.cell_genome() (the explicit genomes) and numpy."""
 import numpy as np
 
@@ -17,8 +19,22 @@ import oracle
 from process_b200 import _abi as A
 
 
-def expected_tables(f, coverage, purity, R, with_normal=True):
+def insert_law(mean, sd):
+    """support and probabilities of the insert size, src/seq_simulation.cpp:431-451"""
+    from scipy import stats
+    p = 1 - sd * sd / mean
+    t = int(mean / p)
+    k = np.arange(0, t + 1)
+    pk = stats.binom.pmf(k, t, p)
+    keep = pk > 1e-15
+    return k[keep], pk[keep] / pk[keep].sum()
+
+
+def expected_tables(f, coverage, purity, R, with_normal=True, insert=None):
+    """insert = (mean, sd) for paired reads, None for single reads"""
     assert ((f.mut_ref_len == 1) & (f.mut_alt_len == 1)).all(), "closed form is written for SNV-only forests"
+    mates = 2 if insert else 1
+    ks, pk = insert_law(*insert) if insert else (np.zeros(1, np.int64), np.ones(1))
     n_s = f.n_samples
     S = n_s + (1 if with_normal else 0)
     e_cov = np.zeros((S, f.n_mut))
@@ -27,7 +43,7 @@ def expected_tables(f, coverage, purity, R, with_normal=True):
     for c in range(f.n_chr):
         rows = np.flatnonzero(f.mut_chr == c)
         x = f.mut_pos[rows].astype(np.int64)
-        N = round(coverage * int(f.chr_len[c]) / R)
+        N = int(np.floor(coverage * int(f.chr_len[c]) / (R * mates) + 0.5))
 
         def molecules(kind, cell):
             frags, sids = oracle.cell_genome(f, kind, cell, c)
@@ -48,7 +64,13 @@ def expected_tables(f, coverage, purity, R, with_normal=True):
                 mol += [(1 - p,) + m for m in normal]
             W = sum(w * (e - b + 1) for w, o, b, e, car in mol)
             for w, o, b, e, car in mol:
-                n_starts = np.maximum(0, np.minimum(x, e - R + 1) - np.maximum(b, x - R + 1) + 1)
+                n_starts = np.zeros(len(x))
+                for k, pr in zip(ks, pk):
+                    tlen = R if not insert else 2 * R + int(k)
+                    last = e - tlen + 1  # last start whose template fits the fragment
+                    n_starts += pr * np.maximum(0, np.minimum(x, last) - np.maximum(b, x - R + 1) + 1)
+                    if insert:  # second mate: starts R + k after the first
+                        n_starts += pr * np.maximum(0, np.minimum(x - R - k, last) - np.maximum(b, x - 2 * R - k + 1) + 1)
                 has = np.array([(int(r) in car) or (((germ.get(int(r), 0) >> o) & 1) == 1 and b <= xx <= e)
                                 for r, xx in zip(rows, x)], bool)
                 e_cov[s, rows] += N / W * w * n_starts

@@ -18,15 +18,16 @@ pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("PCS_EXTRA_GPU_TESTS") != "1", reason="not yet confirmed on a B200 (set PCS_EXTRA_GPU_TESTS=1)")]
 
 
-@pytest.mark.parametrize("purity", [0.7, 1.0])
-def test_sampler_matches_closed_form_expectations(purity):
+@pytest.mark.parametrize("purity,insert", [(0.7, None), (1.0, None), (0.7, (180, 9))])
+def test_sampler_matches_closed_form_expectations(purity, insert):
     import closed_form as CF
     f = synth_forest(CF.snv_only_spec())
     coverage, R = 3000.0, 100
-    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R)
+    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R, insert=insert)
+    kw = dict(insert_size_mean=insert[0], insert_size_stddev=insert[1]) if insert else {}
     ctx = L.Context(0)
     dev = L.Forest(ctx, f)
-    occ, cov, st = dev.simulate(make_params(coverage=coverage, purity=purity, read_size=R, seed=11))
+    occ, cov, st = dev.simulate(make_params(coverage=coverage, purity=purity, read_size=R, seed=11, **kw))
     dev.close()
     ctx.close()
     assert st.n_reads > 1_000_000
