@@ -30,8 +30,9 @@ def insert_law(mean, sd):
     return k[keep], pk[keep] / pk[keep].sum()
 
 
-def expected_tables(f, coverage, purity, R, with_normal=True, insert=None):
-    """insert = (mean, sd) for paired reads, None for single reads"""
+def expected_tables(f, coverage, purity, R, with_normal=True, insert=None, preneoplastic_in_normal=False):
+    """insert = (mean, sd) for paired reads, None for single reads; preneoplastic_in_normal: the normal cells are
+    one per root, each with its root's pre-neoplastic SIDs (A10)"""
     assert ((f.mut_ref_len == 1) & (f.mut_alt_len == 1)).all(), "closed form is written for SNV-only forests"
     mates = 2 if insert else 1
     ks, pk = insert_law(*insert) if insert else (np.zeros(1, np.int64), np.ones(1))
@@ -52,7 +53,11 @@ def expected_tables(f, coverage, purity, R, with_normal=True, insert=None):
                 carried.setdefault(a, set()).add(int(r))
             return [(o, b, e, carried.get(a, set())) for a, o, b, e in frags if b > 0]
 
-        normal = molecules(A.PCS_PLACE_NORMAL_PLAIN, 0)
+        if preneoplastic_in_normal:
+            n_roots = int((f.node_parent < 0).sum())
+            normal = [(1.0 / n_roots,) + m for r in range(n_roots) for m in molecules(A.PCS_PLACE_NORMAL_PRENEO, r)]
+        else:
+            normal = [(1.0,) + m for m in molecules(A.PCS_PLACE_NORMAL_PLAIN, 0)]
         for s in range(S):
             cells = [] if s >= n_s else [l for l in range(f.n_leaves) if f.leaf_sample[l] == s]
             p = purity if cells else 0.0
@@ -61,7 +66,7 @@ def expected_tables(f, coverage, purity, R, with_normal=True, insert=None):
                 for l in cells:
                     mol += [(p / len(cells),) + m for m in molecules(A.PCS_PLACE_TUMOUR, l)]
             if p < 1:
-                mol += [(1 - p,) + m for m in normal]
+                mol += [((1 - p) * m[0],) + m[1:] for m in normal]
             W = sum(w * (e - b + 1) for w, o, b, e, car in mol)
             for w, o, b, e, car in mol:
                 n_starts = np.zeros(len(x))

@@ -130,8 +130,9 @@ def test_oracle_rejects_malformed_input():
         oracle.simulate(f, make_params(insert_size_mean=10, insert_size_stddev=10))  # sd^2 > mean
 
 
-@pytest.mark.parametrize("purity,error_rate,insert", [(0.7, 0.0, None), (1.0, 0.0, None), (0.7, 0.1, None), (0.7, 0.0, (180, 9))])
-def test_oracle_matches_closed_form_expectations(purity, error_rate, insert):
+@pytest.mark.parametrize("purity,error_rate,insert,preneo", [(0.7, 0.0, None, 0), (1.0, 0.0, None, 0), (0.7, 0.1, None, 0),
+                                                             (0.7, 0.0, (180, 9), 0), (0.5, 0.0, None, 1)])
+def test_oracle_matches_closed_form_expectations(purity, error_rate, insert, preneo):
     """E[depth] and E[occurrences] of every (sample, row), written down in closed form from the explicit genomes
     (tests/closed_form.py: amplified, deleted and WGD-doubled alleles, purity, the normal sample, reads that fall
     off a fragment end, constant-quality sequencing errors, paired reads with the Binomial insert law), against a
@@ -142,8 +143,9 @@ def test_oracle_matches_closed_form_expectations(purity, error_rate, insert):
     assert (f.ev_kind == A.PCS_EV_WGD).sum() >= 1 and (f.ev_kind == A.PCS_EV_CNA_AMP).sum() >= 1 and \
         (f.ev_kind == A.PCS_EV_CNA_DEL).sum() >= 1
     coverage, R = 3000.0, 100
-    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R, insert=insert)
+    e_cov, e_occ = CF.expected_tables(f, coverage, purity, R, insert=insert, preneoplastic_in_normal=bool(preneo))
     kw = dict(sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=error_rate) if error_rate else {}
+    kw["preneoplastic_in_normal"] = preneo
     if insert:
         kw.update(insert_size_mean=insert[0], insert_size_stddev=insert[1])
     r = oracle.simulate(f, make_params(coverage=coverage, purity=purity, read_size=R, seed=11, **kw), n_threads=4)
