@@ -1,9 +1,10 @@
 """The GPU sampler against CLOSED-FORM expectations (tests/closed_form.py) instead of against the oracle's
 Monte Carlo: E[depth] and E[occurrences] of every (sample, row) from the explicit genomes.
 
-Written in round 1 after the GPU budget was spent, so it has never run on a B200: it is skipped unless
-PCS_EXTRA_GPU_TESTS=1 until one run has confirmed it (its CPU twin, on the oracle, is
-test_oracle_golden.py::test_oracle_matches_closed_form_expectations)."""
+Written in round 1 after the GPU budget was spent, so it has never run on a B200.  Until one run has confirmed it,
+it is marked xfail(strict=False): it runs with the rest of `-m gpu`, a pass shows as XPASS and a failure cannot
+turn the suite red.  PCS_EXTRA_GPU_TESTS=1 makes it an ordinary test.  Its CPU twin, on the oracle, is
+test_oracle_golden.py::test_oracle_matches_closed_form_expectations."""
 import os
 
 import numpy as np
@@ -14,8 +15,9 @@ from process_b200.synth import synth_forest
 
 from conftest import make_params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PCS_EXTRA_GPU_TESTS") != "1", reason="not yet confirmed on a B200 (set PCS_EXTRA_GPU_TESTS=1)")]
+pytestmark = [pytest.mark.gpu]
+if os.environ.get("PCS_EXTRA_GPU_TESTS") != "1":
+    pytestmark.append(pytest.mark.xfail(reason="first run on a B200: not yet confirmed", strict=False))
 
 
 @pytest.mark.parametrize("purity,insert", [(0.7, None), (1.0, None), (0.7, (180, 9))])
