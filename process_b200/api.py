@@ -194,11 +194,12 @@ def _chr_mask(forest, chromosomes):
 
 
 def _resolve_seed(seed):
-    """get_random_seed<int>(), src/utility.hpp:41-64"""
+    """get_random_seed<int>(), src/utility.hpp:41-64: a number is cast; NULL draws runif(INT_MIN, INT_MAX) from the
+    session's RNG state, so that set.seed() governs the run -- here NumPy's global state (np.random.seed())."""
     if seed is None:
-        return int(np.random.default_rng().integers(-2**31, 2**31 - 1))
+        return int(np.random.uniform(-2.0**31, 2.0**31 - 1))
     if isinstance(seed, bool) or not isinstance(seed, (int, float, np.integer, np.floating)):
-        raise ValueError("The seed must be a number or NULL.")
+        raise ValueError("The seed must be either a number or NILL.")
     return int(seed)
 
 

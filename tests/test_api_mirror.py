@@ -60,7 +60,12 @@ def test_cell_labelling_splits_samples_in_order_of_first_appearance():
 def test_seed_resolution():
     assert api._resolve_seed(7) == 7 and api._resolve_seed(7.0) == 7
     assert -2**31 <= api._resolve_seed(None) < 2**31
-    with pytest.raises(ValueError):
+    # NULL: drawn from the session's RNG state, so seeding the session governs the run (src/utility.hpp:50-57)
+    np.random.seed(3)
+    a = [api._resolve_seed(None) for _ in range(3)]
+    np.random.seed(3)
+    assert a == [api._resolve_seed(None) for _ in range(3)] and len(set(a)) == 3
+    with pytest.raises(ValueError, match="The seed must be either a number or NILL."):
         api._resolve_seed("x")
 
 
