@@ -225,7 +225,7 @@ def main():
 
     torch.cuda.set_device(local)
     # the ranks share the host's cores: split them, or every rank's flattener oversubscribes the box
-    os.environ.setdefault("PCS_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // world)))
+    os.environ.setdefault("PCS_HOST_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // world))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))

@@ -49,14 +49,16 @@ void require(bool ok, const char* msg) {
   if (!ok) throw std::domain_error(msg);
 }
 
-// threads of the host flattener: PCS_HOST_THREADS, else every core
+// threads of the host phases (flattener, sample groups, planner): PCS_HOST_THREADS, else every core up to 32 --
+// the phases are short and memory-bound, and every one of them starts its own threads: past a few dozen the
+// thread start-up costs more than the extra cores give
 unsigned host_threads() {
   const char* s = std::getenv("PCS_HOST_THREADS");
   if (s) {
     long v = std::atol(s);
     if (v >= 1 && v <= 1024) return static_cast<unsigned>(v);
   }
-  return std::max(1u, std::thread::hardware_concurrency());
+  return std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
 }
 
 void parallel_copy(void* dst, const void* src, size_t bytes) {
