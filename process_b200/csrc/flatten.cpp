@@ -422,7 +422,10 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
   out.chr_len.assign(d.chr_len, d.chr_len + d.n_chr);
   out.chr_n_alleles.assign(d.chr_n_alleles, d.chr_n_alleles + d.n_chr);
   out.leaf_sample.assign(d.leaf_sample, d.leaf_sample + d.n_leaves);
-  for (uint32_t c = 0; c < d.n_chr; ++c) check(d.chr_len[c] >= 1, "chromosome length must be positive");
+  for (uint32_t c = 0; c < d.n_chr; ++c) {
+    check(d.chr_len[c] >= 1, "chromosome length must be positive");
+    check(d.chr_len[c] < (1u << 31), "chromosome length must be below 2^31");  // 32-bit positions on the device
+  }
 
   // ---- cell tree
   Tree t;

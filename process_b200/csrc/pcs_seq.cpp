@@ -521,18 +521,30 @@ void validate(const pcs_seq_params& P) {
 void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& alias, uint32_t& kmin, uint32_t& kmax) {
   double q = static_cast<double>(sd) * sd / mean;
   double p = 1 - q;
-  uint32_t t = static_cast<uint32_t>(mean / p);
-  std::vector<double> pmf(t + 1);
+  if (!(p > 0)) {  // sd^2 == mean: Binomial(., 0) is always 0
+    kmin = kmax = 0;
+    alias.assign({4294967295u, 0u});
+    return;
+  }
+  const double td = mean / p;
+  require(td < 4294967296.0, "the insert size law Binomial(mean / p, p), p = 1 - sd^2 / mean, has too many trials");
+  uint32_t t = static_cast<uint32_t>(td);
+  // The law is tabulated where it is not negligible (pmf >= 1e-18).  That support lies within 9-13 standard
+  // deviations of the mean, so only the window mean +- (16 sd + 128) is evaluated: t = mean / p itself can be
+  // billions when sd^2 is close to the mean.
+  const uint32_t w_lo = static_cast<uint32_t>(std::max(0.0, static_cast<double>(mean) - 16.0 * sd - 128.0));
+  const uint32_t w_hi = static_cast<uint32_t>(std::min(static_cast<double>(t), static_cast<double>(mean) + 16.0 * sd + 128.0));
+  std::vector<double> win(static_cast<size_t>(w_hi - w_lo) + 1, 0.0);
+  double* pmf = win.data() - w_lo;  // pmf[k] for k in [w_lo, w_hi]
   if (p >= 1.0) {
-    std::fill(pmf.begin(), pmf.end(), 0.0);
     pmf[t] = 1.0;
   } else {
-    for (uint32_t k = 0; k <= t; ++k)
+    for (uint32_t k = w_lo; k <= w_hi; ++k)
       pmf[k] = std::exp(std::lgamma(t + 1.0) - std::lgamma(k + 1.0) - std::lgamma(t - k + 1.0) +
                         k * std::log(p) + (t - k) * std::log1p(-p));
   }
-  kmin = 0;
-  kmax = t;
+  kmin = w_lo;
+  kmax = w_hi;
   while (kmin < kmax && pmf[kmin] < 1e-18) ++kmin;
   while (kmax > kmin && pmf[kmax] < 1e-18) --kmax;
   // Walker / Vose alias table over the support [kmin, kmax]
@@ -631,8 +643,12 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
   ps.R = P.read_size;
   ps.paired = P.insert_size_mean > 0;
   ps.mates = ps.paired ? 2 : 1;
+  const char* too_long = "the template (both reads and the insert) must be shorter than 2^30 bases";
+  require(2ull * ps.R + P.insert_size_mean < (1ull << 30), too_long);  // before the insert law is tabulated
   if (ps.paired) insert_table(P.insert_size_mean, P.insert_size_stddev, ps.insert_alias, ps.kmin, ps.kmax);
   ps.reach = ps.paired ? 2ull * ps.R + ps.kmax : ps.R;
+  // positions are 32-bit on the device: chromosome (< 2^31, checked by the flattener) + template must not wrap
+  require(ps.reach <= (1ull << 30), too_long);
   if (!P.normal_only)
     for (uint32_t g = 0; g < fo.n_groups; ++g) ps.samples.push_back({false, g});
   if (P.normal_only || P.with_normal_sample) ps.samples.push_back({true, 0});

@@ -234,6 +234,22 @@ def test_parameter_validation_messages():
         fl.plan(make_params(sequencer=9))
     info, _ = fl.plan(make_params(normal_only=1, purity=7.0))  # purity is ignored for the normal sample
     assert info.n_out_samples == 1
+    # the insert law is tabulated on its support only: sd^2 close to the mean (billions of Binomial trials) is as
+    # quick as sd = 10, and sd^2 == mean (p = 0: the insert is always 0) is a table of one column
+    import time
+    t0 = time.perf_counter()
+    for mean, sd in ((100_000, 316), (500_000_000, 20_000), (289, 17), (300, 10)):
+        info, _ = fl.plan(make_params(insert_size_mean=mean, insert_size_stddev=sd))
+        assert info.reads_per_template == 2
+    assert time.perf_counter() - t0 < 5.0
+    # 32-bit positions on the device: a template that could wrap them is refused, not sampled
+    with pytest.raises(L.PcsError, match="shorter than 2\\^30 bases"):
+        fl.plan(make_params(insert_size_mean=4_000_000_000, insert_size_stddev=0))
+    f = MF.forest()
+    f.chr_len = f.chr_len.copy()
+    f.chr_len[0] = 2**31
+    with pytest.raises(L.PcsError, match="below 2\\^31"):
+        L.Flat(f)
 
 
 _THREAD_PROBE = r"""
