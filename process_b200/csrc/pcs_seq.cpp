@@ -535,24 +535,24 @@ void insert_table(uint32_t mean, uint32_t sd, std::vector<uint32_t>& alias, uint
   const uint32_t w_lo = static_cast<uint32_t>(std::max(0.0, static_cast<double>(mean) - 16.0 * sd - 128.0));
   const uint32_t w_hi = static_cast<uint32_t>(std::min(static_cast<double>(t), static_cast<double>(mean) + 16.0 * sd + 128.0));
   std::vector<double> win(static_cast<size_t>(w_hi - w_lo) + 1, 0.0);
-  double* pmf = win.data() - w_lo;  // pmf[k] for k in [w_lo, w_hi]
+  auto pmf = [&](uint32_t k) -> double& { return win[k - w_lo]; };  // k in [w_lo, w_hi]
   if (p >= 1.0) {
-    pmf[t] = 1.0;
+    pmf(t) = 1.0;
   } else {
     for (uint32_t k = w_lo; k <= w_hi; ++k)
-      pmf[k] = std::exp(std::lgamma(t + 1.0) - std::lgamma(k + 1.0) - std::lgamma(t - k + 1.0) +
+      pmf(k) = std::exp(std::lgamma(t + 1.0) - std::lgamma(k + 1.0) - std::lgamma(t - k + 1.0) +
                         k * std::log(p) + (t - k) * std::log1p(-p));
   }
   kmin = w_lo;
   kmax = w_hi;
-  while (kmin < kmax && pmf[kmin] < 1e-18) ++kmin;
-  while (kmax > kmin && pmf[kmax] < 1e-18) --kmax;
+  while (kmin < kmax && pmf(kmin) < 1e-18) ++kmin;
+  while (kmax > kmin && pmf(kmax) < 1e-18) --kmax;
   // Walker / Vose alias table over the support [kmin, kmax]
   const uint32_t n = kmax - kmin + 1;
   std::vector<double> scaled(n);
   double total = 0;
-  for (uint32_t i = 0; i < n; ++i) total += pmf[kmin + i];
-  for (uint32_t i = 0; i < n; ++i) scaled[i] = pmf[kmin + i] / total * n;
+  for (uint32_t i = 0; i < n; ++i) total += pmf(kmin + i);
+  for (uint32_t i = 0; i < n; ++i) scaled[i] = pmf(kmin + i) / total * n;
   std::vector<uint32_t> small, large;
   for (uint32_t i = 0; i < n; ++i) (scaled[i] < 1.0 ? small : large).push_back(i);
   alias.assign(2 * static_cast<size_t>(n), 0);
