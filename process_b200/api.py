@@ -235,17 +235,45 @@ def release_device_cache():
 atexit.register(release_device_cache)
 
 
+def _string_column(codes, table):
+    """The column table[codes] (None in the table = NA) as pandas would infer it from Python strings, but built from
+    the dictionary encoding: millions of rows draw from a handful of distinct strings (chromosome names, bases,
+    signature names, class names), so no Python object is made per row (the data frame, not the
+    sampler, is what a 5 M row result waits for)."""
+    import pandas as pd
+    codes = np.asarray(codes)
+    table = np.asarray(table, dtype=object)
+    try:
+        import pyarrow as pa
+        dtype = pd.Series(["x"]).dtype  # str (pyarrow-backed) from pandas 3 on
+        if getattr(dtype, "storage", None) != "pyarrow":
+            raise TypeError("strings are not arrow-backed in this pandas")
+        is_na = np.asarray([x is None for x in table], bool)
+        values = pa.array(["" if x is None else x for x in table], type=pa.large_string())
+        mask = is_na[codes] if is_na.any() else None
+        if len(codes) == 0 or (mask is not None and mask.all()):
+            return table[codes]  # nothing to infer a string type from: the object column pandas makes of it
+        idx = pa.array(codes.astype(np.int32), mask=mask)
+        arr = pa.DictionaryArray.from_arrays(idx, values).cast(pa.large_string())
+        return dtype.construct_array_type()(arr, dtype=dtype)
+    except Exception:  # older pandas / no pyarrow: plain object strings, the same values
+        return table[codes]
+
+
 def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, params=None):
     """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181.
     Sample columns in name order (std::map iteration), rows in SID order."""
     import pandas as pd
     rows = dev.active_rows(occ, include_non_sequenced, params)
-    ref, alt = forest.row_strings(rows)
+    ref_codes, ref_table, alt_codes, alt_table = forest.row_string_codes(rows)
+    cause = forest.mut_cause[rows]
+    class_table = [";".join(sorted(A.NATURE_DESCRIPTIONS[b] for b in range(4) if (m >> b) & 1)) for m in range(16)]
     cols = {
-        "chr": np.asarray(forest.chr_names, dtype=object)[forest.mut_chr[rows]],
+        "chr": _string_column(forest.mut_chr[rows], forest.chr_names),
         "chr_pos": forest.mut_pos[rows].astype(np.int32),
-        "ref": ref, "alt": alt,
-        "causes": forest.row_causes(rows), "classes": forest.row_classes(rows),
+        "ref": _string_column(ref_codes, ref_table), "alt": _string_column(alt_codes, alt_table),
+        "causes": _string_column(np.where(cause < 0, len(forest.cause_names), cause), list(forest.cause_names) + [None]),
+        "classes": _string_column(forest.mut_nature_mask[rows] & 15, class_table),
     }
     for s in sorted(range(len(names)), key=lambda i: names[i]):
         o = occ[s, rows].astype(np.int32)
@@ -255,7 +283,7 @@ def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, param
         cols[f"{names[s]}.occurrences"] = o
         cols[f"{names[s]}.coverage"] = c
         cols[f"{names[s]}.VAF"] = vaf
-    return pd.DataFrame(cols)
+    return pd.DataFrame(cols, copy=False)
 
 
 def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,

@@ -141,6 +141,31 @@ class PhylogeneticForest:
             alt[i] = a + b * (int(al[i]) - 1)
         return ref, alt
 
+    def row_string_codes(self, rows: np.ndarray):
+        """The same strings as row_strings(), dictionary-encoded: (ref_codes, ref_table, alt_codes, alt_table) with
+        ref = ref_table[ref_codes], alt = alt_table[alt_codes].  A row's strings depend on (first base, repeated
+        base, length) only, so the tables are tiny and nothing is done per row in Python."""
+        rows = np.asarray(rows)
+        rc = (self.mut_ref_code[rows] & 3).astype(np.int64)
+        ac = (self.mut_alt_code[rows] & 3).astype(np.int64)
+        rl, al = self.mut_ref_len[rows].astype(np.int64), self.mut_alt_len[rows].astype(np.int64)
+        indel = ((rl != 1) | (al != 1)).astype(np.int64)
+        out = []
+        for length, snv_base in ((rl, rc), (al, ac)):
+            key = rc | (ac << 2) | (indel << 4) | (length << 5)   # < 2^13: lengths are u8
+            present = np.flatnonzero(np.bincount(key, minlength=1 << 13))
+            index = np.zeros(1 << 13, np.int32)
+            index[present] = np.arange(len(present), dtype=np.int32)
+            table = np.empty(len(present), dtype=object)
+            for j, k in enumerate(present):
+                a, b, is_indel, n = _BASES[k & 3], _BASES[(k >> 2) & 3], (k >> 4) & 1, int(k >> 5)
+                if is_indel:
+                    table[j] = str(a) + str(b) * (n - 1)
+                else:  # SNV: ref is the first base, alt the other one
+                    table[j] = str(a) if length is rl else str(b)
+            out += [index[key], table]
+        return tuple(out)
+
     def alt_table(self):
         """(alt_off [n_mut+1] uint32, alt_bytes) of every row, the layout pcs_forest_set_alt takes."""
         _, alt = self.row_strings(np.arange(self.n_mut))

@@ -140,3 +140,46 @@ def test_get_seq_data_and_depth_ratio_follow_the_plot_helpers():
     assert {"DP.tumour", "DP.normal", "VAF.tumour", "VAF.normal", "NV.tumour", "NV.normal"} <= set(dr.columns)
     with pytest.raises(ValueError, match='mandatory normal sample "normal_sample"'):
         api.depth_ratio(wide.drop(columns=["normal_sample.VAF"]), "Sample.A")
+
+
+def test_result_dataframe_from_dictionary_codes_equals_per_row_strings():
+    """SURVEY.md 8 f2: the string columns are built from their dictionary encoding (no Python object per row);
+    the frame must be the one the per-row construction gives -- values, NA positions, dtypes -- also when there
+    are no rows and when no row has a cause"""
+    import pandas as pd
+    from conftest import small_spec
+    from process_b200.synth import synth_forest
+
+    class FakeDevice:
+        def __init__(self, rows):
+            self.rows = rows
+
+        def active_rows(self, occ, include_non_sequenced, params):
+            return self.rows
+
+    def per_row(forest, rows, occ, cov, names):
+        ref, alt = forest.row_strings(rows)
+        cols = {"chr": np.asarray(forest.chr_names, dtype=object)[forest.mut_chr[rows]],
+                "chr_pos": forest.mut_pos[rows].astype(np.int32), "ref": ref, "alt": alt,
+                "causes": forest.row_causes(rows), "classes": forest.row_classes(rows)}
+        for s in sorted(range(len(names)), key=lambda i: names[i]):
+            o, c = occ[s, rows].astype(np.int32), cov[s, rows].astype(np.int32)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                vaf = o.astype(np.float64) / c
+            cols[f"{names[s]}.occurrences"], cols[f"{names[s]}.coverage"], cols[f"{names[s]}.VAF"] = o, c, vaf
+        return pd.DataFrame(cols)
+
+    for f in (MF.forest(), synth_forest(small_spec(0)), synth_forest(small_spec(4))):
+        names = list(f.sample_names) + ["normal_sample"]
+        rng = np.random.default_rng(1)
+        cov = rng.poisson(30, (len(names), f.n_mut)).astype(np.uint32)
+        occ = rng.integers(0, 20, (len(names), f.n_mut)).astype(np.uint32)
+        indels = np.flatnonzero((f.mut_ref_len != 1) | (f.mut_alt_len != 1)).astype(np.uint32)
+        for rows in (np.arange(f.n_mut, dtype=np.uint32), np.zeros(0, np.uint32),
+                     np.arange(0, f.n_mut, 3, dtype=np.uint32), indels):
+            a = api._result_dataframe(f, FakeDevice(rows), occ, cov, names, False)
+            b = per_row(f, rows, occ, cov, names)
+            assert list(a.columns) == list(b.columns) and (a.dtypes == b.dtypes).all() and a.equals(b)
+    ref_codes, ref_table, alt_codes, alt_table = f.row_string_codes(indels)
+    ref, alt = f.row_strings(indels)
+    assert len(indels) > 5 and list(ref_table[ref_codes]) == list(ref) and list(alt_table[alt_codes]) == list(alt)
