@@ -260,6 +260,13 @@ def _string_column(codes, table):
         return table[codes]
 
 
+def _int32_rows(table_row, rows):
+    """table_row[rows] as int32 (IntegerVector, src/seq_simulation.cpp:110) in one gather"""
+    if table_row.dtype == np.uint32 and table_row.flags.c_contiguous:
+        return table_row.view(np.int32).take(rows)
+    return table_row[rows].astype(np.int32)
+
+
 def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, params=None):
     """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181.
     Sample columns in name order (std::map iteration), rows in SID order."""
@@ -276,8 +283,8 @@ def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, param
         "classes": _string_column(forest.mut_nature_mask[rows] & 15, class_table),
     }
     for s in sorted(range(len(names)), key=lambda i: names[i]):
-        o = occ[s, rows].astype(np.int32)
-        c = cov[s, rows].astype(np.int32)
+        o = _int32_rows(occ[s], rows)
+        c = _int32_rows(cov[s], rows)
         with np.errstate(divide="ignore", invalid="ignore"):
             vaf = o.astype(np.float64) / c
         cols[f"{names[s]}.occurrences"] = o

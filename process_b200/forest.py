@@ -146,13 +146,12 @@ class PhylogeneticForest:
         ref = ref_table[ref_codes], alt = alt_table[alt_codes].  A row's strings depend on (first base, repeated
         base, length) only, so the tables are tiny and nothing is done per row in Python."""
         rows = np.asarray(rows)
-        rc = (self.mut_ref_code[rows] & 3).astype(np.int64)
-        ac = (self.mut_alt_code[rows] & 3).astype(np.int64)
-        rl, al = self.mut_ref_len[rows].astype(np.int64), self.mut_alt_len[rows].astype(np.int64)
-        indel = ((rl != 1) | (al != 1)).astype(np.int64)
+        rl, al = self.mut_ref_len[rows], self.mut_alt_len[rows]
+        base = ((self.mut_ref_code[rows] & 3) | ((self.mut_alt_code[rows] & 3) << 2)).astype(np.uint16)
+        base |= ((rl != 1) | (al != 1)).astype(np.uint16) << 4
         out = []
-        for length, snv_base in ((rl, rc), (al, ac)):
-            key = rc | (ac << 2) | (indel << 4) | (length << 5)   # < 2^13: lengths are u8
+        for length in (rl, al):
+            key = base | (length.astype(np.uint16) << 5)   # < 2^13: lengths are u8
             present = np.flatnonzero(np.bincount(key, minlength=1 << 13))
             index = np.zeros(1 << 13, np.int32)
             index[present] = np.arange(len(present), dtype=np.int32)
