@@ -340,6 +340,18 @@ int pcs_flat_plan(const pcs_flat* flat, const pcs_seq_params* params, pcs_plan_i
                   uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,
                   uint32_t* tile_begin, uint32_t* tile_len);
 
+/* hap_list[offset, offset + n): the haplotype indices of a sampling list */
+int pcs_flat_hap_list(const pcs_flat* flat, uint32_t offset, uint32_t n, uint32_t* haps);
+/* the sampling entries of one tile of the (single-shard) plan: entry e owns the haplotype draw words
+ * (thr[e-1], thr[e]] (from 0 for e = 0) and draws uniformly from the list of list_n[e] haplotypes at
+ * hap_list[list_off[e]] -- every cell / allele of a class equiprobable (src/sequencing.cpp:155-163) */
+int pcs_flat_tile_entries(const pcs_flat* flat, const pcs_seq_params* params, uint32_t tile_id, uint32_t cap,
+                          uint32_t* thr, uint32_t* list_off, uint32_t* list_n, uint32_t* frag_end, uint32_t* n);
+/* the haplotype draw of the sampler kernels evaluated on the host (same inline function, dev.hpp::exact_leaf):
+ * haplotype index (inside the tile's chromosome) and entry index each 32-bit draw word u[i] selects */
+int pcs_flat_draw(const pcs_flat* flat, const pcs_seq_params* params, uint32_t tile_id, uint64_t n_draws,
+                  const uint32_t* u, uint32_t* hap, uint32_t* entry);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,7 @@ EXPORTS = [
     "pcs_plan_materialize",
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan", "pcs_flat_group_list",
+    "pcs_flat_tile_entries", "pcs_flat_draw", "pcs_flat_hap_list",
 ]
 
 
@@ -121,6 +122,29 @@ class Flat:
         n = int(min(cap, info.n_tiles))
         keys = ["id", "templates", "sample", "chr", "begin", "len"]
         return info, {k: a[:n] for k, a in zip(keys, arrs)}
+
+
+    def hap_list(self, offset, n):
+        h = np.zeros(n, np.uint32)
+        _ok(lib().pcs_flat_hap_list(self._h, C.c_uint32(offset), C.c_uint32(n), A.ptr(h, C.c_uint32)))
+        return h
+
+    def tile_entries(self, params: A.SeqParams, tile_id, cap=64):
+        """sampling entries of one tile: dict of thr, list_off, list_n, frag_end (uint32 arrays)"""
+        arrs = [np.zeros(cap, np.uint32) for _ in range(4)]
+        n = C.c_uint32(0)
+        _ok(lib().pcs_flat_tile_entries(self._h, C.byref(params), C.c_uint32(tile_id), C.c_uint32(cap),
+                                        *[A.ptr(a, C.c_uint32) for a in arrs], C.byref(n)))
+        assert n.value <= cap
+        return {k: a[:n.value] for k, a in zip(["thr", "list_off", "list_n", "frag_end"], arrs)}
+
+    def draw(self, params: A.SeqParams, tile_id, u):
+        """(haplotype index, entry index) the sampler's haplotype draw maps each 32-bit word of u to"""
+        u = _u32(u)
+        hap = np.zeros(len(u), np.uint32); ent = np.zeros(len(u), np.uint32)
+        _ok(lib().pcs_flat_draw(self._h, C.byref(params), C.c_uint32(tile_id), C.c_uint64(len(u)),
+                                A.ptr(u, C.c_uint32), A.ptr(hap, C.c_uint32), A.ptr(ent, C.c_uint32)))
+        return hap, ent
 
 
 # --------------------------------------------------------------------------- device objects

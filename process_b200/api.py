@@ -203,6 +203,26 @@ def _resolve_seed(seed):
     return int(seed)
 
 
+def _agree_over_ranks(c_seed, group, names):
+    """More than one rank (torch.distributed initialised): every rank must plan THE SAME call, or their tile sets
+    are not a partition of the job -- the per-tile template counts and the shard assignment both follow the seed.
+    seed=NULL is resolved on rank 0 and broadcast (each rank would otherwise draw its own from its own RNG state);
+    the sample partition (names and the cells of every group) must be identical, else the call is refused."""
+    rank, world = _shard()
+    if world == 1:
+        return c_seed
+    import hashlib
+    import torch.distributed as dist
+    box = [c_seed]
+    dist.broadcast_object_list(box, src=0)
+    digest = hashlib.sha256(repr(list(names)).encode() + (b"" if group is None else np.ascontiguousarray(group).tobytes())).hexdigest()
+    seen = [None] * world
+    dist.all_gather_object(seen, digest)
+    if len(set(seen)) != 1:
+        raise ValueError("simulate_seq over several ranks: the ranks' sample partitions (cell_labelling) differ")
+    return int(box[0])
+
+
 _ctx_cache = {}
 _forest_cache = weakref.WeakKeyDictionary()
 
@@ -285,8 +305,9 @@ def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, param
     for s in sorted(range(len(names)), key=lambda i: names[i]):
         o = _int32_rows(occ[s], rows)
         c = _int32_rows(cov[s], rows)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            vaf = o.astype(np.float64) / c
+        # VAF = occurrences / coverage; a row the sample never covered has no occurrence: VAF 0, as the rows
+        # the reference does not find in the sample's data (src/seq_simulation.cpp:121-131)
+        vaf = np.divide(o, c, out=np.zeros(len(o), np.float64), where=c != 0)
         cols[f"{names[s]}.occurrences"] = o
         cols[f"{names[s]}.coverage"] = c
         cols[f"{names[s]}.VAF"] = vaf
@@ -381,6 +402,7 @@ def simulate_seq(phylo_forest, sequencer=None, reference_genome=None, chromosome
     (src/seq_simulation.cpp:84-89, 137-139, 586-600)."""
     c_seed = _resolve_seed(seed)
     group, names = _apply_FACS_labels(phylo_forest, cell_labelling)
+    c_seed = _agree_over_ranks(c_seed, group, names)
     df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
                   insert_size_stddev, write_SAM, group, names, purity, with_normal_sample,
                   preneoplastic_in_normal, False, include_non_sequenced_mutations, c_seed, device, cache, _shard(),
@@ -402,7 +424,7 @@ def simulate_normal_seq(phylo_forest, sequencer=None, reference_genome=None, chr
                         include_non_sequenced_mutations=False, seed=None, *, device=0, cache=True):
     """Simulate the sequencing of a normal sample (purity forced to 1,
     src/seq_simulation.cpp:650-657)."""
-    c_seed = _resolve_seed(seed)
+    c_seed = _agree_over_ranks(_resolve_seed(seed), None, [])
     df, st = _run(phylo_forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
                   insert_size_stddev, write_SAM, None, [], 1.0, False, with_preneoplastic, True,
                   include_non_sequenced_mutations, c_seed, device, cache, _shard(),

@@ -6,18 +6,55 @@
 
 namespace pcs {
 
+#if defined(__CUDACC__)
+#define PCS_HD __host__ __device__ __forceinline__
+#else
+#define PCS_HD inline
+#endif
+
 // One way of drawing a haplotype for a read that starts inside a tile: the
 // haplotype leaves of one (sample group | normal cells, fragment set) list.
 // A single 32-bit draw u picks the entry (first with u <= thr) and the leaf inside
-// it: leaf = umulhi(u - base, scale), base = previous entry's thr + 1 (0 for the first),
-// scale = floor(list_n * 2^32 / (thr - base + 1)).  16 bytes: one LDS.128 per read.
+// it.  With x = u - base (base = previous entry's thr + 1, 0 for the first) and
+// width = thr - base + 1 the leaf is EXACTLY floor(x * list_n / width): every leaf of
+// an entry owns floor(width / list_n) or ceil(width / list_n) of the entry's draw
+// values -- as uniform as 32 bits allow (every cell / allele of a class is
+// equiprobable: src/sequencing.cpp:155-163, src/seq_simulation.cpp:572-578).
+// The quotient is a 64-bit fixed-point multiply by scale64 = ceil(list_n * 2^64 / width)
+// (exact_leaf_scale / exact_leaf below): `scale` holds its high word here, the low
+// word lives in the parallel array entry_lo[] (one extra LDS.32 per read that reaches
+// the walk; the 16-byte entry stays one LDS.128).
 struct Entry {
   uint32_t thr;       // last draw value belonging to this entry (cumulative)
-  uint32_t scale;
+  uint32_t scale;     // high word of scale64
   uint32_t list_off;  // into hap_list
   uint32_t frag_end;  // last position of the fragment the tile lies in (reads never cross it)
 };
 static_assert(sizeof(Entry) == 16, "Entry layout");
+
+// floor(x * list_n / width) for every 0 <= x < width <= 2^32 when list_n < width:
+// x * scale64 / 2^64 = x * list_n / width + x * delta / 2^64 with 0 <= delta < 1, and the excess
+// (< 2^-32) cannot reach the next integer because frac(x * list_n / width) <= 1 - 1 / width.
+PCS_HD uint32_t exact_leaf(uint32_t x, uint32_t scale_hi, uint32_t scale_lo) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t carry = __umulhi(x, scale_lo);
+#else
+  const uint32_t carry = static_cast<uint32_t>((static_cast<uint64_t>(x) * scale_lo) >> 32);
+#endif
+  return static_cast<uint32_t>((static_cast<uint64_t>(x) * scale_hi + carry) >> 32);
+}
+
+// host: scale64 = ceil(list_n * 2^64 / width).  list_n >= width (a class so light that it owns fewer
+// draw values than it has haplotypes) saturates: leaf = x - 1 (0 for x = 0), inside the list.
+inline void exact_leaf_scale(uint64_t list_n, uint64_t width, uint32_t& hi, uint32_t& lo) {
+  if (width == 0 || list_n >= width) {
+    hi = lo = 0xffffffffu;
+    return;
+  }
+  const unsigned __int128 s = ((static_cast<unsigned __int128>(list_n) << 64) + (width - 1)) / width;
+  hi = static_cast<uint32_t>(static_cast<uint64_t>(s >> 32));
+  lo = static_cast<uint32_t>(static_cast<uint64_t>(s));
+}
 
 constexpr uint32_t kMaxStagedEntries = 16;  // tiles drawing from more lists use the global kernel
 

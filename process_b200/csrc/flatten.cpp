@@ -79,6 +79,7 @@ struct ChrWork {
   std::vector<uint32_t> ev_off;       // [n_nodes+1], indexed by preorder position
   std::vector<uint32_t> ev_nodes;     // the preorder positions that have events of this chromosome, increasing
   bool has_wgd = false;
+  uint32_t row_lo = 0, row_hi = 0;    // rows of this chromosome in the mutation table
   std::vector<Inst> inst;
   std::vector<HapRec> haps;           // fragset is a LOCAL id until merge
   std::vector<FragKey> fragsets;
@@ -152,7 +153,13 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
 
 // haplotype numbering of one chromosome: leaves (w.haps), the SOMATIC placements sorted by row (w.inst),
 // the interval below each germline allele, the pieces its fragment sets cut the chromosome into
-void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
+//
+// A haplotype carries at most ONE SID per position (the kernels' walk and the read materialiser rely on it; the
+// oracle refuses anything else): `occupied` has one bit per position of the chromosome, set while a SID at that
+// position is carried by the haplotypes being numbered -- the germline SIDs of the germline allele the walk
+// descends from, and every open somatic instance.  A SID that finds its bit set is a second SID of the haplotype
+// at that position: std::domain_error, as the oracle.
+void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std::atomic<uint8_t>* row_mask) {
   const uint32_t chr = w.chr;
   const uint32_t clen = d.chr_len[chr];
   const uint8_t n0 = d.chr_n_alleles[chr];
@@ -166,7 +173,9 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
       e.y = d.mut_pos[m];
       e.meta = static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8);
     }
-  if (w.has_wgd) wgd_prepass(d, t, w);
+  // allele ids along every lineage: WGD copies get their ids, and an amplification into an id the lineage
+  // already has is refused -- with or without a WGD in the forest
+  wgd_prepass(d, t, w);
 
   const uint32_t full = w.intern_set(FragKey{{1u, clen}});
   uint32_t counter = 0;
@@ -205,6 +214,8 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   std::vector<Scan> scans;
   std::vector<Undo> undo;
   std::vector<uint32_t> open;  // instances whose interval is still growing
+  std::vector<uint64_t> occupied((static_cast<size_t>(clen) >> 6) + 2, 0);
+  auto occupied_bit = [&](uint32_t pos) -> uint64_t& { return occupied[pos >> 6]; };
   const uint32_t* leaf_pos = t.leaf_pos.data();
   const uint32_t* leaf_id = t.leaf_id.data();
   const uint32_t n_leaf_pos = static_cast<uint32_t>(t.leaf_pos.size());
@@ -214,12 +225,20 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
     for (size_t k = open_size; k < open.size(); ++k) {
       Inst& in = w.inst[open[k]];
       in.span = counter - in.lo;
+      const uint32_t pos = d.mut_pos[in.row];
+      occupied_bit(pos) &= ~(1ull << (pos & 63));
     }
     open.resize(open_size);
   };
 
   w.inst.reserve(w.ev.size());
   for (uint16_t g = 0; g < n0; ++g) {
+    for (uint32_t m = w.row_lo; m < w.row_hi; ++m)  // the germline SIDs of allele g
+      if ((row_mask[m].load(std::memory_order_relaxed) >> g) & 1u) {
+        const uint32_t pos = d.mut_pos[m];
+        check(!((occupied_bit(pos) >> (pos & 63)) & 1ull), "two germline SIDs at one position of one allele");
+        occupied_bit(pos) |= 1ull << (pos & 63);
+      }
     germ_lo[g] = counter;
     w.haps.push_back({0u, full, g, HAP_NORMAL_PLAIN});
     ++counter;
@@ -293,6 +312,8 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
             if (e.allele != sc.allele) continue;
             if (e.kind == PCS_EV_SID) {
               if (holds(w.fragsets[sc.fs], e.y)) {
+                check(!((occupied_bit(e.y) >> (e.y & 63)) & 1ull), "two SIDs at one position of one allele");
+                occupied_bit(e.y) |= 1ull << (e.y & 63);
                 open.push_back(static_cast<uint32_t>(w.inst.size()));
                 w.inst.push_back({counter, 0u, e.x, e.meta});
               }
@@ -337,6 +358,11 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
       }
     }
     germ_hi[g] = counter;
+    for (uint32_t m = w.row_lo; m < w.row_hi; ++m)
+      if ((row_mask[m].load(std::memory_order_relaxed) >> g) & 1u) {
+        const uint32_t pos = d.mut_pos[m];
+        occupied_bit(pos) &= ~(1ull << (pos & 63));
+      }
   }
 
   // a SID no sampled haplotype inherited has an empty interval: drop it
@@ -666,22 +692,14 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     });
   }
   timer.lap("events by chromosome");
-  // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
-  std::vector<uint32_t> chr_order(d.n_chr);
-  for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
-  std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
-    return chr_load[a] != chr_load[b] ? chr_load[a] > chr_load[b] : a < b;
-  });
-  parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]]); });
-  timer.lap("haplotype numbering");
-
   // ---- germline SIDs by row.  The caller's list comes in any order; a SID is normally listed once, so the
-  // list is scattered into one allele-mask byte per row (0 = not germline).  Should a row be listed twice, a
-  // stably sorted copy of the list is walked instead (same result, slower).
+  // list is scattered into one allele-mask byte per row (0 = not germline; a row listed twice gets the union
+  // of its masks).  Should a row be listed twice, a stably sorted copy of the list is walked for the instances
+  // instead (same result, slower).  Built before the haplotype numbering, which checks somatic SIDs against it.
   const uint64_t G = d.n_germline;
   check(G <= 0xffffffffull, "too many germline SIDs");
   const uint32_t g_chunks = G ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (G + 65535) / 65536)) : 0;
-  // relaxed atomics (plain byte moves): a row listed twice may be written by two threads
+  // relaxed atomic ORs: a row listed twice may be written by two threads
   std::unique_ptr<std::atomic<uint8_t>[]> row_mask(new std::atomic<uint8_t>[static_cast<size_t>(d.n_mut) + 1]());
   {
     // Threads must not write mask bytes of the same cache line, or the line bounces between cores for every
@@ -712,7 +730,7 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
       // chunk k writes rows [germ_mut[lo], germ_mut[hi-1]]: only the two edge bytes can share a line
       parallel_for(g_chunks, [&](uint32_t k) {
         const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
-        for (uint64_t i = lo; i < hi; ++i) row_mask[d.germ_mut[i]].store(d.germ_allele_mask[i], std::memory_order_relaxed);
+        for (uint64_t i = lo; i < hi; ++i) row_mask[d.germ_mut[i]].fetch_or(d.germ_allele_mask[i], std::memory_order_relaxed);
       });
     } else {
       // hist -> where chunk k writes its entries of bucket b: buckets in order, chunks in order inside a bucket
@@ -744,10 +762,24 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
       });
       parallel_for(n_buckets, [&](uint32_t b) {  // bucket = 2^shift rows, shift >= 6: whole cache lines
         for (uint64_t i = bucket_off[b]; i < bucket_off[b + 1]; ++i)
-          row_mask[part[i] & 0x3fffffffu].store(static_cast<uint8_t>(part[i] >> 30), std::memory_order_relaxed);
+          row_mask[part[i] & 0x3fffffffu].fetch_or(static_cast<uint8_t>(part[i] >> 30), std::memory_order_relaxed);
       });
     }
   }
+  timer.lap("germline masks");
+  // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
+  std::vector<uint32_t> chr_order(d.n_chr);
+  for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
+  std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
+    return chr_load[a] != chr_load[b] ? chr_load[a] > chr_load[b] : a < b;
+  });
+  for (uint32_t c = 0; c < d.n_chr; ++c) {
+    work[c].row_lo = chr_row_off[c];
+    work[c].row_hi = chr_row_off[c + 1];
+  }
+  parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]], row_mask.get()); });
+  timer.lap("haplotype numbering");
+
   // chunks of loci (a locus never straddles two chunks); germline rows per chunk
   const uint32_t m_chunks = n_loci ? std::min<uint32_t>(4 * n_threads, (n_loci + 65535) / 65536) : 0;
   auto chunk_locus = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n_loci) * k / m_chunks); };
@@ -771,6 +803,9 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     for (uint64_t i = 0; i < G; ++i) {
       g_mut[i] = static_cast<uint32_t>(key[i] >> 32);
       g_mask[i] = d.germ_allele_mask[key[i] & 0xffffffffull];
+      if (i > 0 && g_mut[i] == g_mut[i - 1])  // masks of one row must name different alleles
+        for (uint64_t j = i; j-- > 0 && g_mut[j] == g_mut[i];)
+          check((g_mask[j] & g_mask[i]) == 0, "a germline SID is listed twice for one allele");
     }
     for (uint32_t k = 0; k <= m_chunks; ++k)
       germ_before[k] = std::lower_bound(g_mut.begin(), g_mut.end(), out.locus_first_row[chunk_locus(k)]) - g_mut.begin();

@@ -296,7 +296,10 @@ __device__ __forceinline__ bool walk_global(const GlobalView& V, uint32_t i, uin
     } else {
       for (uint32_t k = L.k0; k < L.k0 + L.n_multi; ++k) {
         const uint4 in = V.instance(k);
-        if (h - in.x < in.y && !carried_sid(V, p, in.w, in.z, false, R, frag_end, w, err)) return true;
+        if (h - in.x < in.y) {  // a haplotype carries at most one SID per position (enforced by the flattener)
+          if (!carried_sid(V, p, in.w, in.z, false, R, frag_end, w, err)) return true;
+          break;
+        }
       }
     }
   }
@@ -316,7 +319,10 @@ __device__ __forceinline__ bool walk_shared(const SharedView& V, uint32_t i, uin
     } else {
       for (uint32_t k = r.y; k < r.y + r.w; ++k) {
         const uint4 in = V.instance(k);
-        if (h - in.x < in.y && !carried_sid(V, r.x, in.w, in.z, true, R, frag_end, w, err)) return true;
+        if (h - in.x < in.y) {
+          if (!carried_sid(V, r.x, in.w, in.z, true, R, frag_end, w, err)) return true;
+          break;
+        }
       }
     }
   }
@@ -339,15 +345,15 @@ struct Template {
 };
 
 template <class EntryPtr>
-__device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const DevForest& F, uint32_t u_start, uint32_t u_hap,
-                                      uint32_t tlen, Template& out) {
+__device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const uint32_t* ent_lo, const DevForest& F,
+                                      uint32_t u_start, uint32_t u_hap, uint32_t tlen, Template& out) {
   out.x = T.begin + __umulhi(u_start, T.len);
   uint32_t e = 0, base = 0;
   while (u_hap > ent[e].thr) {  // the last entry's thr is 0xffffffff
     base = ent[e].thr + 1u;
     ++e;
   }
-  const uint32_t leaf = __umulhi(u_hap - base, ent[e].scale);
+  const uint32_t leaf = exact_leaf(u_hap - base, ent[e].scale, __ldg(ent_lo + e));
   out.h = __ldg(F.hap_list + (ent[e].list_off + leaf));
   out.frag_end = ent[e].frag_end;
   return out.x + (tlen - 1u) <= out.frag_end;  // else the template falls off its molecule
@@ -430,8 +436,9 @@ struct StagedTile {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(dir + bucket * 8u));
     return v;
   }
-  // the sampling entry a haplotype draw falls in: {thr, scale, list_off, frag_end}; base = first draw value of the entry
-  __device__ __forceinline__ uint4 entry_of(uint32_t u_hap, uint32_t& base) const {
+  // the sampling entry a haplotype draw falls in: {thr, scale high word, list_off, frag_end}; base = first draw
+  // value of the entry, lo_addr = shared address of the low word of its scale
+  __device__ __forceinline__ uint4 entry_of(uint32_t u_hap, uint32_t& base, uint32_t& lo_addr) const {
     uint32_t addr = ent;
     base = 0;
     uint4 a = lds128(addr);
@@ -440,6 +447,7 @@ struct StagedTile {
       addr += 16u;
       a = lds128(addr);
     }
+    lo_addr = ent + kMaxStagedEntries * 16u + ((addr - ent) >> 2);
     return a;
   }
 };
@@ -451,9 +459,9 @@ template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
                                             uint32_t* depth, uint32_t* alt, uint4 item) {
   const uint32_t R = M.read_size;
-  uint32_t base;
-  const uint4 a = S.entry_of(item.y, base);
-  const uint32_t h = __ldg(F.hap_list + (a.z + __umulhi(item.y - base, a.y)));
+  uint32_t base, lo_addr;
+  const uint4 a = S.entry_of(item.y, base, lo_addr);
+  const uint32_t h = __ldg(F.hap_list + (a.z + exact_leaf(item.y - base, a.y, lds32(lo_addr))));
   const uint32_t xs = T.begin + item.x, read_id = item.z, i = item.w, frag_end = a.w;
   Walk w;
   w.init(xs, R, frag_end);
@@ -527,15 +535,17 @@ __device__ __noinline__ void settle_carried(ErrModel E, uint32_t slots, uint32_t
 
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 __global__ void __launch_bounds__(kStagedThreads, MIN_CTAS)
-sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
-                           StageDims D, uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
+sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries,
+                           const uint32_t* __restrict__ entry_lo, DevForest F, SeqModel M, StageDims D,
+                           uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
                            unsigned long long* __restrict__ n_reads) {
   extern __shared__ __align__(16) unsigned char smem[];
   uint4* s_rec = reinterpret_cast<uint4*>(smem);
   uint4* s_queue = s_rec + D.max_loci + 1;
   uint4* s_carried = s_queue + (kStagedThreads / 32) * kQueueSlots;
   uint4* s_ent = s_carried + (ERRORS ? (kStagedThreads / 32) * kCarriedSlots : 0u);
-  uint2* s_dir = reinterpret_cast<uint2*>(s_ent + kMaxStagedEntries);
+  uint32_t* s_ent_lo = reinterpret_cast<uint32_t*>(s_ent + kMaxStagedEntries);  // [kMaxStagedEntries]
+  uint2* s_dir = reinterpret_cast<uint2*>(s_ent_lo + kMaxStagedEntries);
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
   __shared__ uint32_t s_safe;
@@ -563,8 +573,10 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   }
   if (threadIdx.x == 0) s_rec[n] = make_uint4(0xffffffffu, 0u, 0u, 0u);  // sentinel: past every read
   for (uint32_t r = threadIdx.x; r < T.n_rows; r += kStagedThreads) s_alt[r] = 0;
-  if (threadIdx.x < T.n_entries)
+  if (threadIdx.x < T.n_entries) {
     s_ent[threadIdx.x] = __ldg(reinterpret_cast<const uint4*>(entries + T.entry_off) + threadIdx.x);
+    s_ent_lo[threadIdx.x] = __ldg(entry_lo + T.entry_off + threadIdx.x);
+  }
   if (threadIdx.x == 32) {
     // start offsets below s_safe fit their molecule whatever haplotype is drawn: the longest template
     // (M.reach bases) ends at or before the nearest fragment end of any entry
@@ -609,8 +621,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
   // does a template of tlen bases starting at offset off fit the fragment its haplotype draw selects?
   auto fits = [&](uint32_t u_hap, uint32_t off, uint32_t tlen) {
-    uint32_t base;
-    return T.begin + off + (tlen - 1u) <= S.entry_of(u_hap, base).w;
+    uint32_t base, lo_addr;
+    return T.begin + off + (tlen - 1u) <= S.entry_of(u_hap, base, lo_addr).w;
   };
   // probe: the directory gives index and offset of the first staged locus at or after the read's bucket in one
   // load; the read goes to the queue if that locus lies before its end (the sentinel covers empty buckets)
@@ -714,7 +726,8 @@ __device__ __forceinline__ void global_read(const Tile& T, const DevForest& F, c
 
 template <bool TRACE>
 __global__ void __launch_bounds__(256)
-sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
+sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries,
+                           const uint32_t* __restrict__ entry_lo, DevForest F, SeqModel M,
                            uint32_t* __restrict__ depth, uint32_t* __restrict__ alt,
                            unsigned long long* __restrict__ n_reads, DevPlacement* __restrict__ trace,
                            uint32_t* __restrict__ trace_masks, unsigned long long trace_cap,
@@ -726,6 +739,7 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
                       TRACE ? nullptr : alt + static_cast<size_t>(T.sample) * F.n_mut};
   const uint32_t R = M.read_size;
   const Entry* ent = entries + T.entry_off;
+  const uint32_t* ent_lo = entry_lo + T.entry_off;
   uint32_t placed = 0;
 
   if (M.paired) {
@@ -733,7 +747,7 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       const uint4 u = philox4x32_10(make_uint4(t, T.id, 0u, M.seed));
       const uint32_t ins = draw_insert(M, u.z);
       Template tp;
-      if (!place(T, ent, F, u.x, u.y, 2u * R + ins, tp)) continue;
+      if (!place(T, ent, ent_lo, F, u.x, u.y, 2u * R + ins, tp)) continue;
       global_read<TRACE>(T, F, M, GV, chr_l1, 2u * t, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
       global_read<TRACE>(T, F, M, GV, chr_l1, 2u * t + 1u, tp.x + R + ins, tp.h, tp.frag_end, trace, trace_masks,
                          trace_cap, trace_n);
@@ -744,11 +758,11 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
       const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
       Template tp;
-      if (place(T, ent, F, u.x, u.y, R, tp)) {
+      if (place(T, ent, ent_lo, F, u.x, u.y, R, tp)) {
         global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
         ++placed;
       }
-      if (2u * j + 1u < T.n_templates && place(T, ent, F, u.z, u.w, R, tp)) {
+      if (2u * j + 1u < T.n_templates && place(T, ent, ent_lo, F, u.z, u.w, R, tp)) {
         global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j + 1u, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap,
                            trace_n);
         ++placed;
@@ -875,14 +889,16 @@ __device__ void materialize_read(const DevForest& F, const SeqModel& M, const Se
 }
 
 __global__ void __launch_bounds__(128)
-materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
-                         SeqData D, SamHeader* __restrict__ hdr, uint32_t* __restrict__ masks,
+materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries,
+                         const uint32_t* __restrict__ entry_lo, DevForest F, SeqModel M, SeqData D,
+                         SamHeader* __restrict__ hdr, uint32_t* __restrict__ masks,
                          uint8_t* __restrict__ seq, uint8_t* __restrict__ qual, unsigned long long cap,
                          unsigned long long* __restrict__ n_out) {
   const Tile T = tiles[blockIdx.x];
   const uint32_t chr_l1 = F.chr_locus_off[T.chr + 1];
   const uint32_t R = M.read_size;
   const Entry* ent = entries + T.entry_off;
+  const uint32_t* ent_lo = entry_lo + T.entry_off;
   const uint32_t n_blocks = M.paired ? T.n_templates : (T.n_templates + 1u) >> 1;
   for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
     const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
@@ -892,13 +908,13 @@ materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict
       int32_t tlen = 0;
       if (M.paired) {
         ins = draw_insert(M, u.z);
-        if (!place(T, ent, F, u.x, u.y, 2u * R + ins, tp)) break;
+        if (!place(T, ent, ent_lo, F, u.x, u.y, 2u * R + ins, tp)) break;
         xs = tp.x + k * (R + ins);
         mate_start = tp.x + (1u - k) * (R + ins);
         tlen = static_cast<int32_t>(2u * R + ins) * (k == 0 ? 1 : -1);
       } else {
         if (2u * j + k >= T.n_templates) break;
-        if (!place(T, ent, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) continue;
+        if (!place(T, ent, ent_lo, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) continue;
         xs = tp.x;
       }
       const unsigned long long idx = atomicAdd(n_out, 1ull);
@@ -921,11 +937,11 @@ materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict
 }
 
 cudaError_t launch_materialize_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                     const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
+                                     const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
                                      uint32_t* masks, uint8_t* seq, uint8_t* qual, unsigned long long cap,
                                      unsigned long long* n_out) {
   if (n_tiles == 0) return cudaSuccess;
-  materialize_tiles_kernel<<<n_tiles, 128, 0, st>>>(tiles, entries, F, M, D, hdr, masks, seq, qual, cap, n_out);
+  materialize_tiles_kernel<<<n_tiles, 128, 0, st>>>(tiles, entries, entry_lo, F, M, D, hdr, masks, seq, qual, cap, n_out);
   return cudaGetLastError();
 }
 
@@ -973,6 +989,7 @@ size_t staged_smem_bytes(const StageDims& D, bool errors) {
   size_t b = static_cast<size_t>(D.max_loci) * (sizeof(uint4) + sizeof(uint32_t));
   b += (1 + static_cast<size_t>(kStagedThreads / 32) * (kQueueSlots + (errors ? kCarriedSlots : 0u)) + kMaxStagedEntries) *
        sizeof(uint4);
+  b += kMaxStagedEntries * sizeof(uint32_t);  // low words of the entries' leaf scales
   b += static_cast<size_t>(D.max_rows) * sizeof(uint32_t);
   b += static_cast<size_t>(D.max_buckets) * sizeof(uint2);
   return (b + 15) & ~static_cast<size_t>(15);
@@ -991,57 +1008,57 @@ static int staged_min_ctas(bool errors) {
 
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
 static cudaError_t launch_staged_occ(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                     const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                     const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                      uint32_t* alt, unsigned long long* n_reads) {
   const size_t smem = staged_smem_bytes(D, ERRORS);
   auto kern = sample_tiles_staged_kernel<PAIRED, ERRORS, MIN_CTAS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kern<<<n_tiles, kStagedThreads, smem, st>>>(tiles, entries, F, M, D, depth, alt, n_reads);
+  kern<<<n_tiles, kStagedThreads, smem, st>>>(tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
   return cudaGetLastError();
 }
 
 template <bool PAIRED, bool ERRORS>
 static cudaError_t launch_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                 const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                 const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                  uint32_t* alt, unsigned long long* n_reads) {
   switch (staged_min_ctas(ERRORS)) {
-    case 3: return launch_staged_occ<PAIRED, ERRORS, 3>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
-    case 5: return launch_staged_occ<PAIRED, ERRORS, 5>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
-    case 6: return launch_staged_occ<PAIRED, ERRORS, 6>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
-    case 8: return launch_staged_occ<PAIRED, ERRORS, 8>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
-    default: return launch_staged_occ<PAIRED, ERRORS, 4>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    case 3: return launch_staged_occ<PAIRED, ERRORS, 3>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
+    case 5: return launch_staged_occ<PAIRED, ERRORS, 5>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
+    case 6: return launch_staged_occ<PAIRED, ERRORS, 6>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
+    case 8: return launch_staged_occ<PAIRED, ERRORS, 8>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
+    default: return launch_staged_occ<PAIRED, ERRORS, 4>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
   }
 }
 
 cudaError_t launch_sample_tiles_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                       const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                       const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                        uint32_t* alt, unsigned long long* n_reads) {
   if (n_tiles == 0) return cudaSuccess;
   const bool errors = M.sequencer != PCS_SEQ_ERRORLESS;
   if (M.paired) {
-    return errors ? launch_staged<true, true>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads)
-                  : launch_staged<true, false>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+    return errors ? launch_staged<true, true>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads)
+                  : launch_staged<true, false>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
   }
-  return errors ? launch_staged<false, true>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads)
-                : launch_staged<false, false>(st, tiles, n_tiles, entries, F, M, D, depth, alt, n_reads);
+  return errors ? launch_staged<false, true>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads)
+                : launch_staged<false, false>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
 }
 
 cudaError_t launch_sample_tiles_global(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                       const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
+                                       const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
                                        unsigned long long* n_reads) {
   if (n_tiles == 0) return cudaSuccess;
-  sample_tiles_global_kernel<false><<<n_tiles, 256, 0, st>>>(tiles, entries, F, M, depth, alt, n_reads, nullptr,
+  sample_tiles_global_kernel<false><<<n_tiles, 256, 0, st>>>(tiles, entries, entry_lo, F, M, depth, alt, n_reads, nullptr,
                                                               nullptr, 0ull, nullptr);
   return cudaGetLastError();
 }
 
 cudaError_t launch_trace_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                               const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
+                               const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
                                DevPlacement* trace, uint32_t* trace_masks, unsigned long long cap,
                                unsigned long long* trace_n) {
   if (n_tiles == 0) return cudaSuccess;
-  sample_tiles_global_kernel<true><<<n_tiles, 256, 0, st>>>(tiles, entries, F, M, nullptr, nullptr, n_reads, trace,
+  sample_tiles_global_kernel<true><<<n_tiles, 256, 0, st>>>(tiles, entries, entry_lo, F, M, nullptr, nullptr, n_reads, trace,
                                                              trace_masks, cap, trace_n);
   return cudaGetLastError();
 }

@@ -12,17 +12,17 @@ namespace pcs {
 
 size_t staged_smem_bytes(const StageDims& D, bool errors);
 cudaError_t launch_sample_tiles_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                       const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
+                                       const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                        uint32_t* alt, unsigned long long* n_reads);
 cudaError_t launch_sample_tiles_global(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                       const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
+                                       const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, uint32_t* depth, uint32_t* alt,
                                        unsigned long long* n_reads);
 cudaError_t launch_trace_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                               const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
+                               const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, unsigned long long* n_reads,
                                DevPlacement* trace, uint32_t* trace_masks, unsigned long long cap,
                                unsigned long long* trace_n);
 cudaError_t launch_materialize_tiles(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                     const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
+                                     const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const SeqData& D, SamHeader* hdr,
                                      uint32_t* masks, uint8_t* seq, uint8_t* qual, unsigned long long cap,
                                      unsigned long long* n_out);
 cudaError_t launch_count_injected(cudaStream_t st, const DevPlacement* rec, const uint32_t* masks,

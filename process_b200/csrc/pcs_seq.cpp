@@ -440,6 +440,7 @@ struct HostPlan {
   std::vector<uint32_t> sample_tile_off;    // [n_out_samples + 1]
   pcs::StageDims dims{};
   std::vector<pcs::Entry> entries;
+  std::vector<uint32_t> entry_lo;      // low word of every entry's leaf scale (dev.hpp: exact_leaf)
   std::vector<uint32_t> insert_alias;  // [n][2] {keep threshold, alias column}
   pcs::SeqModel model{};
   pcs_plan_info info{};
@@ -452,6 +453,7 @@ struct pcs_plan {
   // the staged tiles once more, grouped by output sample (host-output runs launch sample by sample)
   DevBuf<pcs::Tile> d_tiles_by_sample;  // uploaded by the first run that needs it
   DevBuf<pcs::Entry> d_entries;
+  DevBuf<uint32_t> d_entry_lo;
   DevBuf<uint32_t> d_insert_alias;
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
   DevBuf<unsigned long long> d_counters;  // [0] reads placed [1] sum depth [2] sum occ [3] trace count
@@ -702,6 +704,7 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
 // the tiles with the RNG stream of (seed, sample, chromosome)); entry_off is relative to `entries`
 struct SampleChrPlan {
   std::vector<pcs::Entry> entries;
+  std::vector<uint32_t> entry_lo;
   std::vector<pcs::Tile> tiles;
   uint64_t total_templates = 0;
 };
@@ -761,9 +764,11 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
         if (static_cast<uint64_t>(thr[i]) + 1 <= base) continue;
         const uint64_t width = static_cast<uint64_t>(thr[i]) + 1 - base;
         es[i].thr = thr[i];
-        // leaf = umulhi(u - base, scale) < list_n, base = previous kept entry's thr + 1
-        es[i].scale = static_cast<uint32_t>(std::min<uint64_t>(0xffffffffull, (static_cast<uint64_t>(es_n[i]) << 32) / width));
+        // leaf = floor((u - base) * list_n / width), base = previous kept entry's thr + 1: uniform inside the entry
+        uint32_t lo = 0;
+        pcs::exact_leaf_scale(es_n[i], width, es[i].scale, lo);
         entries.push_back(es[i]);
+        task.entry_lo.push_back(lo);
         ++n_kept;
         base = static_cast<uint64_t>(thr[i]) + 1;
       }
@@ -850,11 +855,13 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     }
     all.reserve(n_tiles);
     entries.reserve(n_entries);
+    pl.entry_lo.reserve(n_entries);
   }
   uint64_t total_templates = 0;
   for (auto& task : per) {
     const uint32_t base = static_cast<uint32_t>(entries.size());
     entries.insert(entries.end(), task.entries.begin(), task.entries.end());
+    pl.entry_lo.insert(pl.entry_lo.end(), task.entry_lo.begin(), task.entry_lo.end());
     for (auto& t : task.tiles) {
       t.entry_off += base;
       t.id = static_cast<uint32_t>(all.size());
@@ -939,6 +946,7 @@ void upload_plan(pcs_plan& pl) {
   pl.h2d_bytes += pl.d_tiles_global.upload(pl.host.tiles_global, st);
   pl.d_tiles_by_sample.release();
   pl.h2d_bytes += pl.d_entries.upload(pl.host.entries, st);
+  pl.h2d_bytes += pl.d_entry_lo.upload(pl.host.entry_lo, st);
   pl.h2d_bytes += pl.d_insert_alias.upload(pl.host.insert_alias, st);
   pl.host.model.insert_alias = pl.d_insert_alias.p;
   const size_t S = pl.host.info.n_out_samples;
@@ -991,7 +999,7 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
     const size_t row_bytes = M * sizeof(uint32_t);
     for (size_t smp = 0; smp < S; ++smp) {
       const uint32_t t0 = pl.host.sample_tile_off[smp], t1 = pl.host.sample_tile_off[smp + 1];
-      CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles_by_sample.p + t0, t1 - t0, pl.d_entries.p, DF, pl.host.model,
+      CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles_by_sample.p + t0, t1 - t0, pl.d_entries.p, pl.d_entry_lo.p, DF, pl.host.model,
                                               pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
       CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p + smp * L, fo.d_row_locus.p, 1u, static_cast<uint32_t>(L),
                                    static_cast<uint32_t>(M), d_cov + smp * M));
@@ -1012,9 +1020,9 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
     CUDA_OK(cudaEventRecord(cx.ev[2], st));
   } else {
     CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
-                                            DF, pl.host.model, pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
+                                            pl.d_entry_lo.p, DF, pl.host.model, pl.host.dims, pl.d_depth.p, d_occ, pl.d_counters.p));
     CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
-                                            pl.d_entries.p, DF, pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
+                                            pl.d_entries.p, pl.d_entry_lo.p, DF, pl.host.model, pl.d_depth.p, d_occ, pl.d_counters.p));
     launches += (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
     CUDA_OK(cudaEventRecord(cx.ev[2], st));
     CUDA_OK(pcs::launch_finalize(st, pl.d_depth.p, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
@@ -1098,9 +1106,9 @@ void accumulate_plan(pcs_plan& pl, uint32_t* d_depth, uint32_t* d_occ, pcs_run_s
   CUDA_OK(cudaEventRecord(cx.ev[1], st));
   const pcs::DevForest DF = fo.dev();
   CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
-                                          DF, pl.host.model, pl.host.dims, d_depth, d_occ, pl.d_counters.p));
+                                          pl.d_entry_lo.p, DF, pl.host.model, pl.host.dims, d_depth, d_occ, pl.d_counters.p));
   CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
-                                          pl.d_entries.p, DF, pl.host.model, d_depth, d_occ, pl.d_counters.p));
+                                          pl.d_entries.p, pl.d_entry_lo.p, DF, pl.host.model, d_depth, d_occ, pl.d_counters.p));
   CUDA_OK(cudaEventRecord(cx.ev[2], st));
   unsigned long long counters[4] = {0, 0, 0, 0};
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
@@ -1170,7 +1178,7 @@ void materialize_tiles(pcs_plan& pl, const std::vector<pcs::Tile>& tiles, uint64
   d_seq.alloc(cap * R, st);
   d_qual.alloc(cap * R, st);
   CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
-  CUDA_OK(pcs::launch_materialize_tiles(st, d_tiles.p, static_cast<uint32_t>(tiles.size()), pl.d_entries.p, fo.dev(),
+  CUDA_OK(pcs::launch_materialize_tiles(st, d_tiles.p, static_cast<uint32_t>(tiles.size()), pl.d_entries.p, pl.d_entry_lo.p, fo.dev(),
                                         pl.host.model, D, d_hdr.p, d_masks.p, d_seq.p, d_qual.p, cap, pl.d_counters.p + 3));
   unsigned long long counters[4];
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
@@ -1188,6 +1196,12 @@ void materialize_tiles(pcs_plan& pl, const std::vector<pcs::Tile>& tiles, uint64
     CUDA_OK(cudaMemcpyAsync(out.qual.data(), d_qual.p, out.qual.size(), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
   }
+  // a CIGAR the record cannot hold would no longer describe SEQ: refuse, never truncate
+  for (const auto& h : out.hdr)
+    if (h.flags & 4u)
+      throw std::domain_error("a read carries more indels than a CIGAR of " + std::to_string(pcs::kMaxCigar) +
+                              " operations can describe (tile " + std::to_string(h.tile_id) + ", read " +
+                              std::to_string(h.read_id) + ")");
 }
 
 void placement_of(const pcs::FlatForest& F, const pcs::SamHeader& h, pcs_read_placement& r) {
@@ -1689,6 +1703,8 @@ int pcs_plan_materialize(pcs_plan* pl, uint64_t cap, pcs_read_placement* placeme
                          uint8_t* qual, uint32_t* cigar, uint32_t* n_cigar, uint32_t* lengths, uint64_t* n_out) {
   return guarded([&] {
     require(pl && placements && seq && qual && cigar && n_cigar && lengths && n_out, "bad arguments");
+    require(!err_masks || pl->host.info.read_size <= 32u * PCS_ERRMASK_WORDS,
+            "error masks cover 256 read offsets: reads longer than that cannot be materialised with masks");
     std::vector<pcs::Tile> tiles = pl->host.tiles;
     tiles.insert(tiles.end(), pl->host.tiles_global.begin(), pl->host.tiles_global.end());
     Materialized m;
@@ -1781,6 +1797,8 @@ int pcs_memcpy_d2h(pcs_ctx* cx, void* host_dst, const void* dev_src, size_t byte
 int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint64_t cap, uint64_t* n_out) {
   return guarded([&] {
     require(pl && rec && n_out, "bad arguments");
+    require(!masks || pl->host.model.sequencer == PCS_SEQ_ERRORLESS || pl->host.info.read_size <= 32u * PCS_ERRMASK_WORDS,
+            "error masks cover 256 read offsets: reads longer than that cannot be traced with masks");
     pcs_forest& fo = *pl->forest;
     pcs_ctx& cx = *fo.ctx;
     cx.bind();
@@ -1791,10 +1809,10 @@ int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint6
     if (masks) d_masks.alloc(cap * PCS_ERRMASK_WORDS, st);
     CUDA_OK(cudaMemsetAsync(pl->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
     CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
-                                    fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p, cap,
+                                    pl->d_entry_lo.p, fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p, cap,
                                     pl->d_counters.p + 3));
     CUDA_OK(pcs::launch_trace_tiles(st, pl->d_tiles_global.p, static_cast<uint32_t>(pl->host.tiles_global.size()),
-                                    pl->d_entries.p, fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p,
+                                    pl->d_entries.p, pl->d_entry_lo.p, fo.dev(), pl->host.model, pl->d_counters.p, d_rec.p, d_masks.p,
                                     cap, pl->d_counters.p + 3));
     unsigned long long counters[4];
     CUDA_OK(cudaMemcpyAsync(counters, pl->d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
@@ -1837,6 +1855,8 @@ int pcs_count_injected(pcs_forest* fo, uint32_t n_out_samples, uint32_t read_siz
     require(fo && occ && cov && (rec || n == 0), "bad arguments");
     require(read_size >= 1 && read_size <= 65535, "read_size must be in [1, 65535]");
     require(n_out_samples >= 1 && n_out_samples <= 65535, "n_out_samples out of range");
+    require(!masks || read_size <= 32u * PCS_ERRMASK_WORDS,
+            "error masks cover 256 read offsets: reads longer than that cannot be injected with masks");
     const pcs::FlatForest& F = fo->host.flat;
     fo->host.build_lookup();
     std::vector<pcs::DevPlacement> h(n);
@@ -1923,6 +1943,9 @@ int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples,
       const bool normals = !params || normal_only || params->with_normal_sample || params->purity < 1.0;
       carried.assign(F.n_mut, 0);
       for (uint32_t c = 0; c < F.n_chr; ++c) {
+        // the reference hands only the chromosomes of `chr_ids` to the simulator (src/seq_simulation.cpp:570,577):
+        // rows of the others never reach its data frame
+        if (params && params->chr_mask && !params->chr_mask[c]) continue;
         std::vector<uint32_t> seq_haps;  // sorted haplotype indices of the sequenced cells
         const auto& haps = F.chr_haps[c];
         for (uint32_t h = 0; h < haps.size(); ++h) {
@@ -1933,8 +1956,18 @@ int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples,
         for (uint32_t l = F.chr_locus_off[c]; l < F.chr_locus_off[c + 1]; ++l)
           for (uint32_t i = F.locus_inst_off[l]; i < F.locus_inst_off[l + 1]; ++i) {
             const pcs::Inst& in = F.inst[i];
-            auto it = std::lower_bound(seq_haps.begin(), seq_haps.end(), in.lo);
-            if (it != seq_haps.end() && *it - in.lo < in.span) carried[in.row] = 1;
+            if (carried[in.row]) continue;
+            // a haplotype of the interval that still HOLDS the position (a later CNA deletion may have taken it)
+            const uint32_t pos = F.locus_pos[l];
+            for (auto it = std::lower_bound(seq_haps.begin(), seq_haps.end(), in.lo);
+                 it != seq_haps.end() && *it - in.lo < in.span; ++it) {
+              bool has = false;
+              for (const auto& fr : F.fragsets[haps[*it].fragset]) has |= pos >= fr.b && pos <= fr.e;
+              if (has) {
+                carried[in.row] = 1;
+                break;
+              }
+            }
           }
       }
     }
@@ -2092,6 +2125,72 @@ int pcs_flat_plan(const pcs_flat* fl, const pcs_seq_params* params, pcs_plan_inf
       if (tile_begin) tile_begin[i] = both[i].begin;
       if (tile_len) tile_len[i] = both[i].len;
     }
+  });
+}
+
+
+int pcs_flat_hap_list(const pcs_flat* fl, uint32_t offset, uint32_t n, uint32_t* haps) {
+  return guarded([&] {
+    require(fl && (n == 0 || haps), "bad arguments");
+    require(static_cast<size_t>(offset) + n <= fl->host.hap_list.size(), "slice outside hap_list");
+    std::copy_n(fl->host.hap_list.begin() + offset, n, haps);
+  });
+}
+
+int pcs_flat_tile_entries(const pcs_flat* fl, const pcs_seq_params* params, uint32_t tile_id, uint32_t cap,
+                          uint32_t* thr, uint32_t* list_off, uint32_t* list_n, uint32_t* frag_end, uint32_t* n) {
+  return guarded([&] {
+    require(fl && params && n, "bad arguments");
+    validate(*params);
+    pcs_seq_params P = *params;
+    P.shard_rank = 0;
+    P.shard_count = 1;
+    const HostPlan pl = make_host_plan(fl->host, P);
+    std::unordered_map<uint32_t, uint32_t> n_of;  // list offset -> haplotypes in the list
+    for (const auto& kv : fl->host.list_index) n_of[kv.second.first] = kv.second.second;
+    for (const auto* v : {&pl.tiles, &pl.tiles_global})
+      for (const pcs::Tile& t : *v) {
+        if (t.id != tile_id) continue;
+        *n = t.n_entries;
+        for (uint32_t e = 0; e < t.n_entries && e < cap; ++e) {
+          const pcs::Entry& en = pl.entries[t.entry_off + e];
+          if (thr) thr[e] = en.thr;
+          if (list_off) list_off[e] = en.list_off;
+          if (list_n) list_n[e] = n_of.at(en.list_off);
+          if (frag_end) frag_end[e] = en.frag_end;
+        }
+        return;
+      }
+    throw std::domain_error("no tile with that id holds templates");
+  });
+}
+
+int pcs_flat_draw(const pcs_flat* fl, const pcs_seq_params* params, uint32_t tile_id, uint64_t n_draws,
+                  const uint32_t* u, uint32_t* hap, uint32_t* entry) {
+  return guarded([&] {
+    require(fl && params && (n_draws == 0 || (u && hap)), "bad arguments");
+    validate(*params);
+    pcs_seq_params P = *params;
+    P.shard_rank = 0;
+    P.shard_count = 1;
+    const HostPlan pl = make_host_plan(fl->host, P);
+    for (const auto* v : {&pl.tiles, &pl.tiles_global})
+      for (const pcs::Tile& t : *v) {
+        if (t.id != tile_id) continue;
+        const pcs::Entry* ent = pl.entries.data() + t.entry_off;
+        const uint32_t* lo = pl.entry_lo.data() + t.entry_off;
+        for (uint64_t i = 0; i < n_draws; ++i) {  // the device's place() / staged_read(), word for word
+          uint32_t e = 0, base = 0;
+          while (u[i] > ent[e].thr) {
+            base = ent[e].thr + 1u;
+            ++e;
+          }
+          hap[i] = fl->host.hap_list[ent[e].list_off + pcs::exact_leaf(u[i] - base, ent[e].scale, lo[e])];
+          if (entry) entry[i] = e;
+        }
+        return;
+      }
+    throw std::domain_error("no tile with that id holds templates");
   });
 }
 

@@ -369,7 +369,7 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
       const uint32_t o = occ[s * M + r], cv = cov[s * M + r];
       col.occurrences.push_back(static_cast<int>(o));
       col.coverage.push_back(static_cast<int>(cv));
-      col.VAF.push_back(static_cast<double>(o) / cv);  // :126
+      col.VAF.push_back(cv ? static_cast<double>(o) / cv : 0.0);  // :126; never covered: 0 (:129-131)
     }
     res.samples.push_back(std::move(col));
   }

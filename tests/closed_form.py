@@ -83,6 +83,42 @@ def expected_tables(f, coverage, purity, R, with_normal=True, insert=None, prene
     return e_cov, e_occ
 
 
+def expected_haplotype_reads(f, coverage, purity, R, with_normal=True, preneoplastic_in_normal=False):
+    """single-end: E[reads placed] of every (sample, chromosome, PCS_PLACE_* kind, cell, allele) -- N / W * w *
+    (fragment length - R + 1)+ summed over the allele's fragments (a start is uniform over the fragment and the read
+    is dropped when it does not fit, A11).  Inside a class (the tumour cells of a sample; the normal cells) every
+    cell weighs the same: src/sequencing.cpp:155-163."""
+    n_s = f.n_samples
+    S = n_s + (1 if with_normal else 0)
+    out = {}
+    for c in range(f.n_chr):
+        N = int(np.floor(coverage * int(f.chr_len[c]) / R + 0.5))
+
+        def molecules(kind, cell, weight):
+            frags, _ = oracle.cell_genome(f, kind, cell, c)
+            return [(weight, kind, cell, a, b, e) for a, o, b, e in frags if b > 0]
+
+        if preneoplastic_in_normal:
+            n_roots = int((f.node_parent < 0).sum())
+            normal = [m for r in range(n_roots) for m in molecules(A.PCS_PLACE_NORMAL_PRENEO, r, 1.0 / n_roots)]
+        else:
+            normal = molecules(A.PCS_PLACE_NORMAL_PLAIN, 0, 1.0)
+        for s in range(S):
+            cells = [] if s >= n_s else [l for l in range(f.n_leaves) if f.leaf_sample[l] == s]
+            p = purity if cells else 0.0
+            mol = []
+            if p > 0:
+                for l in cells:
+                    mol += molecules(A.PCS_PLACE_TUMOUR, l, p / len(cells))
+            if p < 1:
+                mol += [((1 - p) * m[0],) + m[1:] for m in normal]
+            W = sum(w * (e - b + 1) for w, kind, cell, a, b, e in mol)
+            for w, kind, cell, a, b, e in mol:
+                key = (s, c, kind, cell, a)
+                out[key] = out.get(key, 0.0) + N / W * w * max(0, e - b + 1 - R + 1)
+    return out
+
+
 def z_scores(obs, exp, min_expected=20.0):
     """Poisson z-scores of the cells whose expectation is large enough for the normal approximation; and the
     number of cells that are non-zero although their expectation is exactly zero"""
@@ -91,8 +127,15 @@ def z_scores(obs, exp, min_expected=20.0):
     return z, int((obs[exp == 0] != 0).sum())
 
 
-def snv_only_spec(seed=5):
+def snv_only_spec(seed=5, **kw):
     from conftest import small_spec
-    return small_spec(seed, chr_names=["1", "X"], chr_len=[120_000, 80_000], chr_n_alleles=[2, 1], sample_cells=[5, 7],
-                      germline_density=3e-3, germline_indel_frac=0.0, n_preneo_snv=20, n_preneo_indel=0, indel_frac=0.0,
-                      node_snv_mean=6, n_clones=2, clone_cna=3, wgd_clones=1, cna_len=(3000, 40000))
+    d = dict(chr_names=["1", "X"], chr_len=[120_000, 80_000], chr_n_alleles=[2, 1], sample_cells=[5, 7],
+             germline_density=3e-3, germline_indel_frac=0.0, n_preneo_snv=20, n_preneo_indel=0, indel_frac=0.0,
+             node_snv_mean=6, n_clones=2, clone_cna=3, wgd_clones=1, cna_len=(3000, 40000))
+    d.update(kw)
+    return small_spec(seed, **d)
+
+
+def cna_dense_spec(seed=9):
+    """many short CNAs: most tiles draw from several sampling entries even at purity 1"""
+    return snv_only_spec(seed, sample_cells=[6, 9], n_clones=3, clone_cna=12, wgd_clones=1, cna_len=(1500, 15000))

@@ -177,6 +177,53 @@ def test_malformed_forests_are_refused():
         L.Flat(f)
 
 
+def _micro_with_events(extra, node):
+    """the micro forest with `extra` events (kind, pos, len, allele, dest, mut, nature) appended to `node`"""
+    d = {k: (list(v) if isinstance(v, list) else v) for k, v in MF.FOREST.items()}
+    at = d["node_event_off"][node + 1]
+    for j, (kind, pos, ln, allele, dest, mut, nature) in enumerate(extra):
+        for key, val in (("ev_kind", kind), ("ev_chr", 0), ("ev_pos", pos), ("ev_len", ln), ("ev_allele", allele),
+                         ("ev_dest", dest), ("ev_mut", mut), ("ev_nature", nature)):
+            d[key].insert(at + j, val)
+    d["node_event_off"] = [o + (len(extra) if i > node else 0) for i, o in enumerate(d["node_event_off"])]
+    from process_b200.forest import PhylogeneticForest
+    kw = {k: (v if k in ("chr_names", "sample_names") else np.asarray(v)) for k, v in d.items()}
+    return PhylogeneticForest(**kw).normalise()
+
+
+def test_a_haplotype_carries_at_most_one_sid_per_position():
+    """the kernels' walk counts one SID per position of a haplotype; the flattener must refuse anything else,
+    exactly where the oracle does (its explicit genomes are position-keyed maps)"""
+    SID, AMP = A.PCS_EV_SID, A.PCS_EV_CNA_AMP
+    refused = {
+        "the root's SID again in a child, same allele": ([(SID, 0, 0, 1, 0, 2, 1)], 1),
+        "the same SID twice in one node": ([(SID, 0, 0, 0, 0, 4, 1)], 1),
+        "a somatic SID on a germline SID of the allele": ([(SID, 0, 0, 0, 0, 0, 1)], 1),
+        "inherited through an amplified copy": ([(AMP, 350, 100, 0, 3, 0, 1), (SID, 0, 0, 3, 0, 4, 1)], 1),
+        "amplification into an allele id the lineage has (no WGD anywhere)": ([(AMP, 350, 100, 0, 1, 0, 1)], 1),
+    }
+    for why, (extra, node) in refused.items():
+        f = _micro_with_events(extra, node)
+        with pytest.raises(L.PcsError):
+            L.Flat(f)
+        with pytest.raises(oracle.OracleError):
+            oracle.cell_genome(f, A.PCS_PLACE_TUMOUR, 0, 0)
+    accepted = {
+        "the same position on the other allele": [(SID, 0, 0, 1, 0, 4, 1)],
+        "a germline position of the OTHER allele": [(SID, 0, 0, 1, 0, 0, 1)],
+        "a position the allele has lost": [(A.PCS_EV_CNA_DEL, 380, 40, 0, 0, 0, 1), (SID, 0, 0, 0, 0, 4, 1)],
+    }
+    for why, extra in accepted.items():
+        f = _micro_with_events(extra, 2 if "lost" not in why else 1)
+        check_flat_against_explicit_genomes(f)
+    # a germline SID listed twice for one allele
+    f = MF.forest()
+    f.germ_mut = np.asarray([0, 1, 3, 7, 0], np.uint32)
+    f.germ_allele_mask = np.asarray([1, 3, 2, 1, 1], np.uint8)
+    with pytest.raises(L.PcsError):
+        L.Flat(f)
+
+
 def test_planner_tile_grid_and_template_counts():
     f = synth_forest(small_spec(1))
     fl = L.Flat(f)

@@ -55,6 +55,29 @@ def _worker(rank, world, port, out_dir):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         assert hi.item() - lo.item() <= float(t_all["templates"].max())
+        # seed=None: every rank draws from its OWN RNG state; the call must still plan one job.  The seed is resolved
+        # on rank 0 and broadcast, and the shards planned with it partition the tile grid
+        np.random.seed(1000 + rank)
+        own = api._resolve_seed(None)
+        seeds = [None] * world
+        dist.all_gather_object(seeds, own)
+        assert len(set(seeds)) == world  # the ranks did draw different seeds
+        agreed = api._agree_over_ranks(own, None, list(f.sample_names))
+        assert agreed == seeds[0]
+        info_all, t_all = fl.plan(make_params(coverage=30.0, purity=0.7, seed=agreed))
+        info, t = fl.plan(make_params(coverage=30.0, purity=0.7, seed=agreed, shard_rank=rank, shard_count=world))
+        ids = torch.zeros(int(info_all.n_tiles_total), dtype=torch.int32)
+        ids[torch.from_numpy(t["id"].astype(np.int64))] = 1
+        dist.all_reduce(ids)
+        owned = torch.zeros_like(ids)
+        owned[torch.from_numpy(t_all["id"].astype(np.int64))] = 1
+        assert torch.equal(ids, owned)
+        # ranks that disagree on the sample partition are refused
+        try:
+            api._agree_over_ranks(own, np.full(f.n_leaves, rank, np.uint32), ["a", "b"])
+            raise AssertionError("differing partitions were accepted")
+        except ValueError:
+            pass
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
