@@ -130,6 +130,45 @@ typedef struct pcs_forest_desc {
   const uint8_t*  germ_allele_mask; /* [n_germline] bit a set: allele a carries the SID */
 } pcs_forest_desc;
 
+/*
+ * The same forest as EXPLICIT PER-CELL GENOMES -- what the seam of the reference really hands over:
+ * forest.get_sample_mutations_list() (per sample a list of CellGenomeMutations, src/seq_simulation.cpp:566) and
+ * forest.get_normal_sample("normal_sample", true) (src/seq_simulation.cpp:572), each genome walked as
+ * chromosome -> allele -> fragment -> SID (src/phylogenetic_forest.cpp:279-290, 332-335).  No tree is needed: the
+ * library recovers the haplotype intervals from the genomes' contents.  Cells 0 .. n_cells-1 are the sampled
+ * tumour cells; cells n_cells .. n_cells+n_normal_preneo-1 are the normal cells that carry the germline plus the
+ * pre-neoplastic SIDs (needed only for preneoplastic_in_normal; the plain normal cell is the germline itself).
+ * Alleles are listed in any order; an allele's fragments sorted by position; its SIDs in any order.
+ */
+typedef struct pcs_cell_genomes_desc {
+  uint32_t n_chr;
+  const uint32_t* chr_len;          /* [n_chr] */
+  const uint8_t*  chr_n_alleles;    /* [n_chr] alleles of the germline genome */
+  uint32_t n_samples;
+  uint32_t n_cells;
+  const uint32_t* cell_sample;      /* [n_cells] */
+  uint32_t n_normal_preneo;
+  uint64_t n_alleles;
+  const uint32_t* allele_cell;      /* [n_alleles] */
+  const uint16_t* allele_chr;       /* [n_alleles] */
+  const uint16_t* allele_id;        /* [n_alleles] AlleleId inside the cell */
+  const uint8_t*  allele_origin;    /* [n_alleles] germline allele it descends from (the source chain of its CNAs) */
+  const uint64_t* allele_frag_off;  /* [n_alleles+1] */
+  const uint32_t* frag_begin;       /* inclusive, 1-based */
+  const uint32_t* frag_end;
+  const uint64_t* allele_sid_off;   /* [n_alleles+1] */
+  const uint32_t* sid_row;          /* somatic SIDs the allele carries: rows of the mutation table */
+  /* mutation table and germline SIDs: as in pcs_forest_desc */
+  uint32_t n_mut;
+  const uint16_t* mut_chr;
+  const uint32_t* mut_pos;
+  const uint8_t*  mut_ref_len;
+  const uint8_t*  mut_alt_len;
+  uint64_t n_germline;
+  const uint32_t* germ_mut;
+  const uint8_t*  germ_allele_mask;
+} pcs_cell_genomes_desc;
+
 /* arguments of one simulate_seq()/simulate_normal_seq() call
  * (src/seq_simulation.hpp:28-54; defaults src/sequencing.cpp:193-209) */
 typedef struct pcs_seq_params {
@@ -202,7 +241,10 @@ typedef struct pcs_plan pcs_plan;
 /* flags of pcs_plan_run */
 enum {
   PCS_RUN_HOST_OUTPUT = 0,    /* occ/cov are host pointers  */
-  PCS_RUN_DEVICE_OUTPUT = 1   /* occ/cov are device pointers on the context's device */
+  PCS_RUN_DEVICE_OUTPUT = 1,  /* occ/cov are device pointers on the context's device */
+  PCS_RUN_NO_CHECKSUMS = 2,   /* skip the two table checksums (sum_depth / sum_occurrences stay 0) */
+  PCS_RUN_ASYNC = 4           /* with DEVICE_OUTPUT: return once the kernels are queued; stats are not filled,
+                                 the plan's counters accumulate until pcs_plan_counters() reads them */
 };
 
 int pcs_abi_version(void);
@@ -217,6 +259,8 @@ int pcs_device_name(pcs_ctx* ctx, char* buf, size_t buf_len);
 
 /* flatten the forest (haplotype numbering, loci, fragment sets) and copy it to HBM */
 int pcs_forest_upload(pcs_ctx* ctx, const pcs_forest_desc* desc, pcs_forest** forest);
+/* the same from explicit per-cell genomes (pcs_cell_genomes_desc): identical tables for identical reads */
+int pcs_forest_upload_genomes(pcs_ctx* ctx, const pcs_cell_genomes_desc* genomes, pcs_forest** forest);
 int pcs_forest_free(pcs_forest* forest);
 /* repartition the sampled cells into `n_groups` output samples (FACS labelling);
  * leaf_group == NULL restores the forest's own samples */
@@ -248,12 +292,18 @@ int pcs_shared_open(pcs_ctx* ctx, const unsigned char ipc_handle[64], void** dev
 int pcs_shared_close(pcs_ctx* ctx, void* dev_ptr);
 int pcs_enable_peer(pcs_ctx* ctx, int peer_device);
 int pcs_memset_u32(pcs_ctx* ctx, uint32_t* dev_ptr, size_t count);   /* async on the context's stream */
+int pcs_memset_u32_stream(pcs_ctx* ctx, uint32_t* dev_ptr, size_t count, void* stream); /* async on a cudaStream_t */
 int pcs_memcpy_d2h(pcs_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes); /* synchronous */
-/* run this shard's sampler adding into the given tables: no zeroing, no finalize */
+/* run this shard's sampler adding into the given tables: no zeroing, no finalize.  stats == NULL: asynchronous --
+ * the call returns once the kernels are queued on the context's stream and the plan's counters accumulate */
 int pcs_plan_accumulate(pcs_plan* plan, uint32_t* depth, uint32_t* occurrences, pcs_run_stats* stats);
-/* coverage[s][row] = depth[s][locus(row)] (device pointers) + table checksums in stats */
+/* coverage[s][row] = depth[s][locus(row)] (device pointers) + table checksums in stats; stats == NULL:
+ * asynchronous, no checksums */
 int pcs_plan_finalize(pcs_plan* plan, const uint32_t* depth, const uint32_t* occurrences, uint32_t* coverage,
                       pcs_run_stats* stats);
+/* wait for the plan's queued work, read and reset its counters: n_reads / checksums accumulated by the asynchronous
+ * calls since the last read, kernel_ms of the last sampler launch */
+int pcs_plan_counters(pcs_plan* plan, pcs_run_stats* stats);
 
 /* ---- one process, several GPUs (what the single-threaded R session needs) ----
  * pcs_forest_replicate: a second device copy of an uploaded forest, sharing its flattened host view.
@@ -313,11 +363,42 @@ int pcs_count_injected(pcs_forest* forest, uint32_t n_out_samples, uint32_t read
 int pcs_active_rows(pcs_forest* forest, const uint32_t* occurrences, uint32_t n_out_samples,
                     int include_non_sequenced, const pcs_seq_params* params, uint32_t* rows_out, uint32_t* n_rows);
 
+/* ---- result assembly on the device (get_result_dataframe / get_active_mutations / add_sample_statistics,
+ * src/seq_simulation.cpp:92-181): the rows of the data frame -- occurrences > 0 in some sample, or carried by a
+ * sequenced cell with include_non_sequenced -- compacted in row order into one column per sample:
+ * occurrences (int), coverage (int), VAF (double, occurrences / coverage; 0 where coverage is 0, :129-131).
+ * Only these columns cross the link.  pcs_simulate_result = plan + sample + assemble (the call the Rcpp shim
+ * makes); pcs_plan_result assembles the tables the last pcs_plan_run of the plan left on the device.
+ * pcs_result_fetch copies into caller-owned columns (R vectors): rows[n_rows], and per sample s the pointers
+ * occ_cols[s] / cov_cols[s] / vaf_cols[s] to n_rows elements each (any array or pointer may be NULL = skip). */
+typedef struct pcs_result pcs_result;
+int pcs_simulate_result(pcs_forest* forest, const pcs_seq_params* params, int include_non_sequenced, int with_vaf,
+                        pcs_result** result, pcs_run_stats* stats);
+int pcs_plan_result(pcs_plan* plan, int include_non_sequenced, const pcs_seq_params* params, int with_vaf,
+                    pcs_result** result);
+int pcs_result_info(const pcs_result* result, uint32_t* n_rows, uint32_t* n_samples, int* has_vaf);
+int pcs_result_fetch(pcs_result* result, uint32_t* rows, int32_t* const* occ_cols, int32_t* const* cov_cols,
+                     double* const* vaf_cols, uint64_t* d2h_bytes);
+int pcs_result_free(pcs_result* result);
+
+/* ---- host-side column builders for the annotation columns of the data frame (chr, chr_pos, ref, alt, causes,
+ * classes; src/seq_simulation.cpp:52-90), parallel over the host cores; no GPU involved.
+ * pcs_host_gather: dst[i] = src[rows[i]] for elements of 1, 2, 4 or 8 bytes.
+ * pcs_host_string_column: the strings table[codes[rows[i]]] as an Arrow large_string column -- offsets[n + 1]
+ * (int64), the concatenated bytes in `data` (capacity data_cap; NULL: only offsets, *data_len and the validity
+ * bits are produced, so that the caller can size `data` and call again), and, when `validity` is not NULL, one
+ * bit per row (LSB first, ceil(n / 8) bytes; 0 = the table entry is NULL = NA). */
+int pcs_host_gather(const uint32_t* rows, uint64_t n, const void* src, uint32_t elem_bytes, void* dst);
+int pcs_host_string_column(const uint32_t* rows, uint64_t n, const uint16_t* codes, const char* const* table,
+                           uint32_t n_table, int64_t* offsets, char* data, uint64_t data_cap, uint8_t* validity,
+                           uint64_t* data_len, uint64_t* null_count);
+
 /* ---- host-only introspection of the flattened view (no GPU needed).  Used by the
  * CPU test-suite to check the haplotype-interval view against explicit per-cell
  * genomes and the planner's shard partition; not needed by the Rcpp shim. ---- */
 typedef struct pcs_flat pcs_flat;
 int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** flat);
+int pcs_flat_create_genomes(const pcs_cell_genomes_desc* genomes, pcs_flat** flat);
 int pcs_flat_free(pcs_flat* flat);
 int pcs_flat_set_groups(pcs_flat* flat, const uint32_t* leaf_group, uint32_t n_groups);
 int pcs_flat_info(const pcs_flat* flat, uint64_t out[6]);

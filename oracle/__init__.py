@@ -63,7 +63,10 @@ def simulate(forest, params: A.SeqParams, leaf_group=None, n_groups=None, n_thre
         A.ptr(masks, C.c_uint32), C.c_uint64(trace_cap), C.byref(tn), C.byref(nr)))
     if rec is not None and tn.value > trace_cap:
         raise OracleError(f"trace capacity {trace_cap} < {tn.value} reads")
+    tm = (C.c_double * 4)()
+    lib().oracle_last_timing(tm)
     return dict(occ=occ, cov=cov, n_reads=nr.value,
+                timing=dict(genomes_cpu_s=tm[0], fixed_cpu_s=tm[1], read_loop_cpu_s=tm[2], wall_s=tm[3]),
                 trace=None if rec is None else rec[:tn.value],
                 masks=None if masks is None else masks[:tn.value])
 
@@ -115,3 +118,50 @@ def materialize(forest, ref_off, ref_bases: bytes, alt_off, alt_bytes: bytes, re
         A.ptr(em, C.c_uint32), C.c_uint64(n), A.ptr(seq, C.c_uint8), A.ptr(qual, C.c_uint8), A.ptr(cigar, C.c_uint32),
         A.ptr(nc, C.c_uint32), A.ptr(ln, C.c_uint32)))
     return seq, qual, cigar, nc, ln
+
+
+def chr_genomes(forest, chrom, with_preneo=True):
+    """every explicit genome of one chromosome: dict of CSR arrays (allele_cell, allele_id, allele_origin,
+    allele_frag_off, frag_begin, frag_end, allele_sid_off, sid_row); cells >= n_leaves are the normal cells with the
+    pre-neoplastic SIDs (one per root)"""
+    d = forest.as_desc()
+    n = (C.c_uint64 * 3)()
+    null = lambda ct: C.cast(None, C.POINTER(ct))
+    _check(lib().oracle_chr_genomes(C.byref(d), C.c_uint32(chrom), C.c_int(1 if with_preneo else 0), C.c_uint64(0),
+                                    C.c_uint64(0), C.c_uint64(0), null(C.c_uint32), null(C.c_uint16), null(C.c_uint8),
+                                    null(C.c_uint64), null(C.c_uint32), null(C.c_uint32), null(C.c_uint64),
+                                    null(C.c_uint32), n))
+    na, nf, ns = int(n[0]), int(n[1]), int(n[2])
+    out = dict(allele_cell=np.zeros(na, np.uint32), allele_id=np.zeros(na, np.uint16), allele_origin=np.zeros(na, np.uint8),
+               allele_frag_off=np.zeros(na + 1, np.uint64), frag_begin=np.zeros(max(nf, 1), np.uint32),
+               frag_end=np.zeros(max(nf, 1), np.uint32), allele_sid_off=np.zeros(na + 1, np.uint64),
+               sid_row=np.zeros(max(ns, 1), np.uint32))
+    _check(lib().oracle_chr_genomes(C.byref(d), C.c_uint32(chrom), C.c_int(1 if with_preneo else 0), C.c_uint64(max(na, 1)),
+                                    C.c_uint64(max(nf, 1)), C.c_uint64(max(ns, 1)), A.ptr(out["allele_cell"], C.c_uint32),
+                                    A.ptr(out["allele_id"], C.c_uint16), A.ptr(out["allele_origin"], C.c_uint8),
+                                    A.ptr(out["allele_frag_off"], C.c_uint64), A.ptr(out["frag_begin"], C.c_uint32),
+                                    A.ptr(out["frag_end"], C.c_uint32), A.ptr(out["allele_sid_off"], C.c_uint64),
+                                    A.ptr(out["sid_row"], C.c_uint32), n))
+    out["frag_begin"], out["frag_end"], out["sid_row"] = out["frag_begin"][:nf], out["frag_end"][:nf], out["sid_row"][:ns]
+    return out
+
+
+def cell_genomes(forest, with_preneo=True):
+    """the forest as explicit per-cell genomes (process_b200.genomes.CellGenomes): what the reference's
+    get_sample_mutations_list() / get_normal_sample() hand to the sequencing simulator"""
+    from process_b200.genomes import CellGenomes
+    parts = [chr_genomes(forest, c, with_preneo) for c in range(forest.n_chr)]
+    cat = lambda k, dt: np.concatenate([p[k] for p in parts]).astype(dt)
+    frag_off = np.concatenate([[0]] + [p["allele_frag_off"][1:] + sum(len(q["frag_begin"]) for q in parts[:i])
+                                       for i, p in enumerate(parts)]).astype(np.uint64)
+    sid_off = np.concatenate([[0]] + [p["allele_sid_off"][1:] + sum(len(q["sid_row"]) for q in parts[:i])
+                                      for i, p in enumerate(parts)]).astype(np.uint64)
+    n_roots = int((np.asarray(forest.node_parent) < 0).sum())
+    return CellGenomes(
+        source=forest, n_cells=forest.n_leaves, cell_sample=np.asarray(forest.leaf_sample, np.uint32),
+        n_normal_preneo=n_roots if with_preneo else 0,
+        allele_cell=cat("allele_cell", np.uint32),
+        allele_chr=np.concatenate([np.full(len(p["allele_cell"]), c, np.uint16) for c, p in enumerate(parts)]),
+        allele_id=cat("allele_id", np.uint16), allele_origin=cat("allele_origin", np.uint8),
+        allele_frag_off=frag_off, frag_begin=cat("frag_begin", np.uint32), frag_end=cat("frag_end", np.uint32),
+        allele_sid_off=sid_off, sid_row=cat("sid_row", np.uint32))

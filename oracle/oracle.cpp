@@ -31,6 +31,8 @@
  */
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -47,6 +49,18 @@
 namespace {
 
 thread_local std::string g_err;
+
+// where the time of the last oracle_simulate went, in CPU-seconds summed over its worker threads:
+// [0] building explicit genomes, [1] per (sample, chromosome) fixed work (zeroing the per-base coverage vector,
+// drawing the per-fragment template counts, gathering the tables), [2] the read loop, [3] wall-clock of the call
+std::atomic<double> g_timing[4];
+void add_time(int k, double sec) {
+  double old = g_timing[k].load();
+  while (!g_timing[k].compare_exchange_weak(old, old + sec)) {}
+}
+double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 // ---------------------------------------------------------------- genome model
 struct Fragment {
@@ -428,6 +442,8 @@ void simulate_sample_chr(const Forest& f, const ChrGenomes& G, uint32_t chr, uin
                          std::vector<uint32_t>& occ_row, std::vector<uint32_t>& cov_row, Trace* trace,
                          uint64_t* n_reads_out) {
   const pcs_forest_desc* d = f.d;
+  const double t_begin = now_s();
+  std::atomic<double> t_loop{0.0};
   const uint32_t R = P.read_size;
   const bool paired = P.insert_size_mean > 0;
   const uint32_t mates = paired ? 2 : 1;
@@ -487,6 +503,7 @@ void simulate_sample_chr(const Forest& f, const ChrGenomes& G, uint32_t chr, uin
     auto ins = insert_dist;
     ErrMask m1, m2;
     size_t lo = frags.size() * t / n_threads, hi = frags.size() * (t + 1) / n_threads;
+    const double t_loop_begin = now_s();
     for (size_t i = lo; i < hi; ++i) {
       const FragRef& fr = frags[i];
       std::uniform_int_distribution<uint32_t> start(fr.fr->begin, fr.fr->end);
@@ -524,6 +541,11 @@ void simulate_sample_chr(const Forest& f, const ChrGenomes& G, uint32_t chr, uin
         }
       }
     }
+    {
+      const double dt = now_s() - t_loop_begin;
+      double old = t_loop.load();
+      while (!t_loop.compare_exchange_weak(old, old + dt)) {}
+    }
     cov[t] = std::move(out.cov);
   };
 
@@ -541,6 +563,9 @@ void simulate_sample_chr(const Forest& f, const ChrGenomes& G, uint32_t chr, uin
     }
     *n_reads_out += placed[t];
   }
+  add_time(2, t_loop.load());
+  // everything else of this task, in CPU-seconds: with inner threads the zeroing runs on all of them
+  add_time(1, std::max(0.0, (now_s() - t_begin) * n_threads - t_loop.load()));
 }
 
 bool chr_selected(const pcs_seq_params& P, uint32_t c) { return !P.chr_mask || P.chr_mask[c]; }
@@ -559,6 +584,12 @@ extern "C" {
 
 const char* oracle_last_error(void) { return g_err.c_str(); }
 
+/* CPU-seconds of the last oracle_simulate of the process: out[0] explicit genomes, out[1] fixed work per
+ * (sample, chromosome), out[2] the read loop, out[3] wall-clock seconds of the call */
+void oracle_last_timing(double out[4]) {
+  for (int k = 0; k < 4; ++k) out[k] = g_timing[k].load();
+}
+
 /* free-running simulation.  occ/cov: [n_out_samples][n_mut].  trace_* may be NULL. */
 int oracle_simulate(const pcs_forest_desc* desc, const pcs_seq_params* params, const uint32_t* leaf_group,
                     uint32_t n_groups, uint32_t n_threads, uint32_t* occ, uint32_t* cov,
@@ -573,13 +604,55 @@ int oracle_simulate(const pcs_forest_desc* desc, const pcs_seq_params* params, c
     auto cov_v = occ_v;
     Trace tr{trace_rec, trace_masks, trace_cap, 0};
     uint64_t placed = 0;
-    for (uint32_t c = 0; c < desc->n_chr; ++c) {
-      if (!chr_selected(*params, c)) continue;
-      ChrGenomes G = build_chr_genomes(f, c);
-      for (uint32_t s = 0; s < samples.size(); ++s)
-        simulate_sample_chr(f, G, c, s, samples[s], *params, n_threads, occ_v[s], cov_v[s],
-                            trace_rec ? &tr : nullptr, &placed);
+    for (auto& t : g_timing) t.store(0.0);
+    const double t_call = now_s();
+    std::vector<uint32_t> chrs;
+    for (uint32_t c = 0; c < desc->n_chr; ++c)
+      if (chr_selected(*params, c)) chrs.push_back(c);
+    if (n_threads > 1 && chrs.size() >= 2 && !trace_rec) {
+      // several chromosomes: one worker per chromosome (longest first), each single-threaded inside -- the
+      // tables are those of a one-thread run (the RNG streams are keyed by (seed, chromosome, sample, thread 0)),
+      // and no thread zeroes a per-base coverage vector it does not fill
+      std::sort(chrs.begin(), chrs.end(), [&](uint32_t a, uint32_t b) {
+        return desc->chr_len[a] != desc->chr_len[b] ? desc->chr_len[a] > desc->chr_len[b] : a < b;
+      });
+      std::atomic<size_t> next{0};
+      std::atomic<uint64_t> placed_all{0};
+      std::vector<std::string> errors(chrs.size());
+      auto worker = [&] {
+        for (size_t k = next.fetch_add(1); k < chrs.size(); k = next.fetch_add(1)) {
+          try {
+            const uint32_t c = chrs[k];
+            const double t0 = now_s();
+            ChrGenomes G = build_chr_genomes(f, c);
+            add_time(0, now_s() - t0);
+            uint64_t mine = 0;
+            for (uint32_t s = 0; s < samples.size(); ++s)  // rows of chromosome c only: no two workers share a cell
+              simulate_sample_chr(f, G, c, s, samples[s], *params, 1, occ_v[s], cov_v[s], nullptr, &mine);
+            placed_all += mine;
+          } catch (const std::exception& e) {
+            errors[k] = e.what();
+          }
+        }
+      };
+      std::vector<std::thread> th;
+      for (uint32_t w = 1; w < std::min<size_t>(n_threads, chrs.size()); ++w) th.emplace_back(worker);
+      worker();
+      for (auto& t : th) t.join();
+      for (const auto& e : errors)
+        if (!e.empty()) throw std::domain_error(e);
+      placed = placed_all.load();
+    } else {
+      for (uint32_t c : chrs) {
+        const double t0 = now_s();
+        ChrGenomes G = build_chr_genomes(f, c);
+        add_time(0, now_s() - t0);
+        for (uint32_t s = 0; s < samples.size(); ++s)
+          simulate_sample_chr(f, G, c, s, samples[s], *params, n_threads, occ_v[s], cov_v[s],
+                              trace_rec ? &tr : nullptr, &placed);
+      }
     }
+    g_timing[3].store(now_s() - t_call);
     for (uint32_t s = 0; s < samples.size(); ++s) {
       std::memcpy(occ + static_cast<size_t>(s) * desc->n_mut, occ_v[s].data(), sizeof(uint32_t) * desc->n_mut);
       std::memcpy(cov + static_cast<size_t>(s) * desc->n_mut, cov_v[s].data(), sizeof(uint32_t) * desc->n_mut);
@@ -746,6 +819,59 @@ int oracle_materialize(const pcs_forest_desc* desc, const uint64_t* ref_off, con
         lengths[i] = o;
       }
     }
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+/* Every explicit genome of one chromosome at once, as CSR arrays: the sampled cells 0 .. n_leaves-1, then (if
+ * with_preneo) the normal cells carrying the pre-neoplastic SIDs, one per root, as cells n_leaves + root ordinal.
+ * Alleles without DNA are listed with no fragment.  Two calls: with every capacity 0 to size the arrays
+ * (n_out = {alleles, fragments, SIDs}), then to fill them. */
+int oracle_chr_genomes(const pcs_forest_desc* desc, uint32_t chr, int with_preneo, uint64_t cap_alleles,
+                       uint64_t cap_frags, uint64_t cap_sids, uint32_t* allele_cell, uint16_t* allele_id,
+                       uint8_t* allele_origin, uint64_t* allele_frag_off, uint32_t* frag_begin, uint32_t* frag_end,
+                       uint64_t* allele_sid_off, uint32_t* sid_row, uint64_t n_out[3]) {
+  try {
+    Forest f = build_forest(desc);
+    check(chr < desc->n_chr, "chromosome out of range");
+    ChrGenomes G = build_chr_genomes(f, chr);
+    uint64_t na = 0, nf = 0, ns = 0;
+    auto emit = [&](const ChrGenome& g, uint32_t cell) {
+      for (const auto& [aid, al] : g.alleles) {
+        if (na < cap_alleles) {
+          allele_cell[na] = cell;
+          allele_id[na] = aid;
+          allele_origin[na] = static_cast<uint8_t>(al.origin);
+          allele_frag_off[na] = nf;
+          allele_sid_off[na] = ns;
+        }
+        ++na;
+        for (const auto& [b, fr] : al.fragments) {
+          if (nf < cap_frags) {
+            frag_begin[nf] = fr.begin;
+            frag_end[nf] = fr.end;
+          }
+          ++nf;
+          for (const auto& [pos, row] : fr.sids) {
+            if (ns < cap_sids) sid_row[ns] = row;
+            ++ns;
+          }
+        }
+      }
+    };
+    for (uint32_t l = 0; l < desc->n_leaves; ++l) emit(G.leaf[l], l);
+    if (with_preneo)
+      for (uint32_t r = 0; r < G.normal_preneo.size(); ++r) emit(G.normal_preneo[r], desc->n_leaves + r);
+    if (na <= cap_alleles && cap_alleles) {
+      allele_frag_off[na] = nf;
+      allele_sid_off[na] = ns;
+    }
+    n_out[0] = na;
+    n_out[1] = nf;
+    n_out[2] = ns;
     return 0;
   } catch (const std::exception& e) {
     g_err = e.what();

@@ -11,7 +11,7 @@ NATURE_DESCRIPTIONS = ("driver", "passenger", "germinal", "preneoplastic")
 PCS_SEQ_ERRORLESS, PCS_SEQ_BASIC_CONSTANT, PCS_SEQ_BASIC_RANDOM = 0, 1, 2
 PCS_PLACE_TUMOUR, PCS_PLACE_NORMAL_PLAIN, PCS_PLACE_NORMAL_PRENEO = 0, 1, 2
 PCS_ERRMASK_WORDS = 8
-PCS_RUN_HOST_OUTPUT, PCS_RUN_DEVICE_OUTPUT = 0, 1
+PCS_RUN_HOST_OUTPUT, PCS_RUN_DEVICE_OUTPUT, PCS_RUN_NO_CHECKSUMS, PCS_RUN_ASYNC = 0, 1, 2, 4
 
 _u8p = C.POINTER(C.c_uint8)
 _u16p = C.POINTER(C.c_uint16)
@@ -30,6 +30,18 @@ class ForestDesc(C.Structure):
         ("ev_allele", _u16p), ("ev_dest", _u16p), ("ev_mut", _u32p), ("ev_nature", _u8p),
         ("n_mut", C.c_uint32), ("mut_chr", _u16p), ("mut_pos", _u32p),
         ("mut_ref_len", _u8p), ("mut_alt_len", _u8p),
+        ("n_germline", C.c_uint64), ("germ_mut", _u32p), ("germ_allele_mask", _u8p),
+    ]
+
+
+class CellGenomesDesc(C.Structure):
+    _fields_ = [
+        ("n_chr", C.c_uint32), ("chr_len", _u32p), ("chr_n_alleles", _u8p),
+        ("n_samples", C.c_uint32), ("n_cells", C.c_uint32), ("cell_sample", _u32p), ("n_normal_preneo", C.c_uint32),
+        ("n_alleles", C.c_uint64), ("allele_cell", _u32p), ("allele_chr", _u16p), ("allele_id", _u16p),
+        ("allele_origin", _u8p), ("allele_frag_off", _u64p), ("frag_begin", _u32p), ("frag_end", _u32p),
+        ("allele_sid_off", _u64p), ("sid_row", _u32p),
+        ("n_mut", C.c_uint32), ("mut_chr", _u16p), ("mut_pos", _u32p), ("mut_ref_len", _u8p), ("mut_alt_len", _u8p),
         ("n_germline", C.c_uint64), ("germ_mut", _u32p), ("germ_allele_mask", _u8p),
     ]
 

@@ -29,6 +29,9 @@ EXPORTS = [
     "pcs_flat_create", "pcs_flat_free", "pcs_flat_set_groups", "pcs_flat_info", "pcs_flat_cell_haps",
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan", "pcs_flat_group_list",
     "pcs_flat_tile_entries", "pcs_flat_draw", "pcs_flat_hap_list",
+    "pcs_host_gather", "pcs_host_string_column", "pcs_plan_counters", "pcs_memset_u32_stream",
+    "pcs_forest_upload_genomes", "pcs_flat_create_genomes",
+    "pcs_simulate_result", "pcs_plan_result", "pcs_result_info", "pcs_result_fetch", "pcs_result_free",
 ]
 
 
@@ -62,6 +65,43 @@ def _u32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
 
 
+# --------------------------------------------------------------------------- host-side column builders
+def host_gather(rows, src):
+    """src[rows] on all host cores (rows: uint32)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    src = np.ascontiguousarray(src)
+    dst = np.empty(len(rows), src.dtype)
+    _ok(lib().pcs_host_gather(A.ptr(rows, C.c_uint32), C.c_uint64(len(rows)), C.c_void_p(src.ctypes.data),
+                              C.c_uint32(src.dtype.itemsize), C.c_void_p(dst.ctypes.data)))
+    return dst
+
+
+def host_string_column(rows, codes, table):
+    """the strings table[codes[rows]] (None in the table = NA) as Arrow large_string buffers:
+    (offsets int64 [n+1], data uint8 [len], validity uint8 [ceil(n/8)] or None, null_count)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint16)
+    n = len(rows)
+    enc = [None if x is None else str(x).encode() for x in table]
+    tab = (C.c_char_p * max(1, len(enc)))(*enc)
+    offsets = np.empty(n + 1, np.int64)
+    has_na = any(x is None for x in enc)
+    validity = np.zeros((n + 7) // 8, np.uint8) if has_na else None
+    length, nulls = C.c_uint64(0), C.c_uint64(0)
+    args = lambda data, cap: (A.ptr(rows, C.c_uint32), C.c_uint64(n), A.ptr(codes, C.c_uint16), tab, C.c_uint32(len(enc)),
+                              offsets.ctypes.data_as(C.POINTER(C.c_int64)), data, C.c_uint64(cap),
+                              A.ptr(validity, C.c_uint8), C.byref(length), C.byref(nulls))
+    bound = n * max([1] + [len(x) for x in enc if x is not None])
+    if bound <= (1 << 31):  # one call: pages of `data` past the real length are never touched
+        data = np.empty(max(1, bound), np.uint8)
+        _ok(lib().pcs_host_string_column(*args(C.c_void_p(data.ctypes.data), len(data))))
+    else:  # size it first
+        _ok(lib().pcs_host_string_column(*args(None, 0)))
+        data = np.empty(max(1, length.value), np.uint8)
+        _ok(lib().pcs_host_string_column(*args(C.c_void_p(data.ctypes.data), len(data))))
+    return offsets, data[:length.value], validity, nulls.value
+
+
 # --------------------------------------------------------------------------- host-only view
 class Flat:
     """flattened (haplotype-interval) view of a forest, host side only."""
@@ -69,8 +109,12 @@ class Flat:
     def __init__(self, forest):
         self.forest = forest
         self._h = C.c_void_p()
-        d = forest.as_desc()
-        _ok(lib().pcs_flat_create(C.byref(d), C.byref(self._h)))
+        if hasattr(forest, "as_genomes_desc"):  # explicit per-cell genomes (process_b200.genomes.CellGenomes)
+            d = forest.as_genomes_desc()
+            _ok(lib().pcs_flat_create_genomes(C.byref(d), C.byref(self._h)))
+        else:
+            d = forest.as_desc()
+            _ok(lib().pcs_flat_create(C.byref(d), C.byref(self._h)))
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -184,8 +228,11 @@ class Context:
     def enable_peer(self, device):
         _ok(lib().pcs_enable_peer(self._h, C.c_int(device)))
 
-    def memset_u32(self, ptr, n_words):
-        _ok(lib().pcs_memset_u32(self._h, C.c_void_p(ptr), C.c_size_t(n_words)))
+    def memset_u32(self, ptr, n_words, stream=None):
+        if stream is None:
+            _ok(lib().pcs_memset_u32(self._h, C.c_void_p(ptr), C.c_size_t(n_words)))
+        else:
+            _ok(lib().pcs_memset_u32_stream(self._h, C.c_void_p(ptr), C.c_size_t(n_words), C.c_void_p(stream)))
 
     def to_host(self, ptr, n_words):
         out = np.zeros(n_words, np.uint32)
@@ -198,6 +245,39 @@ class Context:
         return buf.value.decode()
 
 
+class Result:
+    """compact, column-major result of one call, resident on the device until fetched
+    (pcs_simulate_result / pcs_plan_result: the data frame's rows, assembled on the GPU)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        n, s, v = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+        _ok(lib().pcs_result_info(self._h, C.byref(n), C.byref(s), C.byref(v)))
+        self.n_rows, self.n_samples, self.has_vaf = n.value, s.value, bool(v.value)
+        self.d2h_bytes = 0
+
+    def fetch(self, vaf=True):
+        """(rows uint32 [n], occurrences int32 [S, n], coverage int32 [S, n], VAF float64 [S, n] or None)"""
+        n, S = self.n_rows, self.n_samples
+        rows = np.empty(n, np.uint32)
+        occ = np.empty((S, n), np.int32)
+        cov = np.empty((S, n), np.int32)
+        vf = np.empty((S, n), np.float64) if (vaf and self.has_vaf) else None
+        ptrs = lambda a, ct: (C.POINTER(ct) * S)(*[a[s].ctypes.data_as(C.POINTER(ct)) for s in range(S)])
+        b = C.c_uint64(0)
+        _ok(lib().pcs_result_fetch(self._h, A.ptr(rows, C.c_uint32), ptrs(occ, C.c_int32), ptrs(cov, C.c_int32),
+                                   ptrs(vf, C.c_double) if vf is not None else None, C.byref(b)))
+        self.d2h_bytes = b.value
+        return rows, occ, cov, vf
+
+    def close(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.pcs_result_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
 class Forest:
     """a forest flattened and resident in HBM."""
 
@@ -205,8 +285,12 @@ class Forest:
         self.ctx = ctx
         self.forest = forest
         self._h = C.c_void_p()
-        d = forest.as_desc()
-        _ok(lib().pcs_forest_upload(ctx._h, C.byref(d), C.byref(self._h)))
+        if hasattr(forest, "as_genomes_desc"):  # explicit per-cell genomes (process_b200.genomes.CellGenomes)
+            d = forest.as_genomes_desc()
+            _ok(lib().pcs_forest_upload_genomes(ctx._h, C.byref(d), C.byref(self._h)))
+        else:
+            d = forest.as_desc()
+            _ok(lib().pcs_forest_upload(ctx._h, C.byref(d), C.byref(self._h)))
         self.n_groups = forest.n_samples
 
     def close(self):
@@ -254,6 +338,14 @@ class Forest:
         st = A.RunStats()
         _ok(lib().pcs_simulate(self._h, C.byref(params), A.ptr(occ, C.c_uint32), A.ptr(cov, C.c_uint32), C.byref(st)))
         return occ, cov, st
+
+    def simulate_result(self, params: A.SeqParams, include_non_sequenced=False, with_vaf=True):
+        """plan + sample + assemble the data frame's rows on the device; returns (Result, stats)."""
+        h = C.c_void_p()
+        st = A.RunStats()
+        _ok(lib().pcs_simulate_result(self._h, C.byref(params), C.c_int(1 if include_non_sequenced else 0),
+                                      C.c_int(1 if with_vaf else 0), C.byref(h), C.byref(st)))
+        return Result(h), st
 
     def count_injected(self, n_out, read_size, placements, err_masks=None):
         placements = np.ascontiguousarray(placements, dtype=A.PLACEMENT_DTYPE)
@@ -326,23 +418,37 @@ class Plan:
                                A.ptr(cov, C.c_uint32), C.byref(st)))
         return occ, cov, st
 
-    def run_device(self, occ_ptr: int, cov_ptr: int):
-        """occ_ptr / cov_ptr: device addresses of uint32 [n_out_samples, n_mut] buffers."""
-        st = A.RunStats()
-        _ok(lib().pcs_plan_run(self._h, C.c_int(A.PCS_RUN_DEVICE_OUTPUT), C.c_void_p(occ_ptr),
-                               C.c_void_p(cov_ptr), C.byref(st)))
-        return st
+    def result(self, include_non_sequenced=False, with_vaf=True):
+        """assemble the tables the last run() left on the device (pcs_plan_result)."""
+        h = C.c_void_p()
+        _ok(lib().pcs_plan_result(self._h, C.c_int(1 if include_non_sequenced else 0), C.byref(self.params),
+                                  C.c_int(1 if with_vaf else 0), C.byref(h)))
+        return Result(h)
 
-    def accumulate(self, depth_ptr: int, occ_ptr: int):
+    def run_device(self, occ_ptr: int, cov_ptr: int, checksums=True, wait=True):
+        """occ_ptr / cov_ptr: device addresses of uint32 [n_out_samples, n_mut] buffers.  wait=False: the call
+        returns once the kernels are queued (no stats; counters() reads what accumulated)."""
+        flags = A.PCS_RUN_DEVICE_OUTPUT | (0 if checksums else A.PCS_RUN_NO_CHECKSUMS) | (0 if wait else A.PCS_RUN_ASYNC)
+        st = A.RunStats()
+        _ok(lib().pcs_plan_run(self._h, C.c_int(flags), C.c_void_p(occ_ptr), C.c_void_p(cov_ptr), C.byref(st)))
+        return st if wait else None
+
+    def accumulate(self, depth_ptr: int, occ_ptr: int, wait=True):
         """this shard's sampler adding into depth [S, n_loci] / occ [S, n_mut] (device or peer pointers)."""
         st = A.RunStats()
-        _ok(lib().pcs_plan_accumulate(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.byref(st)))
-        return st
+        _ok(lib().pcs_plan_accumulate(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.byref(st) if wait else None))
+        return st if wait else None
 
-    def finalize(self, depth_ptr: int, occ_ptr: int, cov_ptr: int):
+    def finalize(self, depth_ptr: int, occ_ptr: int, cov_ptr: int, wait=True):
         st = A.RunStats()
         _ok(lib().pcs_plan_finalize(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.c_void_p(cov_ptr),
-                                    C.byref(st)))
+                                    C.byref(st) if wait else None))
+        return st if wait else None
+
+    def counters(self):
+        """wait for the queued work; n_reads / checksums accumulated by the wait=False calls since the last read"""
+        st = A.RunStats()
+        _ok(lib().pcs_plan_counters(self._h, C.byref(st)))
         return st
 
     def materialize(self, cap):

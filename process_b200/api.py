@@ -255,63 +255,85 @@ def release_device_cache():
 atexit.register(release_device_cache)
 
 
-def _string_column(codes, table):
-    """The column table[codes] (None in the table = NA) as pandas would infer it from Python strings, but built from
-    the dictionary encoding: millions of rows draw from a handful of distinct strings (chromosome names, bases,
-    signature names, class names), so no Python object is made per row (the data frame, not the
-    sampler, is what a 5 M row result waits for)."""
+def _string_array(arrow_array):
+    """a pyarrow large_string array as the column pandas would infer from Python strings, or None when this pandas
+    does not keep strings in Arrow memory"""
     import pandas as pd
-    codes = np.asarray(codes)
-    table = np.asarray(table, dtype=object)
+    dtype = pd.Series(["x"]).dtype  # str (pyarrow-backed) from pandas 3 on
+    if getattr(dtype, "storage", None) != "pyarrow":
+        return None
+    return dtype.construct_array_type()(arrow_array, dtype=dtype)
+
+
+def _string_column(rows, codes, table):
+    """The column table[codes[rows]] (None in the table = NA) as pandas would infer it from Python strings, but built
+    from the dictionary encoding: millions of rows draw from a handful of distinct strings (chromosome names,
+    bases, signature names, class names), so no Python object is made per row -- the library's host threads write
+    the Arrow buffers (offsets + bytes + validity) in one parallel pass and pandas wraps them without a copy
+    (the data frame, not the sampler, is what a 5 M row result waits for)."""
+    table = list(table)
+    plain = lambda: np.asarray(table + [None], dtype=object)[:-1][np.asarray(codes)[np.asarray(rows, dtype=np.int64)]]
+    if len(rows) == 0:
+        return plain()
     try:
         import pyarrow as pa
-        dtype = pd.Series(["x"]).dtype  # str (pyarrow-backed) from pandas 3 on
-        if getattr(dtype, "storage", None) != "pyarrow":
-            raise TypeError("strings are not arrow-backed in this pandas")
-        is_na = np.asarray([x is None for x in table], bool)
-        values = pa.array(["" if x is None else x for x in table], type=pa.large_string())
-        mask = is_na[codes] if is_na.any() else None
-        if len(codes) == 0 or (mask is not None and mask.all()):
-            return table[codes]  # nothing to infer a string type from: the object column pandas makes of it
-        idx = pa.array(codes.astype(np.int32), mask=mask)
-        arr = pa.DictionaryArray.from_arrays(idx, values).cast(pa.large_string())
-        return dtype.construct_array_type()(arr, dtype=dtype)
-    except Exception:  # older pandas / no pyarrow: plain object strings, the same values
-        return table[codes]
+        offsets, data, validity, nulls = L.host_string_column(rows, codes, table)
+        if nulls == len(rows):
+            return plain()  # nothing to infer a string type from: the object column pandas makes of it
+        arr = pa.LargeStringArray.from_buffers(len(rows), pa.py_buffer(offsets), pa.py_buffer(data),
+                                               pa.py_buffer(validity) if validity is not None else None, int(nulls))
+        col = _string_array(arr)
+        return plain() if col is None else col
+    except ImportError:  # no pyarrow: plain object strings, the same values
+        return plain()
 
 
-def _int32_rows(table_row, rows):
-    """table_row[rows] as int32 (IntegerVector, src/seq_simulation.cpp:110) in one gather"""
-    if table_row.dtype == np.uint32 and table_row.flags.c_contiguous:
-        return table_row.view(np.int32).take(rows)
-    return table_row[rows].astype(np.int32)
+_CLASS_TABLE = [";".join(sorted(A.NATURE_DESCRIPTIONS[b] for b in range(4) if (m >> b) & 1)) for m in range(16)]
 
 
-def _result_dataframe(forest, dev, occ, cov, names, include_non_sequenced, params=None):
-    """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181.
-    Sample columns in name order (std::map iteration), rows in SID order."""
+def _row_codes(forest):
+    """dictionary codes of the annotation columns for every row of the forest's mutation table, made once per forest
+    (src/seq_simulation.cpp:52-90 builds these strings row by row on every call)"""
+    cache = getattr(forest, "_row_code_cache", None)
+    if cache is None or cache["n_mut"] != forest.n_mut:
+        ref_codes, ref_table, alt_codes, alt_table = forest.row_string_codes(np.arange(forest.n_mut))
+        cause = np.where(forest.mut_cause < 0, len(forest.cause_names), forest.mut_cause)
+        cache = dict(n_mut=forest.n_mut,
+                     chr=(forest.mut_chr.astype(np.uint16), list(forest.chr_names)),
+                     ref=(ref_codes.astype(np.uint16), list(ref_table)), alt=(alt_codes.astype(np.uint16), list(alt_table)),
+                     causes=(cause.astype(np.uint16), list(forest.cause_names) + [None]),
+                     classes=((forest.mut_nature_mask & 15).astype(np.uint16), _CLASS_TABLE))
+        forest._row_code_cache = cache
+    return cache
+
+
+def _frame(forest, names, rows, occ_cols, cov_cols, vaf_cols):
+    """get_result_dataframe()/add_sample_statistics(), src/seq_simulation.cpp:52-181, from the compact columns the
+    device assembled: `rows` (ascending = SID order) and per sample occurrences / coverage / VAF of those rows.
+    Sample columns in name order (std::map iteration)."""
     import pandas as pd
-    rows = dev.active_rows(occ, include_non_sequenced, params)
-    ref_codes, ref_table, alt_codes, alt_table = forest.row_string_codes(rows)
-    cause = forest.mut_cause[rows]
-    class_table = [";".join(sorted(A.NATURE_DESCRIPTIONS[b] for b in range(4) if (m >> b) & 1)) for m in range(16)]
-    cols = {
-        "chr": _string_column(forest.mut_chr[rows], forest.chr_names),
-        "chr_pos": forest.mut_pos[rows].astype(np.int32),
-        "ref": _string_column(ref_codes, ref_table), "alt": _string_column(alt_codes, alt_table),
-        "causes": _string_column(np.where(cause < 0, len(forest.cause_names), cause), list(forest.cause_names) + [None]),
-        "classes": _string_column(forest.mut_nature_mask[rows] & 15, class_table),
-    }
+    codes = _row_codes(forest)
+    cols = {"chr": _string_column(rows, *codes["chr"]),
+            "chr_pos": L.host_gather(rows, forest.mut_pos).view(np.int32),
+            "ref": _string_column(rows, *codes["ref"]), "alt": _string_column(rows, *codes["alt"]),
+            "causes": _string_column(rows, *codes["causes"]), "classes": _string_column(rows, *codes["classes"])}
     for s in sorted(range(len(names)), key=lambda i: names[i]):
-        o = _int32_rows(occ[s], rows)
-        c = _int32_rows(cov[s], rows)
-        # VAF = occurrences / coverage; a row the sample never covered has no occurrence: VAF 0, as the rows
-        # the reference does not find in the sample's data (src/seq_simulation.cpp:121-131)
-        vaf = np.divide(o, c, out=np.zeros(len(o), np.float64), where=c != 0)
-        cols[f"{names[s]}.occurrences"] = o
-        cols[f"{names[s]}.coverage"] = c
-        cols[f"{names[s]}.VAF"] = vaf
+        cols[f"{names[s]}.occurrences"] = occ_cols[s]
+        cols[f"{names[s]}.coverage"] = cov_cols[s]
+        cols[f"{names[s]}.VAF"] = vaf_cols[s]
     return pd.DataFrame(cols, copy=False)
+
+
+def _frame_from_tables(forest, dev, occ, cov, names, include_non_sequenced, params=None):
+    """the same frame from full host tables (several ranks: the tables are summed over ranks first): active rows by
+    pcs_active_rows, columns gathered by the library's host threads"""
+    rows = dev.active_rows(occ, include_non_sequenced, params)
+    occ_cols = [L.host_gather(rows, occ[s]).view(np.int32) for s in range(len(names))]
+    cov_cols = [L.host_gather(rows, cov[s]).view(np.int32) for s in range(len(names))]
+    # VAF = occurrences / coverage; a row the sample never covered has no occurrence: VAF 0, as the rows the
+    # reference does not find in the sample's data (src/seq_simulation.cpp:121-131)
+    vaf_cols = [np.divide(o, c, out=np.zeros(len(o), np.float64), where=c != 0) for o, c in zip(occ_cols, cov_cols)]
+    return _frame(forest, names, rows, occ_cols, cov_cols, vaf_cols)
 
 
 def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, insert_size_mean,
@@ -355,13 +377,23 @@ def _run(forest, sequencer, reference_genome, chromosomes, coverage, read_size, 
             try:
                 occ, cov, st = plan.run()
                 plan.write_sam(output_dir, out_names, filename_prefix, template_name_prefix, update_SAM)
+                res = plan.result(include_non_sequenced)
             finally:
                 plan.close()
-        else:
+        elif shard[1] > 1:
             occ, cov, st = dev.simulate(P)
-        if shard[1] > 1:
             occ, cov = _reduce_over_ranks(occ, cov)
-        df = _result_dataframe(forest, dev, occ, cov, out_names, include_non_sequenced, P)
+            res = None
+        else:
+            res, st = dev.simulate_result(P, include_non_sequenced)
+        if res is None:
+            df = _frame_from_tables(forest, dev, occ, cov, out_names, include_non_sequenced, P)
+        else:
+            try:  # the data frame's rows were assembled on the device: only they cross the link
+                rows, occ_c, cov_c, vaf_c = res.fetch()
+            finally:
+                res.close()
+            df = _frame(forest, out_names, rows, occ_c, cov_c, vaf_c)
     finally:
         if owned:
             dev.close()

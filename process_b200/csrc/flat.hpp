@@ -115,7 +115,10 @@ struct FlatForest {
 
 // throws std::domain_error on malformed input.  A block lent through out.store before the call is kept and used.
 void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads);
+// the same view from explicit per-cell genomes (what get_sample_mutations_list() / get_normal_sample() hand over)
+void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads);
 // bytes of lent memory that are always enough for the tables of `d` (FlatStore::capacity)
 size_t flat_store_bytes(const pcs_forest_desc& d);
+size_t flat_store_bytes(const pcs_cell_genomes_desc& g);
 
 }  // namespace pcs

@@ -80,6 +80,7 @@ struct ChrWork {
   std::vector<uint32_t> ev_nodes;     // the preorder positions that have events of this chromosome, increasing
   bool has_wgd = false;
   uint32_t row_lo = 0, row_hi = 0;    // rows of this chromosome in the mutation table
+  uint32_t clen = 0;                  // its length
   std::vector<Inst> inst;
   std::vector<HapRec> haps;           // fragset is a LOCAL id until merge
   std::vector<FragKey> fragsets;
@@ -151,15 +152,70 @@ void wgd_prepass(const pcs_forest_desc& d, const Tree& t, ChrWork& w) {
   }
 }
 
+// what every numbering ends with: placements without carriers dropped, the rest sorted by row; the pieces the
+// fragment sets in use cut the chromosome into, each with the fragment sets that cover it
+void finish_chr(ChrWork& w) {
+  const uint32_t chr = w.chr, clen = w.clen;
+  // a SID no sampled haplotype inherited has an empty interval: drop it
+  w.inst.erase(std::remove_if(w.inst.begin(), w.inst.end(), [](const Inst& in) { return in.span == 0; }), w.inst.end());
+  // by row, placements of one row in DFS order: stable LSD radix sort on (row - smallest row), 11 bits a pass
+  if (w.inst.size() > 1) {
+    uint32_t row_min = 0xffffffffu, row_max = 0;
+    for (const Inst& in : w.inst) {
+      row_min = std::min(row_min, in.row);
+      row_max = std::max(row_max, in.row);
+    }
+    std::vector<Inst> tmp(w.inst.size());
+    Inst* src = w.inst.data();
+    Inst* dst = tmp.data();
+    const size_t n_inst = w.inst.size();
+    for (uint32_t shift = 0; shift < 32 && ((row_max - row_min) >> shift) != 0; shift += 11) {
+      uint32_t cnt[2049] = {0};
+      for (size_t i = 0; i < n_inst; ++i) ++cnt[(((src[i].row - row_min) >> shift) & 2047u) + 1];
+      for (uint32_t b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
+      for (size_t i = 0; i < n_inst; ++i) dst[cnt[((src[i].row - row_min) >> shift) & 2047u]++] = src[i];
+      std::swap(src, dst);
+    }
+    if (src != w.inst.data()) w.inst.swap(tmp);
+  }
+
+  // pieces: maximal intervals on which the set of covering fragments is constant
+  std::vector<uint8_t> used(w.fragsets.size(), 0);
+  for (const auto& h : w.haps) used[h.fragset] = 1;
+  std::vector<uint32_t> bp{1u, clen + 1};
+  for (size_t k = 0; k < w.fragsets.size(); ++k)
+    if (used[k])
+      for (const auto& p : w.fragsets[k]) {
+        bp.push_back(p.first);
+        bp.push_back(p.second + 1);
+      }
+  std::sort(bp.begin(), bp.end());
+  bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
+  for (size_t i = 0; i + 1 < bp.size(); ++i) {
+    Piece pc{chr, bp[i], bp[i + 1] - 1, static_cast<uint32_t>(w.covers.size()), 0};
+    for (size_t k = 0; k < w.fragsets.size(); ++k) {
+      if (!used[k]) continue;
+      for (const auto& p : w.fragsets[k])
+        if (p.first <= pc.begin && pc.end <= p.second) {
+          w.covers.push_back({static_cast<uint32_t>(k), p.second});
+          ++pc.cover_n;
+          break;
+        }
+    }
+    if (pc.cover_n) w.pieces.push_back(pc);
+  }
+}
+
 // haplotype numbering of one chromosome: leaves (w.haps), the SOMATIC placements sorted by row (w.inst),
 // the interval below each germline allele, the pieces its fragment sets cut the chromosome into
 //
 // A haplotype carries at most ONE SID per position (the kernels' walk and the read materialiser rely on it; the
-// oracle refuses anything else): `occupied` has one bit per position of the chromosome, set while a SID at that
-// position is carried by the haplotypes being numbered -- the germline SIDs of the germline allele the walk
-// descends from, and every open somatic instance.  A SID that finds its bit set is a second SID of the haplotype
-// at that position: std::domain_error, as the oracle.
-void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std::atomic<uint8_t>* row_mask) {
+// oracle refuses anything else).  Rows of one position are neighbours in the mutation table (one locus), so the
+// check looks at the few rows of the new SID's locus: a germline SID of the germline allele the walk descends
+// from (row_mask), or a somatic instance that is still open (row_open) -- a second SID of the haplotype at that
+// position: std::domain_error, as the oracle.
+void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std::atomic<uint8_t>* row_mask,
+                 const uint32_t* row_locus, const uint32_t* locus_first_row) {
   const uint32_t chr = w.chr;
   const uint32_t clen = d.chr_len[chr];
   const uint8_t n0 = d.chr_n_alleles[chr];
@@ -214,8 +270,17 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std:
   std::vector<Scan> scans;
   std::vector<Undo> undo;
   std::vector<uint32_t> open;  // instances whose interval is still growing
-  std::vector<uint64_t> occupied((static_cast<size_t>(clen) >> 6) + 2, 0);
-  auto occupied_bit = [&](uint32_t pos) -> uint64_t& { return occupied[pos >> 6]; };
+  std::vector<uint8_t> row_open(w.row_hi - w.row_lo, 0);  // the row has an open somatic instance
+  // two germline rows of one position must not share an allele
+  if (w.row_hi > w.row_lo)
+    for (uint32_t l = row_locus[w.row_lo]; l <= row_locus[w.row_hi - 1]; ++l) {
+      uint32_t seen = 0;
+      for (uint32_t m = locus_first_row[l]; m < locus_first_row[l + 1]; ++m) {
+        const uint32_t mask = row_mask[m].load(std::memory_order_relaxed);
+        check((seen & mask) == 0, "two germline SIDs at one position of one allele");
+        seen |= mask;
+      }
+    }
   const uint32_t* leaf_pos = t.leaf_pos.data();
   const uint32_t* leaf_id = t.leaf_id.data();
   const uint32_t n_leaf_pos = static_cast<uint32_t>(t.leaf_pos.size());
@@ -225,20 +290,13 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std:
     for (size_t k = open_size; k < open.size(); ++k) {
       Inst& in = w.inst[open[k]];
       in.span = counter - in.lo;
-      const uint32_t pos = d.mut_pos[in.row];
-      occupied_bit(pos) &= ~(1ull << (pos & 63));
+      row_open[in.row - w.row_lo] = 0;
     }
     open.resize(open_size);
   };
 
   w.inst.reserve(w.ev.size());
   for (uint16_t g = 0; g < n0; ++g) {
-    for (uint32_t m = w.row_lo; m < w.row_hi; ++m)  // the germline SIDs of allele g
-      if ((row_mask[m].load(std::memory_order_relaxed) >> g) & 1u) {
-        const uint32_t pos = d.mut_pos[m];
-        check(!((occupied_bit(pos) >> (pos & 63)) & 1ull), "two germline SIDs at one position of one allele");
-        occupied_bit(pos) |= 1ull << (pos & 63);
-      }
     germ_lo[g] = counter;
     w.haps.push_back({0u, full, g, HAP_NORMAL_PLAIN});
     ++counter;
@@ -312,8 +370,13 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std:
             if (e.allele != sc.allele) continue;
             if (e.kind == PCS_EV_SID) {
               if (holds(w.fragsets[sc.fs], e.y)) {
-                check(!((occupied_bit(e.y) >> (e.y & 63)) & 1ull), "two SIDs at one position of one allele");
-                occupied_bit(e.y) |= 1ull << (e.y & 63);
+                const uint32_t l = row_locus[e.x];
+                for (uint32_t m = locus_first_row[l]; m < locus_first_row[l + 1]; ++m) {
+                  check(!((row_mask[m].load(std::memory_order_relaxed) >> g) & 1u),
+                        "somatic SID at a germline SID position of the same allele");
+                  check(!row_open[m - w.row_lo], "two SIDs at one position of one allele");
+                }
+                row_open[e.x - w.row_lo] = 1;
                 open.push_back(static_cast<uint32_t>(w.inst.size()));
                 w.inst.push_back({counter, 0u, e.x, e.meta});
               }
@@ -358,61 +421,9 @@ void flatten_chr(const pcs_forest_desc& d, const Tree& t, ChrWork& w, const std:
       }
     }
     germ_hi[g] = counter;
-    for (uint32_t m = w.row_lo; m < w.row_hi; ++m)
-      if ((row_mask[m].load(std::memory_order_relaxed) >> g) & 1u) {
-        const uint32_t pos = d.mut_pos[m];
-        occupied_bit(pos) &= ~(1ull << (pos & 63));
-      }
   }
 
-  // a SID no sampled haplotype inherited has an empty interval: drop it
-  w.inst.erase(std::remove_if(w.inst.begin(), w.inst.end(), [](const Inst& in) { return in.span == 0; }), w.inst.end());
-  // by row, placements of one row in DFS order: stable LSD radix sort on (row - smallest row), 11 bits a pass
-  if (w.inst.size() > 1) {
-    uint32_t row_min = 0xffffffffu, row_max = 0;
-    for (const Inst& in : w.inst) {
-      row_min = std::min(row_min, in.row);
-      row_max = std::max(row_max, in.row);
-    }
-    std::vector<Inst> tmp(w.inst.size());
-    Inst* src = w.inst.data();
-    Inst* dst = tmp.data();
-    const size_t n_inst = w.inst.size();
-    for (uint32_t shift = 0; shift < 32 && ((row_max - row_min) >> shift) != 0; shift += 11) {
-      uint32_t cnt[2049] = {0};
-      for (size_t i = 0; i < n_inst; ++i) ++cnt[(((src[i].row - row_min) >> shift) & 2047u) + 1];
-      for (uint32_t b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
-      for (size_t i = 0; i < n_inst; ++i) dst[cnt[((src[i].row - row_min) >> shift) & 2047u]++] = src[i];
-      std::swap(src, dst);
-    }
-    if (src != w.inst.data()) w.inst.swap(tmp);
-  }
-
-  // pieces: maximal intervals on which the set of covering fragments is constant
-  std::vector<uint8_t> used(w.fragsets.size(), 0);
-  for (const auto& h : w.haps) used[h.fragset] = 1;
-  std::vector<uint32_t> bp{1u, clen + 1};
-  for (size_t k = 0; k < w.fragsets.size(); ++k)
-    if (used[k])
-      for (const auto& p : w.fragsets[k]) {
-        bp.push_back(p.first);
-        bp.push_back(p.second + 1);
-      }
-  std::sort(bp.begin(), bp.end());
-  bp.erase(std::unique(bp.begin(), bp.end()), bp.end());
-  for (size_t i = 0; i + 1 < bp.size(); ++i) {
-    Piece pc{chr, bp[i], bp[i + 1] - 1, static_cast<uint32_t>(w.covers.size()), 0};
-    for (size_t k = 0; k < w.fragsets.size(); ++k) {
-      if (!used[k]) continue;
-      for (const auto& p : w.fragsets[k])
-        if (p.first <= pc.begin && pc.end <= p.second) {
-          w.covers.push_back({static_cast<uint32_t>(k), p.second});
-          ++pc.cover_n;
-          break;
-        }
-    }
-    if (pc.cover_n) w.pieces.push_back(pc);
-  }
+  finish_chr(w);
 }
 
 }  // namespace
@@ -430,10 +441,25 @@ struct PhaseTimer {
 };
 }  // namespace
 
-void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads) {
+// what the path-specific haplotype numbering of flatten_with() works on
+struct Numbering {
+  const pcs_forest_desc& d;
+  FlatForest& out;
+  std::vector<ChrWork>& work;              // [n_chr]: chr, row_lo, row_hi set; the numbering fills the rest
+  const std::atomic<uint8_t>* row_mask;    // [n_mut] germline allele mask of every row
+  const std::function<void(uint32_t, const std::function<void(uint32_t)>&)>& parallel_for;
+  PhaseTimer& timer;
+};
+
+// The flattened view of a forest given in any form: the mutation table and the germline of `d` are turned into
+// loci, germline masks and -- after `number` has produced, per chromosome, the haplotype leaves, the somatic
+// placements (sorted by row), the interval below each germline allele, fragment sets and pieces -- the merged
+// instance table.  `number` is the only part that depends on how the forest is described (an event-labelled
+// tree: flatten_forest; explicit per-cell genomes: flatten_cell_genomes).
+template <class NumberFn>
+void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, NumberFn&& number) {
   PhaseTimer timer;
   check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
-  check(d.n_nodes >= 1, "the forest has no nodes");
   {
     FlatStore keep = std::move(out.store);  // a block lent by the caller survives the reset
     keep.used = 0;
@@ -453,72 +479,6 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     check(d.chr_len[c] < (1u << 31), "chromosome length must be below 2^31");  // 32-bit positions on the device
   }
 
-  // ---- cell tree
-  Tree t;
-  t.child_off.assign(d.n_nodes + 1, 0);
-  for (uint32_t v = 0; v < d.n_nodes; ++v) {
-    int32_t p = d.node_parent[v];
-    if (p < 0) {
-      t.roots.push_back(v);
-    } else {
-      check(static_cast<uint32_t>(p) < v, "node_parent must precede the child");
-      ++t.child_off[p + 1];
-    }
-  }
-  for (uint32_t v = 0; v < d.n_nodes; ++v) t.child_off[v + 1] += t.child_off[v];
-  t.child_idx.resize(t.child_off[d.n_nodes]);
-  {
-    std::vector<uint32_t> fill(t.child_off.begin(), t.child_off.end() - 1);
-    for (uint32_t v = 0; v < d.n_nodes; ++v)
-      if (d.node_parent[v] >= 0) t.child_idx[fill[d.node_parent[v]]++] = v;
-  }
-  out.n_roots = static_cast<uint32_t>(t.roots.size());
-  t.node_leaf.assign(d.n_nodes, -1);
-  for (uint32_t l = 0; l < d.n_leaves; ++l) {
-    check(d.leaf_node[l] < d.n_nodes, "leaf_node out of range");
-    check(t.child_off[d.leaf_node[l] + 1] == t.child_off[d.leaf_node[l]], "a sampled cell must be a leaf");
-    check(d.leaf_sample[l] < d.n_samples, "leaf_sample out of range");
-    t.node_leaf[d.leaf_node[l]] = l;
-  }
-
-  // preorder layout
-  {
-    const uint32_t n = d.n_nodes;
-    t.pre_node.resize(n);
-    t.pre_end.resize(n);
-    t.pre_leaf.resize(n);
-    std::vector<uint32_t> pos_of(n);
-    std::vector<uint32_t> stack;
-    uint32_t next = 0;
-    for (uint32_t r : t.roots) {
-      t.root_pos.push_back(next);
-      stack.push_back(r);
-      while (!stack.empty()) {
-        const uint32_t v = stack.back();
-        stack.pop_back();
-        pos_of[v] = next;
-        t.pre_node[next] = v;
-        t.pre_leaf[next] = t.node_leaf[v];
-        ++next;
-        for (uint32_t c = t.child_off[v + 1]; c > t.child_off[v]; --c) stack.push_back(t.child_idx[c - 1]);  // smallest on top
-      }
-    }
-    check(next == n, "internal: preorder does not cover the tree");
-    // subtree ends: a node's subtree ends where its last child's does; children come after their parent
-    for (uint32_t i = n; i-- > 0;) {
-      const uint32_t v = t.pre_node[i];
-      const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
-      t.pre_end[i] = nc ? t.pre_end[pos_of[t.child_idx[t.child_off[v + 1] - 1]]] : i + 1;
-    }
-    t.leaf_pos.reserve(d.n_leaves);
-    t.leaf_id.reserve(d.n_leaves);
-    for (uint32_t i = 0; i < n; ++i)
-      if (t.pre_leaf[i] >= 0) {
-        t.leaf_pos.push_back(i);
-        t.leaf_id.push_back(static_cast<uint32_t>(t.pre_leaf[i]));
-      }
-  }
-  timer.lap("cell tree");
   n_threads = std::max(1u, n_threads);
   // run fn(task) for task in [0, n_tasks) on up to n_threads threads; the first exception is rethrown
   auto parallel_for = [&](uint32_t n_tasks, const std::function<void(uint32_t)>& fn) {
@@ -620,78 +580,6 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     out.chr_locus_off[c] = chr_row_off[c] < d.n_mut ? out.row_locus[chr_row_off[c]] : n_loci;
 
   timer.lap("loci");
-  // ---- events: validated and dealt to their chromosomes in WALK order (by preorder position of the node, then
-  // in the node's own order), with what the walk needs of the rows they name.  One counting pass and one filling
-  // pass over chunks of preorder positions: every event is read twice, whatever the number of chromosomes; a
-  // WGD goes to every chromosome.
-  std::vector<ChrWork> work(d.n_chr);
-  for (uint32_t c = 0; c < d.n_chr; ++c) work[c].chr = c;
-  check(d.node_event_off[0] == 0 && d.node_event_off[d.n_nodes] == d.n_events, "node_event_off is not a CSR of the events");
-  check(d.n_events <= 0xffffffffull, "too many events");
-  for (uint32_t v = 0; v < d.n_nodes; ++v)
-    check(d.node_event_off[v] <= d.node_event_off[v + 1], "node_event_off must be non-decreasing");
-  std::vector<uint64_t> chr_load(d.n_chr, 0);
-  {
-    const uint32_t n = d.n_nodes, n_chr = d.n_chr;
-    const uint32_t p_chunks = std::max(1u, std::min<uint32_t>(4 * n_threads, (n + 4095) / 4096));
-    auto pos_lo = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n) * k / p_chunks); };
-    parallel_for(n_chr, [&](uint32_t c) { work[c].ev_off.assign(static_cast<size_t>(n) + 1, 0); });
-    std::atomic<bool> any_wgd{false};
-    parallel_for(p_chunks, [&](uint32_t k) {  // ev_off[c][i + 1] = events of chromosome c in the node at position i
-      bool wgd = false;
-      for (uint32_t i = pos_lo(k); i < pos_lo(k + 1); ++i) {
-        const uint32_t v = t.pre_node[i];
-        for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
-          const uint8_t kind = d.ev_kind[e];
-          check(kind <= PCS_EV_WGD, "unknown event kind");
-          if (kind == PCS_EV_WGD) {
-            wgd = true;
-            for (uint32_t c = 0; c < n_chr; ++c) ++work[c].ev_off[i + 1];
-          } else {
-            check(d.ev_chr[e] < n_chr, "event chromosome out of range");
-            ++work[d.ev_chr[e]].ev_off[i + 1];
-          }
-        }
-      }
-      if (wgd) any_wgd.store(true, std::memory_order_relaxed);
-    });
-    parallel_for(n_chr, [&](uint32_t c) {
-      ChrWork& w = work[c];
-      for (uint32_t i = 0; i < n; ++i) {
-        if (w.ev_off[i + 1]) w.ev_nodes.push_back(i);
-        w.ev_off[i + 1] += w.ev_off[i];
-      }
-      w.ev.resize(w.ev_off[n]);
-      w.has_wgd = any_wgd.load(std::memory_order_relaxed);
-      chr_load[c] = w.ev_off[n];
-    });
-    parallel_for(p_chunks, [&](uint32_t k) {
-      const uint32_t i0 = pos_lo(k), i1 = pos_lo(k + 1);
-      std::vector<uint32_t> at(n_chr);  // where the next event of each chromosome goes
-      for (uint32_t c = 0; c < n_chr; ++c) at[c] = work[c].ev_off[i0];
-      for (uint32_t i = i0; i < i1; ++i) {
-        const uint32_t v = t.pre_node[i];
-        for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
-          const uint8_t kind = d.ev_kind[e];
-          if (kind == PCS_EV_WGD) {
-            for (uint32_t c = 0; c < n_chr; ++c)
-              work[c].ev[at[c]++] = Ev{static_cast<uint32_t>(e), 0u, 0u, 0, 0, kind, d.ev_nature[e]};
-            continue;
-          }
-          const uint32_t c = d.ev_chr[e];
-          if (kind == PCS_EV_SID) {  // position and lengths of the row: looked up per chromosome (flatten_chr)
-            work[c].ev[at[c]++] = Ev{d.ev_mut[e], 0u, 0u, d.ev_allele[e], 0, kind, d.ev_nature[e]};
-          } else {
-            check(d.ev_len[e] >= 1, "CNA length must be positive");
-            work[c].ev[at[c]++] = Ev{d.ev_pos[e], d.ev_len[e], 0u, d.ev_allele[e], d.ev_dest[e], kind, d.ev_nature[e]};
-          }
-        }
-      }
-      for (uint32_t c = 0; c < n_chr; ++c)
-        check(at[c] == work[c].ev_off[i1], "internal: events dealt out of step");
-    });
-  }
-  timer.lap("events by chromosome");
   // ---- germline SIDs by row.  The caller's list comes in any order; a SID is normally listed once, so the
   // list is scattered into one allele-mask byte per row (0 = not germline; a row listed twice gets the union
   // of its masks).  Should a row be listed twice, a stably sorted copy of the list is walked for the instances
@@ -767,17 +655,18 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     }
   }
   timer.lap("germline masks");
-  // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
-  std::vector<uint32_t> chr_order(d.n_chr);
-  for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
-  std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
-    return chr_load[a] != chr_load[b] ? chr_load[a] > chr_load[b] : a < b;
-  });
+  std::vector<ChrWork> work(d.n_chr);
   for (uint32_t c = 0; c < d.n_chr; ++c) {
+    work[c].chr = c;
+    work[c].clen = d.chr_len[c];
     work[c].row_lo = chr_row_off[c];
     work[c].row_hi = chr_row_off[c + 1];
   }
-  parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]], row_mask.get()); });
+  {
+    const std::function<void(uint32_t, const std::function<void(uint32_t)>&)> pf = parallel_for;
+    Numbering nb{d, out, work, row_mask.get(), pf, timer};
+    number(nb);
+  }
   timer.lap("haplotype numbering");
 
   // chunks of loci (a locus never straddles two chunks); germline rows per chunk
@@ -898,6 +787,330 @@ void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_thread
     }
   });
   timer.lap("merge");
+}
+
+void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads) {
+  check(d.n_nodes >= 1, "the forest has no nodes");
+  flatten_with(d, out, n_threads, [&](Numbering& nb) {
+    FlatForest& out = nb.out;
+    std::vector<ChrWork>& work = nb.work;
+    const std::atomic<uint8_t>* row_mask = nb.row_mask;
+    const auto& parallel_for = nb.parallel_for;
+    PhaseTimer& timer = nb.timer;
+    // ---- cell tree
+    Tree t;
+    t.child_off.assign(d.n_nodes + 1, 0);
+    for (uint32_t v = 0; v < d.n_nodes; ++v) {
+      int32_t p = d.node_parent[v];
+      if (p < 0) {
+        t.roots.push_back(v);
+      } else {
+        check(static_cast<uint32_t>(p) < v, "node_parent must precede the child");
+        ++t.child_off[p + 1];
+      }
+    }
+    for (uint32_t v = 0; v < d.n_nodes; ++v) t.child_off[v + 1] += t.child_off[v];
+    t.child_idx.resize(t.child_off[d.n_nodes]);
+    {
+      std::vector<uint32_t> fill(t.child_off.begin(), t.child_off.end() - 1);
+      for (uint32_t v = 0; v < d.n_nodes; ++v)
+        if (d.node_parent[v] >= 0) t.child_idx[fill[d.node_parent[v]]++] = v;
+    }
+    out.n_roots = static_cast<uint32_t>(t.roots.size());
+    t.node_leaf.assign(d.n_nodes, -1);
+    for (uint32_t l = 0; l < d.n_leaves; ++l) {
+      check(d.leaf_node[l] < d.n_nodes, "leaf_node out of range");
+      check(t.child_off[d.leaf_node[l] + 1] == t.child_off[d.leaf_node[l]], "a sampled cell must be a leaf");
+      check(d.leaf_sample[l] < d.n_samples, "leaf_sample out of range");
+      t.node_leaf[d.leaf_node[l]] = l;
+    }
+
+    // preorder layout
+    {
+      const uint32_t n = d.n_nodes;
+      t.pre_node.resize(n);
+      t.pre_end.resize(n);
+      t.pre_leaf.resize(n);
+      std::vector<uint32_t> pos_of(n);
+      std::vector<uint32_t> stack;
+      uint32_t next = 0;
+      for (uint32_t r : t.roots) {
+        t.root_pos.push_back(next);
+        stack.push_back(r);
+        while (!stack.empty()) {
+          const uint32_t v = stack.back();
+          stack.pop_back();
+          pos_of[v] = next;
+          t.pre_node[next] = v;
+          t.pre_leaf[next] = t.node_leaf[v];
+          ++next;
+          for (uint32_t c = t.child_off[v + 1]; c > t.child_off[v]; --c) stack.push_back(t.child_idx[c - 1]);  // smallest on top
+        }
+      }
+      check(next == n, "internal: preorder does not cover the tree");
+      // subtree ends: a node's subtree ends where its last child's does; children come after their parent
+      for (uint32_t i = n; i-- > 0;) {
+        const uint32_t v = t.pre_node[i];
+        const uint32_t nc = t.child_off[v + 1] - t.child_off[v];
+        t.pre_end[i] = nc ? t.pre_end[pos_of[t.child_idx[t.child_off[v + 1] - 1]]] : i + 1;
+      }
+      t.leaf_pos.reserve(d.n_leaves);
+      t.leaf_id.reserve(d.n_leaves);
+      for (uint32_t i = 0; i < n; ++i)
+        if (t.pre_leaf[i] >= 0) {
+          t.leaf_pos.push_back(i);
+          t.leaf_id.push_back(static_cast<uint32_t>(t.pre_leaf[i]));
+        }
+    }
+    timer.lap("cell tree");
+    // ---- events: validated and dealt to their chromosomes in WALK order (by preorder position of the node, then
+    // in the node's own order), with what the walk needs of the rows they name.  One counting pass and one filling
+    // pass over chunks of preorder positions: every event is read twice, whatever the number of chromosomes; a
+    // WGD goes to every chromosome.
+    check(d.node_event_off[0] == 0 && d.node_event_off[d.n_nodes] == d.n_events, "node_event_off is not a CSR of the events");
+    check(d.n_events <= 0xffffffffull, "too many events");
+    for (uint32_t v = 0; v < d.n_nodes; ++v)
+      check(d.node_event_off[v] <= d.node_event_off[v + 1], "node_event_off must be non-decreasing");
+    std::vector<uint64_t> chr_load(d.n_chr, 0);
+    {
+      const uint32_t n = d.n_nodes, n_chr = d.n_chr;
+      const uint32_t p_chunks = std::max(1u, std::min<uint32_t>(4 * n_threads, (n + 4095) / 4096));
+      auto pos_lo = [&](uint32_t k) { return static_cast<uint32_t>(static_cast<uint64_t>(n) * k / p_chunks); };
+      parallel_for(n_chr, [&](uint32_t c) { work[c].ev_off.assign(static_cast<size_t>(n) + 1, 0); });
+      std::atomic<bool> any_wgd{false};
+      parallel_for(p_chunks, [&](uint32_t k) {  // ev_off[c][i + 1] = events of chromosome c in the node at position i
+        bool wgd = false;
+        for (uint32_t i = pos_lo(k); i < pos_lo(k + 1); ++i) {
+          const uint32_t v = t.pre_node[i];
+          for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+            const uint8_t kind = d.ev_kind[e];
+            check(kind <= PCS_EV_WGD, "unknown event kind");
+            if (kind == PCS_EV_WGD) {
+              wgd = true;
+              for (uint32_t c = 0; c < n_chr; ++c) ++work[c].ev_off[i + 1];
+            } else {
+              check(d.ev_chr[e] < n_chr, "event chromosome out of range");
+              ++work[d.ev_chr[e]].ev_off[i + 1];
+            }
+          }
+        }
+        if (wgd) any_wgd.store(true, std::memory_order_relaxed);
+      });
+      parallel_for(n_chr, [&](uint32_t c) {
+        ChrWork& w = work[c];
+        for (uint32_t i = 0; i < n; ++i) {
+          if (w.ev_off[i + 1]) w.ev_nodes.push_back(i);
+          w.ev_off[i + 1] += w.ev_off[i];
+        }
+        w.ev.resize(w.ev_off[n]);
+        w.has_wgd = any_wgd.load(std::memory_order_relaxed);
+        chr_load[c] = w.ev_off[n];
+      });
+      parallel_for(p_chunks, [&](uint32_t k) {
+        const uint32_t i0 = pos_lo(k), i1 = pos_lo(k + 1);
+        std::vector<uint32_t> at(n_chr);  // where the next event of each chromosome goes
+        for (uint32_t c = 0; c < n_chr; ++c) at[c] = work[c].ev_off[i0];
+        for (uint32_t i = i0; i < i1; ++i) {
+          const uint32_t v = t.pre_node[i];
+          for (uint64_t e = d.node_event_off[v]; e < d.node_event_off[v + 1]; ++e) {
+            const uint8_t kind = d.ev_kind[e];
+            if (kind == PCS_EV_WGD) {
+              for (uint32_t c = 0; c < n_chr; ++c)
+                work[c].ev[at[c]++] = Ev{static_cast<uint32_t>(e), 0u, 0u, 0, 0, kind, d.ev_nature[e]};
+              continue;
+            }
+            const uint32_t c = d.ev_chr[e];
+            if (kind == PCS_EV_SID) {  // position and lengths of the row: looked up per chromosome (flatten_chr)
+              work[c].ev[at[c]++] = Ev{d.ev_mut[e], 0u, 0u, d.ev_allele[e], 0, kind, d.ev_nature[e]};
+            } else {
+              check(d.ev_len[e] >= 1, "CNA length must be positive");
+              work[c].ev[at[c]++] = Ev{d.ev_pos[e], d.ev_len[e], 0u, d.ev_allele[e], d.ev_dest[e], kind, d.ev_nature[e]};
+            }
+          }
+        }
+        for (uint32_t c = 0; c < n_chr; ++c)
+          check(at[c] == work[c].ev_off[i1], "internal: events dealt out of step");
+      });
+    }
+    timer.lap("events by chromosome");
+    // ---- per-chromosome haplotype numbering, chromosomes in parallel (most events first)
+    std::vector<uint32_t> chr_order(d.n_chr);
+    for (uint32_t c = 0; c < d.n_chr; ++c) chr_order[c] = c;
+    std::sort(chr_order.begin(), chr_order.end(), [&](uint32_t a, uint32_t b) {
+      return chr_load[a] != chr_load[b] ? chr_load[a] > chr_load[b] : a < b;
+    });
+    parallel_for(d.n_chr, [&](uint32_t k) { flatten_chr(d, t, work[chr_order[k]], row_mask, out.row_locus.data(), out.locus_first_row.data()); });
+
+  });
+}
+
+// ---------------------------------------------------------------- explicit per-cell genomes
+// What the seam of the reference actually hands over (src/seq_simulation.cpp:566-575): per sample a list of per-cell
+// genomes, chromosome -> allele -> fragment -> SID (traversal idiom src/phylogenetic_forest.cpp:279-290, 332-335),
+// plus the normal sample's cells.  No tree comes with them, so the haplotype numbering is recovered from the
+// contents: the carriers of a SID form a clade of the (unknown) haplotype tree, clades are nested, and sorting
+// the haplotypes lexicographically by their SID lists -- every list ordered by decreasing number of carriers --
+// lays every clade out as one run of consecutive haplotypes: a haplotype's list then starts with the chain of
+// clades it belongs to, outermost first, so two members of a clade share the whole prefix down to it.  A SID whose
+// carriers are NOT one clade (a later CNA deletion took it from part of one) simply gets one placement per run.
+namespace {
+
+void number_from_genomes(const pcs_cell_genomes_desc& g, const std::vector<uint64_t>& alleles, ChrWork& w,
+                         const pcs_forest_desc& d, const std::atomic<uint8_t>* row_mask, const uint32_t* row_locus,
+                         const uint32_t* locus_first_row) {
+  const uint32_t chr = w.chr, clen = w.clen;
+  const uint8_t n0 = d.chr_n_alleles[chr];
+  check(n0 >= 1 && n0 <= 2, "chr_n_alleles must be 1 or 2");
+  const uint32_t n_rows = w.row_hi - w.row_lo;
+  const uint32_t full = w.intern_set(FragKey{{1u, clen}});
+  // two germline rows of one position must not share an allele
+  if (n_rows)
+    for (uint32_t l = row_locus[w.row_lo]; l <= row_locus[w.row_hi - 1]; ++l) {
+      uint32_t seen = 0;
+      for (uint32_t m = locus_first_row[l]; m < locus_first_row[l + 1]; ++m) {
+        const uint32_t mask = row_mask[m].load(std::memory_order_relaxed);
+        check((seen & mask) == 0, "two germline SIDs at one position of one allele");
+        seen |= mask;
+      }
+    }
+  // carriers per row, and the rank of every row when rows are ordered by (carriers descending, row)
+  std::vector<uint32_t> carriers(n_rows, 0);
+  for (uint64_t a : alleles)
+    for (uint64_t k = g.allele_sid_off[a]; k < g.allele_sid_off[a + 1]; ++k) {
+      const uint32_t m = g.sid_row[k];
+      check(m >= w.row_lo && m < w.row_hi, "an allele carries a SID of another chromosome");
+      ++carriers[m - w.row_lo];
+    }
+  std::vector<uint32_t> by_count(n_rows), rank(n_rows);
+  for (uint32_t i = 0; i < n_rows; ++i) by_count[i] = i;
+  std::stable_sort(by_count.begin(), by_count.end(), [&](uint32_t x, uint32_t y) { return carriers[x] > carriers[y]; });
+  for (uint32_t i = 0; i < n_rows; ++i) rank[by_count[i]] = i;
+  // haplotypes: the normal cell's germline alleles (no somatic SID: they sort first in their block) and every
+  // allele that still has DNA
+  struct Hap {
+    uint32_t cell, fragset;
+    uint16_t allele;
+    uint8_t kind, origin;
+    uint64_t key_off;
+    uint32_t key_n;
+  };
+  std::vector<Hap> haps;
+  std::vector<uint32_t> keys;  // ranks of the SIDs of every haplotype, ascending
+  for (uint16_t a0 = 0; a0 < n0; ++a0) haps.push_back({0u, full, a0, HAP_NORMAL_PLAIN, static_cast<uint8_t>(a0), 0, 0});
+  std::vector<uint32_t> positions;
+  for (uint64_t a : alleles) {
+    check(g.allele_origin[a] < n0, "allele_origin names a missing germline allele");
+    FragKey fk;
+    for (uint64_t k = g.allele_frag_off[a]; k < g.allele_frag_off[a + 1]; ++k) {
+      check(g.frag_begin[k] >= 1 && g.frag_begin[k] <= g.frag_end[k] && g.frag_end[k] <= clen, "fragment outside the chromosome");
+      check(fk.empty() || fk.back().second < g.frag_begin[k], "the fragments of an allele must be disjoint and sorted");
+      fk.emplace_back(g.frag_begin[k], g.frag_end[k]);
+    }
+    if (fk.empty()) continue;  // an allele that lost all its DNA is never read
+    const uint32_t cell = g.allele_cell[a];
+    check(cell < g.n_cells + g.n_normal_preneo, "allele_cell out of range");
+    Hap h{cell < g.n_cells ? cell : cell - g.n_cells, w.intern_set(fk), g.allele_id[a],
+          static_cast<uint8_t>(cell < g.n_cells ? HAP_TUMOUR : HAP_NORMAL_PRENEO), g.allele_origin[a], keys.size(), 0};
+    positions.clear();
+    for (uint64_t k = g.allele_sid_off[a]; k < g.allele_sid_off[a + 1]; ++k) {
+      const uint32_t m = g.sid_row[k], pos = d.mut_pos[m];
+      check(holds(fk, pos), "an allele carries a SID outside its fragments");
+      // one SID per position of a haplotype: not on a germline SID of the allele it descends from ...
+      const uint32_t l = row_locus[m];
+      for (uint32_t q = locus_first_row[l]; q < locus_first_row[l + 1]; ++q)
+        check(!((row_mask[q].load(std::memory_order_relaxed) >> h.origin) & 1u),
+              "somatic SID at a germline SID position of the same allele");
+      positions.push_back(pos);
+      keys.push_back(rank[m - w.row_lo]);
+    }
+    std::sort(positions.begin(), positions.end());  // ... and no two somatic ones
+    check(std::adjacent_find(positions.begin(), positions.end()) == positions.end(), "two SIDs at one position of one allele");
+    h.key_n = static_cast<uint32_t>(keys.size() - h.key_off);
+    std::sort(keys.begin() + static_cast<std::ptrdiff_t>(h.key_off), keys.end());
+    haps.push_back(h);
+  }
+  std::vector<uint32_t> order(haps.size());
+  for (uint32_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+    const Hap &hx = haps[x], &hy = haps[y];
+    if (hx.origin != hy.origin) return hx.origin < hy.origin;
+    return std::lexicographical_compare(keys.begin() + static_cast<std::ptrdiff_t>(hx.key_off),
+                                        keys.begin() + static_cast<std::ptrdiff_t>(hx.key_off + hx.key_n),
+                                        keys.begin() + static_cast<std::ptrdiff_t>(hy.key_off),
+                                        keys.begin() + static_cast<std::ptrdiff_t>(hy.key_off + hy.key_n));
+  });
+  // leaves in that order; the interval below each germline allele
+  for (uint16_t a0 = 0; a0 < 2; ++a0) w.germ_lo[a0] = w.germ_hi[a0] = 0;
+  w.haps.reserve(order.size());
+  for (uint32_t i = 0; i < order.size(); ++i) {
+    const Hap& h = haps[order[i]];
+    if (i == 0 || haps[order[i - 1]].origin != h.origin) w.germ_lo[h.origin] = i;
+    w.germ_hi[h.origin] = i + 1;
+    w.haps.push_back({h.cell, h.fragset, h.allele, h.kind});
+  }
+  // placements: the runs of consecutive haplotypes that carry a row
+  std::vector<uint32_t> last(n_rows, 0xffffffffu);  // index in w.inst of the row's run that ends at the previous haplotype
+  for (uint32_t i = 0; i < order.size(); ++i) {
+    const Hap& h = haps[order[i]];
+    for (uint32_t k = 0; k < h.key_n; ++k) {
+      const uint32_t r = by_count[keys[h.key_off + k]];  // row - row_lo
+      if (last[r] != 0xffffffffu && w.inst[last[r]].lo + w.inst[last[r]].span == i) {
+        ++w.inst[last[r]].span;
+      } else {
+        const uint32_t m = w.row_lo + r;
+        last[r] = static_cast<uint32_t>(w.inst.size());
+        w.inst.push_back({i, 1u, m, static_cast<uint32_t>(d.mut_ref_len[m]) | (static_cast<uint32_t>(d.mut_alt_len[m]) << 8)});
+      }
+    }
+  }
+  finish_chr(w);
+}
+
+pcs_forest_desc common_desc(const pcs_cell_genomes_desc& g) {
+  pcs_forest_desc d{};
+  d.n_chr = g.n_chr;
+  d.chr_len = g.chr_len;
+  d.chr_n_alleles = g.chr_n_alleles;
+  d.n_samples = g.n_samples;
+  d.n_leaves = g.n_cells;
+  d.leaf_sample = g.cell_sample;
+  d.n_mut = g.n_mut;
+  d.mut_chr = g.mut_chr;
+  d.mut_pos = g.mut_pos;
+  d.mut_ref_len = g.mut_ref_len;
+  d.mut_alt_len = g.mut_alt_len;
+  d.n_germline = g.n_germline;
+  d.germ_mut = g.germ_mut;
+  d.germ_allele_mask = g.germ_allele_mask;
+  return d;
+}
+
+}  // namespace
+
+void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads) {
+  const pcs_forest_desc d = common_desc(g);
+  for (uint32_t c = 0; c < g.n_cells; ++c) check(g.cell_sample[c] < g.n_samples, "cell_sample out of range");
+  check(g.n_alleles == 0 || (g.allele_frag_off[0] == 0 && g.allele_sid_off[0] == 0), "allele offsets are not CSR arrays");
+  flatten_with(d, out, n_threads, [&](Numbering& nb) {
+    nb.out.n_roots = g.n_normal_preneo;
+    std::vector<std::vector<uint64_t>> by_chr(g.n_chr);
+    for (uint64_t a = 0; a < g.n_alleles; ++a) {
+      check(g.allele_chr[a] < g.n_chr, "allele_chr out of range");
+      check(g.allele_frag_off[a] <= g.allele_frag_off[a + 1] && g.allele_sid_off[a] <= g.allele_sid_off[a + 1],
+            "allele offsets must be non-decreasing");
+      by_chr[g.allele_chr[a]].push_back(a);
+    }
+    nb.parallel_for(g.n_chr, [&](uint32_t c) {
+      number_from_genomes(g, by_chr[c], nb.work[c], d, nb.row_mask, nb.out.row_locus.data(), nb.out.locus_first_row.data());
+    });
+  });
+}
+
+size_t flat_store_bytes(const pcs_cell_genomes_desc& g) {
+  auto padded = [](size_t n, size_t elem) { return (std::max<size_t>(n * elem, 1) + 255) & ~static_cast<size_t>(255); };
+  const size_t n_sid = g.n_alleles ? static_cast<size_t>(g.allele_sid_off[g.n_alleles]) : 0;
+  return 2 * padded(g.n_mut, 4) + 2 * padded(static_cast<size_t>(g.n_mut) + 1, 4) +
+         padded(n_sid + static_cast<size_t>(g.n_germline), sizeof(Inst));
 }
 
 size_t flat_store_bytes(const pcs_forest_desc& d) {

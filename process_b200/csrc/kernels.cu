@@ -455,6 +455,9 @@ struct StagedTile {
 // one queued read {start offset in the tile, haplotype draw, read id, first staged locus to look at} through the
 // staged loci (and past them, if a carried deletion stretches it that far).  The haplotype is resolved here, not
 // where the read was drawn: three reads out of four never get this far and never need it.
+// (Measured alternative, round 2: one locus per visit to the queue, a read with a further locus going back to
+// it, so that every visit runs with a full warp -- 21.9 ms against 19.5 ms for this loop on C3: the pop, the
+// push and their ballots cost more than the idle lanes of a loop that makes 2.4 trips per drain.)
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
                                             uint32_t* depth, uint32_t* alt, uint4 item) {
@@ -982,6 +985,147 @@ __global__ void sum_u32_kernel(const uint32_t* __restrict__ v, size_t n, unsigne
     acc += v[i];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------- result assembly
+// get_result_dataframe()/get_active_mutations()/add_sample_statistics() (src/seq_simulation.cpp:92-181) on the
+// device: a row is active iff some sample saw it (occurrences > 0) or -- include_non_sequenced_mutations -- some
+// sequenced cell carries it (`carried`, host-made, may be null); active rows are compacted IN ROW ORDER (the
+// std::map<SID, ...> order of the reference) into column-major per-sample columns: occurrences, coverage =
+// depth at the row's locus (this replaces finalize_kernel on this path), VAF = occurrences / coverage as double
+// (0 where the sample never covered the locus, :129-131).  HBM-bound: reads the occurrence tables twice, writes
+// the compact columns once.
+constexpr int kActiveThreads = 256, kActivePerThread = 8;
+constexpr uint32_t kActiveRowsPerBlock = kActiveThreads * kActivePerThread;
+
+__device__ __forceinline__ bool row_active(const uint32_t* __restrict__ occ, const uint8_t* __restrict__ carried,
+                                           uint32_t S, uint32_t M, uint32_t m) {
+  if (carried && carried[m]) return true;
+  uint32_t any = 0;
+  for (uint32_t s = 0; s < S; ++s) any |= __ldg(occ + static_cast<size_t>(s) * M + m);
+  return any != 0;
+}
+
+__global__ void __launch_bounds__(kActiveThreads)
+active_count_kernel(const uint32_t* __restrict__ occ, const uint8_t* __restrict__ carried, uint32_t S, uint32_t M,
+                    uint32_t* __restrict__ block_count) {
+  const uint32_t base = blockIdx.x * kActiveRowsPerBlock;
+  uint32_t n = 0;
+#pragma unroll
+  for (int j = 0; j < kActivePerThread; ++j) {
+    const uint32_t m = base + j * kActiveThreads + threadIdx.x;
+    n += (m < M && row_active(occ, carried, S, M, m)) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  __shared__ uint32_t s_w[kActiveThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kActiveThreads / 32; ++w) t += s_w[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+// exclusive scan of the block counts in place (one CTA: a few thousand values); total[0] = number of active rows
+__global__ void __launch_bounds__(1024) active_scan_kernel(uint32_t* __restrict__ block_count, uint32_t n_blocks,
+                                                           uint32_t* __restrict__ total) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (uint32_t i0 = 0; i0 < n_blocks; i0 += 1024) {
+    const uint32_t i = i0 + threadIdx.x;
+    const uint32_t v = i < n_blocks ? block_count[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= static_cast<uint32_t>(o)) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = s_w[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= static_cast<uint32_t>(o)) w += y;
+      }
+      s_w[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t before = s_carry + (warp ? s_w[warp - 1] : 0u) + x - v;
+    if (i < n_blocks) block_count[i] = before;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = before + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) total[0] = s_carry;
+}
+
+__global__ void __launch_bounds__(kActiveThreads)
+active_scatter_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ depth,
+                      const uint32_t* __restrict__ row_locus, const uint8_t* __restrict__ carried, uint32_t S,
+                      uint32_t M, uint32_t L, const uint32_t* __restrict__ block_off, uint32_t n_active,
+                      uint32_t* __restrict__ rows_out, uint32_t* __restrict__ occ_c, uint32_t* __restrict__ cov_c,
+                      double* __restrict__ vaf_c) {
+  __shared__ uint32_t s_w[kActiveThreads / 32];
+  const uint32_t base = blockIdx.x * kActiveRowsPerBlock;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t lanes_below;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
+  uint32_t running = block_off[blockIdx.x];
+  for (int j = 0; j < kActivePerThread; ++j) {
+    const uint32_t m = base + j * kActiveThreads + threadIdx.x;
+    const bool on = m < M && row_active(occ, carried, S, M, m);
+    const uint32_t ballot = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) s_w[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kActiveThreads / 32; ++w) {
+      const uint32_t c = s_w[w];
+      before += w < static_cast<int>(warp) ? c : 0u;
+      all += c;
+    }
+    if (on) {
+      const uint32_t k = running + before + __popc(ballot & lanes_below);
+      rows_out[k] = m;
+      const uint32_t l = __ldg(row_locus + m);
+      for (uint32_t s = 0; s < S; ++s) {
+        const uint32_t o = __ldg(occ + static_cast<size_t>(s) * M + m);
+        const uint32_t c = __ldg(depth + static_cast<size_t>(s) * L + l);
+        const size_t at = static_cast<size_t>(s) * n_active + k;
+        occ_c[at] = o;
+        cov_c[at] = c;
+        if (vaf_c) vaf_c[at] = c ? static_cast<double>(o) / static_cast<double>(c) : 0.0;
+      }
+    }
+    running += all;
+    __syncthreads();
+  }
+}
+
+uint32_t active_blocks(uint32_t n_mut) { return (n_mut + kActiveRowsPerBlock - 1) / kActiveRowsPerBlock; }
+
+cudaError_t launch_active_count(cudaStream_t st, const uint32_t* occ, const uint8_t* carried, uint32_t S, uint32_t M,
+                                uint32_t* block_count, uint32_t* total) {
+  const uint32_t nb = active_blocks(M);
+  if (nb == 0) return cudaMemsetAsync(total, 0, sizeof(uint32_t), st);
+  active_count_kernel<<<nb, kActiveThreads, 0, st>>>(occ, carried, S, M, block_count);
+  active_scan_kernel<<<1, 1024, 0, st>>>(block_count, nb, total);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const uint32_t* depth, const uint32_t* row_locus,
+                                  const uint8_t* carried, uint32_t S, uint32_t M, uint32_t L, const uint32_t* block_off,
+                                  uint32_t n_active, uint32_t* rows_out, uint32_t* occ_c, uint32_t* cov_c,
+                                  double* vaf_c) {
+  const uint32_t nb = active_blocks(M);
+  if (nb == 0 || n_active == 0) return cudaSuccess;
+  active_scatter_kernel<<<nb, kActiveThreads, 0, st>>>(occ, depth, row_locus, carried, S, M, L, block_off, n_active,
+                                                       rows_out, occ_c, cov_c, vaf_c);
+  return cudaGetLastError();
 }
 
 // ----------------------------------------------------------------- launchers

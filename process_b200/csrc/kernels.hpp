@@ -30,6 +30,14 @@ cudaError_t launch_count_injected(cudaStream_t st, const DevPlacement* rec, cons
                                   uint32_t* alt);
 cudaError_t launch_finalize(cudaStream_t st, const uint32_t* depth, const uint32_t* row_locus, uint32_t n_samples,
                             uint32_t n_loci, uint32_t n_mut, uint32_t* coverage);
+// result assembly: active rows compacted in row order into column-major per-sample columns
+uint32_t active_blocks(uint32_t n_mut);  // length of the block_count scratch array
+cudaError_t launch_active_count(cudaStream_t st, const uint32_t* occ, const uint8_t* carried, uint32_t S, uint32_t M,
+                                uint32_t* block_count, uint32_t* total);
+cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const uint32_t* depth, const uint32_t* row_locus,
+                                  const uint8_t* carried, uint32_t S, uint32_t M, uint32_t L, const uint32_t* block_off,
+                                  uint32_t n_active, uint32_t* rows_out, uint32_t* occ_c, uint32_t* cov_c,
+                                  double* vaf_c);
 cudaError_t launch_sum_u32(cudaStream_t st, const uint32_t* v, size_t n, unsigned long long* out);
 
 }  // namespace pcs

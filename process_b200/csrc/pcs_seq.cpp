@@ -140,7 +140,15 @@ struct Lap {
 
 }  // namespace
 
+struct pcs_ctx;
+void release_ctx(pcs_ctx* cx);  // one user less; the last one of a destroyed context frees it
+
 struct pcs_ctx {
+  // Forests (and the flattened host views that borrowed a pinned block) keep their context alive: pcs_destroy on
+  // a context that still has users only marks it, and the last user to go frees it -- a caller that tears things
+  // down in the wrong order (an exception between the two frees, an interpreter shutting down) does not crash.
+  std::atomic<int> users{0};
+  std::atomic<bool> destroyed{false};
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -211,11 +219,60 @@ struct pcs_ctx {
     if (!pinned_counters) CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned_counters), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
     return pinned_counters;
   }
+  // tables other devices of this process add into (pcs_simulate_multi): plain cudaMalloc, kept between calls
+  void* peer_tables = nullptr;
+  size_t peer_tables_bytes = 0;
+  void* peer_table(size_t bytes) {
+    if (bytes > peer_tables_bytes) {
+      if (peer_tables) cudaFree(peer_tables);
+      peer_tables = nullptr;
+      peer_tables_bytes = 0;
+      CUDA_OK(cudaMalloc(&peer_tables, bytes));
+      peer_tables_bytes = bytes;
+    }
+    return peer_tables;
+  }
   // second stream: the tables of one sample travel to the host while the next sample is being sampled
   cudaStream_t copy_stream = nullptr;
   cudaStream_t copier() {
     if (!copy_stream) CUDA_OK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     return copy_stream;
+  }
+  // timing events of the per-sample sampler launches of a pipelined call (created on first use)
+  std::vector<cudaEvent_t> time_ev;
+  cudaEvent_t time_event(size_t i) {
+    while (time_ev.size() <= i) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreate(&e));
+      time_ev.push_back(e);
+    }
+    return time_ev[i];
+  }
+  // pinned slots the per-sample plan slices are uploaded from: slot k is written again only after its last DMA
+  struct PlanSlot {
+    char* p = nullptr;
+    size_t bytes = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+  };
+  PlanSlot plan_slots[5];  // [4]: the haplotype lists of a forest's sample groups
+  PlanSlot& group_slot(size_t bytes) { return plan_slot(4, bytes); }
+  PlanSlot& plan_slot(size_t k, size_t bytes) {  // k in [0, 4]
+    PlanSlot& sl = plan_slots[k];
+    if (!sl.done) CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    if (sl.in_flight) {
+      CUDA_OK(cudaEventSynchronize(sl.done));
+      sl.in_flight = false;
+    }
+    if (bytes > sl.bytes) {
+      if (sl.p) cudaFreeHost(sl.p);
+      sl.p = nullptr;
+      sl.bytes = 0;
+      bytes += bytes / 4;
+      CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&sl.p), bytes, cudaHostAllocDefault));
+      sl.bytes = bytes;
+    }
+    return sl;
   }
   // events that mark the chunks of a pipelined device-to-host copy (created on first use)
   std::vector<cudaEvent_t> chunk_ev;
@@ -240,11 +297,15 @@ struct HostForest {
   HostForest(const HostForest&) = delete;
   HostForest& operator=(const HostForest&) = delete;
   ~HostForest() {
-    if (lender) lender->give_back(block);
+    if (lender) {
+      lender->give_back(block);
+      release_ctx(lender);
+    }
   }
   void borrow(pcs_ctx* cx, size_t bytes) {
     block = cx->lend(bytes);
     lender = cx;
+    ++cx->users;
     flat.store.base = static_cast<char*>(block.p);
     flat.store.capacity = block.bytes;
   }
@@ -327,6 +388,18 @@ struct pcs_flat {
 };
 
 struct pcs_forest {
+  // declared first = destroyed last: the device buffers below are freed on the context's stream before the
+  // context loses this user
+  struct CtxUser {
+    pcs_ctx* cx = nullptr;
+    void hold(pcs_ctx* c) {
+      cx = c;
+      ++c->users;
+    }
+    ~CtxUser() {
+      if (cx) release_ctx(cx);
+    }
+  } user;
   pcs_ctx* ctx = nullptr;
   std::shared_ptr<HostForest> host_ptr = std::make_shared<HostForest>();
   HostForest& host = *host_ptr;  // several devices may hold one flattened forest
@@ -384,8 +457,19 @@ struct pcs_forest {
   }
   uint64_t uploaded_groups = 0;
   void upload_groups() {
+    // through a pinned slot and left in flight, behind the flat tables' own DMA: the caller goes on to plan
     ctx->bind();
-    h2d_bytes += d_hap_list.upload(host.hap_list, ctx->stream);
+    cudaStream_t st = ctx->stream;
+    const size_t bytes = host.hap_list.size() * sizeof(uint32_t);
+    d_hap_list.alloc(host.hap_list.size(), st);
+    if (bytes) {
+      pcs_ctx::PlanSlot& slot = ctx->group_slot(bytes);
+      parallel_copy(slot.p, host.hap_list.data(), bytes);
+      CUDA_OK(cudaMemcpyAsync(d_hap_list.p, slot.p, bytes, cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaEventRecord(slot.done, st));
+      slot.in_flight = true;
+    }
+    h2d_bytes += bytes;
     uploaded_groups = host.groups_version;
   }
   // a replica whose sibling changed the sample groups re-uploads the haplotype lists
@@ -458,6 +542,17 @@ struct pcs_plan {
   DevBuf<uint32_t> d_depth, d_occ, d_cov;
   DevBuf<unsigned long long> d_counters;  // [0] reads placed [1] sum depth [2] sum occ [3] trace count
   uint64_t h2d_bytes = 0;
+  const uint32_t* last_occ = nullptr;  // occurrence table of the last pcs_plan_run (device), for pcs_plan_result
+  uint64_t launches_since_read = 0;    // kernels launched since the counters were last read (asynchronous steps)
+};
+
+// compact, column-major result of one call, resident on the device until fetched (include/pcs_seq.h)
+struct pcs_result {
+  pcs_forest* forest = nullptr;
+  uint32_t n_rows = 0, n_samples = 0;
+  DevBuf<uint32_t> d_rows, d_occ, d_cov;
+  DevBuf<double> d_vaf;
+  pcs_run_stats stats{};
 };
 
 namespace {
@@ -725,7 +820,10 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
   tile_w.reserve(g.tiles.size());
   // normal cells: every one carries each germline allele whole
   auto nit = fo.list_index.find(HostForest::list_key(ps.normal_group, F.full_fragset[c]));
-  require(nit != fo.list_index.end(), "internal: normal haplotype list missing");
+  require(nit != fo.list_index.end(),
+          P.preneoplastic_in_normal ? "preneoplastic_in_normal: the forest was uploaded without the normal cells that carry "
+                                      "the pre-neoplastic mutations (pcs_cell_genomes_desc.n_normal_preneo = 0)"
+                                    : "internal: normal haplotype list missing");
   const uint32_t n_normal_cells = P.preneoplastic_in_normal ? F.n_roots : 1;
   std::vector<double> w;
   std::vector<pcs::Entry> es;
@@ -832,16 +930,36 @@ void set_model(HostPlan& pl, const PlanSetup& ps) {
   M.dir_shift = ps.dir_shift;
 }
 
-HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
-  HostPlan pl;
+// what a tile costs the sampler, in warp instructions per 32 templates (profiles/: Philox + draw + probe ~35
+// for every read, queue + walk + counting ~160 x the fraction of reads that reach a locus): shards are balanced
+// on this, not on templates -- tiles differ in locus density
+uint64_t tile_cost(const pcs::Tile& t, const PlanSetup& ps) {
+  static const bool by_templates = [] {  // PCS_BALANCE=templates: the round-1 rule, for A/B measurements
+    const char* e = std::getenv("PCS_BALANCE");
+    return e && std::string(e) == "templates";
+  }();
+  if (by_templates) return t.n_templates;
+  const double span = static_cast<double>(t.len) + static_cast<double>(ps.reach);
+  const double hit = std::min(1.0, static_cast<double>(t.l1 - t.l0) * ps.R * ps.mates / span / ps.mates);
+  return static_cast<uint64_t>(static_cast<double>(t.n_templates) * ps.mates * (35.0 + 160.0 * hit));
+}
+
+// The plan of the output samples [s0, s1) of the job: the slice of the whole job's plan that belongs to them.
+// Tile ids are positions in the (sample, chromosome, position) order of the WHOLE job, so `id_base` = tiles of
+// the samples before s0 (info.n_tiles_total of their plans); template counts come from the RNG stream of
+// (seed, sample, chromosome).  Results do not depend on how the job is cut into plans or shards.
+// `all_shards`: one plan per shard of ps.shards (one process driving several GPUs plans the job once); else only
+// the plan of shard ps.P.shard_rank.
+std::vector<HostPlan> make_host_plans(const PlanSetup& ps, uint32_t s0, uint32_t s1, uint32_t id_base, bool all_shards) {
+  std::vector<HostPlan> plans(all_shards ? ps.shards : 1u);
+  HostPlan& pl = plans[0];
   Lap lap;
+  const HostForest& fo = *ps.fo;
   const pcs::FlatForest& F = fo.flat;
-  PlanSetup ps = plan_setup(fo, P);
-  lap("  plan: tile geometry");
   // every (output sample, chromosome) is an independent task with its own RNG stream
-  std::vector<SampleChrPlan> per(ps.samples.size() * static_cast<size_t>(F.n_chr));
+  std::vector<SampleChrPlan> per(static_cast<size_t>(s1 - s0) * F.n_chr);
   host_tasks(per.size(), [&](size_t k) {
-    plan_sample_chr(ps, static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr), per[k]);
+    plan_sample_chr(ps, s0 + static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr), per[k]);
   });
   lap("  plan: entries + templates");
   // merged in (sample, chromosome) order: the position in this order is the tile id
@@ -864,13 +982,13 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
     pl.entry_lo.insert(pl.entry_lo.end(), task.entry_lo.begin(), task.entry_lo.end());
     for (auto& t : task.tiles) {
       t.entry_off += base;
-      t.id = static_cast<uint32_t>(all.size());
+      t.id = id_base + static_cast<uint32_t>(all.size());
       all.push_back(t);
     }
     total_templates += task.total_templates;
   }
   lap("  plan: merge");
-  // shard: longest-processing-time greedy on templates; ties by tile id => deterministic
+  // shard: longest-processing-time greedy on the tiles' cost, heaviest first; ties by tile id => deterministic
   const std::vector<uint32_t> order = heaviest_first(all);
   // tiles whose loci / instances / rows fit the staging capacity go to the staged kernel
   const uint32_t lcap = ps.lcap, dir_shift = ps.dir_shift, shards = ps.shards;
@@ -878,22 +996,22 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
   auto stageable = [&](const pcs::Tile& t) {
     return lcap > 0 && t.l1 - t.l0 <= lcap && t.n_rows <= 2 * lcap && t.n_entries <= pcs::kMaxStagedEntries;
   };
-  auto take = [&](const pcs::Tile& t) {
+  auto take = [&](HostPlan& dst, const pcs::Tile& t) {
     if (stageable(t)) {
-      pl.tiles.push_back(t);
-      pl.dims.max_loci = std::max(pl.dims.max_loci, t.l1 - t.l0);
-      pl.dims.max_rows = std::max(pl.dims.max_rows, t.n_rows);
-      pl.dims.max_buckets = std::max<uint32_t>(pl.dims.max_buckets, static_cast<uint32_t>(((t.len + reach) >> dir_shift) + 1));
+      dst.tiles.push_back(t);
+      dst.dims.max_loci = std::max(dst.dims.max_loci, t.l1 - t.l0);
+      dst.dims.max_rows = std::max(dst.dims.max_rows, t.n_rows);
+      dst.dims.max_buckets = std::max<uint32_t>(dst.dims.max_buckets, static_cast<uint32_t>(((t.len + reach) >> dir_shift) + 1));
     } else {
-      pl.tiles_global.push_back(t);
+      dst.tiles_global.push_back(t);
     }
   };
-  pl.tiles.reserve(all.size() / shards + 16);
-  uint64_t mine = 0;
+  for (auto& q : plans) q.tiles.reserve(all.size() / shards + 16);
+  std::vector<uint64_t> templates(shards, 0);
   if (shards == 1) {
     for (uint32_t i : order)
-      if (all[i].n_templates) take(all[i]);
-    mine = total_templates;
+      if (all[i].n_templates) take(pl, all[i]);
+    templates[0] = total_templates;
   } else {
     std::vector<uint64_t> load(shards, 0);
     for (uint32_t i : order) {
@@ -901,41 +1019,58 @@ HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
       uint32_t best = 0;
       for (uint32_t r = 1; r < shards; ++r)
         if (load[r] < load[best]) best = r;
-      load[best] += all[i].n_templates;
-      if (best == P.shard_rank) take(all[i]);
+      load[best] += tile_cost(all[i], ps);
+      templates[best] += all[i].n_templates;
+      if (all_shards) take(plans[best], all[i]);
+      else if (best == ps.P.shard_rank) take(pl, all[i]);
     }
-    mine = load[P.shard_rank];
-  }
-  // the staged tiles once more, grouped by output sample, heaviest first inside a sample: host-output runs
-  // launch sample by sample
-  const size_t S = ps.samples.size();
-  pl.sample_tile_off.assign(S + 1, 0);
-  for (const auto& t : pl.tiles) ++pl.sample_tile_off[t.sample + 1];
-  for (size_t i = 0; i < S; ++i) pl.sample_tile_off[i + 1] += pl.sample_tile_off[i];
-  {
-    std::vector<uint32_t> at(pl.sample_tile_off.begin(), pl.sample_tile_off.end() - 1);
-    pl.tiles_by_sample.resize(pl.tiles.size());
-    for (const auto& t : pl.tiles) pl.tiles_by_sample[at[t.sample]++] = t;
   }
   lap("  plan: order + shard");
-  // round the capacities so that plans of similar forests share one shared-memory footprint
-  pl.dims.max_loci = (pl.dims.max_loci + 63) & ~63u;
-  pl.dims.max_rows = (pl.dims.max_rows + 63) & ~63u;
-  pl.dims.max_buckets = (pl.dims.max_buckets + 63) & ~63u;
+  const size_t S = ps.samples.size();
+  for (size_t q = 0; q < plans.size(); ++q) {
+    HostPlan& d = plans[q];
+    if (q != 0) {  // every shard's tiles index the same sampling entries
+      d.entries = pl.entries;
+      d.entry_lo = pl.entry_lo;
+    }
+    // the staged tiles once more, grouped by output sample, heaviest first inside a sample: host-output runs
+    // launch sample by sample
+    d.sample_tile_off.assign(S + 1, 0);
+    for (const auto& t : d.tiles) ++d.sample_tile_off[t.sample + 1];
+    for (size_t i = 0; i < S; ++i) d.sample_tile_off[i + 1] += d.sample_tile_off[i];
+    {
+      std::vector<uint32_t> at(d.sample_tile_off.begin(), d.sample_tile_off.end() - 1);
+      d.tiles_by_sample.resize(d.tiles.size());
+      for (const auto& t : d.tiles) d.tiles_by_sample[at[t.sample]++] = t;
+    }
+    // round the capacities so that plans of similar forests share one shared-memory footprint
+    d.dims.max_loci = (d.dims.max_loci + 63) & ~63u;
+    d.dims.max_rows = (d.dims.max_rows + 63) & ~63u;
+    d.dims.max_buckets = (d.dims.max_buckets + 63) & ~63u;
+    d.insert_alias = ps.insert_alias;
+    set_model(d, ps);
+    d.info.n_out_samples = static_cast<uint32_t>(ps.samples.size());
+    d.info.n_mut = F.n_mut;
+    d.info.n_loci = static_cast<uint32_t>(F.locus_pos.size());
+    d.info.n_tiles = d.tiles.size() + d.tiles_global.size();
+    d.info.n_tiles_total = all.size();
+    d.info.n_templates = templates[all_shards ? q : (shards == 1 ? 0 : ps.P.shard_rank)];
+    d.info.n_templates_total = total_templates;
+    d.info.reads_per_template = ps.mates;
+    d.info.read_size = ps.R;
+  }
+  return plans;
+}
 
-  pl.insert_alias = ps.insert_alias;
-  set_model(pl, ps);
+HostPlan make_host_plan(const PlanSetup& ps, uint32_t s0, uint32_t s1, uint32_t id_base) {
+  return std::move(make_host_plans(ps, s0, s1, id_base, false)[0]);
+}
 
-  pl.info.n_out_samples = static_cast<uint32_t>(ps.samples.size());
-  pl.info.n_mut = F.n_mut;
-  pl.info.n_loci = static_cast<uint32_t>(F.locus_pos.size());
-  pl.info.n_tiles = pl.tiles.size() + pl.tiles_global.size();
-  pl.info.n_tiles_total = all.size();
-  pl.info.n_templates = mine;
-  pl.info.n_templates_total = total_templates;
-  pl.info.reads_per_template = ps.mates;
-  pl.info.read_size = ps.R;
-  return pl;
+HostPlan make_host_plan(const HostForest& fo, const pcs_seq_params& P) {
+  Lap lap;
+  const PlanSetup ps = plan_setup(fo, P);
+  lap("  plan: tile geometry");
+  return make_host_plan(ps, 0, static_cast<uint32_t>(ps.samples.size()), 0);
 }
 
 void upload_plan(pcs_plan& pl) {
@@ -962,17 +1097,20 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
   cx.bind();
   cudaStream_t st = cx.stream;
   const bool dev_out = (flags & PCS_RUN_DEVICE_OUTPUT) != 0;
+  const bool checksums = (flags & PCS_RUN_NO_CHECKSUMS) == 0;
+  const bool async = dev_out && (flags & PCS_RUN_ASYNC) != 0;  // nothing comes back to the host: no need to wait
   const size_t S = pl.host.info.n_out_samples, M = pl.host.info.n_mut, L = pl.host.info.n_loci;
   uint32_t* d_occ = dev_out ? occ : pl.d_occ.p;
   uint32_t* d_cov = dev_out ? cov : pl.d_cov.p;
   require(S * M == 0 || (occ && cov), "occurrences/coverage output pointers are NULL");
+  pl.last_occ = d_occ;
   const double t0 = now_ms();
   uint64_t launches = 0;
 
   CUDA_OK(cudaEventRecord(cx.ev[0], st));
   if (S * L != 0) CUDA_OK(cudaMemsetAsync(pl.d_depth.p, 0, S * L * sizeof(uint32_t), st));
   if (S * M != 0) CUDA_OK(cudaMemsetAsync(d_occ, 0, S * M * sizeof(uint32_t), st));
-  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  if (!async) CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));  // async: they accumulate
   CUDA_OK(cudaEventRecord(cx.ev[1], st));
   const pcs::DevForest DF = fo.dev();
   uint64_t d2h = 0;
@@ -1029,10 +1167,14 @@ void run_plan(pcs_plan& pl, int flags, uint32_t* occ, uint32_t* cov, pcs_run_sta
                                  static_cast<uint32_t>(M), d_cov));
     launches += S * M != 0 ? 1 : 0;
   }
-  CUDA_OK(pcs::launch_sum_u32(st, pl.d_depth.p, S * L, pl.d_counters.p + 1));
-  CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
-  launches += (S * M != 0 ? 1 : 0) + (S * L != 0 ? 1 : 0);
+  if (checksums) {
+    CUDA_OK(pcs::launch_sum_u32(st, pl.d_depth.p, S * L, pl.d_counters.p + 1));
+    CUDA_OK(pcs::launch_sum_u32(st, d_occ, S * M, pl.d_counters.p + 2));
+    launches += (S * M != 0 ? 1 : 0) + (S * L != 0 ? 1 : 0);
+  }
   CUDA_OK(cudaEventRecord(cx.ev[3], st));
+  pl.launches_since_read += launches;
+  if (async) return;
   if (!by_sample && !dev_out && table_bytes != 0) {
     char* stage = static_cast<char*>(cx.staging(2 * table_bytes));
     const size_t cb = std::max<size_t>(4u << 20, ((2 * table_bytes / 16) + 4095) & ~static_cast<size_t>(4095));
@@ -1102,7 +1244,9 @@ void accumulate_plan(pcs_plan& pl, uint32_t* d_depth, uint32_t* d_occ, pcs_run_s
   require(S * M == 0 || (d_depth && d_occ), "depth/occurrences table pointers are NULL");
   (void)L;
   const double t0 = now_ms();
-  CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+  // stats == NULL: asynchronous -- nothing is read back, the call returns once the kernels are queued and the
+  // counters keep accumulating until pcs_plan_counters() reads them
+  if (stats) CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
   CUDA_OK(cudaEventRecord(cx.ev[1], st));
   const pcs::DevForest DF = fo.dev();
   CUDA_OK(pcs::launch_sample_tiles_staged(st, pl.d_tiles.p, static_cast<uint32_t>(pl.host.tiles.size()), pl.d_entries.p,
@@ -1110,6 +1254,8 @@ void accumulate_plan(pcs_plan& pl, uint32_t* d_depth, uint32_t* d_occ, pcs_run_s
   CUDA_OK(pcs::launch_sample_tiles_global(st, pl.d_tiles_global.p, static_cast<uint32_t>(pl.host.tiles_global.size()),
                                           pl.d_entries.p, pl.d_entry_lo.p, DF, pl.host.model, d_depth, d_occ, pl.d_counters.p));
   CUDA_OK(cudaEventRecord(cx.ev[2], st));
+  pl.launches_since_read += (pl.host.tiles.empty() ? 0 : 1) + (pl.host.tiles_global.empty() ? 0 : 1);
+  if (!stats) return;
   unsigned long long counters[4] = {0, 0, 0, 0};
   CUDA_OK(cudaMemcpyAsync(counters, pl.d_counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
@@ -1135,6 +1281,12 @@ void finalize_tables(pcs_plan& pl, const uint32_t* d_depth, const uint32_t* d_oc
   const size_t S = pl.host.info.n_out_samples, M = pl.host.info.n_mut, L = pl.host.info.n_loci;
   require(S * M == 0 || (d_depth && d_occ && d_cov), "table pointers are NULL");
   const double t0 = now_ms();
+  if (!stats) {  // asynchronous, no table checksums: just the coverage gather, queued
+    CUDA_OK(pcs::launch_finalize(st, d_depth, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
+                                 static_cast<uint32_t>(M), d_cov));
+    pl.launches_since_read += S * M != 0 ? 1 : 0;
+    return;
+  }
   CUDA_OK(cudaMemsetAsync(pl.d_counters.p, 0, 4 * sizeof(unsigned long long), st));
   CUDA_OK(pcs::launch_finalize(st, d_depth, fo.d_row_locus.p, static_cast<uint32_t>(S), static_cast<uint32_t>(L),
                                static_cast<uint32_t>(M), d_cov));
@@ -1151,6 +1303,302 @@ void finalize_tables(pcs_plan& pl, const uint32_t* d_depth, const uint32_t* d_oc
     stats->sum_occurrences = counters[2];
     stats->d2h_bytes = sizeof(counters);
   }
+}
+
+// ------------------------------------------------------------ device -> caller copies
+// Device memory to the caller's (pageable) buffers: the DMA lands in pinned staging chunk by chunk and host
+// threads copy chunk k out while chunk k+1 is still on the link.
+struct OutCopy {
+  void* dst;
+  const void* src;
+  size_t bytes;
+};
+
+struct ChunkCopy {
+  char* dst;
+  const char* src;
+  size_t bytes;
+};
+
+// wait for the chunks' events (cx.chunk_ev[k], recorded by the caller) and copy them out with host threads
+void drain_chunks(pcs_ctx& cx, const std::vector<ChunkCopy>& chunks) {
+  if (chunks.empty()) return;
+  const unsigned nt = std::max(1u, std::min(16u, host_threads()));
+  std::vector<cudaError_t> werr(nt, cudaSuccess);
+  std::vector<std::thread> th;
+  for (unsigned w = 0; w < nt; ++w)
+    th.emplace_back([&, w] {
+      cudaSetDevice(cx.device);
+      for (size_t k = 0; k < chunks.size(); ++k) {
+        const cudaError_t e = cudaEventSynchronize(cx.chunk_ev[k]);
+        if (e != cudaSuccess) {
+          werr[w] = e;
+          return;
+        }
+        const size_t lo = (chunks[k].bytes * w / nt) & ~static_cast<size_t>(63);
+        const size_t hi = w + 1 == nt ? chunks[k].bytes : (chunks[k].bytes * (w + 1) / nt) & ~static_cast<size_t>(63);
+        if (hi > lo) std::memcpy(chunks[k].dst + lo, chunks[k].src + lo, hi - lo);
+      }
+    });
+  for (auto& t : th) t.join();
+  for (cudaError_t e : werr) CUDA_OK(e);
+}
+
+uint64_t copy_out(pcs_ctx& cx, cudaStream_t st, const std::vector<OutCopy>& items) {
+  size_t total = 0;
+  for (const auto& it : items) total += (it.bytes + 255) & ~static_cast<size_t>(255);
+  if (total == 0) return 0;
+  char* stage = static_cast<char*>(cx.staging(total));
+  const size_t cb = std::max<size_t>(4u << 20, ((total / 16) + 4095) & ~static_cast<size_t>(4095));
+  std::vector<ChunkCopy> chunks;
+  size_t at = 0;
+  for (const auto& it : items) {
+    for (size_t off = 0; off < it.bytes; off += cb) {
+      const size_t nb = std::min(cb, it.bytes - off);
+      CUDA_OK(cudaMemcpyAsync(stage + at + off, static_cast<const char*>(it.src) + off, nb, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(cudaEventRecord(cx.chunk_event(chunks.size()), st));
+      chunks.push_back({static_cast<char*>(it.dst) + off, stage + at + off, nb});
+    }
+    at += (it.bytes + 255) & ~static_cast<size_t>(255);
+  }
+  drain_chunks(cx, chunks);
+  CUDA_OK(cudaStreamSynchronize(st));
+  uint64_t bytes = 0;
+  for (const auto& it : items) bytes += it.bytes;
+  return bytes;
+}
+
+// ------------------------------------------------------------ one call, sample by sample
+// pcs_simulate() and pcs_simulate_result(): the call is planned AND launched one output sample at a time, so the
+// host plans sample s+1 (entries, multinomial template counts, tile order) while the GPU samples s -- of the
+// planner's time only the first sample's share stays in front of the kernels.  A sample's slice of the plan goes
+// up through a pinned slot with one DMA per array.  Same tile ids, template counts and Philox counters as the
+// one-piece plan of pcs_plan_create(): the tables are identical, bit for bit.
+struct CallTables {
+  DevBuf<uint32_t> depth, occ, cov;
+  DevBuf<unsigned long long> counters;
+  DevBuf<uint32_t> insert_alias;
+  size_t S = 0, M = 0, L = 0;
+};
+
+template <class AfterSample>
+void run_pipelined(pcs_forest& fo, const pcs_seq_params& P, bool want_cov, CallTables& T, pcs_run_stats& rs,
+                   AfterSample&& after_sample) {
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  Lap lap;
+  fo.sync_groups();
+  const PlanSetup ps = plan_setup(fo.host, P);
+  lap("  plan: tile geometry");
+  const pcs::FlatForest& F = fo.host.flat;
+  const size_t S = T.S = ps.samples.size(), M = T.M = F.n_mut, L = T.L = F.locus_pos.size();
+  T.depth.alloc(S * L, st);
+  T.occ.alloc(S * M, st);
+  if (want_cov) T.cov.alloc(S * M, st);
+  T.counters.alloc(4, st);
+  if (S * L != 0) CUDA_OK(cudaMemsetAsync(T.depth.p, 0, T.depth.bytes(), st));
+  if (S * M != 0) CUDA_OK(cudaMemsetAsync(T.occ.p, 0, T.occ.bytes(), st));
+  CUDA_OK(cudaMemsetAsync(T.counters.p, 0, T.counters.bytes(), st));
+  uint64_t h2d = 0, launches = 0, templates = 0;
+  if (!ps.insert_alias.empty()) h2d += T.insert_alias.upload(ps.insert_alias, st);
+  const pcs::DevForest DF = fo.dev();
+  uint32_t id_base = 0;
+  rs = pcs_run_stats{};
+  for (uint32_t smp = 0; smp < S; ++smp) {
+    HostPlan hp = make_host_plan(ps, smp, smp + 1, id_base);
+    id_base += static_cast<uint32_t>(hp.info.n_tiles_total);
+    templates += hp.info.n_templates;
+    hp.model.insert_alias = T.insert_alias.p;
+    // the slice goes up from one pinned slot, one DMA per array; the buffers are freed in stream order
+    auto padded = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t b_tiles = hp.tiles.size() * sizeof(pcs::Tile), b_glob = hp.tiles_global.size() * sizeof(pcs::Tile),
+                 b_ent = hp.entries.size() * sizeof(pcs::Entry), b_lo = hp.entry_lo.size() * sizeof(uint32_t);
+    pcs_ctx::PlanSlot& slot = cx.plan_slot(smp % 4, padded(b_tiles) + padded(b_glob) + padded(b_ent) + padded(b_lo) + 256);
+    DevBuf<pcs::Tile> d_tiles, d_glob;
+    DevBuf<pcs::Entry> d_ent;
+    DevBuf<uint32_t> d_lo;
+    size_t at = 0;
+    auto up = [&](auto& buf, const auto& vec, size_t bytes) {
+      buf.alloc(vec.size(), st);
+      if (bytes) {
+        std::memcpy(slot.p + at, vec.data(), bytes);
+        CUDA_OK(cudaMemcpyAsync(buf.p, slot.p + at, bytes, cudaMemcpyHostToDevice, st));
+      }
+      at += padded(bytes);
+      h2d += bytes;
+    };
+    up(d_tiles, hp.tiles, b_tiles);
+    up(d_glob, hp.tiles_global, b_glob);
+    up(d_ent, hp.entries, b_ent);
+    up(d_lo, hp.entry_lo, b_lo);
+    CUDA_OK(cudaEventRecord(slot.done, st));
+    slot.in_flight = true;
+    CUDA_OK(cudaEventRecord(cx.time_event(2 * smp), st));
+    CUDA_OK(pcs::launch_sample_tiles_staged(st, d_tiles.p, static_cast<uint32_t>(hp.tiles.size()), d_ent.p, d_lo.p, DF,
+                                            hp.model, hp.dims, T.depth.p, T.occ.p, T.counters.p));
+    CUDA_OK(pcs::launch_sample_tiles_global(st, d_glob.p, static_cast<uint32_t>(hp.tiles_global.size()), d_ent.p, d_lo.p,
+                                            DF, hp.model, T.depth.p, T.occ.p, T.counters.p));
+    CUDA_OK(cudaEventRecord(cx.time_event(2 * smp + 1), st));
+    launches += (hp.tiles.empty() ? 0 : 1) + (hp.tiles_global.empty() ? 0 : 1);
+    after_sample(smp, launches);
+    rs.n_templates += hp.info.n_templates;
+    if (smp == 0) {
+      rs.h2d_bytes = 0;  // filled below
+      if (lap.on)
+        std::fprintf(stderr, "[pcs host]    sample 0: %zu staged tiles, %zu global; staged smem %zu B\n", hp.tiles.size(),
+                     hp.tiles_global.size(), pcs::staged_smem_bytes(hp.dims, hp.model.sequencer != PCS_SEQ_ERRORLESS));
+    }
+  }
+  lap("  plan + launch, all samples");
+  rs.kernel_launches = launches;
+  rs.h2d_bytes = h2d;
+  (void)templates;
+}
+
+// kernel time of a pipelined call: the per-sample sampler launches, summed (events of run_pipelined)
+double pipelined_kernel_ms(pcs_ctx& cx, size_t S) {
+  double total = 0;
+  for (size_t s = 0; s < S; ++s) {
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, cx.time_ev[2 * s], cx.time_ev[2 * s + 1]));
+    total += ms;
+  }
+  return total;
+}
+
+// pcs_simulate(): full tables back to the caller.  The tables of sample s cross the link on the copy stream while
+// sample s+1 is being sampled.
+void simulate_tables(pcs_forest& fo, const pcs_seq_params& P, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  cudaStream_t cs = cx.copier();
+  const double t0 = now_ms();
+  CallTables T;
+  pcs_run_stats rs{};
+  std::vector<ChunkCopy> chunks;
+  char* stage = nullptr;
+  const size_t M = fo.host.flat.n_mut, L = fo.host.flat.locus_pos.size();
+  const size_t row_bytes = M * sizeof(uint32_t);
+  uint64_t fin_launches = 0;
+  run_pipelined(fo, P, true, T, rs, [&](uint32_t smp, uint64_t) {
+    if (M == 0) return;
+    require(occ && cov, "occurrences/coverage output pointers are NULL");
+    if (!stage) stage = static_cast<char*>(cx.staging(2 * T.S * row_bytes));
+    CUDA_OK(pcs::launch_finalize(st, T.depth.p + smp * L, fo.d_row_locus.p, 1u, static_cast<uint32_t>(L),
+                                 static_cast<uint32_t>(M), T.cov.p + smp * M));
+    ++fin_launches;
+    cudaEvent_t done = cx.chunk_event(2 * T.S + smp);
+    CUDA_OK(cudaEventRecord(done, st));
+    CUDA_OK(cudaStreamWaitEvent(cs, done, 0));
+    const char* dev_tbl[2] = {reinterpret_cast<const char*>(T.occ.p + smp * M), reinterpret_cast<const char*>(T.cov.p + smp * M)};
+    char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M), reinterpret_cast<char*>(cov + smp * M)};
+    for (int t = 0; t < 2; ++t) {
+      char* sp = stage + (2 * smp + t) * row_bytes;
+      CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], row_bytes, cudaMemcpyDeviceToHost, cs));
+      CUDA_OK(cudaEventRecord(cx.chunk_event(chunks.size()), cs));
+      chunks.push_back({host_tbl[t], sp, row_bytes});
+    }
+  });
+  if (stats) {
+    CUDA_OK(pcs::launch_sum_u32(st, T.depth.p, T.S * L, T.counters.p + 1));
+    CUDA_OK(pcs::launch_sum_u32(st, T.occ.p, T.S * M, T.counters.p + 2));
+    fin_launches += (T.S * M != 0 ? 1 : 0) + (T.S * L != 0 ? 1 : 0);
+  }
+  unsigned long long* counters = cx.counters_home();
+  CUDA_OK(cudaMemcpyAsync(counters, T.counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  drain_chunks(cx, chunks);
+  CUDA_OK(cudaStreamSynchronize(st));
+  CUDA_OK(cudaStreamSynchronize(cs));
+  if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "simulate (plan + kernels + D2H)", now_ms() - t0);
+  if (stats) {
+    rs.kernel_ms = pipelined_kernel_ms(cx, T.S);
+    rs.total_ms = now_ms() - t0;
+    rs.kernel_launches += fin_launches;
+    rs.n_reads = counters[0];
+    rs.sum_depth = counters[1];
+    rs.sum_occurrences = counters[2];
+    rs.d2h_bytes = 2 * T.S * row_bytes + 4 * sizeof(unsigned long long);
+    *stats = rs;
+  }
+}
+
+// rows some SEQUENCED cell inherits (include_non_sequenced_mutations): an instance whose haplotype interval holds
+// a haplotype of a sequenced kind (tumour cells unless normal_only; the normal cells that are in the mix) that
+// still holds the position, on a sequenced chromosome
+std::vector<uint8_t> carried_rows(const HostForest& host, const pcs_seq_params* params) {
+  const pcs::FlatForest& F = host.flat;
+  const bool normal_only = params && params->normal_only;
+  const bool preneo = params && params->preneoplastic_in_normal;
+  const bool normals = !params || normal_only || params->with_normal_sample || params->purity < 1.0;
+  std::vector<uint8_t> carried(F.n_mut, 0);
+  host_tasks(F.n_chr, [&](size_t ci) {
+    const uint32_t c = static_cast<uint32_t>(ci);
+    // the reference hands only the chromosomes of `chr_ids` to the simulator (src/seq_simulation.cpp:570,577):
+    // rows of the others never reach its data frame
+    if (params && params->chr_mask && !params->chr_mask[c]) return;
+    std::vector<uint32_t> seq_haps;  // sorted haplotype indices of the sequenced cells
+    const auto& haps = F.chr_haps[c];
+    for (uint32_t h = 0; h < haps.size(); ++h) {
+      const bool on = haps[h].kind == pcs::HAP_TUMOUR ? !normal_only
+                      : normals && (haps[h].kind == (preneo ? pcs::HAP_NORMAL_PRENEO : pcs::HAP_NORMAL_PLAIN));
+      if (on) seq_haps.push_back(h);
+    }
+    for (uint32_t l = F.chr_locus_off[c]; l < F.chr_locus_off[c + 1]; ++l)
+      for (uint32_t i = F.locus_inst_off[l]; i < F.locus_inst_off[l + 1]; ++i) {
+        const pcs::Inst& in = F.inst[i];
+        if (carried[in.row]) continue;
+        // a haplotype of the interval that still HOLDS the position (a later CNA deletion may have taken it)
+        const uint32_t pos = F.locus_pos[l];
+        for (auto it = std::lower_bound(seq_haps.begin(), seq_haps.end(), in.lo);
+             it != seq_haps.end() && *it - in.lo < in.span; ++it) {
+          bool has = false;
+          for (const auto& fr : F.fragsets[haps[*it].fragset]) has |= pos >= fr.b && pos <= fr.e;
+          if (has) {
+            carried[in.row] = 1;
+            break;
+          }
+        }
+      }
+  });
+  return carried;
+}
+
+// active rows of the tables (d_occ, d_depth) compacted on the device into a pcs_result
+std::unique_ptr<pcs_result> assemble_result(pcs_forest& fo, const uint32_t* d_occ, const uint32_t* d_depth, size_t S,
+                                            int include_non_sequenced, const pcs_seq_params* params, bool want_vaf) {
+  pcs_ctx& cx = *fo.ctx;
+  cx.bind();
+  cudaStream_t st = cx.stream;
+  const pcs::FlatForest& F = fo.host.flat;
+  const uint32_t M = F.n_mut, L = static_cast<uint32_t>(F.locus_pos.size());
+  auto res = std::make_unique<pcs_result>();
+  res->forest = &fo;
+  res->n_samples = static_cast<uint32_t>(S);
+  if (M == 0 || S == 0) return res;
+  DevBuf<uint8_t> d_carried;
+  if (include_non_sequenced) {
+    const std::vector<uint8_t> carried = carried_rows(fo.host, params);
+    d_carried.upload(carried, st);
+  }
+  DevBuf<uint32_t> d_blocks;
+  d_blocks.alloc(static_cast<size_t>(pcs::active_blocks(M)) + 1, st);
+  uint32_t* d_total = d_blocks.p + pcs::active_blocks(M);
+  CUDA_OK(pcs::launch_active_count(st, d_occ, d_carried.p, static_cast<uint32_t>(S), M, d_blocks.p, d_total));
+  unsigned long long* home = cx.counters_home();
+  uint32_t* n_home = reinterpret_cast<uint32_t*>(home + 3);  // the trace counter's slot: unused on this path
+  CUDA_OK(cudaMemcpyAsync(n_home, d_total, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  const uint32_t n = *n_home;
+  res->n_rows = n;
+  res->d_rows.alloc(n, st);
+  res->d_occ.alloc(S * n, st);
+  res->d_cov.alloc(S * n, st);
+  if (want_vaf) res->d_vaf.alloc(S * n, st);
+  CUDA_OK(pcs::launch_active_scatter(st, d_occ, d_depth, fo.d_row_locus.p, d_carried.p, static_cast<uint32_t>(S), M, L,
+                                     d_blocks.p, n, res->d_rows.p, res->d_occ.p, res->d_cov.p, res->d_vaf.p));
+  return res;
 }
 
 // reads of a set of tiles as binary records (host vectors)
@@ -1262,6 +1710,20 @@ void append_sam_line(std::string& s, const pcs::SamHeader& h, const uint8_t* seq
   s.push_back('\n');
 }
 
+// peer access between two devices of this process, both directions (idempotent)
+void enable_peer_both_ways(int a, int b) {
+  if (a == b) return;
+  const int pair[2][2] = {{a, b}, {b, a}};
+  for (const auto& pr : pair) {
+    CUDA_OK(cudaSetDevice(pr[0]));
+    int can = 0;
+    CUDA_OK(cudaDeviceCanAccessPeer(&can, pr[0], pr[1]));
+    if (!can) throw CudaError("the devices cannot access each other's memory");
+    const cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CUDA_OK(e);
+  }
+}
+
 template <class Fn>
 int guarded(Fn&& fn) {
   try {
@@ -1322,19 +1784,36 @@ int pcs_create(pcs_ctx** out, int device_id, void* stream) {
   });
 }
 
-int pcs_destroy(pcs_ctx* cx) {
-  return guarded([&] {
-    if (!cx) return;
+extern "C++" {
+static void free_ctx(pcs_ctx* cx) {
     cudaSetDevice(cx->device);
     for (auto& ev : cx->ev)
       if (ev) cudaEventDestroy(ev);
     if (cx->own_stream && cx->stream) cudaStreamDestroy(cx->stream);
     if (cx->pinned) cudaFreeHost(cx->pinned);
     if (cx->pinned_counters) cudaFreeHost(cx->pinned_counters);
+    if (cx->peer_tables) cudaFree(cx->peer_tables);
     for (auto& b : cx->pool) cudaFreeHost(b.p);
     for (auto& ev : cx->chunk_ev) cudaEventDestroy(ev);
+    for (auto& ev : cx->time_ev) cudaEventDestroy(ev);
+    for (auto& sl : cx->plan_slots) {
+      if (sl.p) cudaFreeHost(sl.p);
+      if (sl.done) cudaEventDestroy(sl.done);
+    }
     if (cx->copy_stream) cudaStreamDestroy(cx->copy_stream);
     delete cx;
+}
+
+void release_ctx(pcs_ctx* cx) {
+  if (--cx->users == 0 && cx->destroyed.load()) free_ctx(cx);
+}
+}  // extern "C++"
+
+int pcs_destroy(pcs_ctx* cx) {
+  return guarded([&] {
+    if (!cx) return;
+    cx->destroyed.store(true);
+    if (cx->users.load() == 0) free_ctx(cx);  // else: the last forest to be freed does it
   });
 }
 
@@ -1351,8 +1830,10 @@ int pcs_device_name(pcs_ctx* cx, char* buf, size_t len) {
 int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out) {
   return guarded([&] {
     require(cx && desc && out, "bad arguments");
+    require(!cx->destroyed.load(), "the context has been destroyed");
     auto fo = std::make_unique<pcs_forest>();
     fo->ctx = cx;
+    fo->user.hold(cx);
     Lap lap;
     fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
     lap("pinned block");
@@ -1366,11 +1847,30 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
   });
 }
 
+int pcs_forest_upload_genomes(pcs_ctx* cx, const pcs_cell_genomes_desc* desc, pcs_forest** out) {
+  return guarded([&] {
+    require(cx && desc && out, "bad arguments");
+    require(!cx->destroyed.load(), "the context has been destroyed");
+    auto fo = std::make_unique<pcs_forest>();
+    fo->ctx = cx;
+    fo->user.hold(cx);
+    Lap lap;
+    fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
+    pcs::flatten_cell_genomes(*desc, fo->host.flat, host_threads());
+    lap("flatten_cell_genomes");
+    fo->upload_flat();
+    fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
+    lap("upload");
+    *out = fo.release();
+  });
+}
+
 int pcs_forest_free(pcs_forest* fo) {
   return guarded([&] {
     if (!fo) return;
-    cudaSetDevice(fo->ctx->device);
-    cudaStreamSynchronize(fo->ctx->stream);  // an upload may still be reading the forest's pinned block
+    pcs_ctx* cx = fo->ctx;
+    cudaSetDevice(cx->device);
+    cudaStreamSynchronize(cx->stream);  // an upload may still be reading the forest's pinned block
     delete fo;
   });
 }
@@ -1456,6 +1956,38 @@ int pcs_plan_finalize(pcs_plan* pl, const uint32_t* depth, const uint32_t* occur
   });
 }
 
+int pcs_plan_counters(pcs_plan* pl, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(pl && stats, "bad arguments");
+    pcs_ctx& cx = *pl->forest->ctx;
+    cx.bind();
+    cudaStream_t st = cx.stream;
+    unsigned long long* counters = cx.counters_home();
+    CUDA_OK(cudaMemcpyAsync(counters, pl->d_counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemsetAsync(pl->d_counters.p, 0, 4 * sizeof(unsigned long long), st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    *stats = pcs_run_stats{};
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, cx.ev[1], cx.ev[2]));  // the last sampler launch
+    stats->kernel_ms = ms;
+    stats->kernel_launches = pl->launches_since_read;
+    stats->n_templates = pl->host.info.n_templates;
+    stats->n_reads = counters[0];
+    stats->sum_depth = counters[1];
+    stats->sum_occurrences = counters[2];
+    stats->d2h_bytes = 4 * sizeof(unsigned long long);
+    pl->launches_since_read = 0;
+  });
+}
+
+int pcs_memset_u32_stream(pcs_ctx* cx, uint32_t* dev_ptr, size_t count, void* stream) {
+  return guarded([&] {
+    require(cx && (dev_ptr || count == 0), "bad arguments");
+    cx->bind();
+    if (count) CUDA_OK(cudaMemsetAsync(dev_ptr, 0, count * sizeof(uint32_t), static_cast<cudaStream_t>(stream)));
+  });
+}
+
 int pcs_shared_alloc(pcs_ctx* cx, size_t bytes, void** dev_ptr, unsigned char ipc_handle[64]) {
   return guarded([&] {
     require(cx && dev_ptr && bytes > 0, "bad arguments");
@@ -1530,103 +2062,202 @@ int pcs_memset_u32(pcs_ctx* cx, uint32_t* dev_ptr, size_t count) {
 int pcs_forest_replicate(pcs_forest* src, pcs_ctx* cx, pcs_forest** out) {
   return guarded([&] {
     require(src && cx && out, "bad arguments");
+    require(!cx->destroyed.load(), "the context has been destroyed");
     auto fo = std::make_unique<pcs_forest>(*src, cx);  // shares the flattened host view: no second flatten
-    fo->upload_flat();
-    fo->upload_groups();
+    fo->user.hold(cx);
+    pcs_ctx& sx = *src->ctx;
+    if (sx.device == cx->device) {
+      fo->upload_flat();
+      fo->upload_groups();
+    } else {
+      // device to device over NVLink: the tables are already in the source's HBM
+      src->sync_groups();
+      sx.bind();
+      CUDA_OK(cudaStreamSynchronize(sx.stream));  // the source's own upload may still be in flight
+      enable_peer_both_ways(sx.device, cx->device);
+      cx->bind();
+      cudaStream_t st = cx->stream;
+      auto clone = [&](auto& dst, const auto& from) {
+        dst.alloc(from.n, st);
+        if (from.n) CUDA_OK(cudaMemcpyPeerAsync(dst.p, cx->device, from.p, sx.device, from.bytes(), st));
+      };
+      clone(fo->d_chr_locus_off, src->d_chr_locus_off);
+      clone(fo->d_locus_pos, src->d_locus_pos);
+      clone(fo->d_locus_inst_off, src->d_locus_inst_off);
+      clone(fo->d_row_locus, src->d_row_locus);
+      clone(fo->d_inst, src->d_inst);
+      clone(fo->d_hap_list, src->d_hap_list);
+      fo->uploaded_groups = src->uploaded_groups;
+      CUDA_OK(cudaStreamSynchronize(st));
+    }
     *out = fo.release();
   });
 }
 
+// One process, several GPUs (the single-threaded R session).  The job is planned ONCE, sample by sample, for all
+// shards (make_host_plans); the calling thread queues every device's slice and kernels on that device's stream --
+// launches are asynchronous, no worker threads -- while it plans the next sample.  Every device's sampler adds
+// straight into the tables on forests[0]'s device (peer memory over NVLink); when the last device has finished a
+// sample, that sample's coverage gather and its copy to the host run on device 0's copy stream, behind the other
+// samples' kernels.
 int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_params* params, uint32_t* occ,
                        uint32_t* cov, pcs_run_stats* stats) {
   return guarded([&] {
-    require(forests && n >= 1 && n <= 64 && params && occ && cov, "bad arguments");
+    require(forests && n >= 1 && n <= 64 && params, "bad arguments");
     for (uint32_t i = 0; i < n; ++i) require(forests[i] != nullptr, "forest is NULL");
     for (uint32_t i = 1; i < n; ++i)
       require(forests[i]->host_ptr == forests[0]->host_ptr, "the forests must be replicas of forests[0] (pcs_forest_replicate)");
     validate(*params);
     const double t0 = now_ms();
+    Lap lap;
     pcs_forest& owner = *forests[0];
     pcs_ctx& cx0 = *owner.ctx;
-    // one plan per device: shard i of n
-    std::vector<std::unique_ptr<pcs_plan>> plans(n);
-    std::vector<std::string> errors(n);
-    std::vector<pcs_run_stats> rs(n);
-    auto on_each = [&](const std::function<void(uint32_t)>& fn) {
-      std::vector<std::thread> th;
-      for (uint32_t i = 0; i < n; ++i)
-        th.emplace_back([&, i] {
-          try {
-            fn(i);
-          } catch (const std::exception& e) {
-            errors[i] = e.what();
-            if (errors[i].empty()) errors[i] = "device worker failed";
-          }
-        });
-      for (auto& t : th) t.join();
-      for (const auto& e : errors)
-        if (!e.empty()) throw CudaError(e);
-    };
-    on_each([&](uint32_t i) {
-      pcs_seq_params P = *params;
-      P.shard_rank = i;
-      P.shard_count = n;
-      auto pl = std::make_unique<pcs_plan>();
-      pl->forest = forests[i];
-      forests[i]->sync_groups();
-      pl->host = make_host_plan(forests[i]->host, P);
-      upload_plan(*pl);
-      plans[i] = std::move(pl);
-      if (forests[i]->ctx->device != cx0.device) {
-        forests[i]->ctx->bind();
-        int can = 0;
-        CUDA_OK(cudaDeviceCanAccessPeer(&can, forests[i]->ctx->device, cx0.device));
-        if (!can) throw CudaError("the devices cannot access each other's memory");
-        cudaError_t e = cudaDeviceEnablePeerAccess(cx0.device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CUDA_OK(e);
-      }
-    });
-    // the tables live on the first device; every device's sampler flushes into them.  Plain cudaMalloc:
-    // peers cannot reach stream-ordered pool memory through cudaDeviceEnablePeerAccess.
-    pcs_plan& p0 = *plans[0];
-    const size_t S = p0.host.info.n_out_samples, M = p0.host.info.n_mut, L = p0.host.info.n_loci;
+    pcs_seq_params P = *params;
+    P.shard_rank = 0;
+    P.shard_count = n;
+    for (uint32_t i = 0; i < n; ++i) forests[i]->sync_groups();
+    const PlanSetup ps = plan_setup(owner.host, P);
+    lap("  plan: tile geometry");
+    const pcs::FlatForest& F = owner.host.flat;
+    const size_t S = ps.samples.size(), M = F.n_mut, L = F.locus_pos.size();
+    require(S * M == 0 || (occ && cov), "occurrences/coverage output pointers are NULL");
+    for (uint32_t i = 1; i < n; ++i) enable_peer_both_ways(cx0.device, forests[i]->ctx->device);
+    // the tables live on the first device.  Plain cudaMalloc, kept by the context: peers cannot reach stream-ordered
+    // pool memory through cudaDeviceEnablePeerAccess
     cx0.bind();
-    struct Tables {
-      uint32_t* p = nullptr;
-      ~Tables() { if (p) cudaFree(p); }
-    } tb;
     const size_t words = S * L + 2 * S * M;
-    if (words) CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tb.p), words * sizeof(uint32_t)));
-    uint32_t* t_depth = tb.p;
-    uint32_t* t_occ = tb.p + S * L;
+    uint32_t* tb = static_cast<uint32_t*>(cx0.peer_table(words * sizeof(uint32_t)));
+    uint32_t* t_depth = tb;
+    uint32_t* t_occ = tb + S * L;
     uint32_t* t_cov = t_occ + S * M;
-    if (words) CUDA_OK(cudaMemsetAsync(tb.p, 0, (S * L + S * M) * sizeof(uint32_t), cx0.stream));
-    CUDA_OK(cudaStreamSynchronize(cx0.stream));
-    on_each([&](uint32_t i) { accumulate_plan(*plans[i], t_depth, t_occ, &rs[i]); });
-    pcs_run_stats fin{};
-    finalize_tables(p0, t_depth, t_occ, t_cov, &fin);
+    cudaStream_t st0 = cx0.stream, cs0 = cx0.copier();
+    if (words) CUDA_OK(cudaMemsetAsync(tb, 0, (S * L + S * M) * sizeof(uint32_t), st0));
+    // events live on the device whose stream records them (any stream may wait for them): in every context's pool,
+    // [0, 2S) mark D2H chunks (context 0), 2S = tables zeroed (context 0), 2S + 1 + s = this device is through with sample s
+    cudaEvent_t zeroed = cx0.chunk_event(2 * S);
+    CUDA_OK(cudaEventRecord(zeroed, st0));
+    std::vector<DevBuf<unsigned long long>> d_counters(n);
+    std::vector<DevBuf<uint32_t>> d_alias(n);
+    uint64_t h2d = 0, launches = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+      pcs_ctx& cx = *forests[i]->ctx;
+      cx.bind();
+      d_counters[i].alloc(4, cx.stream);
+      CUDA_OK(cudaMemsetAsync(d_counters[i].p, 0, 4 * sizeof(unsigned long long), cx.stream));
+      if (!ps.insert_alias.empty()) h2d += d_alias[i].upload(ps.insert_alias, cx.stream);
+      if (i) CUDA_OK(cudaStreamWaitEvent(cx.stream, zeroed, 0));
+    }
+    std::vector<ChunkCopy> chunks;
+    const size_t row_bytes = M * sizeof(uint32_t);
+    char* stage = row_bytes ? static_cast<char*>(cx0.staging(2 * S * row_bytes)) : nullptr;
+    uint32_t id_base = 0;
+    uint64_t templates = 0;
+    auto padded = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    for (uint32_t smp = 0; smp < S; ++smp) {
+      std::vector<HostPlan> plans = make_host_plans(ps, smp, smp + 1, id_base, true);
+      id_base += static_cast<uint32_t>(plans[0].info.n_tiles_total);
+      for (uint32_t i = 0; i < n; ++i) {
+        HostPlan& hp = plans[i];
+        pcs_forest& fo = *forests[i];
+        pcs_ctx& cx = *fo.ctx;
+        cx.bind();
+        cudaStream_t st = cx.stream;
+        templates += hp.info.n_templates;
+        hp.model.insert_alias = d_alias[i].p;
+        const size_t b_tiles = hp.tiles.size() * sizeof(pcs::Tile), b_glob = hp.tiles_global.size() * sizeof(pcs::Tile),
+                     b_ent = hp.entries.size() * sizeof(pcs::Entry), b_lo = hp.entry_lo.size() * sizeof(uint32_t);
+        pcs_ctx::PlanSlot& slot = cx.plan_slot(smp % 4, padded(b_tiles) + padded(b_glob) + padded(b_ent) + padded(b_lo) + 256);
+        DevBuf<pcs::Tile> d_tiles, d_glob;
+        DevBuf<pcs::Entry> d_ent;
+        DevBuf<uint32_t> d_lo;
+        size_t at = 0;
+        auto up = [&](auto& buf, const auto& vec, size_t bytes) {
+          buf.alloc(vec.size(), st);
+          if (bytes) {
+            std::memcpy(slot.p + at, vec.data(), bytes);
+            CUDA_OK(cudaMemcpyAsync(buf.p, slot.p + at, bytes, cudaMemcpyHostToDevice, st));
+          }
+          at += padded(bytes);
+          h2d += bytes;
+        };
+        up(d_tiles, hp.tiles, b_tiles);
+        up(d_glob, hp.tiles_global, b_glob);
+        up(d_ent, hp.entries, b_ent);
+        up(d_lo, hp.entry_lo, b_lo);
+        CUDA_OK(cudaEventRecord(slot.done, st));
+        slot.in_flight = true;
+        const pcs::DevForest DF = fo.dev();
+        CUDA_OK(cudaEventRecord(cx.time_event(2 * smp), st));
+        CUDA_OK(pcs::launch_sample_tiles_staged(st, d_tiles.p, static_cast<uint32_t>(hp.tiles.size()), d_ent.p, d_lo.p, DF,
+                                                hp.model, hp.dims, t_depth, t_occ, d_counters[i].p));
+        CUDA_OK(pcs::launch_sample_tiles_global(st, d_glob.p, static_cast<uint32_t>(hp.tiles_global.size()), d_ent.p,
+                                                d_lo.p, DF, hp.model, t_depth, t_occ, d_counters[i].p));
+        CUDA_OK(cudaEventRecord(cx.time_event(2 * smp + 1), st));
+        launches += (hp.tiles.empty() ? 0 : 1) + (hp.tiles_global.empty() ? 0 : 1);
+        // this device is through with the sample
+        CUDA_OK(cudaEventRecord(cx.chunk_event(2 * S + 1 + smp), st));
+      }
+      if (M == 0) continue;
+      // device 0, copy stream: once every device has flushed the sample, gather its coverage and send it home
+      cx0.bind();
+      for (uint32_t i = 0; i < n; ++i) CUDA_OK(cudaStreamWaitEvent(cs0, forests[i]->ctx->chunk_event(2 * S + 1 + smp), 0));
+      CUDA_OK(pcs::launch_finalize(cs0, t_depth + smp * L, owner.d_row_locus.p, 1u, static_cast<uint32_t>(L),
+                                   static_cast<uint32_t>(M), t_cov + smp * M));
+      ++launches;
+      const char* dev_tbl[2] = {reinterpret_cast<const char*>(t_occ + smp * M), reinterpret_cast<const char*>(t_cov + smp * M)};
+      char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M), reinterpret_cast<char*>(cov + smp * M)};
+      for (int t = 0; t < 2; ++t) {
+        char* sp = stage + (2 * smp + t) * row_bytes;
+        CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], row_bytes, cudaMemcpyDeviceToHost, cs0));
+        CUDA_OK(cudaEventRecord(cx0.chunk_event(chunks.size()), cs0));
+        chunks.push_back({host_tbl[t], sp, row_bytes});
+      }
+    }
+    lap("  plan + launch, all samples");
     cx0.bind();
-    if (S * M != 0) {
-      CUDA_OK(cudaMemcpyAsync(occ, t_occ, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx0.stream));
-      CUDA_OK(cudaMemcpyAsync(cov, t_cov, S * M * sizeof(uint32_t), cudaMemcpyDeviceToHost, cx0.stream));
-      CUDA_OK(cudaStreamSynchronize(cx0.stream));
+    DevBuf<unsigned long long> d_sums;
+    d_sums.alloc(4, cs0);
+    CUDA_OK(cudaMemsetAsync(d_sums.p, 0, 4 * sizeof(unsigned long long), cs0));
+    if (stats) {
+      CUDA_OK(pcs::launch_sum_u32(cs0, t_depth, S * L, d_sums.p + 1));
+      CUDA_OK(pcs::launch_sum_u32(cs0, t_occ, S * M, d_sums.p + 2));
+      launches += (S * M != 0 ? 1 : 0) + (S * L != 0 ? 1 : 0);
     }
-    for (uint32_t i = 0; i < n; ++i) {  // free each plan on its own device
-      cudaSetDevice(forests[i]->ctx->device);
-      plans[i].reset();
+    unsigned long long* sums = cx0.counters_home();  // [0..2] checksums, [3] reads placed by this device
+    CUDA_OK(cudaMemcpyAsync(sums, d_sums.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, cs0));
+    std::vector<unsigned long long*> placed(n, nullptr);
+    for (uint32_t i = 0; i < n; ++i) {  // every device's own read counter, into its context's pinned slot
+      pcs_ctx& cx = *forests[i]->ctx;
+      cx.bind();
+      placed[i] = cx.counters_home() + 3;
+      CUDA_OK(cudaMemcpyAsync(placed[i], d_counters[i].p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cx.stream));
     }
+    cx0.bind();
+    drain_chunks(cx0, chunks);
+    for (uint32_t i = 0; i < n; ++i) {
+      pcs_ctx& cx = *forests[i]->ctx;
+      cx.bind();
+      CUDA_OK(cudaStreamSynchronize(cx.stream));
+      d_counters[i].release();
+      d_alias[i].release();
+    }
+    cx0.bind();
+    CUDA_OK(cudaStreamSynchronize(cs0));
+    d_sums.release();
+    if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "simulate_multi", now_ms() - t0);
     if (stats) {
       *stats = pcs_run_stats{};
       for (uint32_t i = 0; i < n; ++i) {
-        stats->kernel_ms = std::max(stats->kernel_ms, rs[i].kernel_ms);
-        stats->kernel_launches += rs[i].kernel_launches;
-        stats->n_templates += rs[i].n_templates;
-        stats->n_reads += rs[i].n_reads;
+        forests[i]->ctx->bind();
+        stats->kernel_ms = std::max(stats->kernel_ms, pipelined_kernel_ms(*forests[i]->ctx, S));
+        stats->n_reads += *placed[i];
       }
-      stats->kernel_launches += fin.kernel_launches;
-      stats->sum_depth = fin.sum_depth;
-      stats->sum_occurrences = fin.sum_occurrences;
-      stats->d2h_bytes = 2 * S * M * sizeof(uint32_t);
+      stats->kernel_launches = launches;
+      stats->n_templates = templates;
+      stats->sum_depth = sums[1];
+      stats->sum_occurrences = sums[2];
+      stats->h2d_bytes = h2d;
+      stats->d2h_bytes = 2 * S * M * sizeof(uint32_t) + (4 + n) * sizeof(unsigned long long);
       stats->total_ms = now_ms() - t0;
     }
   });
@@ -1838,6 +2469,12 @@ int pcs_plan_trace(pcs_plan* pl, pcs_read_placement* rec, uint32_t* masks, uint6
 }
 
 int pcs_simulate(pcs_forest* fo, const pcs_seq_params* params, uint32_t* occ, uint32_t* cov, pcs_run_stats* stats) {
+  if (std::getenv("PCS_NO_PIPELINE") == nullptr)
+    return guarded([&] {
+      require(fo && params, "bad arguments");
+      validate(*params);
+      simulate_tables(*fo, *params, occ, cov, stats);
+    });
   pcs_plan* pl = nullptr;
   int rc = pcs_plan_create(fo, params, &pl);
   if (rc != PCS_OK) return rc;
@@ -1935,42 +2572,7 @@ int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples,
     require(fo && occ && rows_out && n_rows, "bad arguments");
     const pcs::FlatForest& F = fo->host.flat;
     std::vector<uint8_t> carried;
-    if (include_non_sequenced) {
-      // rows some SEQUENCED cell inherits: an instance whose haplotype interval holds a haplotype of a
-      // sequenced kind (tumour cells unless normal_only; the normal cells that are in the mix)
-      const bool normal_only = params && params->normal_only;
-      const bool preneo = params && params->preneoplastic_in_normal;
-      const bool normals = !params || normal_only || params->with_normal_sample || params->purity < 1.0;
-      carried.assign(F.n_mut, 0);
-      for (uint32_t c = 0; c < F.n_chr; ++c) {
-        // the reference hands only the chromosomes of `chr_ids` to the simulator (src/seq_simulation.cpp:570,577):
-        // rows of the others never reach its data frame
-        if (params && params->chr_mask && !params->chr_mask[c]) continue;
-        std::vector<uint32_t> seq_haps;  // sorted haplotype indices of the sequenced cells
-        const auto& haps = F.chr_haps[c];
-        for (uint32_t h = 0; h < haps.size(); ++h) {
-          const bool on = haps[h].kind == pcs::HAP_TUMOUR ? !normal_only
-                          : normals && (haps[h].kind == (preneo ? pcs::HAP_NORMAL_PRENEO : pcs::HAP_NORMAL_PLAIN));
-          if (on) seq_haps.push_back(h);
-        }
-        for (uint32_t l = F.chr_locus_off[c]; l < F.chr_locus_off[c + 1]; ++l)
-          for (uint32_t i = F.locus_inst_off[l]; i < F.locus_inst_off[l + 1]; ++i) {
-            const pcs::Inst& in = F.inst[i];
-            if (carried[in.row]) continue;
-            // a haplotype of the interval that still HOLDS the position (a later CNA deletion may have taken it)
-            const uint32_t pos = F.locus_pos[l];
-            for (auto it = std::lower_bound(seq_haps.begin(), seq_haps.end(), in.lo);
-                 it != seq_haps.end() && *it - in.lo < in.span; ++it) {
-              bool has = false;
-              for (const auto& fr : F.fragsets[haps[*it].fragset]) has |= pos >= fr.b && pos <= fr.e;
-              if (has) {
-                carried[in.row] = 1;
-                break;
-              }
-            }
-          }
-      }
-    }
+    if (include_non_sequenced) carried = carried_rows(fo->host, params);
     uint32_t k = 0;
     for (uint32_t m = 0; m < F.n_mut; ++m) {
       bool on = include_non_sequenced && carried[m];
@@ -1978,6 +2580,168 @@ int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples,
       if (on) rows_out[k++] = m;
     }
     *n_rows = k;
+  });
+}
+
+int pcs_simulate_result(pcs_forest* fo, const pcs_seq_params* params, int include_non_sequenced, int with_vaf,
+                        pcs_result** out, pcs_run_stats* stats) {
+  return guarded([&] {
+    require(fo && params && out, "bad arguments");
+    validate(*params);
+    pcs_ctx& cx = *fo->ctx;
+    cx.bind();
+    cudaStream_t st = cx.stream;
+    const double t0 = now_ms();
+    CallTables T;
+    pcs_run_stats rs{};
+    run_pipelined(*fo, *params, false, T, rs, [](uint32_t, uint64_t) {});
+    uint64_t extra = 0;
+    if (stats) {
+      CUDA_OK(pcs::launch_sum_u32(st, T.depth.p, T.S * T.L, T.counters.p + 1));
+      CUDA_OK(pcs::launch_sum_u32(st, T.occ.p, T.S * T.M, T.counters.p + 2));
+      extra += (T.S * T.M != 0 ? 1 : 0) + (T.S * T.L != 0 ? 1 : 0);
+    }
+    unsigned long long* counters = cx.counters_home();
+    CUDA_OK(cudaMemcpyAsync(counters, T.counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    std::unique_ptr<pcs_result> res = assemble_result(*fo, T.occ.p, T.depth.p, T.S, include_non_sequenced, params, with_vaf != 0);
+    extra += T.S * T.M != 0 ? 3 : 0;
+    CUDA_OK(cudaStreamSynchronize(st));
+    rs.kernel_ms = pipelined_kernel_ms(cx, T.S);
+    rs.total_ms = now_ms() - t0;
+    rs.kernel_launches += extra;
+    rs.n_reads = counters[0];
+    rs.sum_depth = counters[1];
+    rs.sum_occurrences = counters[2];
+    rs.d2h_bytes = 4 * sizeof(unsigned long long) + sizeof(uint32_t);
+    res->stats = rs;
+    if (stats) *stats = rs;
+    if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "simulate_result (to compact)", rs.total_ms);
+    *out = res.release();
+  });
+}
+
+int pcs_plan_result(pcs_plan* pl, int include_non_sequenced, const pcs_seq_params* params, int with_vaf, pcs_result** out) {
+  return guarded([&] {
+    require(pl && out, "bad arguments");
+    require(pl->last_occ != nullptr || static_cast<size_t>(pl->host.info.n_out_samples) * pl->host.info.n_mut == 0,
+            "the plan has not been run (pcs_plan_run)");
+    std::unique_ptr<pcs_result> res = assemble_result(*pl->forest, pl->last_occ, pl->d_depth.p, pl->host.info.n_out_samples,
+                                                      include_non_sequenced, params, with_vaf != 0);
+    CUDA_OK(cudaStreamSynchronize(pl->forest->ctx->stream));
+    *out = res.release();
+  });
+}
+
+int pcs_result_info(const pcs_result* res, uint32_t* n_rows, uint32_t* n_samples, int* has_vaf) {
+  return guarded([&] {
+    require(res != nullptr, "result is NULL");
+    if (n_rows) *n_rows = res->n_rows;
+    if (n_samples) *n_samples = res->n_samples;
+    if (has_vaf) *has_vaf = res->d_vaf.p != nullptr || res->n_rows == 0;
+  });
+}
+
+int pcs_result_fetch(pcs_result* res, uint32_t* rows, int32_t* const* occ_cols, int32_t* const* cov_cols,
+                     double* const* vaf_cols, uint64_t* d2h_bytes) {
+  return guarded([&] {
+    require(res != nullptr, "result is NULL");
+    const size_t n = res->n_rows, S = res->n_samples;
+    std::vector<OutCopy> items;
+    if (n) {
+      if (rows) items.push_back({rows, res->d_rows.p, n * sizeof(uint32_t)});
+      for (size_t sm = 0; sm < S; ++sm) {
+        if (occ_cols && occ_cols[sm]) items.push_back({occ_cols[sm], res->d_occ.p + sm * n, n * sizeof(uint32_t)});
+        if (cov_cols && cov_cols[sm]) items.push_back({cov_cols[sm], res->d_cov.p + sm * n, n * sizeof(uint32_t)});
+        if (vaf_cols && vaf_cols[sm]) {
+          require(res->d_vaf.p != nullptr, "the result was assembled without VAF columns");
+          items.push_back({vaf_cols[sm], res->d_vaf.p + sm * n, n * sizeof(double)});
+        }
+      }
+    }
+    pcs_ctx& cx = *res->forest->ctx;
+    cx.bind();
+    const uint64_t b = copy_out(cx, cx.stream, items);
+    if (d2h_bytes) *d2h_bytes = b;
+  });
+}
+
+int pcs_result_free(pcs_result* res) {
+  return guarded([&] {
+    if (!res) return;
+    cudaSetDevice(res->forest->ctx->device);
+    delete res;
+  });
+}
+
+// ------------------------------------------------ host-side column builders
+// The annotation columns of the data frame (chr, ref, alt, causes, classes: src/seq_simulation.cpp:52-90) draw
+// millions of rows from a handful of distinct strings.  The caller keeps one small code per ROW OF THE FOREST and
+// the table of distinct strings; these build the column of the ACTIVE rows in one parallel pass, straight into
+// the layout an Arrow large_string array (pandas) wraps without a copy.  (An R shim does the same with one
+// mkChar per distinct string and one SET_STRING_ELT per row.)
+int pcs_host_gather(const uint32_t* rows, uint64_t n, const void* src, uint32_t elem_bytes, void* dst) {
+  return guarded([&] {
+    require((rows && src && dst) || n == 0, "bad arguments");
+    require(elem_bytes == 1 || elem_bytes == 2 || elem_bytes == 4 || elem_bytes == 8, "element size must be 1, 2, 4 or 8");
+    const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(64, n >> 16));
+    host_tasks(n_chunks, [&](size_t k) {
+      const uint64_t lo = n * k / n_chunks, hi = n * (k + 1) / n_chunks;
+      switch (elem_bytes) {
+        case 1: for (uint64_t i = lo; i < hi; ++i) static_cast<uint8_t*>(dst)[i] = static_cast<const uint8_t*>(src)[rows[i]]; break;
+        case 2: for (uint64_t i = lo; i < hi; ++i) static_cast<uint16_t*>(dst)[i] = static_cast<const uint16_t*>(src)[rows[i]]; break;
+        case 4: for (uint64_t i = lo; i < hi; ++i) static_cast<uint32_t*>(dst)[i] = static_cast<const uint32_t*>(src)[rows[i]]; break;
+        default: for (uint64_t i = lo; i < hi; ++i) static_cast<uint64_t*>(dst)[i] = static_cast<const uint64_t*>(src)[rows[i]]; break;
+      }
+    });
+  });
+}
+
+int pcs_host_string_column(const uint32_t* rows, uint64_t n, const uint16_t* codes, const char* const* table,
+                           uint32_t n_table, int64_t* offsets, char* data, uint64_t data_cap, uint8_t* validity,
+                           uint64_t* data_len, uint64_t* null_count) {
+  return guarded([&] {
+    require(((rows && codes) || n == 0) && table && offsets && data_len, "bad arguments");
+    std::vector<uint32_t> len(n_table, 0);
+    for (uint32_t t = 0; t < n_table; ++t) len[t] = table[t] ? static_cast<uint32_t>(std::strlen(table[t])) : 0u;
+    // chunks of a multiple of 8 rows: no two threads share a validity byte
+    const size_t n_chunks = std::max<size_t>(1, std::min<size_t>(64, n >> 16));
+    auto chunk_lo = [&](size_t k) { return k == n_chunks ? n : (n * k / n_chunks) & ~static_cast<uint64_t>(7); };
+    std::vector<uint64_t> bytes(n_chunks + 1, 0), nulls(n_chunks, 0);
+    host_tasks(n_chunks, [&](size_t k) {
+      uint64_t b = 0;
+      for (uint64_t i = chunk_lo(k); i < chunk_lo(k + 1); ++i) {
+        const uint32_t c = codes[rows[i]];
+        if (c >= n_table) throw std::domain_error("string code outside the table");
+        b += len[c];
+      }
+      bytes[k + 1] = b;
+    });
+    for (size_t k = 0; k < n_chunks; ++k) bytes[k + 1] += bytes[k];
+    *data_len = bytes[n_chunks];
+    offsets[n] = static_cast<int64_t>(bytes[n_chunks]);
+    const bool fill = data != nullptr;
+    require(!fill || data_cap >= bytes[n_chunks], "data buffer too small");
+    host_tasks(n_chunks, [&](size_t k) {
+      uint64_t at = bytes[k], nn = 0;
+      const uint64_t lo = chunk_lo(k), hi = chunk_lo(k + 1);
+      if (validity) std::memset(validity + lo / 8, 0, (hi - lo + 7) / 8);
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t c = codes[rows[i]];
+        offsets[i] = static_cast<int64_t>(at);
+        if (table[c]) {
+          if (fill) std::memcpy(data + at, table[c], len[c]);
+          if (validity) validity[i >> 3] |= static_cast<uint8_t>(1u << (i & 7));
+          at += len[c];
+        } else {
+          ++nn;
+        }
+      }
+      nulls[k] = nn;
+    });
+    if (null_count) {
+      *null_count = 0;
+      for (uint64_t x : nulls) *null_count += x;
+    }
   });
 }
 
@@ -2000,6 +2764,21 @@ int pcs_flat_create(const pcs_forest_desc* desc, pcs_flat** out) {
     require(fl->host.flat.store.heap.empty(), "internal: the lent block was too small for the flat tables");
     fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
     lap("sample groups");
+    *out = fl.release();
+  });
+}
+
+int pcs_flat_create_genomes(const pcs_cell_genomes_desc* desc, pcs_flat** out) {
+  return guarded([&] {
+    require(desc && out, "bad arguments");
+    auto fl = std::make_unique<pcs_flat>();
+    const size_t bytes = pcs::flat_store_bytes(*desc);
+    fl->block.reset(new char[bytes]);
+    fl->host.flat.store.base = fl->block.get();
+    fl->host.flat.store.capacity = bytes;
+    pcs::flatten_cell_genomes(*desc, fl->host.flat, host_threads());
+    require(fl->host.flat.store.heap.empty(), "internal: the lent block was too small for the flat tables");
+    fl->host.build_groups(fl->host.flat.leaf_sample.data(), fl->host.flat.n_samples);
     *out = fl.release();
   });
 }

@@ -311,8 +311,14 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
     if (c.with_normal_sample) names.push_back("normal_sample");  // :572-575
   }
   const size_t S = names.size(), M = forest.mut_pos.size();
-  std::vector<uint32_t> occ(S * M), cov(S * M);
   SeqResult res;
+  // the rows of the data frame are assembled on the device (get_result_dataframe(): src/seq_simulation.cpp:52-181):
+  // only the active rows' columns cross the link
+  pcs_result* result = nullptr;
+  struct ResultGuard {
+    pcs_result*& r;
+    ~ResultGuard() { pcs_result_free(r); }
+  } result_guard{result};
   if (c.write_SAM) {
     // Mode::CREATE / Mode::UPDATE (src/seq_simulation.cpp:545-549); reads and tables come from one plan
     std::vector<const char*> chr_names, sample_names;
@@ -332,6 +338,7 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
       pcs_plan* p;
       ~PlanGuard() { pcs_plan_free(p); }
     } guard{plan};
+    std::vector<uint32_t> occ(S * M), cov(S * M);
     pcs_check(pcs_plan_run(plan, PCS_RUN_HOST_OUTPUT, occ.data(), cov.data(), &res.stats));
     pcs_sam_options opt{};
     opt.output_dir = c.output_dir.c_str();
@@ -341,15 +348,31 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
     opt.sample_names = sample_names.data();
     opt.update = c.update_SAM_dir ? 1 : 0;
     pcs_check(pcs_plan_write_sam(plan, &opt, nullptr));
+    pcs_check(pcs_plan_result(plan, c.include_non_sequenced_mutations, &P, 1, &result));
   } else {
-    pcs_check(pcs_simulate(fo, &P, occ.data(), cov.data(), &res.stats));
+    pcs_check(pcs_simulate_result(fo, &P, c.include_non_sequenced_mutations, 1, &result, &res.stats));
   }
 
-  // get_result_dataframe(): src/seq_simulation.cpp:52-181
-  std::vector<uint32_t> rows(std::max<size_t>(M, 1));
   uint32_t n = 0;
-  pcs_check(pcs_active_rows(fo, occ.data(), static_cast<uint32_t>(S), c.include_non_sequenced_mutations, &P, rows.data(), &n));
-  rows.resize(n);
+  pcs_check(pcs_result_info(result, &n, nullptr, nullptr));
+  std::vector<uint32_t> rows(n);
+  std::vector<size_t> order(S);
+  for (size_t s = 0; s < S; ++s) order[s] = s;
+  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return names[a] < names[b]; });
+  res.samples.resize(S);
+  std::vector<int32_t*> occ_cols(S), cov_cols(S);
+  std::vector<double*> vaf_cols(S);
+  for (size_t k = 0; k < S; ++k) {  // columns in sample-name order, filled in place by the library
+    SampleColumns& col = res.samples[k];
+    col.name = names[order[k]];
+    col.occurrences.resize(n);
+    col.coverage.resize(n);
+    col.VAF.resize(n);
+    occ_cols[order[k]] = col.occurrences.data();
+    cov_cols[order[k]] = col.coverage.data();
+    vaf_cols[order[k]] = col.VAF.data();  // occurrences / coverage (:126); never covered: 0 (:129-131)
+  }
+  pcs_check(pcs_result_fetch(result, rows.data(), occ_cols.data(), cov_cols.data(), vaf_cols.data(), nullptr));
   for (uint32_t r : rows) {
     res.chr.push_back(forest.chr_names[forest.mut_chr[r]]);
     res.chr_pos.push_back(static_cast<int>(forest.mut_pos[r]));
@@ -358,20 +381,6 @@ inline SeqResult run(const PhylogeneticForest& forest, const Call& c, const std:
     res.alt.push_back(sid.alt);
     res.causes.push_back(sid.causes.empty() ? std::nullopt : std::optional<std::string>(join(sid.causes)));
     res.classes.push_back(join(sid.classes));
-  }
-  std::vector<size_t> order(S);
-  for (size_t s = 0; s < S; ++s) order[s] = s;
-  std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return names[a] < names[b]; });
-  for (size_t s : order) {
-    SampleColumns col;
-    col.name = names[s];
-    for (uint32_t r : rows) {
-      const uint32_t o = occ[s * M + r], cv = cov[s * M + r];
-      col.occurrences.push_back(static_cast<int>(o));
-      col.coverage.push_back(static_cast<int>(cv));
-      col.VAF.push_back(cv ? static_cast<double>(o) / cv : 0.0);  // :126; never covered: 0 (:129-131)
-    }
-    res.samples.push_back(std::move(col));
   }
   echo.reference_genome = c.reference_genome;
   echo.chromosomes = c.chromosome_ids;

@@ -164,8 +164,8 @@ def test_result_dataframe_from_dictionary_codes_equals_per_row_strings():
                 "causes": forest.row_causes(rows), "classes": forest.row_classes(rows)}
         for s in sorted(range(len(names)), key=lambda i: names[i]):
             o, c = occ[s, rows].astype(np.int32), cov[s, rows].astype(np.int32)
-            with np.errstate(divide="ignore", invalid="ignore"):
-                vaf = o.astype(np.float64) / c
+            # a row the sample never covered: VAF 0 (/root/reference/src/seq_simulation.cpp:129-131)
+            vaf = np.asarray([oo / cc if cc else 0.0 for oo, cc in zip(o.tolist(), c.tolist())], np.float64)
             cols[f"{names[s]}.occurrences"], cols[f"{names[s]}.coverage"], cols[f"{names[s]}.VAF"] = o, c, vaf
         return pd.DataFrame(cols)
 
@@ -174,10 +174,12 @@ def test_result_dataframe_from_dictionary_codes_equals_per_row_strings():
         rng = np.random.default_rng(1)
         cov = rng.poisson(30, (len(names), f.n_mut)).astype(np.uint32)
         occ = rng.integers(0, 20, (len(names), f.n_mut)).astype(np.uint32)
+        cov[:, ::7] = 0
+        occ[:, ::7] = 0
         indels = np.flatnonzero((f.mut_ref_len != 1) | (f.mut_alt_len != 1)).astype(np.uint32)
         for rows in (np.arange(f.n_mut, dtype=np.uint32), np.zeros(0, np.uint32),
                      np.arange(0, f.n_mut, 3, dtype=np.uint32), indels):
-            a = api._result_dataframe(f, FakeDevice(rows), occ, cov, names, False)
+            a = api._frame_from_tables(f, FakeDevice(rows), occ, cov, names, False)
             b = per_row(f, rows, occ, cov, names)
             assert list(a.columns) == list(b.columns) and (a.dtypes == b.dtypes).all() and a.equals(b)
     ref_codes, ref_table, alt_codes, alt_table = f.row_string_codes(indels)

@@ -153,7 +153,7 @@ def test_config4_eight_samples_200x_sharded_eight_ways(ctx):
         acc_o += o
         acc_c += c
         reads += s.n_reads
-        assert abs(s.n_reads / (st.n_reads / 8) - 1) < 0.01  # LPT balance: near-linear scaling is possible
+        assert abs(s.n_reads / (st.n_reads / 8) - 1) < 0.05  # LPT balance (on cost, not reads): near-linear scaling is possible
     assert reads == st.n_reads
     assert np.array_equal(acc_o, occ) and np.array_equal(acc_c, cov)
     het, hom = germline_sets(f)

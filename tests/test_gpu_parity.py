@@ -447,15 +447,24 @@ def test_dense_sids_and_insertions_with_error_models(ctx, seqm, rate, insert):
 
 @pytest.mark.parametrize("seqm,rate", [SEQ[0], SEQ[2]])
 def test_sample_by_sample_launches_equal_one_launch(ctx, forests, seqm, rate, monkeypatch):
-    """Host-output runs launch the sampler sample by sample (tables of sample s cross the link while
-    s+1 is sampled); PCS_NO_SPLIT keeps the single launch.  Same tiles, same counters: same tables."""
+    """pcs_simulate plans and launches the call sample by sample (the host plans sample s+1 and the tables of
+    sample s cross the link while the GPU samples); PCS_NO_PIPELINE takes the one-piece plan, whose host-output
+    run still launches by sample unless PCS_NO_SPLIT keeps the single launch.  Same tiles, same counters: same
+    tables, whichever way."""
     f = forests[0]
     P = make_params(coverage=25.0, purity=0.7, sequencer=seqm, error_rate=rate, seed=5)
     dev = L.Forest(ctx, f)
-    occ, cov, st = dev.simulate(P)
-    monkeypatch.setenv("PCS_NO_SPLIT", "1")
-    occ1, cov1, st1 = dev.simulate(P)
-    monkeypatch.delenv("PCS_NO_SPLIT")
-    assert st.n_reads == st1.n_reads and st.kernel_launches > st1.kernel_launches
-    assert np.array_equal(occ, occ1) and np.array_equal(cov, cov1)
-    dev.close()
+    try:
+        occ, cov, st = dev.simulate(P)
+        monkeypatch.setenv("PCS_NO_PIPELINE", "1")
+        occ2, cov2, st2 = dev.simulate(P)
+        monkeypatch.setenv("PCS_NO_SPLIT", "1")
+        occ1, cov1, st1 = dev.simulate(P)
+        monkeypatch.delenv("PCS_NO_SPLIT")
+        monkeypatch.delenv("PCS_NO_PIPELINE")
+        assert st.n_reads == st1.n_reads == st2.n_reads and st.kernel_launches > st1.kernel_launches
+        assert st2.kernel_launches > st1.kernel_launches
+        assert np.array_equal(occ, occ1) and np.array_equal(cov, cov1)
+        assert np.array_equal(occ, occ2) and np.array_equal(cov, cov2)
+    finally:
+        dev.close()

@@ -12,8 +12,9 @@ from conftest import make_params, small_spec
 from golden import micro_forest as MF
 
 
-def check_flat_against_explicit_genomes(f):
-    fl = L.Flat(f)
+def check_flat_against_explicit_genomes(f, flat_of=None):
+    """flat_of: what the flat view is built from (default: the event-labelled forest f itself)"""
+    fl = L.Flat(f if flat_of is None else flat_of)
     germ = {}
     for m, mask in zip(f.germ_mut, f.germ_allele_mask):
         germ.setdefault(int(f.mut_chr[m]), []).append((int(m), int(mask)))
@@ -86,6 +87,54 @@ def test_flat_view_with_two_roots_and_nested_copies():
     # row 4 (pos 400) is copied to a2, a3 and a5, then deleted from a5 together with [380,419]
     assert sorted(sids) == [(0, 4), (2, 4), (3, 4), (5, 5)]
     assert check_flat_against_explicit_genomes(f) >= 10
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_flat_view_from_explicit_per_cell_genomes(seed):
+    """pcs_forest_upload_genomes / pcs_flat_create_genomes: the forest handed over the way the reference's seam does
+    it -- per-cell genomes, chromosome -> allele -> fragment -> SID, no tree
+    (/root/reference/src/seq_simulation.cpp:566-575, src/phylogenetic_forest.cpp:279-290) -- must flatten to a view
+    in which every cell's every allele has its fragments and carries exactly its SIDs"""
+    f = synth_forest(small_spec(seed))
+    g = oracle.cell_genomes(f)
+    assert check_flat_against_explicit_genomes(f, flat_of=g) > 50
+    fl_e, fl_g = L.Flat(f), L.Flat(g)
+    ie, ig = fl_e.info(), fl_g.info()
+    # same loci, same haplotypes; placements: one per run of carriers -- the tree-less ordering keeps clades together,
+    # so there are about as many as events placed them (a SID a later deletion took from part of its clade splits)
+    assert ig["n_loci"] == ie["n_loci"] and ig["n_haplotypes"] == ie["n_haplotypes"]
+    assert ig["n_instances"] <= 1.2 * ie["n_instances"] + 16
+    # the planner sees the same job: same tile grid, same templates per tile (the RNG streams are keyed by
+    # (seed, sample, chromosome), the weights by fragment lengths and head counts)
+    P = make_params(coverage=20.0, purity=0.7)
+    info_e, t_e = fl_e.plan(P)
+    info_g, t_g = fl_g.plan(P)
+    assert info_e.n_templates_total == info_g.n_templates_total and info_e.n_tiles_total == info_g.n_tiles_total
+    oe, og = np.argsort(t_e["id"]), np.argsort(t_g["id"])
+    for k in ("id", "templates", "sample", "chr", "begin", "len"):
+        assert np.array_equal(t_e[k][oe], t_g[k][og]), k
+
+
+def test_explicit_genomes_are_validated():
+    f = MF.forest()
+    g = oracle.cell_genomes(f)
+    check_flat_against_explicit_genomes(f, flat_of=g)
+    bad = oracle.cell_genomes(f)
+    bad.sid_row = bad.sid_row.copy()
+    bad.sid_row[0] = 0  # row 0 is a germline SID of allele 0 ... on whatever allele: outside or duplicate
+    with pytest.raises(L.PcsError):
+        L.Flat(bad)
+    bad = oracle.cell_genomes(f)
+    bad.frag_end = bad.frag_end.copy()
+    bad.frag_end[0] = 5000  # past the chromosome
+    with pytest.raises(L.PcsError):
+        L.Flat(bad)
+    # without the normal cells that carry the pre-neoplastic SIDs, preneoplastic_in_normal is refused, nothing else
+    g0 = oracle.cell_genomes(f, with_preneo=False)
+    fl = L.Flat(g0)
+    fl.plan(make_params(coverage=5.0))
+    with pytest.raises(L.PcsError, match="pre-neoplastic"):
+        fl.plan(make_params(coverage=5.0, preneoplastic_in_normal=1))
 
 
 def _all_hap_rows(f):
@@ -266,7 +315,8 @@ def test_planner_shards_partition_the_tile_grid(shards):
         loads.append(int(tr["templates"].sum()))
         assert loads[-1] == info_r.n_templates
     assert seen == {int(i): int(n) for i, n in zip(t["id"], t["templates"])}
-    assert max(loads) - min(loads) <= int(t["templates"].max())  # LPT balance
+    # LPT balances the tiles' COST (templates x a locus-density term), so template loads agree only roughly
+    assert max(loads) / min(loads) < 1.15
     with pytest.raises(L.PcsError):
         fl.plan(make_params(shard_rank=shards, shard_count=shards))
 
