@@ -419,6 +419,13 @@ def main():
 
     # ---- roofline of the sampler kernel on this rank
     kernel_ms = float(np.mean([plan.run_device(occ.data_ptr(), cov.data_ptr(), checksums=False).kernel_ms for _ in range(3)]))
+    if world > 1:  # every rank's sampler kernel, warm: their spread is the imbalance of the shards
+        mine = torch.tensor([kernel_ms], dtype=torch.float64, device="cuda")
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        all_kernel_ms = [float(t.item()) for t in gathered]
+    else:
+        all_kernel_ms = [kernel_ms]
     reads_per_step = total_reads / args.steps
     rank_reads = float(timed.n_reads) / args.steps
     kbar = float(expect[1].item()) / max(1.0, reads_per_step)   # job-wide: every shard sees the same mix

@@ -340,6 +340,15 @@ int pcs_plan_materialize(pcs_plan* plan, uint64_t cap, pcs_read_placement* place
                          uint8_t* seq, uint8_t* qual, uint32_t* cigar, uint32_t* n_cigar, uint32_t* lengths,
                          uint64_t* n_out);
 
+/* ---- binned depth tracks (the depth behind R/plot_genome_wide_mutations.R:75-108 between the
+ * mutations as well): track[s * n_bins + chr_bin_off[chr] + (pos / bin_bp)] = reference bases the reads of sample s
+ * lay on that bin -- the reads of THIS plan (same Philox counters as pcs_plan_run: the track and the tables describe
+ * the same reads; a read counts the R bases from its start, in the frame it starts in).  bin_bp: a power of two.
+ * chr_bin_off: [n_chr + 1] (filled).  track == NULL: only chr_bin_off and *n_bins are filled (to size the buffer of
+ * n_out_samples * n_bins uint32). */
+int pcs_plan_coverage_track(pcs_plan* plan, uint32_t bin_bp, uint64_t* chr_bin_off, uint32_t* track,
+                            uint64_t cap_bins, uint64_t* n_bins);
+
 /* debug/parity: re-run the plan emitting every placed read as a placement
  * record (+ its error mask when the sequencer has errors) instead of counting.
  * Host buffers of capacity `cap` records; *n_out receives the number written. */

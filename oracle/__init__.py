@@ -37,6 +37,12 @@ def _check(rc):
         raise OracleError(lib().oracle_last_error().decode())
 
 
+def set_placement_rule(rule):
+    """A11 (UNPINNED): 0 = start uniform over the fragment, templates past its end dropped (the product's rule);
+    1 = start uniform over the valid starts.  Returns the previous rule."""
+    return int(lib().oracle_set_placement_rule(C.c_int(rule)))
+
+
 def n_out_samples(forest, params: A.SeqParams, n_groups=None):
     if params.normal_only:
         return 1

@@ -50,6 +50,12 @@ namespace {
 
 thread_local std::string g_err;
 
+// A11, read placement inside a fragment (UNPINNED: RACES-internal).  0 = the rule the product implements: the start
+// is uniform over the fragment and a template that runs past the fragment's end is dropped (it falls off the
+// molecule).  1 = SURVEY.md Appendix A as first written: the start is uniform over the starts from which the
+// template fits, nothing is dropped.  Selectable so that the deviation can be measured (tests/).
+std::atomic<int> g_placement_rule{0};
+
 // where the time of the last oracle_simulate went, in CPU-seconds summed over its worker threads:
 // [0] building explicit genomes, [1] per (sample, chromosome) fixed work (zeroing the per-base coverage vector,
 // drawing the per-fragment template counts, gathering the tables), [2] the read loop, [3] wall-clock of the call
@@ -507,10 +513,15 @@ void simulate_sample_chr(const Forest& f, const ChrGenomes& G, uint32_t chr, uin
     for (size_t i = lo; i < hi; ++i) {
       const FragRef& fr = frags[i];
       std::uniform_int_distribution<uint32_t> start(fr.fr->begin, fr.fr->end);
+      const int rule = g_placement_rule.load();
       for (uint64_t k = 0; k < n_frag[i]; ++k) {
         uint32_t x = start(trng);
         uint32_t gap = paired ? ins(trng) : 0;
         uint64_t tlen = paired ? 2ull * R + gap : R;
+        if (rule == 1) {  // uniform over the valid starts; a fragment shorter than the template yields nothing
+          if (static_cast<uint64_t>(fr.fr->end) - fr.fr->begin + 1 < tlen) continue;
+          x = std::uniform_int_distribution<uint32_t>(fr.fr->begin, static_cast<uint32_t>(fr.fr->end - tlen + 1))(trng);
+        }
         if (static_cast<uint64_t>(x) + tlen - 1 > fr.fr->end) continue;  // falls off the molecule
         for (uint32_t mate = 0; mate < mates; ++mate) {
           uint32_t xs = mate == 0 ? x : x + R + gap;
@@ -583,6 +594,10 @@ void validate_params(const pcs_seq_params& P) {
 extern "C" {
 
 const char* oracle_last_error(void) { return g_err.c_str(); }
+
+/* A11 placement rule of the following oracle_simulate calls: 0 (default) uniform over the fragment + drop,
+ * 1 uniform over the valid starts.  Returns the previous rule. */
+int oracle_set_placement_rule(int rule) { return g_placement_rule.exchange(rule == 1 ? 1 : 0); }
 
 /* CPU-seconds of the last oracle_simulate of the process: out[0] explicit genomes, out[1] fixed work per
  * (sample, chromosome), out[2] the read loop, out[3] wall-clock seconds of the call */

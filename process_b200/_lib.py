@@ -30,7 +30,7 @@ EXPORTS = [
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan", "pcs_flat_group_list",
     "pcs_flat_tile_entries", "pcs_flat_draw", "pcs_flat_hap_list",
     "pcs_host_gather", "pcs_host_string_column", "pcs_plan_counters", "pcs_memset_u32_stream",
-    "pcs_forest_upload_genomes", "pcs_flat_create_genomes",
+    "pcs_forest_upload_genomes", "pcs_flat_create_genomes", "pcs_plan_coverage_track",
     "pcs_simulate_result", "pcs_plan_result", "pcs_result_info", "pcs_result_fetch", "pcs_result_free",
 ]
 
@@ -475,6 +475,18 @@ class Plan:
         n = C.c_uint64(0)
         _ok(lib().pcs_plan_write_sam(self._h, C.byref(opt), C.byref(n)))
         return n.value
+
+    def coverage_track(self, bin_bp=4096):
+        """binned depth of the plan's reads: (chr_bin_off uint64 [n_chr+1], track uint32 [n_out_samples, n_bins]);
+        track[s, chr_bin_off[c] + pos // bin_bp] = reference bases the reads of sample s lay on that bin"""
+        n_chr = self.forest.forest.n_chr
+        off = np.zeros(n_chr + 1, np.uint64)
+        n = C.c_uint64(0)
+        _ok(lib().pcs_plan_coverage_track(self._h, C.c_uint32(bin_bp), A.ptr(off, C.c_uint64), None, C.c_uint64(0), C.byref(n)))
+        track = np.zeros((self.info.n_out_samples, n.value), np.uint32)
+        _ok(lib().pcs_plan_coverage_track(self._h, C.c_uint32(bin_bp), A.ptr(off, C.c_uint64), A.ptr(track, C.c_uint32),
+                                          C.c_uint64(n.value), C.byref(n)))
+        return off, track
 
     def trace(self, cap, with_masks=False):
         rec = np.zeros(cap, A.PLACEMENT_DTYPE)

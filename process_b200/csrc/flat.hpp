@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -114,9 +115,12 @@ struct FlatForest {
 };
 
 // throws std::domain_error on malformed input.  A block lent through out.store before the call is kept and used.
-void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads);
+// loci_ready (optional) is called, on the calling thread, once locus_pos / row_locus / chr_locus_off are final.
+void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
+                    const std::function<void()>& loci_ready = nullptr);
 // the same view from explicit per-cell genomes (what get_sample_mutations_list() / get_normal_sample() hand over)
-void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads);
+void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads,
+                          const std::function<void()>& loci_ready = nullptr);
 // bytes of lent memory that are always enough for the tables of `d` (FlatStore::capacity)
 size_t flat_store_bytes(const pcs_forest_desc& d);
 size_t flat_store_bytes(const pcs_cell_genomes_desc& g);

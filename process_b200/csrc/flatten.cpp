@@ -7,6 +7,7 @@
 //   DEL  on allele a : [pos, pos+len-1] removed from the fragments of a
 //   WGD              : per chromosome, every allele in increasing id order is copied to id next_id++
 #include "flat.hpp"
+#include "host_pool.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -457,7 +458,8 @@ struct Numbering {
 // instance table.  `number` is the only part that depends on how the forest is described (an event-labelled
 // tree: flatten_forest; explicit per-cell genomes: flatten_cell_genomes).
 template <class NumberFn>
-void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, NumberFn&& number) {
+void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, const std::function<void()>& loci_ready,
+                  NumberFn&& number) {
   PhaseTimer timer;
   check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
   {
@@ -482,28 +484,15 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   n_threads = std::max(1u, n_threads);
   // run fn(task) for task in [0, n_tasks) on up to n_threads threads; the first exception is rethrown
   auto parallel_for = [&](uint32_t n_tasks, const std::function<void(uint32_t)>& fn) {
-    std::atomic<uint32_t> next_task{0};
     std::vector<std::string> errors(n_tasks);
-    auto body = [&]() {
-      for (;;) {
-        uint32_t k = next_task.fetch_add(1);
-        if (k >= n_tasks) return;
-        try {
-          fn(k);
-        } catch (const std::exception& e) {
-          errors[k] = e.what();
-          if (errors[k].empty()) errors[k] = "flatten failed";
-        }
+    HostPool::get().run(n_tasks, [&](size_t k) {
+      try {
+        fn(static_cast<uint32_t>(k));
+      } catch (const std::exception& e) {
+        errors[k] = e.what();
+        if (errors[k].empty()) errors[k] = "flatten failed";
       }
-    };
-    const unsigned nt = std::min<unsigned>(n_threads, n_tasks);
-    if (nt <= 1) {
-      body();
-    } else {
-      std::vector<std::thread> th;
-      for (unsigned i = 0; i < nt; ++i) th.emplace_back(body);
-      for (auto& x : th) x.join();
-    }
+    }, n_threads);
     for (const auto& e : errors)
       if (!e.empty()) throw std::domain_error(e);
   };
@@ -580,6 +569,7 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
     out.chr_locus_off[c] = chr_row_off[c] < d.n_mut ? out.row_locus[chr_row_off[c]] : n_loci;
 
   timer.lap("loci");
+  if (loci_ready) loci_ready();  // locus_pos, row_locus, chr_locus_off are final: the caller may start copying them
   // ---- germline SIDs by row.  The caller's list comes in any order; a SID is normally listed once, so the
   // list is scattered into one allele-mask byte per row (0 = not germline; a row listed twice gets the union
   // of its masks).  Should a row be listed twice, a stably sorted copy of the list is walked for the instances
@@ -616,9 +606,31 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
     });
     if (std::find(chunk_sorted.begin(), chunk_sorted.end(), 0) == chunk_sorted.end()) {
       // chunk k writes rows [germ_mut[lo], germ_mut[hi-1]]: only the two edge bytes can share a line
+      // The list is sorted by row: the listings of one row are neighbours, so a chunk gathers a row's masks in a
+      // register and writes the byte once, with a plain store -- except for its first and its last row, which a
+      // neighbouring chunk may hold listings of as well (atomic OR).
       parallel_for(g_chunks, [&](uint32_t k) {
         const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
-        for (uint64_t i = lo; i < hi; ++i) row_mask[d.germ_mut[i]].fetch_or(d.germ_allele_mask[i], std::memory_order_relaxed);
+        if (lo == hi) return;
+        const uint32_t first_row = d.germ_mut[lo], last_row = d.germ_mut[hi - 1];
+        uint32_t row = first_row;
+        uint8_t acc = 0;
+        auto flush = [&]() {
+          if (row == first_row || row == last_row)
+            row_mask[row].fetch_or(acc, std::memory_order_relaxed);
+          else
+            row_mask[row].store(acc, std::memory_order_relaxed);
+        };
+        for (uint64_t i = lo; i < hi; ++i) {
+          const uint32_t m = d.germ_mut[i];
+          if (m != row) {
+            flush();
+            row = m;
+            acc = 0;
+          }
+          acc |= d.germ_allele_mask[i];
+        }
+        flush();
       });
     } else {
       // hist -> where chunk k writes its entries of bucket b: buckets in order, chunks in order inside a bucket
@@ -789,9 +801,9 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   timer.lap("merge");
 }
 
-void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads) {
+void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, const std::function<void()>& loci_ready) {
   check(d.n_nodes >= 1, "the forest has no nodes");
-  flatten_with(d, out, n_threads, [&](Numbering& nb) {
+  flatten_with(d, out, n_threads, loci_ready, [&](Numbering& nb) {
     FlatForest& out = nb.out;
     std::vector<ChrWork>& work = nb.work;
     const std::atomic<uint8_t>* row_mask = nb.row_mask;
@@ -1087,11 +1099,12 @@ pcs_forest_desc common_desc(const pcs_cell_genomes_desc& g) {
 
 }  // namespace
 
-void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads) {
+void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads,
+                          const std::function<void()>& loci_ready) {
   const pcs_forest_desc d = common_desc(g);
   for (uint32_t c = 0; c < g.n_cells; ++c) check(g.cell_sample[c] < g.n_samples, "cell_sample out of range");
   check(g.n_alleles == 0 || (g.allele_frag_off[0] == 0 && g.allele_sid_off[0] == 0), "allele offsets are not CSR arrays");
-  flatten_with(d, out, n_threads, [&](Numbering& nb) {
+  flatten_with(d, out, n_threads, loci_ready, [&](Numbering& nb) {
     nb.out.n_roots = g.n_normal_preneo;
     std::vector<std::vector<uint64_t>> by_chr(g.n_chr);
     for (uint64_t a = 0; a < g.n_alleles; ++a) {

@@ -926,8 +926,9 @@ materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict
       H.hap = tp.h; H.start = xs; H.frag_end = tp.frag_end; H.chr_sample = T.chr | (T.sample << 16);
       H.read_id = 2u * j + k; H.tile_id = T.id; H.flags = (M.paired ? 1u : 0u) | (M.paired && k ? 2u : 0u);
       H.mate_start = mate_start; H.tlen = tlen;
-      uint32_t* mask = masks + idx * PCS_ERRMASK_WORDS;
-      for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) mask[i] = 0;
+      uint32_t* mask = masks ? masks + idx * PCS_ERRMASK_WORDS : nullptr;  // the SAM writer does not need them
+      if (mask)
+        for (int i = 0; i < PCS_ERRMASK_WORDS; ++i) mask[i] = 0;
       BaseWriter W{M, H.read_id, T.id, seq + idx * R, qual + idx * R, mask};
       CigarBuilder C{H.cigar};
       materialize_read(F, M, D, T.chr, lower_bound_pos(F.locus_pos, T.l0, chr_l1, xs), chr_l1, tp.h, xs, tp.frag_end, W, C,
@@ -1125,6 +1126,86 @@ cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const ui
   if (nb == 0 || n_active == 0) return cudaSuccess;
   active_scatter_kernel<<<nb, kActiveThreads, 0, st>>>(occ, depth, row_locus, carried, S, M, L, block_off, n_active,
                                                        rows_out, occ_c, cov_c, vaf_c);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------- coverage tracks
+// Binned depth along the genome (the tables behind depth-ratio plots,
+// R/plot_genome_wide_mutations.R:75-108, want depth between the mutations too).  Reads are never materialised,
+// so the track is made by drawing the templates of the plan ONCE MORE -- same Philox counters, same starts, same
+// templates dropped at fragment ends as the counting kernels: the track and the tables describe the same reads --
+// without haplotypes or loci: a read adds its R reference bases (its span in the frame it starts in) to the bins
+// of 2^bin_shift bp it overlaps.  One CTA per tile, bins of the tile in shared memory, one red.global per touched
+// bin.  About a third of the sampler's work, and only when a track is asked for.
+template <bool PAIRED>
+__global__ void __launch_bounds__(256)
+coverage_track_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, SeqModel M, uint32_t bin_shift,
+                      const uint64_t* __restrict__ chr_bin_off, uint64_t n_bins, uint32_t* __restrict__ track) {
+  extern __shared__ uint32_t s_bins[];
+  const Tile T = tiles[blockIdx.x];
+  const uint32_t R = M.read_size;
+  const uint32_t first_bin = T.begin >> bin_shift;
+  const uint32_t n_local = ((T.begin + T.len + M.reach) >> bin_shift) - first_bin + 1u;
+  for (uint32_t b = threadIdx.x; b < n_local; b += blockDim.x) s_bins[b] = 0;
+  __shared__ uint32_t s_safe;
+  if (threadIdx.x == 0) {
+    uint32_t min_fe = 0xffffffffu;
+    for (uint32_t e = 0; e < T.n_entries; ++e) min_fe = min(min_fe, __ldg(&entries[T.entry_off + e].frag_end));
+    const long long lim = static_cast<long long>(min_fe) + 2 - static_cast<long long>(M.reach) - T.begin;
+    s_safe = lim <= 0 ? 0u : (lim >= static_cast<long long>(T.len) ? T.len : static_cast<uint32_t>(lim));
+  }
+  __syncthreads();
+  const uint32_t safe = s_safe;
+  const Entry* ent = entries + T.entry_off;
+  // does the template fit the fragment its haplotype draw selects?  (only asked past `safe`)
+  auto fits = [&](uint32_t u_hap, uint32_t off, uint32_t tlen) {
+    uint32_t e = 0;
+    while (u_hap > __ldg(&ent[e].thr)) ++e;
+    return T.begin + off + (tlen - 1u) <= __ldg(&ent[e].frag_end);
+  };
+  auto add = [&](uint32_t off) {  // R bases from tile offset `off` on
+    const uint32_t x = T.begin + off, b0 = (x >> bin_shift) - first_bin;
+    const uint32_t in_first = min(R, ((x >> bin_shift) + 1u << bin_shift) - x);
+    atomicAdd(&s_bins[b0], in_first);
+    for (uint32_t left = R - in_first, b = b0 + 1u; left != 0u; ++b) {  // R may span several bins
+      const uint32_t n = min(left, 1u << bin_shift);
+      atomicAdd(&s_bins[b], n);
+      left -= n;
+    }
+  };
+  const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
+  for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
+    const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+    if (PAIRED) {
+      const uint32_t off = __umulhi(u.x, T.len), off2 = off + R + draw_insert(M, u.z);
+      if (off >= safe && !fits(u.y, off, off2 - off + R)) continue;
+      add(off);
+      add(off2);
+    } else {
+      const uint32_t off0 = __umulhi(u.x, T.len), off1 = __umulhi(u.z, T.len);
+      if (off0 < safe || fits(u.y, off0, R)) add(off0);
+      if (2u * j + 1u < T.n_templates && (off1 < safe || fits(u.w, off1, R))) add(off1);
+    }
+  }
+  __syncthreads();
+  uint32_t* out = track + static_cast<size_t>(T.sample) * n_bins + chr_bin_off[T.chr] + first_bin;
+  const uint32_t chr_bins = static_cast<uint32_t>(chr_bin_off[T.chr + 1] - chr_bin_off[T.chr]);
+  for (uint32_t b = threadIdx.x; b < n_local; b += blockDim.x) {
+    const uint32_t v = s_bins[b];
+    if (v && first_bin + b < chr_bins) atomicAdd(out + b, v);
+  }
+}
+
+cudaError_t launch_coverage_track(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
+                                  const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,
+                                  const uint64_t* chr_bin_off, uint64_t n_bins, uint32_t* track) {
+  if (n_tiles == 0) return cudaSuccess;
+  const size_t smem = (((static_cast<size_t>(max_tile_len) + M.reach) >> bin_shift) + 2) * sizeof(uint32_t);
+  if (smem > 200u * 1024u) return cudaErrorInvalidValue;  // bins this fine do not fit: the caller picks a wider bin
+  auto kern = M.paired ? coverage_track_kernel<true> : coverage_track_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return e;
+  kern<<<n_tiles, 256, smem, st>>>(tiles, entries, M, bin_shift, chr_bin_off, n_bins, track);
   return cudaGetLastError();
 }
 

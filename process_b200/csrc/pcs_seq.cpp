@@ -28,6 +28,7 @@
 #include "../../include/pcs_seq.h"
 #include "dev.hpp"
 #include "flat.hpp"
+#include "host_pool.hpp"
 #include "kernels.hpp"
 
 namespace {
@@ -67,11 +68,11 @@ void parallel_copy(void* dst, const void* src, size_t bytes) {
     std::memcpy(dst, src, bytes);
     return;
   }
-  std::vector<std::thread> th;
   const size_t chunk = (bytes / nt + 4095) & ~static_cast<size_t>(4095);
-  for (size_t off = 0; off < bytes; off += chunk)
-    th.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off)); });
-  for (auto& t : th) t.join();
+  pcs::HostPool::get().run((bytes + chunk - 1) / chunk, [=](size_t k) {
+    const size_t off = k * chunk;
+    std::memcpy(static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, std::min(chunk, bytes - off));
+  }, nt);
 }
 
 // device buffer from the device's stream-ordered memory pool (cudaMallocAsync): repeated
@@ -342,15 +343,7 @@ struct HostForest {
     };
     std::vector<uint32_t> count(n_keys + 1, 0);  // key = group * n_fs + fragset: the order of list_key()
     auto per_chr = [&](const std::function<void(uint32_t)>& fn) {
-      std::atomic<uint32_t> next{0};
-      auto worker = [&] {
-        for (uint32_t c = next.fetch_add(1); c < flat.n_chr; c = next.fetch_add(1)) fn(c);
-      };
-      const unsigned nt = std::min<unsigned>(flat.n_chr, host_threads());
-      std::vector<std::thread> th;
-      for (unsigned w = 1; w < nt; ++w) th.emplace_back(worker);
-      worker();
-      for (auto& t : th) t.join();
+      pcs::HostPool::get().run(flat.n_chr, [&](size_t c) { fn(static_cast<uint32_t>(c)); }, host_threads());
     };
     per_chr([&](uint32_t c) {
       for (const pcs::HapRec& r : flat.chr_haps[c]) ++count[static_cast<size_t>(group_of(r)) * n_fs + r.fragset + 1];
@@ -489,16 +482,31 @@ struct pcs_forest {
       staged.emplace_back(&dst, &src);
     }
   }
+  // the tables the flattener finishes first, sent while it is still numbering haplotypes (they are read in place
+  // from the lent pinned block; tables outside it wait for upload_flat)
+  bool loci_uploaded = false;
+  void upload_loci_early() {
+    const pcs::FlatForest& F = host.flat;
+    if (!F.store.lent(F.locus_pos.data(), F.locus_pos.size() * 4) || !F.store.lent(F.row_locus.data(), F.row_locus.size() * 4)) return;
+    ctx->bind();
+    std::vector<std::pair<DevBuf<uint32_t>*, const pcs::Table<uint32_t>*>> none;
+    h2d_bytes += d_chr_locus_off.upload(F.chr_locus_off, ctx->stream);
+    upload_table(d_locus_pos, F.locus_pos, none);
+    upload_table(d_row_locus, F.row_locus, none);
+    loci_uploaded = none.empty();
+  }
   void upload_flat() {
     ctx->bind();
     cudaStream_t st = ctx->stream;
     const pcs::FlatForest& F = host.flat;
     std::vector<std::pair<DevBuf<uint32_t>*, const pcs::Table<uint32_t>*>> staged32;
     std::vector<std::pair<DevBuf<pcs::Inst>*, const pcs::Table<pcs::Inst>*>> staged_inst;
-    h2d_bytes += d_chr_locus_off.upload(F.chr_locus_off, st);  // tiny, pageable, synchronous: before the big ones
-    upload_table(d_locus_pos, F.locus_pos, staged32);
+    if (!loci_uploaded) {
+      h2d_bytes += d_chr_locus_off.upload(F.chr_locus_off, st);  // tiny, pageable, synchronous: before the big ones
+      upload_table(d_locus_pos, F.locus_pos, staged32);
+      upload_table(d_row_locus, F.row_locus, staged32);
+    }
     upload_table(d_locus_inst_off, F.locus_inst_off, staged32);
-    upload_table(d_row_locus, F.row_locus, staged32);
     upload_table(d_inst, F.inst, staged_inst);
     if (staged32.empty() && staged_inst.empty()) return;
     auto padded = [](size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); };
@@ -680,22 +688,14 @@ struct OutSample {
 template <class Fn>
 void host_tasks(size_t n, Fn&& fn) {
   std::vector<std::string> errors(n);
-  std::atomic<size_t> next{0};
-  auto worker = [&] {
-    for (size_t k = next.fetch_add(1); k < n; k = next.fetch_add(1)) {
-      try {
-        fn(k);
-      } catch (const std::exception& e) {
-        errors[k] = e.what();
-        if (errors[k].empty()) errors[k] = "planning failed";
-      }
+  pcs::HostPool::get().run(n, [&](size_t k) {
+    try {
+      fn(k);
+    } catch (const std::exception& e) {
+      errors[k] = e.what();
+      if (errors[k].empty()) errors[k] = "planning failed";
     }
-  };
-  const size_t nt = std::min<size_t>(n, std::max(1u, host_threads()));
-  std::vector<std::thread> th;
-  for (size_t w = 1; w < nt; ++w) th.emplace_back(worker);
-  worker();
-  for (auto& t : th) t.join();
+  }, host_threads());
   for (const auto& e : errors)
     if (!e.empty()) throw std::domain_error(e);
 }
@@ -801,8 +801,39 @@ struct SampleChrPlan {
   std::vector<pcs::Entry> entries;
   std::vector<uint32_t> entry_lo;
   std::vector<pcs::Tile> tiles;
+  std::vector<double> tile_w;        // share of the (sample, chromosome)'s templates every tile is drawn with
+  std::vector<uint64_t> block_n;     // templates of every block of kTemplateBlock consecutive tiles
   uint64_t total_templates = 0;
 };
+
+// Templates per tile: a multinomial over the tiles of a (sample, chromosome), drawn in TWO LEVELS -- first over
+// blocks of kTemplateBlock consecutive tiles (a chain of binomials, RNG stream of (seed, sample, chromosome)),
+// then inside every block (stream of (seed, sample, chromosome, block)).  A multinomial split like this is the
+// same law; the blocks are independent tasks, so the longest chromosome is no longer the planner's critical path.
+constexpr size_t kTemplateBlock = 64;
+
+uint64_t draw_binomial(std::mt19937_64& rng, uint64_t n, double p) {
+  if (p >= 1.0) return n;
+  if (p <= 0.0 || n == 0) return 0;
+  return static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(n), p)(rng));
+}
+
+void plan_block_templates(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan& task, size_t b) {
+  const size_t i0 = b * kTemplateBlock, i1 = std::min(task.tiles.size(), i0 + kTemplateBlock);
+  std::seed_seq sq{static_cast<uint32_t>(ps.P.seed), s, c, 0x7116u, static_cast<uint32_t>(b)};
+  std::mt19937_64 rng(sq);
+  double wleft = 0;
+  for (size_t i = i0; i < i1; ++i) wleft += task.tile_w[i];
+  uint64_t left = task.block_n[b];
+  for (size_t i = i0; i < i1 && left > 0; ++i) {
+    const double p = (i + 1 == i1) ? 1.0 : std::min(1.0, std::max(0.0, task.tile_w[i] / wleft));
+    const uint64_t k = draw_binomial(rng, left, p);
+    require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
+    task.tiles[i].n_templates = static_cast<uint32_t>(k);
+    left -= k;
+    wleft -= task.tile_w[i];
+  }
+}
 
 void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan& task) {
   const HostForest& fo = *ps.fo;
@@ -814,7 +845,7 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
   if (nT == 0) purity = 0.0;
   std::vector<pcs::Entry>& entries = task.entries;
   std::vector<pcs::Tile>& all = task.tiles;
-  std::vector<double> tile_w;
+  std::vector<double>& tile_w = task.tile_w;
   const PlanSetup::ChrGrid& g = ps.grid[c];
   all.reserve(g.tiles.size());
   tile_w.reserve(g.tiles.size());
@@ -881,21 +912,25 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
       tile_w.push_back(wsum * t.len);
     }
   }
-  // templates of this (sample, chromosome), multinomial over its tiles
+  // templates of this (sample, chromosome): N of them, multinomial over its tiles -- here over the BLOCKS of tiles
+  // (the tiles inside a block are drawn by plan_block_templates, one independent task per block)
   const uint64_t N = static_cast<uint64_t>(std::llround(P.coverage * F.chr_len[c] / (static_cast<double>(ps.R) * ps.mates)));
   std::seed_seq sq{static_cast<uint32_t>(P.seed), s, c, 0x7115u};
   std::mt19937_64 rng(sq);
+  const size_t n_blocks = (all.size() + kTemplateBlock - 1) / kTemplateBlock;
+  std::vector<double> block_w(n_blocks, 0.0);
+  for (size_t i = 0; i < all.size(); ++i) block_w[i / kTemplateBlock] += tile_w[i];
   double wleft = 0;
-  for (double x : tile_w) wleft += x;
+  for (double x : block_w) wleft += x;
+  task.block_n.assign(n_blocks, 0);
   uint64_t left = all.empty() ? 0 : N;
-  for (size_t i = 0; i < all.size() && left > 0; ++i) {
-    double p = (i + 1 == all.size()) ? 1.0 : std::min(1.0, std::max(0.0, tile_w[i] / wleft));
-    uint64_t k = p >= 1.0 ? left : static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(left), p)(rng));
-    require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
-    all[i].n_templates = static_cast<uint32_t>(k);
+  task.total_templates = left;
+  for (size_t b = 0; b < n_blocks && left > 0; ++b) {
+    const double p = (b + 1 == n_blocks) ? 1.0 : std::min(1.0, std::max(0.0, block_w[b] / wleft));
+    const uint64_t k = draw_binomial(rng, left, p);
+    task.block_n[b] = k;
     left -= k;
-    wleft -= tile_w[i];
-    task.total_templates += k;
+    wleft -= block_w[b];
   }
 }
 
@@ -961,6 +996,15 @@ std::vector<HostPlan> make_host_plans(const PlanSetup& ps, uint32_t s0, uint32_t
   host_tasks(per.size(), [&](size_t k) {
     plan_sample_chr(ps, s0 + static_cast<uint32_t>(k / F.n_chr), static_cast<uint32_t>(k % F.n_chr), per[k]);
   });
+  {
+    std::vector<std::pair<uint32_t, uint32_t>> blocks;  // (task, block)
+    for (size_t k = 0; k < per.size(); ++k)
+      for (size_t b = 0; b < per[k].block_n.size(); ++b) blocks.emplace_back(static_cast<uint32_t>(k), static_cast<uint32_t>(b));
+    host_tasks(blocks.size(), [&](size_t q) {
+      const uint32_t k = blocks[q].first;
+      plan_block_templates(ps, s0 + k / F.n_chr, k % F.n_chr, per[k], blocks[q].second);
+    });
+  }
   lap("  plan: entries + templates");
   // merged in (sample, chromosome) order: the position in this order is the tile id
   std::vector<pcs::Entry>& entries = pl.entries;
@@ -1325,22 +1369,19 @@ void drain_chunks(pcs_ctx& cx, const std::vector<ChunkCopy>& chunks) {
   if (chunks.empty()) return;
   const unsigned nt = std::max(1u, std::min(16u, host_threads()));
   std::vector<cudaError_t> werr(nt, cudaSuccess);
-  std::vector<std::thread> th;
-  for (unsigned w = 0; w < nt; ++w)
-    th.emplace_back([&, w] {
-      cudaSetDevice(cx.device);
-      for (size_t k = 0; k < chunks.size(); ++k) {
-        const cudaError_t e = cudaEventSynchronize(cx.chunk_ev[k]);
-        if (e != cudaSuccess) {
-          werr[w] = e;
-          return;
-        }
-        const size_t lo = (chunks[k].bytes * w / nt) & ~static_cast<size_t>(63);
-        const size_t hi = w + 1 == nt ? chunks[k].bytes : (chunks[k].bytes * (w + 1) / nt) & ~static_cast<size_t>(63);
-        if (hi > lo) std::memcpy(chunks[k].dst + lo, chunks[k].src + lo, hi - lo);
+  pcs::HostPool::get().run(nt, [&](size_t w) {  // thread w copies its share of every chunk, chunk after chunk
+    cudaSetDevice(cx.device);
+    for (size_t k = 0; k < chunks.size(); ++k) {
+      const cudaError_t e = cudaEventSynchronize(cx.chunk_ev[k]);
+      if (e != cudaSuccess) {
+        werr[w] = e;
+        return;
       }
-    });
-  for (auto& t : th) t.join();
+      const size_t lo = (chunks[k].bytes * w / nt) & ~static_cast<size_t>(63);
+      const size_t hi = w + 1 == nt ? chunks[k].bytes : (chunks[k].bytes * (w + 1) / nt) & ~static_cast<size_t>(63);
+      if (hi > lo) std::memcpy(chunks[k].dst + lo, chunks[k].src + lo, hi - lo);
+    }
+  }, nt);
   for (cudaError_t e : werr) CUDA_OK(e);
 }
 
@@ -1713,6 +1754,10 @@ void append_sam_line(std::string& s, const pcs::SamHeader& h, const uint8_t* seq
 // peer access between two devices of this process, both directions (idempotent)
 void enable_peer_both_ways(int a, int b) {
   if (a == b) return;
+  static std::mutex mu;
+  static std::vector<std::pair<int, int>> done;  // pairs already set up by this process
+  std::lock_guard<std::mutex> lock(mu);
+  if (std::find(done.begin(), done.end(), std::make_pair(std::min(a, b), std::max(a, b))) != done.end()) return;
   const int pair[2][2] = {{a, b}, {b, a}};
   for (const auto& pr : pair) {
     CUDA_OK(cudaSetDevice(pr[0]));
@@ -1721,7 +1766,17 @@ void enable_peer_both_ways(int a, int b) {
     if (!can) throw CudaError("the devices cannot access each other's memory");
     const cudaError_t e = cudaDeviceEnablePeerAccess(pr[1], 0);
     if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else CUDA_OK(e);
+    // the library's buffers come from the stream-ordered pool, which cudaDeviceEnablePeerAccess does not cover:
+    // without this a device-to-device copy of pool memory is staged through the host
+    cudaMemPool_t pool;
+    CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, pr[0]));
+    cudaMemAccessDesc desc{};
+    desc.location.type = cudaMemLocationTypeDevice;
+    desc.location.id = pr[1];
+    desc.flags = cudaMemAccessFlagsProtReadWrite;
+    CUDA_OK(cudaMemPoolSetAccess(pool, &desc, 1));
   }
+  done.emplace_back(std::min(a, b), std::max(a, b));
 }
 
 template <class Fn>
@@ -1837,7 +1892,8 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     Lap lap;
     fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
     lap("pinned block");
-    pcs::flatten_forest(*desc, fo->host.flat, host_threads());
+    pcs_forest* early = fo.get();
+    pcs::flatten_forest(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); });
     lap("flatten_forest");
     fo->upload_flat();
     lap("upload flat arrays");
@@ -1856,7 +1912,8 @@ int pcs_forest_upload_genomes(pcs_ctx* cx, const pcs_cell_genomes_desc* desc, pc
     fo->user.hold(cx);
     Lap lap;
     fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
-    pcs::flatten_cell_genomes(*desc, fo->host.flat, host_threads());
+    pcs_forest* early = fo.get();
+    pcs::flatten_cell_genomes(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); });
     lap("flatten_cell_genomes");
     fo->upload_flat();
     fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
@@ -2063,6 +2120,7 @@ int pcs_forest_replicate(pcs_forest* src, pcs_ctx* cx, pcs_forest** out) {
   return guarded([&] {
     require(src && cx && out, "bad arguments");
     require(!cx->destroyed.load(), "the context has been destroyed");
+    Lap lap;
     auto fo = std::make_unique<pcs_forest>(*src, cx);  // shares the flattened host view: no second flatten
     fo->user.hold(cx);
     pcs_ctx& sx = *src->ctx;
@@ -2090,6 +2148,7 @@ int pcs_forest_replicate(pcs_forest* src, pcs_ctx* cx, pcs_forest** out) {
       fo->uploaded_groups = src->uploaded_groups;
       CUDA_OK(cudaStreamSynchronize(st));
     }
+    lap("replicate forest");
     *out = fo.release();
   });
 }
@@ -2356,11 +2415,62 @@ int pcs_plan_materialize(pcs_plan* pl, uint64_t cap, pcs_read_placement* placeme
   });
 }
 
+// One batch of materialised reads in flight: device records, their pinned landing area, the event that says they
+// have landed.  The SAM writer keeps two: the GPU fills one while the host threads format the other.
+struct SamBatch {
+  DevBuf<pcs::Tile> d_tiles;
+  DevBuf<pcs::SamHeader> d_hdr;
+  DevBuf<uint8_t> d_seq, d_qual;
+  DevBuf<unsigned long long> d_count;
+  char* pinned = nullptr;  // [count (256 B) | hdr | seq | qual]
+  size_t pinned_bytes = 0, cap = 0;
+  cudaEvent_t landed = nullptr;
+  uint32_t R = 0;
+  ~SamBatch() {
+    if (pinned) cudaFreeHost(pinned);
+    if (landed) cudaEventDestroy(landed);
+  }
+  const unsigned long long* count() const { return reinterpret_cast<const unsigned long long*>(pinned); }
+  const pcs::SamHeader* hdr() const { return reinterpret_cast<const pcs::SamHeader*>(pinned + 256); }
+  const uint8_t* seq() const { return reinterpret_cast<const uint8_t*>(pinned + 256 + cap * sizeof(pcs::SamHeader)); }
+  const uint8_t* qual() const { return seq() + cap * R; }
+  // queue: tiles up, kernel, records + count back into pinned memory; nothing waits
+  void launch(pcs_plan& pl, const pcs::SeqData& D, const std::vector<pcs::Tile>& tiles, uint64_t reads) {
+    pcs_forest& fo = *pl.forest;
+    cudaStream_t st = fo.ctx->stream;
+    R = pl.host.info.read_size;
+    if (!landed) CUDA_OK(cudaEventCreateWithFlags(&landed, cudaEventDisableTiming));
+    cap = std::max<uint64_t>(reads, 1);
+    const size_t need = 256 + cap * (sizeof(pcs::SamHeader) + 2 * static_cast<size_t>(R));
+    if (need > pinned_bytes) {
+      if (pinned) cudaFreeHost(pinned);
+      pinned = nullptr;
+      pinned_bytes = 0;
+      CUDA_OK(cudaHostAlloc(reinterpret_cast<void**>(&pinned), need + need / 8, cudaHostAllocDefault));
+      pinned_bytes = need + need / 8;
+    }
+    d_tiles.upload(tiles, st);
+    d_hdr.alloc(cap, st);
+    d_seq.alloc(cap * R, st);
+    d_qual.alloc(cap * R, st);
+    d_count.alloc(1, st);
+    CUDA_OK(cudaMemsetAsync(d_count.p, 0, sizeof(unsigned long long), st));
+    CUDA_OK(pcs::launch_materialize_tiles(st, d_tiles.p, static_cast<uint32_t>(tiles.size()), pl.d_entries.p, pl.d_entry_lo.p,
+                                          fo.dev(), pl.host.model, D, d_hdr.p, nullptr, d_seq.p, d_qual.p, cap, d_count.p));
+    CUDA_OK(cudaMemcpyAsync(pinned, d_count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(pinned + 256, d_hdr.p, cap * sizeof(pcs::SamHeader), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(pinned + 256 + cap * sizeof(pcs::SamHeader), d_seq.p, cap * R, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(pinned + 256 + cap * (sizeof(pcs::SamHeader) + R), d_qual.p, cap * R, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaEventRecord(landed, st));
+  }
+};
+
 int pcs_plan_write_sam(pcs_plan* pl, const pcs_sam_options* opt, uint64_t* n_written) {
   return guarded([&] {
     require(pl && opt && opt->output_dir && opt->chr_names && opt->sample_names, "bad arguments");
     namespace fs = std::filesystem;
-    const pcs::FlatForest& F = pl->forest->host.flat;
+    pcs_forest& fo = *pl->forest;
+    const pcs::FlatForest& F = fo.host.flat;
     const fs::path dir(opt->output_dir);
     // ReadSimulator<>::Mode::CREATE refuses an existing directory, UPDATE adds files to it
     // (src/seq_simulation.cpp:545-549, vignettes/sequencing.Rmd:283-309)
@@ -2372,8 +2482,15 @@ int pcs_plan_write_sam(pcs_plan* pl, const pcs_sam_options* opt, uint64_t* n_wri
     const uint32_t R = pl->host.info.read_size, mates = pl->host.info.reads_per_template;
     std::vector<pcs::Tile> tiles = pl->host.tiles;
     tiles.insert(tiles.end(), pl->host.tiles_global.begin(), pl->host.tiles_global.end());
-    uint64_t written = 0;
-    const uint64_t batch_cap = 1u << 20;
+    for (const auto& t : tiles) require(fo.has_reference(t.chr), "the reference sequence of a sequenced chromosome is not loaded");
+    fo.ctx->bind();
+    const pcs::SeqData D = fo.seq_data();
+    uint64_t written = 0, text_bytes = 0;
+    double ms_wait = 0, ms_format = 0, ms_file = 0;  // PCS_TIMING: where the host's time of a SAM run goes
+    // batches of ~256 k reads: two in flight (the GPU materialises batch k+1 while the host formats batch k)
+    const uint64_t batch_cap = 1u << 18;
+    const unsigned nt = std::max(1u, std::min(32u, host_threads()));
+    SamBatch slots[2];
     for (uint32_t c = 0; c < F.n_chr; ++c) {
       std::vector<pcs::Tile> mine;
       for (const auto& t : tiles)
@@ -2384,33 +2501,122 @@ int pcs_plan_write_sam(pcs_plan* pl, const pcs_sam_options* opt, uint64_t* n_wri
       for (uint32_t k = 1; fs::exists(file); ++k) file = dir / (fprefix + opt->chr_names[c] + "_" + std::to_string(k) + ".sam");
       std::ofstream out(file, std::ios::binary);
       if (!out) throw std::runtime_error("cannot write \"" + file.string() + "\"");
-      std::string text = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:" + std::string(opt->chr_names[c]) + "\tLN:" + std::to_string(F.chr_len[c]) + "\n";
+      std::string head = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:" + std::string(opt->chr_names[c]) + "\tLN:" + std::to_string(F.chr_len[c]) + "\n";
       for (uint32_t s = 0; s < pl->host.info.n_out_samples; ++s)
-        text += std::string("@RG\tID:") + opt->sample_names[s] + "\tSM:" + opt->sample_names[s] + "\tPL:ILLUMINA\n";
-      text += "@PG\tID:pcs_seq\tPN:pcs_seq\n";
-      size_t i = 0;
-      while (i < mine.size()) {
-        std::vector<pcs::Tile> batch;
+        head += std::string("@RG\tID:") + opt->sample_names[s] + "\tSM:" + opt->sample_names[s] + "\tPL:ILLUMINA\n";
+      head += "@PG\tID:pcs_seq\tPN:pcs_seq\n";
+      out.write(head.data(), static_cast<std::streamsize>(head.size()));
+      text_bytes += head.size();
+      // the chromosome's batches
+      std::vector<std::pair<size_t, size_t>> batches;  // [first tile, one past the last)
+      std::vector<uint64_t> batch_reads;
+      for (size_t i = 0; i < mine.size();) {
+        const size_t first = i;
         uint64_t reads = 0;
-        while (i < mine.size() && (batch.empty() || reads + static_cast<uint64_t>(mine[i].n_templates) * mates <= batch_cap)) {
-          reads += static_cast<uint64_t>(mine[i].n_templates) * mates;
-          batch.push_back(mine[i++]);
-        }
-        Materialized m;
-        materialize_tiles(*pl, batch, std::max<uint64_t>(reads, 1), m);
-        for (size_t r = 0; r < m.hdr.size(); ++r) {
-          append_sam_line(text, m.hdr[r], m.seq.data() + r * R, m.qual.data() + r * R, tprefix, opt->chr_names[c],
-                          opt->sample_names[m.hdr[r].chr_sample >> 16]);
-          if (text.size() > (8u << 20)) {
-            out.write(text.data(), static_cast<std::streamsize>(text.size()));
-            text.clear();
-          }
-        }
-        written += m.hdr.size();
+        while (i < mine.size() && (i == first || reads + static_cast<uint64_t>(mine[i].n_templates) * mates <= batch_cap))
+          reads += static_cast<uint64_t>(mine[i++].n_templates) * mates;
+        batches.emplace_back(first, i);
+        batch_reads.push_back(reads);
       }
-      out.write(text.data(), static_cast<std::streamsize>(text.size()));
+      auto launch = [&](size_t k) {
+        slots[k & 1].launch(*pl, D, std::vector<pcs::Tile>(mine.begin() + static_cast<std::ptrdiff_t>(batches[k].first),
+                                                            mine.begin() + static_cast<std::ptrdiff_t>(batches[k].second)),
+                            batch_reads[k]);
+      };
+      launch(0);
+      // two sets of text buffers: a writer thread puts batch k into the file while the others format batch k+1
+      std::vector<std::string> text_sets[2] = {std::vector<std::string>(nt), std::vector<std::string>(nt)};
+      std::thread writer;
+      struct JoinWriter {
+        std::thread& t;
+        ~JoinWriter() { if (t.joinable()) t.join(); }
+      } join_writer{writer};
+      for (size_t k = 0; k < batches.size(); ++k) {
+        std::vector<std::string>& text = text_sets[k & 1];
+        if (k + 1 < batches.size()) launch(k + 1);  // behind batch k on the stream: the GPU never waits for the host
+        SamBatch& sb = slots[k & 1];
+        double t_a = now_ms();
+        CUDA_OK(cudaEventSynchronize(sb.landed));
+        ms_wait += now_ms() - t_a;
+        const uint64_t n = *sb.count();
+        if (n > sb.cap) throw std::domain_error("internal: more reads materialised than planned");
+        t_a = now_ms();
+        std::vector<std::string> errors(nt);
+        pcs::HostPool::get().run(nt, [&](size_t w) {
+            std::string& s = text[w];
+            s.clear();
+            const uint64_t lo = n * w / nt, hi = n * (w + 1) / nt;
+            s.reserve((hi - lo) * (2 * static_cast<size_t>(R) + 96));
+            for (uint64_t r = lo; r < hi; ++r) {
+              const pcs::SamHeader& h = sb.hdr()[r];
+              if (h.flags & 4u) {  // a CIGAR the record cannot hold would no longer describe SEQ: refuse, never truncate
+                errors[w] = "a read carries more indels than a CIGAR of " + std::to_string(pcs::kMaxCigar) + " operations can describe";
+                return;
+              }
+              append_sam_line(s, h, sb.seq() + r * R, sb.qual() + r * R, tprefix, opt->chr_names[c], opt->sample_names[h.chr_sample >> 16]);
+            }
+          }, nt);
+        for (const auto& e : errors)
+          if (!e.empty()) throw std::domain_error(e);
+        ms_format += now_ms() - t_a;
+        t_a = now_ms();
+        if (writer.joinable()) writer.join();  // batch k-1 is in the file (and its buffers are free for batch k+1)
+        ms_file += now_ms() - t_a;
+        for (const auto& s : text) text_bytes += s.size();
+        writer = std::thread([&out, &text] {
+          for (const auto& s : text) out.write(s.data(), static_cast<std::streamsize>(s.size()));
+        });
+        written += n;
+      }
+      {
+        const double t_a = now_ms();
+        if (writer.joinable()) writer.join();
+        out.flush();
+        ms_file += now_ms() - t_a;
+      }
+      if (!out) throw std::runtime_error("writing \"" + file.string() + "\" failed");
     }
+    CUDA_OK(cudaStreamSynchronize(fo.ctx->stream));
+    if (std::getenv("PCS_TIMING"))
+      std::fprintf(stderr, "[pcs sam] reads %llu text_bytes %llu gpu_materialise_ms %.1f host_format_ms %.1f file_write_ms %.1f\n",
+                   static_cast<unsigned long long>(written), static_cast<unsigned long long>(text_bytes), ms_wait, ms_format, ms_file);
     if (n_written) *n_written = written;
+  });
+}
+
+int pcs_plan_coverage_track(pcs_plan* pl, uint32_t bin_bp, uint64_t* chr_bin_off, uint32_t* track, uint64_t cap_bins,
+                            uint64_t* n_bins_out) {
+  return guarded([&] {
+    require(pl && chr_bin_off && n_bins_out, "bad arguments");
+    require(bin_bp >= 64 && (bin_bp & (bin_bp - 1)) == 0, "the bin size must be a power of two, at least 64");
+    uint32_t shift = 0;
+    while ((1u << shift) < bin_bp) ++shift;
+    pcs_forest& fo = *pl->forest;
+    pcs_ctx& cx = *fo.ctx;
+    const pcs::FlatForest& F = fo.host.flat;
+    std::vector<uint64_t> off(F.n_chr + 1, 0);
+    for (uint32_t c = 0; c < F.n_chr; ++c) off[c + 1] = off[c] + (static_cast<uint64_t>(F.chr_len[c]) >> shift) + 1;
+    const uint64_t n_bins = off[F.n_chr];
+    std::copy(off.begin(), off.end(), chr_bin_off);
+    *n_bins_out = n_bins;
+    if (!track) return;  // sizes only
+    const size_t S = pl->host.info.n_out_samples;
+    require(cap_bins >= n_bins, "track capacity too small");
+    cx.bind();
+    cudaStream_t st = cx.stream;
+    DevBuf<uint64_t> d_off;
+    DevBuf<uint32_t> d_track;
+    d_off.upload(off, st);
+    d_track.alloc(S * n_bins, st);
+    CUDA_OK(cudaMemsetAsync(d_track.p, 0, d_track.bytes(), st));
+    uint32_t max_len = 0;
+    for (const auto* v : {&pl->host.tiles, &pl->host.tiles_global})
+      for (const auto& t : *v) max_len = std::max(max_len, t.len);
+    CUDA_OK(pcs::launch_coverage_track(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
+                                       pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
+    CUDA_OK(pcs::launch_coverage_track(st, pl->d_tiles_global.p, static_cast<uint32_t>(pl->host.tiles_global.size()),
+                                       pl->d_entries.p, pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
+    copy_out(cx, st, {{track, d_track.p, d_track.bytes()}});
   });
 }
 
@@ -2660,7 +2866,10 @@ int pcs_result_fetch(pcs_result* res, uint32_t* rows, int32_t* const* occ_cols, 
     }
     pcs_ctx& cx = *res->forest->ctx;
     cx.bind();
+    const double t0 = now_ms();
     const uint64_t b = copy_out(cx, cx.stream, items);
+    if (std::getenv("PCS_TIMING"))
+      std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms (%.1f MB)\n", "result fetch", now_ms() - t0, b / 1e6);
     if (d2h_bytes) *d2h_bytes = b;
   });
 }

@@ -293,6 +293,10 @@ def synth_forest(spec: SynthSpec) -> PhylogeneticForest:
     hom = rng.random(n_germ) < spec.germline_hom_frac
     het_allele = rng.integers(0, 2, n_germ)
     germ_mask = np.where(n_all[gchr] == 1, 1, np.where(hom, 3, 1 << het_allele)).astype(np.uint8)
+    # listed in row order, one entry per row: what a shim gets when it walks its std::map<SID, ...> mutation table,
+    # and the flattener's fast path (any order is accepted; tests/test_host_logic.py shuffles it)
+    by_row = np.argsort(germ_mut, kind="stable")
+    germ_mut, germ_mask = germ_mut[by_row], germ_mask[by_row]
 
     # ---- event table
     cols = 11

@@ -70,6 +70,9 @@ def main():
         row = {"config": name, "cells": int(f.n_leaves), "rows": int(M), "samples": int(S),
                "reads": int(stats[-1].n_reads), "kernel_ms": round(ms, 3),
                "gbases_per_s": round(stats[-1].n_reads * plan.info.read_size / (ms * 1e-3) / 1e9),
+               # A11 (unpinned): templates dropped because they ran past their fragment's end, i.e. the coverage
+               # deficit of "uniform over the fragment + drop" against "uniform over the valid starts"
+               "a11_dropped_fraction": 1.0 - stats[-1].n_reads / float(stats[-1].n_templates * plan.info.reads_per_template),
                "flatten_upload_s": round(upload_s, 3), "plan_s": round(plan_s, 3),
                "device_MB": int(info["device_bytes"] // 1_000_000), "haplotypes": int(info["n_haplotypes"]),
                "tiles": int(plan.info.n_tiles)}

@@ -139,3 +139,194 @@ def snv_only_spec(seed=5, **kw):
 def cna_dense_spec(seed=9):
     """many short CNAs: most tiles draw from several sampling entries even at purity 1"""
     return snv_only_spec(seed, sample_cells=[6, 9], n_clones=3, clone_cna=12, wgd_clones=1, cna_len=(1500, 15000))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# The general form: SNVs AND indels, both error models, paired reads, regrouped samples (FACS), normal_only.
+#
+# A haplotype fragment [b, e] with its carried SIDs is a sequence of TOKENS: a reference position that is present,
+# or an inserted base.  A SID at p with (ref_len r, alt_len a) is its anchor token (position p, the occurrence),
+# a - 1 inserted tokens, and the next token is position p + r (DESIGN.md section 3, A12/A13).  A read starting at a
+# present reference position x is the R tokens from x's token on (fewer if the fragment ends); it covers the
+# reference positions among them; it carries a SID iff the anchor token is among them, and under an error model
+# the occurrence survives iff none of the SID's tokens the read holds is a sequencing error (A14).  A start inside
+# the stretch a carried deletion removed does not see that deletion (the read begins after its anchor): those few
+# starts are walked one by one.  Expected counts are sums over all starts of (expected reads starting there) x
+# (what such a read adds) -- exhaustive, no sampling, nothing shared with the oracle's walk or the kernels'.
+def _ramp(i, R):
+    return 0.5 + i / (R - 1) if R > 1 else np.ones_like(i, dtype=np.float64)
+
+
+def _base_error(i, R, error_rate, random_quality):
+    """P(read base i is a sequencing error), A14: constant model error_rate; random-quality model
+    E[min(1, error_rate * ramp(i) * LogNormal(-sigma^2/2, sigma))] = error_rate * ramp(i) while the cap is out of reach"""
+    i = np.asarray(i, np.float64)
+    if not random_quality:
+        return np.full(i.shape, float(error_rate))
+    p = error_rate * _ramp(i, R)
+    assert (p < 0.2).all(), "closed form ignores the cap at 1: keep error_rate small"
+    return p
+
+
+def _walk_one(x, R, e_frag, sids, pos_of):
+    """reference positions covered and (row, first offset, tokens held) of the SIDs carried by a read of R bases from
+    reference position x on a fragment ending at e_frag; sids: sorted [(pos, row, ref_len, alt_len)] with pos >= x"""
+    covered, carried = [], []
+    q, rem = x, R
+    for pos, row, rl, al in sids:
+        if pos < q:
+            continue
+        if rem == 0 or pos - q >= rem or pos > e_frag:
+            break
+        covered += list(range(q, pos + 1))
+        rem -= pos - q
+        held = min(al, rem)
+        carried.append((row, R - rem, held))
+        rem -= held
+        q = pos + rl
+    if rem > 0 and q <= e_frag:
+        covered += list(range(q, min(q + rem - 1, e_frag) + 1))
+    return covered, carried
+
+
+def expected_tables_general(f, coverage, purity, R, with_normal=True, insert=None, preneoplastic_in_normal=False,
+                            error_rate=0.0, random_quality=False, leaf_group=None, n_groups=None, normal_only=False):
+    """E[coverage], E[occurrences] of every (output sample, row).  leaf_group / n_groups: the FACS repartition of
+    the sampled cells (default: the forest's samples); normal_only: simulate_normal_seq (one sample, purity ignored)"""
+    mates = 2 if insert else 1
+    ks, pk = insert_law(*insert) if insert else (np.zeros(1, np.int64), np.ones(1))
+    group = np.asarray(f.leaf_sample if leaf_group is None else leaf_group)
+    n_s = f.n_samples if leaf_group is None else n_groups
+    samples = [] if normal_only else [("tumour", s) for s in range(n_s)]
+    if normal_only or with_normal:
+        samples.append(("normal", None))
+    S = len(samples)
+    e_cov = np.zeros((S, f.n_mut))
+    e_occ = np.zeros((S, f.n_mut))
+    germ = {int(m): int(mask) for m, mask in zip(f.germ_mut, f.germ_allele_mask)}
+    pos_of, rl_of, al_of = f.mut_pos.astype(np.int64), f.mut_ref_len.astype(np.int64), f.mut_alt_len.astype(np.int64)
+    n_roots = int((f.node_parent < 0).sum())
+    for c in range(f.n_chr):
+        rows_c = np.flatnonzero(f.mut_chr == c)
+        N = int(np.floor(coverage * int(f.chr_len[c]) / (R * mates) + 0.5))
+        clen = int(f.chr_len[c])
+        cache = {}
+
+        def molecules(kind, cell):
+            if (kind, cell) not in cache:
+                frags, sids = oracle.cell_genome(f, kind, cell, c)
+                som = {}
+                for a, r in sids:
+                    som.setdefault(a, []).append(int(r))
+                out = []
+                for a, o, b, e in frags:
+                    if b == 0:
+                        continue
+                    rows = [r for r in som.get(a, []) if b <= pos_of[r] <= e]
+                    rows += [int(r) for r in rows_c if ((germ.get(int(r), 0) >> o) & 1) and b <= pos_of[r] <= e]
+                    out.append((b, e, sorted(set(rows), key=lambda r: pos_of[r])))
+                cache[(kind, cell)] = out
+            return cache[(kind, cell)]
+
+        def contribution(b, e, rows):
+            """per unit of (reads per start): arrays over rows_c of depth and occurrences from all starts of this molecule"""
+            depth = np.zeros(clen + 2)          # by reference position
+            occ = {}
+            sids = [(int(pos_of[r]), r, int(rl_of[r]), int(al_of[r])) for r in rows]
+            # expected reads per start position x, per unit: first mates and second mates
+            x = np.arange(b, e + 1)
+            s = np.zeros(len(x))
+            for k, pr in zip(ks, pk):
+                tlen = R if not insert else 2 * R + int(k)
+                s += pr * (x <= e - tlen + 1)
+                if insert:
+                    first = x - R - int(k)
+                    s += pr * ((first >= b) & (first <= e - tlen + 1))
+            # tokens of the fragment as a read that started before every SID sees it.  A SID inside the stretch an
+            # earlier carried deletion removed is not part of it (only reads starting inside the stretch meet it)
+            deleted = np.zeros(e - b + 2, bool)  # reference positions a carried deletion removed (index x - b)
+            pieces, anchor, at = [], {}, b
+            for p, r, rl, al in sids:
+                if p < at:
+                    continue
+                pieces.append(np.arange(at, p + 1))
+                anchor[r] = sum(len(q) for q in pieces) - 1
+                if al > 1:
+                    pieces.append(np.full(al - 1, -1))
+                deleted[p - b + 1:min(p + rl, e + 1) - b] = True
+                at = p + rl
+            if at <= e:
+                pieces.append(np.arange(at, e + 1))
+            tok = np.concatenate(pieces) if pieces else np.zeros(0, np.int64)
+            is_ref = tok >= 0
+            idx_of = np.full(e - b + 2, -1)
+            idx_of[tok[is_ref] - b] = np.flatnonzero(is_ref)
+            # starts on present positions: weight per token
+            w_tok = np.zeros(len(tok))
+            on = idx_of[x - b] >= 0
+            w_tok[idx_of[x[on] - b]] = s[on]
+            cum = np.concatenate([[0.0], np.cumsum(w_tok)])
+            t = np.arange(len(tok))
+            reads_over = cum[t + 1] - cum[np.maximum(t - R + 1, 0)]   # reads whose R tokens include token t
+            depth[tok[is_ref]] += reads_over[is_ref]
+            for p, r, rl, al in sids:
+                if r not in anchor:
+                    continue
+                ta = anchor[r]
+                lo = max(ta - R + 1, 0)
+                offs = ta - np.arange(lo, ta + 1)                    # read offset of the anchor for a start at token lo..ta
+                surv = np.ones(len(offs))
+                if error_rate > 0:
+                    for kk in range(al):
+                        held = offs + kk < R
+                        surv *= np.where(held, 1 - _base_error(np.minimum(offs + kk, R - 1), R, error_rate, random_quality), 1.0)
+                occ[r] = occ.get(r, 0.0) + float((w_tok[lo:ta + 1] * surv).sum())
+            # starts inside a deleted stretch: the read does not see that deletion
+            for xx in x[~on]:
+                wgt = s[xx - b]
+                if wgt == 0:
+                    continue
+                covered, carried = _walk_one(int(xx), R, e, [q for q in sids if q[0] >= xx], pos_of)
+                for y in covered:
+                    depth[y] += wgt
+                for r, off0, held in carried:
+                    sv = 1.0
+                    if error_rate > 0:
+                        sv = float(np.prod(1 - _base_error(np.arange(off0, off0 + held), R, error_rate, random_quality)))
+                    occ[r] = occ.get(r, 0.0) + wgt * sv
+            return depth, occ
+
+        for si, (what, s_id) in enumerate(samples):
+            cells = [] if what == "normal" else [l for l in range(f.n_leaves) if group[l] == s_id]
+            p = purity if cells else 0.0
+            mol = []
+            if p > 0:
+                for l in cells:
+                    mol += [(p / len(cells),) + m for m in molecules(A.PCS_PLACE_TUMOUR, l)]
+            if p < 1:
+                if preneoplastic_in_normal:
+                    for r in range(n_roots):
+                        mol += [((1 - p) / n_roots,) + m for m in molecules(A.PCS_PLACE_NORMAL_PRENEO, r)]
+                else:
+                    mol += [((1 - p),) + m for m in molecules(A.PCS_PLACE_NORMAL_PLAIN, 0)]
+            W = sum(w * (e - b + 1) for w, b, e, rows in mol)
+            memo = {}
+            for w, b, e, rows in mol:
+                key = (b, e, tuple(rows))
+                if key not in memo:
+                    memo[key] = contribution(b, e, rows)
+                depth, occ = memo[key]
+                e_cov[si, rows_c] += N / W * w * depth[pos_of[rows_c]]
+                for r, v in occ.items():
+                    e_occ[si, r] += N / W * w * v
+    return e_cov, e_occ
+
+
+def indel_spec(seed=6, **kw):
+    """SNVs and indels, germline and somatic, CNAs and a WGD: the forests the general closed form is for"""
+    from conftest import small_spec
+    d = dict(chr_names=["1", "X"], chr_len=[60_000, 40_000], chr_n_alleles=[2, 1], sample_cells=[5, 6],
+             germline_density=4e-3, germline_indel_frac=0.3, n_preneo_snv=15, n_preneo_indel=15, indel_frac=0.3,
+             node_snv_mean=6, n_clones=2, clone_cna=3, wgd_clones=1, cna_len=(3000, 30000))
+    d.update(kw)
+    return small_spec(seed, **d)

@@ -111,3 +111,31 @@ def test_every_haplotype_gets_its_share_of_the_reads(ctx, purity, preneo, spec):
         k0 = (0 << 48) | (0 << 40) | (A.PCS_PLACE_NORMAL_PLAIN << 36) | 0
         c0, c1 = dict(zip(ks.tolist(), counts.tolist()))[k0], dict(zip(ks.tolist(), counts.tolist()))[k0 | 1]
         assert n0 > 10_000 and abs(c0 / c1 - 1) < 6 / np.sqrt(n0)
+
+
+def _general_cases():
+    from test_oracle_golden import GENERAL_CASES
+    return GENERAL_CASES
+
+
+@pytest.mark.parametrize("seqm,rate,insert,extra", _general_cases())
+def test_sampler_matches_the_general_closed_form(ctx, seqm, rate, insert, extra):
+    """the GPU twin of test_oracle_golden.py::test_oracle_matches_the_general_closed_form: indels, both error
+    models, paired reads, FACS groups, normal_only -- all six sequencer x pairing variants against expectations
+    written down without any sampler"""
+    import closed_form as CF
+    from test_oracle_golden import general_case
+    f, pkw, ckw, leaf_group, n_groups = general_case(seqm, rate, insert, extra)
+    coverage, R, purity = 2000.0, 100, 0.7
+    e_cov, e_occ = CF.expected_tables_general(f, coverage, purity, R, **ckw)
+    dev = L.Forest(ctx, f)
+    if leaf_group is not None:
+        dev.set_groups(leaf_group, n_groups)
+    occ, cov, st = dev.simulate(make_params(coverage=coverage, purity=purity, read_size=R, seed=17, **pkw))
+    dev.close()
+    assert cov.shape == e_cov.shape and st.n_reads > 500_000
+    for obs, exp in ((cov, e_cov), (occ, e_occ)):
+        z, impossible = CF.z_scores(obs, exp)
+        assert impossible == 0
+        assert len(z) > 400 and abs(z.mean()) < 0.12 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.5
+        assert abs(obs.sum() / exp.sum() - 1) < 3e-3

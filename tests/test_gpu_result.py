@@ -110,3 +110,28 @@ def test_api_frame_equals_the_host_construction(ctx):
         ref, alt = f.row_strings(dev_rows := np.flatnonzero(np.isin(f.mut_pos, df["chr_pos"].to_numpy())))
         assert set(df["ref"]) <= set(ref) and (df[[c for c in df.columns if c.endswith(".VAF")]].to_numpy() <= 1).all()
     api.release_device_cache()
+
+
+@pytest.mark.parametrize("insert", [0, 250])
+@pytest.mark.parametrize("bin_bp", [256, 4096])
+def test_coverage_track_describes_the_reads_of_the_plan(ctx, insert, bin_bp):
+    """pcs_plan_coverage_track: the binned depth track is drawn with the Philox counters of the
+    counting kernels, so it must be, bin for bin, the track of the very reads pcs_plan_trace lists"""
+    f = synth_forest(small_spec(6))
+    dev = L.Forest(ctx, f)
+    P = make_params(coverage=40.0, purity=0.8, read_size=150, insert_size_mean=insert, seed=9)
+    plan = L.Plan(dev, P)
+    occ, cov, st = plan.run()
+    off, track = plan.coverage_track(bin_bp)
+    rec, _ = plan.trace(cap=int(st.n_reads) + 8)
+    want = np.zeros(track.shape, np.int64)
+    R = P.read_size
+    for k in range(R):  # one base at a time: trivially right
+        pos = rec["start"].astype(np.int64) + k
+        np.add.at(want, (rec["sample"].astype(np.int64), off[rec["chr"]].astype(np.int64) + pos // bin_bp), 1)
+    assert track.sum() == st.n_reads * R and np.array_equal(track.astype(np.int64), want)
+    # mean depth of the track = the requested coverage, for every sample
+    G = float(f.chr_len.sum())
+    assert np.allclose(track.sum(axis=1) / G, 40.0, rtol=2e-2)
+    plan.close()
+    dev.close()

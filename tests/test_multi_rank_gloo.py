@@ -49,12 +49,12 @@ def _worker(rank, world, port, out_dir):
         owned = torch.zeros_like(ids)
         owned[torch.from_numpy(t_all["id"].astype(np.int64))] = 1
         assert torch.equal(ids, owned)
-        # the ranks' loads differ by less than one tile
+        # the shards are balanced (on the tiles' cost: templates x a locus-density term), so the loads are close
         load = torch.tensor([float(info.n_templates)])
         lo, hi = load.clone(), load.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        assert hi.item() - lo.item() <= float(t_all["templates"].max())
+        assert hi.item() / lo.item() < 1.15
         # seed=None: every rank draws from its OWN RNG state; the call must still plan one job.  The seed is resolved
         # on rank 0 and broadcast, and the shards planned with it partition the tile grid
         np.random.seed(1000 + rank)

@@ -155,3 +155,90 @@ def test_oracle_matches_closed_form_expectations(purity, error_rate, insert, pre
         assert impossible == 0
         assert len(z) > 1500 and abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.0
         assert abs(obs.sum() / exp.sum() - 1) < 2e-3
+
+
+def test_placement_rule_deviation_is_the_dropped_templates_and_nothing_else():
+    """A11 is RACES-internal (unpinned).  The product draws a start uniformly over the fragment and drops a template
+    that runs past its end; SURVEY.md Appendix A first had "uniform over the valid starts".  Both are selectable
+    in the oracle: the difference is a coverage deficit of (template length - 1) / fragment length per fragment,
+    concentrated within one read length of fragment ends (CNA breakpoints), and nothing else."""
+    f = synth_forest(small_spec(2, chr_names=["1"], chr_len=[400_000], chr_n_alleles=[2], sample_cells=[10, 12],
+                                cna_len=(4000, 30000), clone_cna=6))
+    P = make_params(coverage=400.0, purity=1.0, read_size=150, seed=3)
+    try:
+        oracle.set_placement_rule(0)
+        a = oracle.simulate(f, P, n_threads=4)
+        oracle.set_placement_rule(1)
+        b = oracle.simulate(f, P, n_threads=4)
+    finally:
+        oracle.set_placement_rule(0)
+    want_reads = round(400.0 * 400_000 / 150) * 3
+    assert b["n_reads"] == want_reads and a["n_reads"] < want_reads
+    deficit = 1 - a["n_reads"] / b["n_reads"]
+    # every molecule loses (R - 1) of its starts: a few 1e-4 here, ~5e-6 on a WGS-sized genome
+    assert 1e-5 < deficit < 5e-3
+    assert abs(a["cov"].mean() / b["cov"].mean() - 1) < 3 * deficit + 2e-3
+
+
+GENERAL_CASES = [
+    # sequencer, error rate, insert, extra
+    (A.PCS_SEQ_ERRORLESS, 0.0, None, {}),
+    (A.PCS_SEQ_BASIC_CONSTANT, 0.05, None, {}),
+    (A.PCS_SEQ_BASIC_RANDOM, 0.05, None, {}),
+    (A.PCS_SEQ_ERRORLESS, 0.0, (180, 9), {}),
+    (A.PCS_SEQ_BASIC_CONSTANT, 0.05, (180, 9), {}),
+    (A.PCS_SEQ_BASIC_RANDOM, 0.05, (180, 9), {}),
+    (A.PCS_SEQ_BASIC_CONSTANT, 0.05, None, {"groups": True, "preneoplastic_in_normal": 1}),
+    (A.PCS_SEQ_BASIC_RANDOM, 0.05, None, {"normal_only": 1, "preneoplastic_in_normal": 1}),
+]
+
+
+def general_case(seqm, rate, insert, extra):
+    """(forest, params kwargs, closed-form kwargs, leaf_group, n_groups) of one GENERAL_CASES entry"""
+    import closed_form as CF
+    f = synth_forest(CF.indel_spec())
+    extra = dict(extra)
+    leaf_group = n_groups = None
+    if extra.pop("groups", False):  # FACS-like repartition: every sample split in two by cell parity
+        leaf_group = (f.leaf_sample * 2 + np.arange(f.n_leaves) % 2).astype(np.uint32)
+        n_groups = 2 * f.n_samples
+    pkw = dict(sequencer=seqm, error_rate=rate, **extra)
+    ckw = dict(error_rate=rate, random_quality=seqm == A.PCS_SEQ_BASIC_RANDOM, leaf_group=leaf_group, n_groups=n_groups,
+               preneoplastic_in_normal=bool(extra.get("preneoplastic_in_normal", 0)), normal_only=bool(extra.get("normal_only", 0)))
+    if insert:
+        pkw.update(insert_size_mean=insert[0], insert_size_stddev=insert[1])
+        ckw["insert"] = insert
+    if extra.get("normal_only"):
+        pkw["with_normal_sample"] = 0
+    return f, pkw, ckw, leaf_group, n_groups
+
+
+@pytest.mark.parametrize("seqm,rate,insert,extra", GENERAL_CASES)
+def test_oracle_matches_the_general_closed_form(seqm, rate, insert, extra):
+    """SNVs AND indels (A12/A13 frame shifts, SIDs hidden inside a carried deletion), both error models (A14: the
+    occurrence survives iff none of the SID's bases the read holds is an error; random-quality ramp), paired reads,
+    FACS groups, normal_only: the expectations are written down by exhaustive enumeration of the starts on a token
+    model of every haplotype (tests/closed_form.py::expected_tables_general) that shares nothing with the oracle's
+    read walk.  All six sequencer x pairing variants."""
+    import closed_form as CF
+    f, pkw, ckw, leaf_group, n_groups = general_case(seqm, rate, insert, extra)
+    assert ((f.mut_ref_len != 1) | (f.mut_alt_len != 1)).sum() > 100
+    coverage, R, purity = 2000.0, 100, 0.7
+    e_cov, e_occ = CF.expected_tables_general(f, coverage, purity, R, **ckw)
+    r = oracle.simulate(f, make_params(coverage=coverage, purity=purity, read_size=R, seed=11, **pkw),
+                        leaf_group=leaf_group, n_groups=n_groups, n_threads=4)
+    assert r["cov"].shape == e_cov.shape
+    for obs, exp in ((r["cov"], e_cov), (r["occ"], e_occ)):
+        z, impossible = CF.z_scores(obs, exp)
+        assert impossible == 0
+        assert len(z) > 400 and abs(z.mean()) < 0.12 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.0
+        assert abs(obs.sum() / exp.sum() - 1) < 3e-3
+
+
+def test_general_closed_form_reduces_to_the_snv_one():
+    import closed_form as CF
+    f = synth_forest(CF.snv_only_spec())
+    for kw in (dict(), dict(insert=(180, 9)), dict(preneoplastic_in_normal=True)):
+        a = CF.expected_tables(f, 3000.0, 0.7, 100, **kw)
+        b = CF.expected_tables_general(f, 3000.0, 0.7, 100, **kw)
+        assert np.allclose(a[0], b[0], rtol=0, atol=1e-6) and np.allclose(a[1], b[1], rtol=0, atol=1e-6)
