@@ -430,6 +430,12 @@ int pcs_flat_plan(const pcs_flat* flat, const pcs_seq_params* params, pcs_plan_i
                   uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,
                   uint32_t* tile_begin, uint32_t* tile_len);
 
+/* thinning of the plan's tiles (single-end reads; dev.hpp: Tile), in the order of pcs_flat_plan's heaviest-first
+ * list is NOT guaranteed -- match by tile_id: thin (0/1), the number of start offsets from which a read can span
+ * a locus or run past its fragment (u_len), the first offset of the tail zone, and how many of the tile's
+ * templates start at such offsets (n_useful <= templates; == templates when the tile is not thinned) */
+int pcs_flat_plan_thinning(const pcs_flat* flat, const pcs_seq_params* params, uint64_t cap, uint32_t* tile_id,
+                           uint32_t* thin, uint32_t* u_len, uint32_t* tail_off, uint32_t* n_useful);
 /* hap_list[offset, offset + n): the haplotype indices of a sampling list */
 int pcs_flat_hap_list(const pcs_flat* flat, uint32_t offset, uint32_t n, uint32_t* haps);
 /* the sampling entries of one tile of the (single-shard) plan: entry e owns the haplotype draw words

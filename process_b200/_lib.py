@@ -30,7 +30,7 @@ EXPORTS = [
     "pcs_flat_fragset", "pcs_flat_hap_rows", "pcs_flat_plan", "pcs_flat_group_list",
     "pcs_flat_tile_entries", "pcs_flat_draw", "pcs_flat_hap_list",
     "pcs_host_gather", "pcs_host_string_column", "pcs_plan_counters", "pcs_memset_u32_stream",
-    "pcs_forest_upload_genomes", "pcs_flat_create_genomes", "pcs_plan_coverage_track",
+    "pcs_forest_upload_genomes", "pcs_flat_create_genomes", "pcs_plan_coverage_track", "pcs_flat_plan_thinning",
     "pcs_simulate_result", "pcs_plan_result", "pcs_result_info", "pcs_result_fetch", "pcs_result_free",
 ]
 
@@ -167,6 +167,14 @@ class Flat:
         keys = ["id", "templates", "sample", "chr", "begin", "len"]
         return info, {k: a[:n] for k, a in zip(keys, arrs)}
 
+
+    def plan_thinning(self, params: A.SeqParams, cap=1 << 22):
+        """per tile of the plan (keyed by tile id): thin, u_len, tail_off, n_useful (dev.hpp: Tile)"""
+        arrs = [np.zeros(cap, np.uint32) for _ in range(5)]
+        _ok(lib().pcs_flat_plan_thinning(self._h, C.byref(params), C.c_uint64(cap), *[A.ptr(a, C.c_uint32) for a in arrs]))
+        info, _ = self.plan(params, cap=1)
+        n = int(min(cap, info.n_tiles))
+        return {k: a[:n] for k, a in zip(["id", "thin", "u_len", "tail_off", "n_useful"], arrs)}
 
     def hap_list(self, offset, n):
         h = np.zeros(n, np.uint32)

@@ -57,6 +57,7 @@ inline void exact_leaf_scale(uint64_t list_n, uint64_t width, uint32_t& hi, uint
 }
 
 constexpr uint32_t kMaxStagedEntries = 16;  // tiles drawing from more lists use the global kernel
+constexpr uint32_t kMaxThinLoci = 1024;     // a thinned tile keeps one cumulative count per locus in shared memory
 
 // A tile: a stretch of one piece of one chromosome for one output sample.  Every
 // template whose start falls in [begin, begin+len) is drawn by the CTA owning it.
@@ -72,8 +73,43 @@ struct Tile {
   uint32_t l0, l1;   // loci with position in [begin, begin+len+reach): staged range
   uint32_t r0;       // first mutation row of locus l0
   uint32_t n_rows;   // rows of the loci [l0, l1)
+  // Thinning (single-end reads, staged tiles).  A read changes the tables only if it spans a locus, i.e. if its
+  // start offset lies in U = the union over the tile's loci p of [p - R + 1, p] (plus the tail zone: the offsets
+  // from which a read may run past the end of its fragment, tail_off on).  Of the tile's n_templates templates,
+  // n_useful ~ Binomial(n_templates, u_len / len) start in U (drawn by the host: a multinomial split), uniformly
+  // over U; the others are never drawn by the counting kernels -- same law for the tables, a fifth of the work.
+  // thin == 0: the tile is not thinned (every template is drawn, start uniform over the tile).
+  uint32_t n_useful;
+  uint32_t u_len;     // |U|, in offsets
+  uint32_t tail_off;  // first offset of the tail zone (== len: none)
+  uint32_t thin;
 };
-static_assert(sizeof(Tile) == 48, "Tile layout");
+static_assert(sizeof(Tile) == 64, "Tile layout");
+
+// The useful offsets of a thinned tile, from its sorted locus positions.  The tile is cut at `limit`, the last
+// position before the tail zone: below it, locus i adds the offsets of its window [max(p_i - R + 1, begin),
+// min(p_i, limit)] that no earlier locus covered -- gain_i of them, the LAST gain_i of the window; from limit + 1
+// on every offset is useful (the tail zone: one more window after the last locus).  Host (planner: u_len) and
+// device (staging: the cumulative gains the draws are mapped through) use this one rule.
+struct UsefulScan {
+  uint32_t begin, last, limit, R;  // tile begin, last position of the tile, last position before the tail zone, read size
+  uint32_t covered_to;             // every position <= covered_to is in U or before the tile
+  PCS_HD void init(uint32_t tile_begin, uint32_t tile_len, uint32_t tail_off, uint32_t read_size) {
+    begin = tile_begin;
+    last = tile_begin + tile_len - 1u;
+    limit = tile_begin + tail_off - 1u;
+    R = read_size;
+    covered_to = tile_begin - 1u;
+  }
+  PCS_HD uint32_t add_window(uint32_t s, uint32_t e) {
+    if (s <= covered_to) s = covered_to + 1u;
+    if (s > e) return 0u;
+    covered_to = e;
+    return e - s + 1u;
+  }
+  PCS_HD uint32_t add_locus(uint32_t p) { return add_window(p + 1u > R ? p + 1u - R : 0u, p < limit ? p : limit); }
+  PCS_HD uint32_t add_tail() { return add_window(limit + 1u, last); }
+};
 
 struct DevForest {
   const uint32_t* locus_pos;       // [L]

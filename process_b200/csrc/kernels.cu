@@ -247,8 +247,17 @@ struct ErrDefer {
   __device__ __forceinline__ void count(const SharedView& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
                                         uint32_t n) const {
     const uint32_t rel = abs_row ? row - V.r0 : row;
-    uint32_t slot;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(slot) : "r"(count_addr) : "memory");
+    // one slot per carried SID, allocated for all the lanes that are here together with ONE shared atomic (on a
+    // thinned tile nearly every lane carries a SID in the same trip of the walk: thirty-two atomics on one word
+    // would be replayed one after the other)
+    const uint32_t together = __activemask();
+    uint32_t below;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
+    const uint32_t rank = __popc(together & below);
+    uint32_t slot = 0;
+    if (rank == 0)
+      asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(slot) : "r"(count_addr), "r"(__popc(together)) : "memory");
+    slot = __shfl_sync(together, slot, __ffs(together) - 1) + rank;
     if (slot < kCarriedSlots) {
       V.add_alt(rel);
       asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slots + slot * 16u), "r"(read), "r"(rel),
@@ -345,9 +354,20 @@ struct Template {
 };
 
 template <class EntryPtr>
+__device__ __forceinline__ bool place_at(const Tile& T, EntryPtr ent, const uint32_t* ent_lo, const DevForest& F,
+                                         uint32_t off, uint32_t u_hap, uint32_t tlen, Template& out);
+
+template <class EntryPtr>
 __device__ __forceinline__ bool place(const Tile& T, EntryPtr ent, const uint32_t* ent_lo, const DevForest& F,
                                       uint32_t u_start, uint32_t u_hap, uint32_t tlen, Template& out) {
-  out.x = T.begin + __umulhi(u_start, T.len);
+  return place_at(T, ent, ent_lo, F, __umulhi(u_start, T.len), u_hap, tlen, out);
+}
+
+// the template that starts at tile offset `off`: haplotype from its draw word, fragment end, does it fit
+template <class EntryPtr>
+__device__ __forceinline__ bool place_at(const Tile& T, EntryPtr ent, const uint32_t* ent_lo, const DevForest& F,
+                                         uint32_t off, uint32_t u_hap, uint32_t tlen, Template& out) {
+  out.x = T.begin + off;
   uint32_t e = 0, base = 0;
   while (u_hap > ent[e].thr) {  // the last entry's thr is 0xffffffff
     base = ent[e].thr + 1u;
@@ -392,6 +412,137 @@ __device__ __forceinline__ void block_sub_u64(unsigned long long total, uint32_t
     if (total > m) atomicAdd(dst, total - m);
   }
 }
+
+// ------------------------------------------------------------ thinned tiles
+// The useful offsets of a thinned tile (dev.hpp: Tile, UsefulScan), as the device sees them: cum[i] = offsets of
+// U contributed by the loci 0..i; cum[n] adds the tail zone, so cum[n] == T.u_len.  A gain depends on nothing but
+// the previous locus' position, so the gains are computed in parallel and scanned.
+// pos(i): position of the tile's i-th locus.  Block-wide (any block size that is a multiple of 32, <= 1024);
+// ends with __syncthreads().
+template <class PosFn>
+__device__ void build_useful_cum(const Tile& T, uint32_t R, uint32_t n_u, PosFn pos, uint32_t* cum) {
+  __shared__ uint32_t s_w[32];
+  __shared__ uint32_t s_carry;
+  const uint32_t begin = T.begin, last = T.begin + T.len - 1u, limit = T.begin + T.tail_off - 1u;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t i0 = 0; i0 <= n_u; i0 += blockDim.x) {
+    const uint32_t i = i0 + threadIdx.x;
+    uint32_t g = 0;
+    if (i <= n_u) {
+      const uint32_t prev_e = i ? min(pos(i - 1u), limit) : begin - 1u;
+      uint32_t s_, e_;
+      if (i < n_u) {
+        const uint32_t p = pos(i);
+        s_ = p + 1u > R ? p + 1u - R : 0u;
+        e_ = min(p, limit);
+      } else {
+        s_ = limit + 1u;
+        e_ = last;
+      }
+      s_ = max(s_, prev_e + 1u);
+      g = s_ <= e_ ? e_ - s_ + 1u : 0u;
+    }
+    uint32_t x = g;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= static_cast<uint32_t>(o)) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < n_warps ? s_w[lane] : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= static_cast<uint32_t>(o)) w += y;
+      }
+      s_w[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t incl = s_carry + (warp ? s_w[warp - 1] : 0u) + x;
+    if (i <= n_u) cum[i] = incl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1u) s_carry = incl;
+    __syncthreads();
+  }
+}
+
+// the i-th window's end, and the offset a useful-draw t (< T.u_len) maps to once i = the window it falls in
+// (smallest i with cum[i] > t): the new offsets of window i are its LAST cum[i] - cum[i-1] positions
+__device__ __forceinline__ uint32_t useful_position(uint32_t t, uint32_t cum_i, uint32_t window_end) {
+  return window_end - (cum_i - 1u - t);
+}
+
+// Enumeration of a tile's reads for the kernels that need ALL of them (trace, SAM records, coverage tracks), from
+// global memory.  Thinned tile: read r < n_useful is the sampler's read r -- Philox block r / 2 of purpose 0, start
+// drawn over U; read r >= n_useful is one of the templates the sampler never draws: block (r - n_useful) / 2 of
+// purpose 2, start drawn over the offsets NOT in U (it spans no locus and cannot fall off its fragment).  A tile
+// that is not thinned: block r / 2 of purpose 0, start uniform over the tile.
+struct TileReads {
+  const uint32_t* pos;  // locus positions of the tile (global)
+  const uint32_t* cum;  // shared: cumulative useful offsets, n_u + 1 entries (thinned tiles)
+  uint32_t n_u, begin, last, limit, len, u_len, n_useful, thin, tile_id, seed;
+  template <class CumBuf>
+  __device__ void init(const Tile& T, const DevForest& F, const SeqModel& M, CumBuf* cum_buf) {
+    pos = F.locus_pos + T.l0;
+    cum = cum_buf;
+    begin = T.begin;
+    len = T.len;
+    last = T.begin + T.len - 1u;
+    limit = T.begin + T.tail_off - 1u;
+    u_len = T.u_len;
+    n_useful = T.n_useful;
+    thin = T.thin && !M.paired;
+    tile_id = T.id;
+    seed = M.seed;
+    n_u = 0;
+    if (thin) {  // block-wide
+      n_u = T.l1 - T.l0;
+      const uint32_t* p = pos;
+      build_useful_cum(T, M.read_size, n_u, [p](uint32_t i) { return __ldg(p + i); }, cum_buf);
+    }
+  }
+  __device__ __forceinline__ uint32_t window_end(uint32_t i) const { return i < n_u ? min(__ldg(pos + i), limit) : last; }
+  // single-end read r of the tile: start offset, haplotype draw; first: index of the first locus the read spans
+  // (n_u: none)
+  __device__ void read(uint32_t r, uint32_t& off, uint32_t& u_hap, uint32_t& first) const {
+    if (!thin) {
+      const uint4 u = philox4x32_10(make_uint4(r >> 1, tile_id, 0u, seed));
+      off = __umulhi((r & 1u) ? u.z : u.x, len);
+      u_hap = (r & 1u) ? u.w : u.y;
+      first = 0xffffffffu;  // unknown: search
+      return;
+    }
+    const bool useful = r < n_useful;
+    const uint32_t q = useful ? r : r - n_useful;
+    const uint4 u = philox4x32_10(make_uint4(q >> 1, tile_id, useful ? 0u : 2u, seed));
+    const uint32_t us = (q & 1u) ? u.z : u.x;
+    u_hap = (q & 1u) ? u.w : u.y;
+    if (useful) {
+      const uint32_t t = __umulhi(us, u_len);
+      uint32_t lo = 0, hi = n_u;  // smallest i with cum[i] > t
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (cum[mid] > t) hi = mid; else lo = mid + 1u;
+      }
+      off = useful_position(t, cum[lo], window_end(lo)) - begin;
+      first = lo;
+    } else {
+      // the t-th offset outside U: outside[i] = offsets of the tile up to window i's end that are not in U
+      const uint32_t t = __umulhi(us, len - u_len);
+      uint32_t lo = 0, hi = n_u;  // smallest i with outside[i] > t
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (window_end(mid) - begin + 1u - cum[mid] > t) hi = mid; else lo = mid + 1u;
+      }
+      const uint32_t prev_e = lo ? window_end(lo - 1u) : begin - 1u;
+      const uint32_t prev_out = lo ? prev_e - begin + 1u - cum[lo - 1u] : 0u;
+      off = prev_e + 1u + (t - prev_out) - begin;
+      first = n_u;
+    }
+  }
+};
 
 // ---------------------------------------------------- staged sampler kernel
 constexpr int kStagedThreads = 256;
@@ -589,15 +740,38 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     s_safe = lim <= 0 ? 0u : (lim >= static_cast<long long>(T.len) ? T.len : static_cast<uint32_t>(lim));
   }
   __syncthreads();
-  // directory: first staged locus at or after the start of each bucket
-  for (uint32_t b = threadIdx.x; b < n_buckets; b += kStagedThreads) {
-    const uint32_t x = T.begin + (b << shift);
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-      uint32_t mid = (lo + hi) >> 1;
-      if (s_rec[mid].x < x) lo = mid + 1; else hi = mid;
+  const bool thin = !PAIRED && T.thin != 0u;  // the same for the whole CTA
+  uint32_t* s_cum = reinterpret_cast<uint32_t*>(s_queue);    // thinned tile: cumulative useful offsets [n_u + 1]
+  uint16_t* s_slot = reinterpret_cast<uint16_t*>(s_dir);     //               window of every 64th useful offset
+  uint32_t n_u = 0;
+  if (!thin) {
+    // directory: first staged locus at or after the start of each bucket
+    for (uint32_t b = threadIdx.x; b < n_buckets; b += kStagedThreads) {
+      const uint32_t x = T.begin + (b << shift);
+      uint32_t lo = 0, hi = n;
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (s_rec[mid].x < x) lo = mid + 1; else hi = mid;
+      }
+      s_dir[b] = make_uint2(lo, s_rec[lo].x - T.begin);  // s_rec[n] is the sentinel at 0xffffffff; offsets from T.begin
     }
-    s_dir[b] = make_uint2(lo, s_rec[lo].x - T.begin);  // s_rec[n] is the sentinel at 0xffffffff; offsets from T.begin
+  } else {
+    // the useful offsets (dev.hpp: Tile): cumulative gains of the loci's windows, and for every 64th useful offset
+    // the window it falls in -- a draw finds its window with one load and, one time in three, one step
+    n_u = n;
+    build_useful_cum(T, M.read_size, n_u, [s_rec](uint32_t i) { return s_rec[i].x; }, s_cum);
+    const uint32_t n_slots = (T.u_len >> 6) + 1u;
+    for (uint32_t b = threadIdx.x; b < n_slots; b += kStagedThreads) {
+      const uint32_t t = b << 6;
+      uint32_t lo = 0, hi = n_u;  // smallest i with cum[i] > t (cum[n_u] = u_len > t for every slot but a last empty one)
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_cum[mid] > t) hi = mid; else lo = mid + 1u;
+      }
+      s_slot[b] = static_cast<uint16_t>(lo);
+    }
+    // the planner drew n_useful with ITS count of the useful offsets: the two must be one number
+    if (threadIdx.x == 0 && s_cum[n_u] != T.u_len) asm volatile("trap;");
   }
   __syncthreads();
 
@@ -646,6 +820,50 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     }
   };
 
+  if (thin) {
+    // Thinned tile: only the templates whose read can span a locus are drawn -- T.n_useful of them, start uniform
+    // over the useful offsets.  Every one of them is walked (no probe, no queue): the draw lands in the new part
+    // of window i, so locus i is the first the read spans; a draw in the tail zone (the last read length of a
+    // fragment) is tested for falling off its fragment and looks its first locus up.
+    const uint32_t cum_a = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_cum)));
+    const uint32_t slot_a = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_slot)));
+    const uint32_t u_len = T.u_len, n_useful = T.n_useful, last = T.begin + T.len - 1u, limit = T.begin + T.tail_off - 1u;
+    const uint32_t n_blocks = (n_useful + 1u) >> 1;
+    for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
+      const uint32_t j = j0 + lane;
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+#pragma unroll
+      for (uint32_t k = 0; k < 2u; ++k) {
+        const uint32_t t = __umulhi(k ? u.z : u.x, u_len), u_hap = k ? u.w : u.y;
+        if (2u * j + k < n_useful) {
+          uint32_t i;
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(i) : "r"(slot_a + (t >> 6) * 2u));
+          uint32_t c = lds32(cum_a + i * 4u);
+          while (c <= t) {
+            ++i;
+            c = lds32(cum_a + i * 4u);
+          }
+          const uint32_t we = i < n_u ? min(lds32(S.SV.rec + i * 16u), limit) : last;
+          const uint32_t xs = useful_position(t, c, we), off = xs - T.begin;
+          if (off >= safe && !fits(u_hap, off, R)) {
+            ++dropped;
+          } else {
+            if (i == n_u) {  // a draw in the tail zone: the first locus at or after the read's start, if any
+              uint32_t lo = 0, hi = n;
+              while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (lds32(S.SV.rec + mid * 16u) < xs) lo = mid + 1u; else hi = mid;
+              }
+              i = lo;
+            }
+            staged_read<ERRORS>(S, T, F, M, depth, alt, make_uint4(off, u_hap, 2u * j + k, i));
+          }
+        }
+      }
+      flush_carried(false);
+    }
+    flush_carried(true);
+  } else {
   // Philox block j: two single-end templates (2j, 2j+1) or one paired template (mates 2j, 2j+1)
   const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
   const uint32_t n_second = PAIRED ? T.n_templates : T.n_templates >> 1;  // blocks whose second read exists
@@ -684,6 +902,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   __syncwarp();
   if (lane < (Q.tail - Q.base) / 16u) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
   flush_carried(true);
+  }
   __syncthreads();
 
   // ---- flush: one reduction per touched counter, coalesced over consecutive loci / rows
@@ -757,17 +976,16 @@ sample_tiles_global_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       placed += 2;
     }
   } else {
-    const uint32_t n_blocks = (T.n_templates + 1u) >> 1;
-    for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
-      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+    // every read of the tile, the ones a thinned tile's sampler never draws included (TileReads)
+    __shared__ uint32_t s_cum[kMaxThinLoci + 2];
+    TileReads TR;
+    TR.init(T, F, M, s_cum);
+    for (uint32_t r = threadIdx.x; r < T.n_templates; r += blockDim.x) {
+      uint32_t off, u_hap, first;
+      TR.read(r, off, u_hap, first);
       Template tp;
-      if (place(T, ent, ent_lo, F, u.x, u.y, R, tp)) {
-        global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
-        ++placed;
-      }
-      if (2u * j + 1u < T.n_templates && place(T, ent, ent_lo, F, u.z, u.w, R, tp)) {
-        global_read<TRACE>(T, F, M, GV, chr_l1, 2u * j + 1u, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap,
-                           trace_n);
+      if (place_at(T, ent, ent_lo, F, off, u_hap, R, tp)) {
+        global_read<TRACE>(T, F, M, GV, chr_l1, r, tp.x, tp.h, tp.frag_end, trace, trace_masks, trace_cap, trace_n);
         ++placed;
       }
     }
@@ -902,10 +1120,15 @@ materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict
   const uint32_t R = M.read_size;
   const Entry* ent = entries + T.entry_off;
   const uint32_t* ent_lo = entry_lo + T.entry_off;
-  const uint32_t n_blocks = M.paired ? T.n_templates : (T.n_templates + 1u) >> 1;
-  for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
-    const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
-    for (uint32_t k = 0; k < 2u; ++k) {
+  __shared__ uint32_t s_cum[kMaxThinLoci + 2];
+  TileReads TR;
+  TR.init(T, F, M, s_cum);  // single-end: every read of the tile, thinned or not
+  // paired: Philox block j is template j (mates 2j, 2j+1); single-end: one read per trip
+  const uint32_t n_trips = T.n_templates;
+  for (uint32_t j = threadIdx.x; j < n_trips; j += blockDim.x) {
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (M.paired) u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+    for (uint32_t k = 0; k < (M.paired ? 2u : 1u); ++k) {
       Template tp;
       uint32_t ins = 0, xs, mate_start = 0;
       int32_t tlen = 0;
@@ -916,15 +1139,16 @@ materialize_tiles_kernel(const Tile* __restrict__ tiles, const Entry* __restrict
         mate_start = tp.x + (1u - k) * (R + ins);
         tlen = static_cast<int32_t>(2u * R + ins) * (k == 0 ? 1 : -1);
       } else {
-        if (2u * j + k >= T.n_templates) break;
-        if (!place(T, ent, ent_lo, F, k ? u.z : u.x, k ? u.w : u.y, R, tp)) continue;
+        uint32_t off, u_hap, first;
+        TR.read(j, off, u_hap, first);
+        if (!place_at(T, ent, ent_lo, F, off, u_hap, R, tp)) continue;
         xs = tp.x;
       }
       const unsigned long long idx = atomicAdd(n_out, 1ull);
       if (idx >= cap) continue;
       SamHeader H{};
       H.hap = tp.h; H.start = xs; H.frag_end = tp.frag_end; H.chr_sample = T.chr | (T.sample << 16);
-      H.read_id = 2u * j + k; H.tile_id = T.id; H.flags = (M.paired ? 1u : 0u) | (M.paired && k ? 2u : 0u);
+      H.read_id = M.paired ? 2u * j + k : j; H.tile_id = T.id; H.flags = (M.paired ? 1u : 0u) | (M.paired && k ? 2u : 0u);
       H.mate_start = mate_start; H.tlen = tlen;
       uint32_t* mask = masks ? masks + idx * PCS_ERRMASK_WORDS : nullptr;  // the SAM writer does not need them
       if (mask)
@@ -1139,8 +1363,9 @@ cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const ui
 // bin.  About a third of the sampler's work, and only when a track is asked for.
 template <bool PAIRED>
 __global__ void __launch_bounds__(256)
-coverage_track_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, SeqModel M, uint32_t bin_shift,
-                      const uint64_t* __restrict__ chr_bin_off, uint64_t n_bins, uint32_t* __restrict__ track) {
+coverage_track_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ entries, DevForest F, SeqModel M,
+                      uint32_t bin_shift, const uint64_t* __restrict__ chr_bin_off, uint64_t n_bins,
+                      uint32_t* __restrict__ track) {
   extern __shared__ uint32_t s_bins[];
   const Tile T = tiles[blockIdx.x];
   const uint32_t R = M.read_size;
@@ -1173,18 +1398,20 @@ coverage_track_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ 
       left -= n;
     }
   };
-  const uint32_t n_blocks = PAIRED ? T.n_templates : (T.n_templates + 1u) >> 1;
-  for (uint32_t j = threadIdx.x; j < n_blocks; j += blockDim.x) {
-    const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+  __shared__ uint32_t s_cum[kMaxThinLoci + 2];
+  TileReads TR;
+  if (!PAIRED) TR.init(T, F, M, s_cum);  // single-end: every read of the tile, thinned or not
+  for (uint32_t j = threadIdx.x; j < T.n_templates; j += blockDim.x) {
     if (PAIRED) {
+      const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
       const uint32_t off = __umulhi(u.x, T.len), off2 = off + R + draw_insert(M, u.z);
       if (off >= safe && !fits(u.y, off, off2 - off + R)) continue;
       add(off);
       add(off2);
     } else {
-      const uint32_t off0 = __umulhi(u.x, T.len), off1 = __umulhi(u.z, T.len);
-      if (off0 < safe || fits(u.y, off0, R)) add(off0);
-      if (2u * j + 1u < T.n_templates && (off1 < safe || fits(u.w, off1, R))) add(off1);
+      uint32_t off, u_hap, first;
+      TR.read(j, off, u_hap, first);
+      if (off < safe || fits(u_hap, off, R)) add(off);
     }
   }
   __syncthreads();
@@ -1197,7 +1424,7 @@ coverage_track_kernel(const Tile* __restrict__ tiles, const Entry* __restrict__ 
 }
 
 cudaError_t launch_coverage_track(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                  const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,
+                                  const DevForest& F, const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,
                                   const uint64_t* chr_bin_off, uint64_t n_bins, uint32_t* track) {
   if (n_tiles == 0) return cudaSuccess;
   const size_t smem = (((static_cast<size_t>(max_tile_len) + M.reach) >> bin_shift) + 2) * sizeof(uint32_t);
@@ -1205,7 +1432,7 @@ cudaError_t launch_coverage_track(cudaStream_t st, const Tile* tiles, uint32_t n
   auto kern = M.paired ? coverage_track_kernel<true> : coverage_track_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
-  kern<<<n_tiles, 256, smem, st>>>(tiles, entries, M, bin_shift, chr_bin_off, n_bins, track);
+  kern<<<n_tiles, 256, smem, st>>>(tiles, entries, F, M, bin_shift, chr_bin_off, n_bins, track);
   return cudaGetLastError();
 }
 
@@ -1222,13 +1449,15 @@ size_t staged_smem_bytes(const StageDims& D, bool errors) {
 
 // CTAs per SM the kernel is compiled for: PCS_MIN_CTAS overrides.  The error-model variants need ~78
 // registers uncapped; capping them at 64 (4 CTAs) spills a little and still wins on occupancy.
-static int staged_min_ctas(bool errors) {
+static int staged_min_ctas(bool errors, bool paired) {
   static const int v = [] {
     const char* s = std::getenv("PCS_MIN_CTAS");
     const int x = s ? std::atoi(s) : 0;
     return (x >= 3 && x <= 8) ? x : 0;
   }();
-  return v ? v : (errors ? 4 : kDefaultMinCtas);
+  // measured on C3 (profiles/r02_*): errorless single-end (thinned tiles) 8.85 / 8.85 / 8.68 / 9.11 ms at 3 / 4 / 5 / 6;
+  // the unthinned loop (paired reads) is fastest at 3
+  return v ? v : (errors ? 4 : (paired ? kDefaultMinCtas : 5));
 }
 
 template <bool PAIRED, bool ERRORS, int MIN_CTAS>
@@ -1247,7 +1476,7 @@ template <bool PAIRED, bool ERRORS>
 static cudaError_t launch_staged(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                  const uint32_t* entry_lo, const DevForest& F, const SeqModel& M, const StageDims& D, uint32_t* depth,
                                  uint32_t* alt, unsigned long long* n_reads) {
-  switch (staged_min_ctas(ERRORS)) {
+  switch (staged_min_ctas(ERRORS, PAIRED)) {
     case 3: return launch_staged_occ<PAIRED, ERRORS, 3>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
     case 5: return launch_staged_occ<PAIRED, ERRORS, 5>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);
     case 6: return launch_staged_occ<PAIRED, ERRORS, 6>(st, tiles, n_tiles, entries, entry_lo, F, M, D, depth, alt, n_reads);

@@ -40,7 +40,7 @@ cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const ui
                                   double* vaf_c);
 // binned depth track of the plan's reads: track[s][chr_bin_off[chr] + (pos >> bin_shift)] += bases
 cudaError_t launch_coverage_track(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
-                                  const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,
+                                  const DevForest& F, const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,
                                   const uint64_t* chr_bin_off, uint64_t n_bins, uint32_t* track);
 cudaError_t launch_sum_u32(cudaStream_t st, const uint32_t* v, size_t n, unsigned long long* out);
 

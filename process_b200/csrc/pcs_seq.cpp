@@ -721,6 +721,7 @@ struct PlanSetup {
   uint32_t R = 0, mates = 1, kmin = 0, kmax = 0, W = 0, lcap = 0, shards = 1, normal_group = 0, dir_shift = 5;
   uint64_t reach = 0;
   bool paired = false;
+  bool thin = false;  // single-end reads: staged tiles draw only the templates that can span a locus (dev.hpp: Tile)
   std::vector<uint32_t> insert_alias;
   struct ChrGrid {
     std::vector<pcs::Tile> tiles;         // chr, begin, len, l0, l1, r0, n_rows
@@ -755,6 +756,10 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
     if (ps.sequenced(c)) sequenced_bp += F.chr_len[c];
   ps.W = tile_bp(sequenced_bp * ps.samples.size());
   ps.lcap = stage_loci_cap();
+  {
+    const char* e = std::getenv("PCS_THIN");  // PCS_THIN=0: draw every template (the round-1 sampler), for A/B runs
+    ps.thin = !ps.paired && ps.lcap > 0 && !(e && std::string(e) == "0");
+  }
   ps.shards = P.shard_count ? P.shard_count : 1;
   while ((((static_cast<uint64_t>(ps.W) + ps.reach) >> ps.dir_shift) + 1) > 4096) ++ps.dir_shift;
 
@@ -786,6 +791,20 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
         t.len = static_cast<uint32_t>(len);
         t.r0 = F.locus_first_row[t.l0];
         t.n_rows = F.locus_first_row[t.l1] - t.r0;
+        t.tail_off = t.len;
+        if (ps.thin && t.l1 - t.l0 <= std::min(ps.lcap, pcs::kMaxThinLoci) && t.n_rows <= 2 * ps.lcap) {
+          // the offsets from which a read can span a locus, plus those from which it may run past the piece's end
+          const uint64_t first_unsafe = static_cast<uint64_t>(pc.end) + 2 > static_cast<uint64_t>(ps.R) + b
+                                            ? static_cast<uint64_t>(pc.end) + 2 - ps.R - b : 0;
+          t.tail_off = static_cast<uint32_t>(std::min<uint64_t>(first_unsafe, len));
+          pcs::UsefulScan us;
+          us.init(t.begin, t.len, t.tail_off, ps.R);
+          uint64_t u = 0;
+          for (uint32_t l = t.l0; l < t.l1; ++l) u += us.add_locus(lp[l]);
+          u += us.add_tail();
+          t.u_len = static_cast<uint32_t>(u);
+          t.thin = 1;
+        }
         g.tiles.push_back(t);
         b += len;
       }
@@ -829,7 +848,10 @@ void plan_block_templates(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChr
     const double p = (i + 1 == i1) ? 1.0 : std::min(1.0, std::max(0.0, task.tile_w[i] / wleft));
     const uint64_t k = draw_binomial(rng, left, p);
     require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
-    task.tiles[i].n_templates = static_cast<uint32_t>(k);
+    pcs::Tile& t = task.tiles[i];
+    t.n_templates = static_cast<uint32_t>(k);
+    // of these, the templates whose read can span a locus: the start is uniform over the tile's offsets
+    t.n_useful = t.thin ? static_cast<uint32_t>(draw_binomial(rng, k, static_cast<double>(t.u_len) / t.len)) : t.n_templates;
     left -= k;
     wleft -= task.tile_w[i];
   }
@@ -908,6 +930,7 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
       t.entry_off = entry_off;
       t.n_entries = n_kept;
       t.sample = s;
+      if (n_kept > pcs::kMaxStagedEntries) t.thin = 0;  // goes to the global-memory kernel: drawn in full
       all.push_back(t);
       tile_w.push_back(wsum * t.len);
     }
@@ -974,6 +997,7 @@ uint64_t tile_cost(const pcs::Tile& t, const PlanSetup& ps) {
     return e && std::string(e) == "templates";
   }();
   if (by_templates) return t.n_templates;
+  if (t.thin) return static_cast<uint64_t>(t.n_useful) * 130u + 2000u;  // every drawn read reaches a locus
   const double span = static_cast<double>(t.len) + static_cast<double>(ps.reach);
   const double hit = std::min(1.0, static_cast<double>(t.l1 - t.l0) * ps.R * ps.mates / span / ps.mates);
   return static_cast<uint64_t>(static_cast<double>(t.n_templates) * ps.mates * (35.0 + 160.0 * hit));
@@ -1046,6 +1070,8 @@ std::vector<HostPlan> make_host_plans(const PlanSetup& ps, uint32_t s0, uint32_t
       dst.dims.max_loci = std::max(dst.dims.max_loci, t.l1 - t.l0);
       dst.dims.max_rows = std::max(dst.dims.max_rows, t.n_rows);
       dst.dims.max_buckets = std::max<uint32_t>(dst.dims.max_buckets, static_cast<uint32_t>(((t.len + reach) >> dir_shift) + 1));
+      // a thinned tile keeps a 2-byte slot per 64 useful offsets where the others keep their 8-byte buckets
+      if (t.thin) dst.dims.max_buckets = std::max<uint32_t>(dst.dims.max_buckets, (t.u_len >> 8) + 2);
     } else {
       dst.tiles_global.push_back(t);
     }
@@ -2613,9 +2639,9 @@ int pcs_plan_coverage_track(pcs_plan* pl, uint32_t bin_bp, uint64_t* chr_bin_off
     for (const auto* v : {&pl->host.tiles, &pl->host.tiles_global})
       for (const auto& t : *v) max_len = std::max(max_len, t.len);
     CUDA_OK(pcs::launch_coverage_track(st, pl->d_tiles.p, static_cast<uint32_t>(pl->host.tiles.size()), pl->d_entries.p,
-                                       pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
+                                       fo.dev(), pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
     CUDA_OK(pcs::launch_coverage_track(st, pl->d_tiles_global.p, static_cast<uint32_t>(pl->host.tiles_global.size()),
-                                       pl->d_entries.p, pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
+                                       pl->d_entries.p, fo.dev(), pl->host.model, shift, max_len, d_off.p, n_bins, d_track.p));
     copy_out(cx, st, {{track, d_track.p, d_track.bytes()}});
   });
 }
@@ -3116,6 +3142,26 @@ int pcs_flat_plan(const pcs_flat* fl, const pcs_seq_params* params, pcs_plan_inf
   });
 }
 
+
+int pcs_flat_plan_thinning(const pcs_flat* fl, const pcs_seq_params* params, uint64_t cap, uint32_t* tile_id,
+                           uint32_t* thin, uint32_t* u_len, uint32_t* tail_off, uint32_t* n_useful) {
+  return guarded([&] {
+    require(fl && params, "bad arguments");
+    validate(*params);
+    const HostPlan pl = make_host_plan(fl->host, *params);
+    size_t i = 0;
+    for (const auto* v : {&pl.tiles, &pl.tiles_global})
+      for (const pcs::Tile& t : *v) {
+        if (i >= cap) return;
+        if (tile_id) tile_id[i] = t.id;
+        if (thin) thin[i] = t.thin;
+        if (u_len) u_len[i] = t.u_len;
+        if (tail_off) tail_off[i] = t.tail_off;
+        if (n_useful) n_useful[i] = t.n_useful;
+        ++i;
+      }
+  });
+}
 
 int pcs_flat_hap_list(const pcs_flat* fl, uint32_t offset, uint32_t n, uint32_t* haps) {
   return guarded([&] {

@@ -386,3 +386,40 @@ def test_flat_view_and_plan_do_not_depend_on_the_number_of_host_threads():
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout.strip())
     assert int(outs[0].split()[0]) > 130_000 and outs[0] == outs[1] == outs[2], outs
+
+
+def test_thinned_tiles_count_the_useful_offsets_exactly():
+    """Single-end reads, staged tiles: the sampler draws only the templates whose read can span a locus (or run past
+    its fragment).  The planner's count of such start offsets (Tile.u_len: the device recomputes it and traps on a
+    mismatch) against a brute-force union of the loci's windows; n_useful ~ Binomial(templates, u_len / len)."""
+    f = synth_forest(small_spec(3))
+    fl = L.Flat(f)
+    for R in (150, 37, 1):
+        P = make_params(coverage=40.0, purity=0.8, read_size=R)
+        info, t = fl.plan(P)
+        th = fl.plan_thinning(P)
+        by_id = {int(i): k for k, i in enumerate(t["id"])}
+        assert set(by_id) == {int(i) for i in th["id"]} and th["thin"].sum() > 0.9 * len(th["id"])
+        z = []
+        for k in range(len(th["id"])):
+            q = by_id[int(th["id"][k])]
+            begin, ln, c, n_t = int(t["begin"][q]), int(t["len"][q]), int(t["chr"][q]), int(t["templates"][q])
+            if not th["thin"][k]:
+                assert th["n_useful"][k] == n_t
+                continue
+            pos = f.mut_pos[f.mut_chr == c].astype(np.int64)
+            useful = np.zeros(ln, bool)
+            for p in np.unique(pos[(pos >= begin) & (pos <= begin + ln + R - 2)]):
+                lo, hi = max(p - R + 1, begin), min(p, begin + ln - 1)
+                useful[lo - begin:hi - begin + 1] = True
+            useful[int(th["tail_off"][k]):] = True  # the tail zone: a read from there may run past its fragment
+            assert int(th["u_len"][k]) == int(useful.sum()), (R, k)
+            assert th["n_useful"][k] <= n_t
+            if n_t > 200 and 0 < useful.sum() < ln:
+                pr = useful.sum() / ln
+                z.append((th["n_useful"][k] - n_t * pr) / np.sqrt(n_t * pr * (1 - pr)))
+        z = np.asarray(z)
+        assert len(z) > 30 and abs(z.mean()) < 0.5 and 0.7 < z.std() < 1.3
+    # paired reads and PCS_THIN=0 draw every template
+    th = fl.plan_thinning(make_params(coverage=40.0, insert_size_mean=300))
+    assert th["thin"].sum() == 0
