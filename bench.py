@@ -349,15 +349,19 @@ def main():
             b = step_no[0] & 1
             step_no[0] += 1
             plan.accumulate(ring[b], ring[b] + 4 * S * Lc, wait=False)
+            if rank == 0:
+                # the side stream's work of the step before (below) is complete before rank 0 joins this step's
+                # collective -- and no rank's next sampler, which adds into the table set zeroed there, starts
+                # before the collective is through
+                stream.wait_stream(side)
             # every rank's flush has landed in rank 0's tables once this (on-stream) collective is through
             dist.all_reduce(token)
             if rank == 0:
-                plan.finalize(ring[b], ring[b] + 4 * S * Lc, cov.data_ptr(), wait=False)
-                # zero this table set for the step after next on a side stream, behind the finalize; the next
-                # step's collective (which every rank's step after that waits for) is ordered behind it
+                # coverage gather of this step and zeroing of its table set for the step after next: on a side
+                # stream, beside the next step's sampler instead of in front of it
                 side.wait_stream(stream)
+                plan.finalize_on(ring[b], cov.data_ptr(), side.cuda_stream)
                 ctx.memset_u32(ring[b], words, stream=side.cuda_stream)
-                stream.wait_stream(side)
             return
         plan.run_device(occ.data_ptr(), cov.data_ptr(), checksums=False, wait=False)
         if world > 1:  # 'nccl': sum the per-sample count tables on rank 0

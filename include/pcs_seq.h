@@ -301,6 +301,9 @@ int pcs_plan_accumulate(pcs_plan* plan, uint32_t* depth, uint32_t* occurrences, 
  * asynchronous, no checksums */
 int pcs_plan_finalize(pcs_plan* plan, const uint32_t* depth, const uint32_t* occurrences, uint32_t* coverage,
                       pcs_run_stats* stats);
+/* the coverage gather alone, queued on the given cudaStream_t (not the context's): the owner of shared tables
+ * runs it beside the next step's sampler instead of in front of it */
+int pcs_plan_finalize_stream(pcs_plan* plan, const uint32_t* depth, uint32_t* coverage, void* stream);
 /* wait for the plan's queued work, read and reset its counters: n_reads / checksums accumulated by the asynchronous
  * calls since the last read, kernel_ms of the last sampler launch */
 int pcs_plan_counters(pcs_plan* plan, pcs_run_stats* stats);
@@ -447,6 +450,10 @@ int pcs_flat_tile_entries(const pcs_flat* flat, const pcs_seq_params* params, ui
  * haplotype index (inside the tile's chromosome) and entry index each 32-bit draw word u[i] selects */
 int pcs_flat_draw(const pcs_flat* flat, const pcs_seq_params* params, uint32_t tile_id, uint64_t n_draws,
                   const uint32_t* u, uint32_t* hap, uint32_t* entry);
+/* `count` draws of the planner's Binomial(n, p) sampler (csrc/plan_rng.hpp) from the stream of `seed`: the
+ * templates of a (sample, chromosome) are split over its tiles with chains of these (a multinomial), as the
+ * reference draws its reads' positions one by one (src/sequencing.cpp:155-163).  Host only; for tests. */
+int pcs_host_binomial(uint32_t seed, uint64_t n, double p, uint64_t count, uint64_t* out);
 
 #ifdef __cplusplus
 }

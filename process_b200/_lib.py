@@ -32,6 +32,7 @@ EXPORTS = [
     "pcs_host_gather", "pcs_host_string_column", "pcs_plan_counters", "pcs_memset_u32_stream",
     "pcs_forest_upload_genomes", "pcs_flat_create_genomes", "pcs_plan_coverage_track", "pcs_flat_plan_thinning",
     "pcs_simulate_result", "pcs_plan_result", "pcs_result_info", "pcs_result_fetch", "pcs_result_free",
+    "pcs_host_binomial", "pcs_plan_finalize_stream",
 ]
 
 
@@ -63,6 +64,13 @@ def _ok(rc):
 
 def _u32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def host_binomial(seed, n, p, count):
+    """`count` draws of the planner's Binomial(n, p) sampler (csrc/plan_rng.hpp); host only."""
+    out = np.empty(count, np.uint64)
+    _ok(lib().pcs_host_binomial(C.c_uint32(seed), C.c_uint64(n), C.c_double(p), C.c_uint64(count), A.ptr(out, C.c_uint64)))
+    return out
 
 
 # --------------------------------------------------------------------------- host-side column builders
@@ -452,6 +460,10 @@ class Plan:
         _ok(lib().pcs_plan_finalize(self._h, C.c_void_p(depth_ptr), C.c_void_p(occ_ptr), C.c_void_p(cov_ptr),
                                     C.byref(st) if wait else None))
         return st if wait else None
+
+    def finalize_on(self, depth_ptr: int, cov_ptr: int, stream: int):
+        """the coverage gather queued on `stream` (a cudaStream_t handle)"""
+        _ok(lib().pcs_plan_finalize_stream(self._h, C.c_void_p(depth_ptr), C.c_void_p(cov_ptr), C.c_void_p(stream)))
 
     def counters(self):
         """wait for the queued work; n_reads / checksums accumulated by the wait=False calls since the last read"""

@@ -111,6 +111,24 @@ struct UsefulScan {
   PCS_HD uint32_t add_tail() { return add_window(limit + 1u, last); }
 };
 
+// |U| of a tile in closed form (host): the loci are sorted and every window has the same length, so what is covered
+// when locus i comes is exactly what locus i - 1 reached -- gain_i depends on p_{i-1} and p_i only (the rule the
+// device scans in parallel, kernels.cu: build_useful_cum).  No branch in the loop: it runs at memory speed.
+inline uint32_t useful_offsets(const uint32_t* pos, uint32_t n, uint32_t tile_begin, uint32_t tile_len, uint32_t tail_off,
+                               uint32_t R) {
+  const uint32_t last = tile_begin + tile_len - 1u, limit = tile_begin + tail_off - 1u;
+  auto gain = [=](uint32_t prev_e, uint32_t p) {
+    const uint32_t e = p < limit ? p : limit;
+    const uint32_t s0 = p + 1u > R ? p + 1u - R : 0u;
+    const uint32_t s = s0 > prev_e + 1u ? s0 : prev_e + 1u;
+    return s <= e ? e - s + 1u : 0u;
+  };
+  uint32_t u = n ? gain(tile_begin - 1u, pos[0]) : 0u;  // |U| <= tile_len: no overflow
+  for (uint32_t i = 1; i < n; ++i) u += gain(pos[i - 1] < limit ? pos[i - 1] : limit, pos[i]);
+  u += last > limit ? last - limit : 0u;  // the tail zone: every offset past `limit`
+  return u;
+}
+
 struct DevForest {
   const uint32_t* locus_pos;       // [L]
   const uint32_t* chr_locus_off;   // [n_chr+1]
@@ -125,7 +143,7 @@ struct SeqModel {
   uint32_t read_size;
   uint32_t paired;          // 0/1
   uint32_t sequencer;       // PCS_SEQ_*
-  uint32_t err_thr;         // floor(error_rate * 2^32), constant-quality model
+  uint32_t err_thr;         // constant quality: floor(error_rate * 2^32); random quality: a bound of every base's error probability
   float error_rate;         // random-quality model
   uint32_t insert_n;        // columns of the insert-size alias table (paired)
   uint32_t insert_min;      // smallest insert with non-zero probability

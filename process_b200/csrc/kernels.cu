@@ -2,14 +2,18 @@
 //
 //   sample_tiles_staged_kernel  the hot kernel.  One CTA per tile: the tile's sorted loci
 //                         are staged in shared memory as 16-byte records {position,
-//                         carrier interval, SID lengths, row} next to a bucket directory;
-//                         every thread draws template starts with Philox4x32-10 (one block =
-//                         two single-end reads) and probes the directory; reads that may span
-//                         a locus wait in a per-warp queue and are walked 32 at a time
-//                         (haplotype resolved there), counting depth / occurrences with
-//                         shared-memory atomics; the error models settle the carried SIDs
-//                         32 bases at a time from a second queue; one coalesced red.global
-//                         per touched counter at the end.
+//                         carrier interval, SID lengths, row}.  Single-end reads, THINNED tile
+//                         (dev.hpp: Tile): only the templates whose read can span a locus are
+//                         drawn, start mapped through the cumulative widths of the loci's
+//                         windows, and every one of them is walked at once.  Otherwise every
+//                         template is drawn (Philox4x32-10, one block = two single-end reads
+//                         or one paired template), probes a bucket directory, and the reads
+//                         that may span a locus wait in a per-warp queue and are walked 32
+//                         at a time.  The walk resolves the haplotype and counts depth /
+//                         occurrences with shared-memory atomics; the error models test a
+//                         carried SID against two bits of an error block drawn, converged,
+//                         before the walk; one coalesced red.global per touched counter at
+//                         the end.
 //   sample_tiles_global_kernel  same walk straight from global memory (tiles too dense
 //                         to stage) and the read-tracing debug mode.
 //   count_injected_kernel the same locus walk over a caller-supplied placement list
@@ -62,29 +66,75 @@ __device__ __forceinline__ float ramp(uint32_t i, uint32_t R) {
   return R > 1 ? 0.5f + static_cast<float>(i) / static_cast<float>(R - 1) : 1.0f;
 }
 
-// is any of the `n` read bases starting at `off` a sequencing error?  One Philox
-// block per tested base, counter (read, tile, (1 + hit) | base << 20, seed): the
-// outcome does not depend on scheduling.
-// Kept out of line on purpose: inlined into the walk it costs the hot kernel ~20 registers (one CTA
-// less per SM) for a branch only one read in six takes.
-__device__ __noinline__ bool draw_base_errors(uint32_t sequencer, uint32_t err_thr, float error_rate, uint32_t R,
-                                              uint32_t seed, uint32_t read, uint32_t tile, uint32_t hit, uint32_t off,
-                                              uint32_t n, uint32_t* mask) {
+// -------------------------------------------------- sequencing errors on SID bases
+// Does a sequencing error hide the read's hit-th carried SID?  It does iff one of the SID's bases in the read is
+// an error.  Base b of that SID at read offset o is an error iff  t < thr  (constant quality) or
+// u01(t) < min(1, error_rate * ramp(o) * exp(sigma * z - sigma^2 / 2))  (random quality), where
+//   t  the TEST WORD:  b == 0 and hit < 2: word 2 * (read & 1) + hit of the ERROR BLOCK of the read's pair,
+//                      Philox(read >> 1, tile, 1, seed) -- one block serves the first two SIDs of both reads
+//                      of a draw block (or both mates of a template), and the samplers compute it once, converged,
+//                      before the walk;  every other base: word x of the base's own block
+//                      Q = Philox(read, tile, 0x40000000 | b << 20 | hit, seed);
+//   z  the quality deviate (random quality only): Box-Muller of words y, z of Q.
+// All kernels (staged / global samplers, trace, SAM records) draw through these functions, so the tables, the
+// traces and the SAM files of one call describe the same reads with the same errors, whatever the scheduling.
+constexpr uint32_t kErrFastHits = 2;
+constexpr uint32_t kPurposeErrorBlock = 1u, kPurposeSidBase = 0x40000000u;
+constexpr uint32_t kPurposeOutside = 2u;  // thinned tiles: the templates the samplers never draw (TileReads)
+
+struct ErrModel {  // what the error draw needs of the sequencer model, by value (registers, also across a call)
+  uint32_t sequencer, err_thr, read_size, seed;
+  float error_rate;
+};
+__device__ __forceinline__ ErrModel err_model(const SeqModel& M) {
+  return ErrModel{M.sequencer, M.err_thr, M.read_size, M.seed, M.error_rate};
+}
+
+__device__ __forceinline__ uint4 error_block(uint32_t read, uint32_t tile, uint32_t seed) {
+  return philox4x32_10(make_uint4(read >> 1, tile, kPurposeErrorBlock, seed));
+}
+
+// the two test words of read `read` in its pair's error block, as "below the model's threshold" bits (bit h:
+// SID hit h).  Constant quality: the outcome.  Random quality: err_thr is an upper bound of every base's error
+// probability (set_model), so a clear bit is "no error" and a set bit is "evaluate the exact test".
+__device__ __forceinline__ uint32_t error_bits(const uint4& e, uint32_t read, uint32_t thr) {
+  const uint32_t t0 = (read & 1u) ? e.z : e.x, t1 = (read & 1u) ? e.w : e.y;
+  return (t0 < thr ? 1u : 0u) | (t1 < thr ? 2u : 0u);
+}
+
+// the exact test for one base (any base; recomputes the blocks it needs).  *quality: the base's error probability
+__device__ __forceinline__ bool sid_base_error(const ErrModel& E, uint32_t read, uint32_t tile, uint32_t hit, uint32_t b,
+                                               uint32_t o, float* quality = nullptr) {
+  const bool fast = b == 0u && hit < kErrFastHits;
+  uint4 q = make_uint4(0u, 0u, 0u, 0u);
+  if (!fast || E.sequencer != PCS_SEQ_BASIC_CONSTANT) q = philox4x32_10(make_uint4(read, tile, kPurposeSidBase | (b << 20) | hit, E.seed));
+  uint32_t t = q.x;
+  if (fast) {
+    const uint4 e = error_block(read, tile, E.seed);
+    t = (read & 1u) ? (hit ? e.w : e.z) : (hit ? e.y : e.x);
+  }
+  if (E.sequencer == PCS_SEQ_BASIC_CONSTANT) {
+    if (quality) *quality = E.error_rate;
+    return t < E.err_thr;
+  }
+  const float z = sqrtf(-2.0f * __logf(u01(q.y))) * cospif(2.0f * u01(q.z));
+  const float p = E.error_rate * ramp(o, E.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
+  if (quality) *quality = p;
+  return u01(t) < fminf(p, 1.0f);
+}
+
+// is any of the `n` read bases of the hit-th SID, starting at read offset `off`, a sequencing error?  Exact, from
+// scratch.  Kept out of line on purpose: it is the cold path of the samplers (a third SID in a read, an insertion,
+// a random-quality test word below the bound) and must not cost the walk its registers.
+__device__ __noinline__ bool sid_errors_slow(ErrModel E, uint32_t read, uint32_t tile, uint32_t hit, uint32_t off,
+                                             uint32_t n, uint32_t* mask) {
   bool any = false;
   for (uint32_t b = 0; b < n; ++b) {
-    const uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), seed));
-    bool e;
-    if (sequencer == PCS_SEQ_BASIC_CONSTANT) {
-      e = w.x < err_thr;
-    } else {
-      const float z = sqrtf(-2.0f * __logf(u01(w.x))) * cospif(2.0f * u01(w.y));
-      const float p = error_rate * ramp(off + b, R) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
-      e = u01(w.z) < fminf(p, 1.0f);
-    }
-    if (e) {
+    if (sid_base_error(E, read, tile, hit, b, off + b)) {
       any = true;
       const uint32_t i = off + b;
       if (mask && i < 32u * PCS_ERRMASK_WORDS) mask[i >> 5] |= 1u << (i & 31);
+      if (!mask) break;
     }
   }
   return any;
@@ -97,16 +147,14 @@ __device__ __forceinline__ void add_alt_row(const View& V, uint32_t row, bool ab
   if (abs_row) V.add_alt_abs(row); else V.add_alt(row);
 }
 
-struct ErrDraw {
+struct ErrDraw {  // global-memory kernels and trace mode: every SID tested from scratch
   const SeqModel& M;
   uint32_t read, tile;
   uint32_t* mask;  // trace mode: error bits found, else nullptr
   template <class View>
   __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
                                         uint32_t n) const {
-    if (M.sequencer != PCS_SEQ_ERRORLESS &&
-        draw_base_errors(M.sequencer, M.err_thr, M.error_rate, M.read_size, M.seed, read, tile, hit, off, n, mask))
-      return;
+    if (M.sequencer != PCS_SEQ_ERRORLESS && sid_errors_slow(err_model(M), read, tile, hit, off, n, mask)) return;
     add_alt_row(V, row, abs_row);
   }
 };
@@ -197,33 +245,15 @@ struct SharedView {
   __device__ __forceinline__ uint4 instance(uint32_t k) const { return __ldg(inst + k); }
 };
 
-// what the error draw needs of the sequencer model, by value (registers, also across a call)
-struct ErrModel {
-  uint32_t sequencer, err_thr, read_size, seed;
-  float error_rate;
-};
-__device__ __forceinline__ ErrModel err_model(const SeqModel& M) {
-  return ErrModel{M.sequencer, M.err_thr, M.read_size, M.seed, M.error_rate};
-}
-
-// is read base `o`, base b of the read's hit-th carried SID, a sequencing error?  The draw of
-// draw_base_errors for that base: block (read, tile, (1 + hit) | b << 20, seed).
-__device__ __forceinline__ bool sid_base_error(const ErrModel& E, uint32_t read, uint32_t tile, uint32_t hit,
-                                               uint32_t b, uint32_t o) {
-  const uint4 w = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), E.seed));
-  if (E.sequencer == PCS_SEQ_BASIC_CONSTANT) return w.x < E.err_thr;
-  const float z = sqrtf(-2.0f * __logf(u01(w.x))) * cospif(2.0f * u01(w.y));
-  const float p = E.error_rate * ramp(o, E.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
-  return u01(w.z) < fminf(p, 1.0f);
-}
-
-// Staged kernel, error models: the error draw of a carried SID costs a Philox block per SID base, and inside
-// the walk it would run with the few lanes that carry a SID at that moment (and as long as the longest
-// insertion among them).  So the walk counts the occurrence at once and queues the carried SID
+// Staged kernel, error models.  The first two SIDs of a read are settled inside the walk from the two bits of its
+// pair's error block (error_bits) when they are SNVs -- nine carried SIDs in ten.  Whatever needs more draws (a
+// third SID, an insertion's further bases, a random-quality test word below the bound) would run inside the walk
+// with the one or two lanes concerned while the others wait, so the walk counts that occurrence at once and
+// queues the carried SID
 // {read, row, hit, read offset | base << 16 | bases left << 24}; the warp settles 32 queued bases at a time,
 // one per lane (settle_carried): a lane draws for the base of its item, puts the item back for the next base
-// if there is one, and the FIRST erroneous base of a SID takes the occurrence back.  Same Philox counters as
-// the immediate draw: an occurrence survives iff none of its bases is an error, whatever the order.
+// if there is one, and the FIRST erroneous base of a SID takes the occurrence back.  The draws are
+// sid_base_error's: an occurrence survives iff none of its bases is an error, whatever the order.
 constexpr uint32_t kCarriedSlots = 96;  // per warp; a SID that finds the queue full is settled on the spot
 
 // out of line: the queue-full path inside the walk is cold and must not cost the walk registers
@@ -237,6 +267,7 @@ __device__ __noinline__ void settle_sid_cold(ErrModel E, uint32_t alt_addr, uint
 struct ErrDefer {
   const SeqModel& M;
   uint32_t read, tile;
+  uint32_t bits;        // error_bits of the read
   uint32_t slots;       // shared address of this warp's kCarriedSlots uint4 slots
   uint32_t count_addr;  // shared address of the number of waiting items
   template <class View>
@@ -247,6 +278,18 @@ struct ErrDefer {
   __device__ __forceinline__ void count(const SharedView& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
                                         uint32_t n) const {
     const uint32_t rel = abs_row ? row - V.r0 : row;
+    if (n == 0u) {  // nothing of the SID is read (a deletion at the read's last base): no base to get wrong
+      V.add_alt(rel);
+      return;
+    }
+    if (n == 1u && hit < kErrFastHits) {
+      if (((bits >> hit) & 1u) == 0u) {  // no error
+        V.add_alt(rel);
+        return;
+      }
+      if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) return;  // an error hides it
+      // random quality: the test word is below the bound -- the exact test is the queue's
+    }
     // one slot per carried SID, allocated for all the lanes that are here together with ONE shared atomic (on a
     // thinned tile nearly every lane carries a SID in the same trip of the walk: thirty-two atomics on one word
     // would be replayed one after the other)
@@ -516,7 +559,7 @@ struct TileReads {
     }
     const bool useful = r < n_useful;
     const uint32_t q = useful ? r : r - n_useful;
-    const uint4 u = philox4x32_10(make_uint4(q >> 1, tile_id, useful ? 0u : 2u, seed));
+    const uint4 u = philox4x32_10(make_uint4(q >> 1, tile_id, useful ? 0u : kPurposeOutside, seed));
     const uint32_t us = (q & 1u) ? u.z : u.x;
     u_hap = (q & 1u) ? u.w : u.y;
     if (useful) {
@@ -611,7 +654,7 @@ struct StagedTile {
 // push and their ballots cost more than the idle lanes of a loop that makes 2.4 trips per drain.)
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
-                                            uint32_t* depth, uint32_t* alt, uint4 item) {
+                                            uint32_t* depth, uint32_t* alt, uint4 item, uint32_t err_bits) {
   const uint32_t R = M.read_size;
   uint32_t base, lo_addr;
   const uint4 a = S.entry_of(item.y, base, lo_addr);
@@ -621,7 +664,7 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   w.init(xs, R, frag_end);
   bool done;
   if (ERRORS) {
-    const ErrDefer err{M, read_id, T.id, S.carried, S.carried_n};
+    const ErrDefer err{M, read_id, T.id, err_bits, S.carried, S.carried_n};
     done = walk_shared(S.SV, i, S.n, h, R, frag_end, w, err);
     if (!done && w.stop > S.stage_end && T.l1 < S.chr_l1) {
       const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
@@ -637,6 +680,16 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
       walk_global(GV, T.l1, S.chr_l1, h, R, frag_end, w, err);
     }
   }
+}
+
+// a queued read: its pair's error block is drawn here, with the whole warp (the reads of a drain come from
+// anywhere in the tile)
+template <bool ERRORS>
+__device__ __forceinline__ void staged_read_queued(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
+                                                   uint32_t* depth, uint32_t* alt, uint4 item) {
+  uint32_t bits = 0;
+  if (ERRORS) bits = error_bits(error_block(item.z, T.id, M.seed), item.z, M.err_thr);
+  staged_read<ERRORS>(S, T, F, M, depth, alt, item, bits);
 }
 
 // Per-warp queue of reads that may span a locus.  Drawing and probing stay converged
@@ -815,7 +868,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
       Q.tail -= 32u * 16u;
       const uint4 mine = lds128(Q.tail + lane * 16u);
       __syncwarp();
-      staged_read<ERRORS>(S, T, F, M, depth, alt, mine);
+      staged_read_queued<ERRORS>(S, T, F, M, depth, alt, mine);
       flush_carried(false);
     }
   };
@@ -832,6 +885,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
       const uint32_t j = j0 + lane;
       const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
+      uint4 e = make_uint4(0u, 0u, 0u, 0u);  // the error block of reads 2j and 2j + 1
+      if (ERRORS) e = philox4x32_10(make_uint4(j, T.id, kPurposeErrorBlock, M.seed));
 #pragma unroll
       for (uint32_t k = 0; k < 2u; ++k) {
         const uint32_t t = __umulhi(k ? u.z : u.x, u_len), u_hap = k ? u.w : u.y;
@@ -856,7 +911,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
               }
               i = lo;
             }
-            staged_read<ERRORS>(S, T, F, M, depth, alt, make_uint4(off, u_hap, 2u * j + k, i));
+            staged_read<ERRORS>(S, T, F, M, depth, alt, make_uint4(off, u_hap, 2u * j + k, i), error_bits(e, k, M.err_thr));
           }
         }
       }
@@ -900,7 +955,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     drain();
   }
   __syncwarp();
-  if (lane < (Q.tail - Q.base) / 16u) staged_read<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
+  if (lane < (Q.tail - Q.base) / 16u) staged_read_queued<ERRORS>(S, T, F, M, depth, alt, lds128(Q.base + lane * 16u));
   flush_carried(true);
   }
   __syncthreads();
@@ -1039,23 +1094,21 @@ struct BaseWriter {
   __device__ void put(uint32_t o, uint8_t base, bool sid, uint32_t hit, uint32_t b) {
     bool err = false;
     uint8_t q = 'I';
-    if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
-      uint32_t word;
-      if (sid) {
-        const uint4 u = philox4x32_10(make_uint4(read, tile, (1u + hit) | (b << 20), M.seed));
-        word = u.x;
-      } else {
-        const uint32_t block = 0x80000000u | (o >> 2);
-        if (block != cached_block) {
-          cached = philox4x32_10(make_uint4(read, tile, block, M.seed));
-          cached_block = block;
-        }
-        word = (o & 3u) == 0 ? cached.x : (o & 3u) == 1 ? cached.y : (o & 3u) == 2 ? cached.z : cached.w;
+    if (sid && M.sequencer != PCS_SEQ_ERRORLESS) {
+      float e;
+      err = sid_base_error(err_model(M), read, tile, hit, b, o, &e);
+      q = (err && M.sequencer == PCS_SEQ_BASIC_CONSTANT) ? '#' : phred(e);
+    } else if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) {
+      const uint32_t block = 0x80000000u | (o >> 2);
+      if (block != cached_block) {
+        cached = philox4x32_10(make_uint4(read, tile, block, M.seed));
+        cached_block = block;
       }
+      const uint32_t word = (o & 3u) == 0 ? cached.x : (o & 3u) == 1 ? cached.y : (o & 3u) == 2 ? cached.z : cached.w;
       err = word < M.err_thr;
       q = err ? '#' : phred(M.error_rate);
     } else if (M.sequencer == PCS_SEQ_BASIC_RANDOM) {
-      const uint4 u = philox4x32_10(make_uint4(read, tile, sid ? ((1u + hit) | (b << 20)) : (0x80000000u | o), M.seed));
+      const uint4 u = philox4x32_10(make_uint4(read, tile, 0x80000000u | o, M.seed));
       const float z = sqrtf(-2.0f * __logf(u01(u.x))) * cospif(2.0f * u01(u.y));
       const float e = M.error_rate * ramp(o, M.read_size) * __expf(kQualSigma * z - 0.5f * kQualSigma * kQualSigma);
       err = u01(u.z) < fminf(e, 1.0f);

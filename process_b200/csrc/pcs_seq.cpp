@@ -30,6 +30,7 @@
 #include "flat.hpp"
 #include "host_pool.hpp"
 #include "kernels.hpp"
+#include "plan_rng.hpp"
 
 namespace {
 
@@ -711,6 +712,25 @@ const uint32_t* gallop(const uint32_t* first, const uint32_t* last, uint32_t key
   return std::lower_bound(lo, std::min(lo + step, last), key);
 }
 
+// first element >= key of the sorted range [first, last), expected near `guess` (a pointer into the range): an
+// exponential search in whichever direction the guess missed -- with a good guess, two or three probes that share
+// a cache line instead of a binary search's dozen misses
+const uint32_t* gallop_from(const uint32_t* first, const uint32_t* last, const uint32_t* guess, uint32_t key) {
+  if (guess >= last) guess = last;
+  if (guess < first) guess = first;
+  if (guess == last || *guess >= key) {  // the answer is at or before the guess
+    size_t step = 1;
+    const uint32_t* hi = guess;          // everything from hi on is >= key
+    while (static_cast<size_t>(hi - first) >= step && hi[-static_cast<ptrdiff_t>(step)] >= key) {
+      hi -= step;
+      step <<= 1;
+    }
+    const uint32_t* lo = static_cast<size_t>(hi - first) >= step ? hi - step : first;
+    return std::lower_bound(lo, hi, key);
+  }
+  return gallop(guess, last, key);
+}
+
 // The part of a plan no output sample changes: parameters resolved, and per chromosome the tile GEOMETRY
 // (window, staged loci, rows) -- pieces cut into windows of <= W bp and <= lcap staged loci.
 struct PlanSetup {
@@ -764,6 +784,7 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
   while ((((static_cast<uint64_t>(ps.W) + ps.reach) >> ps.dir_shift) + 1) > 4096) ++ps.dir_shift;
 
   ps.grid.resize(F.n_chr);
+  Lap lap;
   host_tasks(F.n_chr, [&](size_t ci) {
     const uint32_t c = static_cast<uint32_t>(ci);
     PlanSetup::ChrGrid& g = ps.grid[c];
@@ -773,6 +794,7 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
     const uint32_t* c_lo = lp + F.chr_locus_off[c];
     const uint32_t* c_hi = lp + F.chr_locus_off[c + 1];
     const uint32_t* near = c_lo;  // pieces and windows come in increasing position: searches resume here
+    const double density = static_cast<double>(c_hi - c_lo) / std::max<double>(1.0, F.chr_len[c]);
     for (uint32_t pi = F.chr_piece_off[c]; pi < F.chr_piece_off[c + 1]; ++pi) {
       const pcs::Piece& pc = F.pieces[pi];
       for (uint64_t b = pc.begin; b <= pc.end;) {
@@ -784,7 +806,9 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
         uint64_t len = std::min<uint64_t>(ps.W, pc.end - b + 1);
         for (;;) {  // shrink the window until its loci fit the staging capacity
           uint64_t last = std::min<uint64_t>(b + len + ps.reach, static_cast<uint64_t>(F.chr_len[c]) + 1);
-          t.l1 = static_cast<uint32_t>(gallop(near, c_hi, static_cast<uint32_t>(last)) - lp);
+          // the loci are spread roughly evenly: look for the window's end where the chromosome's mean density puts it
+          const uint32_t* guess = near + static_cast<size_t>(static_cast<double>(last - b) * density);
+          t.l1 = static_cast<uint32_t>(gallop_from(near, c_hi, guess, static_cast<uint32_t>(last)) - lp);
           if (t.l1 - t.l0 <= ps.lcap || len <= 2048) break;
           len = std::max<uint64_t>(2048, len / 2);
         }
@@ -793,17 +817,11 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
         t.n_rows = F.locus_first_row[t.l1] - t.r0;
         t.tail_off = t.len;
         if (ps.thin && t.l1 - t.l0 <= std::min(ps.lcap, pcs::kMaxThinLoci) && t.n_rows <= 2 * ps.lcap) {
-          // the offsets from which a read can span a locus, plus those from which it may run past the piece's end
+          // the offsets from which a read may run past the piece's end: the tail zone
           const uint64_t first_unsafe = static_cast<uint64_t>(pc.end) + 2 > static_cast<uint64_t>(ps.R) + b
                                             ? static_cast<uint64_t>(pc.end) + 2 - ps.R - b : 0;
           t.tail_off = static_cast<uint32_t>(std::min<uint64_t>(first_unsafe, len));
-          pcs::UsefulScan us;
-          us.init(t.begin, t.len, t.tail_off, ps.R);
-          uint64_t u = 0;
-          for (uint32_t l = t.l0; l < t.l1; ++l) u += us.add_locus(lp[l]);
-          u += us.add_tail();
-          t.u_len = static_cast<uint32_t>(u);
-          t.thin = 1;
+          t.thin = 1;  // u_len: second pass below
         }
         g.tiles.push_back(t);
         b += len;
@@ -811,6 +829,26 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
       g.piece_tile_off[pi - F.chr_piece_off[c] + 1] = static_cast<uint32_t>(g.tiles.size());
     }
   });
+  lap("    geometry: windows");
+  if (ps.thin) {
+    // the useful offsets of every thinned tile (one scan of its loci): all tiles of the genome in equal chunks --
+    // per chromosome, the longest one would be a tenth of the whole pass on one thread
+    std::vector<std::pair<uint32_t, uint32_t>> chunks;  // (chromosome, first tile)
+    constexpr uint32_t kChunk = 128;
+    for (uint32_t c = 0; c < F.n_chr; ++c)
+      for (uint32_t i = 0; i < ps.grid[c].tiles.size(); i += kChunk) chunks.emplace_back(c, i);
+    const uint32_t* lp = F.locus_pos.data();
+    host_tasks(chunks.size(), [&](size_t k) {
+      std::vector<pcs::Tile>& tiles = ps.grid[chunks[k].first].tiles;
+      const size_t i1 = std::min<size_t>(tiles.size(), chunks[k].second + kChunk);
+      for (size_t i = chunks[k].second; i < i1; ++i) {
+        pcs::Tile& t = tiles[i];
+        if (!t.thin) continue;
+        t.u_len = pcs::useful_offsets(lp + t.l0, t.l1 - t.l0, t.begin, t.len, t.tail_off, ps.R);
+      }
+    });
+    lap("    geometry: useful offsets");
+  }
   return ps;
 }
 
@@ -831,27 +869,20 @@ struct SampleChrPlan {
 // same law; the blocks are independent tasks, so the longest chromosome is no longer the planner's critical path.
 constexpr size_t kTemplateBlock = 64;
 
-uint64_t draw_binomial(std::mt19937_64& rng, uint64_t n, double p) {
-  if (p >= 1.0) return n;
-  if (p <= 0.0 || n == 0) return 0;
-  return static_cast<uint64_t>(std::binomial_distribution<long long>(static_cast<long long>(n), p)(rng));
-}
-
 void plan_block_templates(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan& task, size_t b) {
   const size_t i0 = b * kTemplateBlock, i1 = std::min(task.tiles.size(), i0 + kTemplateBlock);
-  std::seed_seq sq{static_cast<uint32_t>(ps.P.seed), s, c, 0x7116u, static_cast<uint32_t>(b)};
-  std::mt19937_64 rng(sq);
+  pcs::PlanRng rng(static_cast<uint32_t>(ps.P.seed), 0x7116u, s, c, static_cast<uint32_t>(b));
   double wleft = 0;
   for (size_t i = i0; i < i1; ++i) wleft += task.tile_w[i];
   uint64_t left = task.block_n[b];
   for (size_t i = i0; i < i1 && left > 0; ++i) {
     const double p = (i + 1 == i1) ? 1.0 : std::min(1.0, std::max(0.0, task.tile_w[i] / wleft));
-    const uint64_t k = draw_binomial(rng, left, p);
+    const uint64_t k = pcs::binomial(rng, left, p);
     require(k <= 0xffffffffull, "too many templates in one tile; lower PCS_TILE_BP");
     pcs::Tile& t = task.tiles[i];
     t.n_templates = static_cast<uint32_t>(k);
     // of these, the templates whose read can span a locus: the start is uniform over the tile's offsets
-    t.n_useful = t.thin ? static_cast<uint32_t>(draw_binomial(rng, k, static_cast<double>(t.u_len) / t.len)) : t.n_templates;
+    t.n_useful = t.thin ? static_cast<uint32_t>(pcs::binomial(rng, k, static_cast<double>(t.u_len) / t.len)) : t.n_templates;
     left -= k;
     wleft -= task.tile_w[i];
   }
@@ -938,8 +969,7 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
   // templates of this (sample, chromosome): N of them, multinomial over its tiles -- here over the BLOCKS of tiles
   // (the tiles inside a block are drawn by plan_block_templates, one independent task per block)
   const uint64_t N = static_cast<uint64_t>(std::llround(P.coverage * F.chr_len[c] / (static_cast<double>(ps.R) * ps.mates)));
-  std::seed_seq sq{static_cast<uint32_t>(P.seed), s, c, 0x7115u};
-  std::mt19937_64 rng(sq);
+  pcs::PlanRng rng(static_cast<uint32_t>(P.seed), 0x7115u, s, c, 0u);
   const size_t n_blocks = (all.size() + kTemplateBlock - 1) / kTemplateBlock;
   std::vector<double> block_w(n_blocks, 0.0);
   for (size_t i = 0; i < all.size(); ++i) block_w[i / kTemplateBlock] += tile_w[i];
@@ -950,7 +980,7 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
   task.total_templates = left;
   for (size_t b = 0; b < n_blocks && left > 0; ++b) {
     const double p = (b + 1 == n_blocks) ? 1.0 : std::min(1.0, std::max(0.0, block_w[b] / wleft));
-    const uint64_t k = draw_binomial(rng, left, p);
+    const uint64_t k = pcs::binomial(rng, left, p);
     task.block_n[b] = k;
     left -= k;
     wleft -= block_w[b];
@@ -980,6 +1010,14 @@ void set_model(HostPlan& pl, const PlanSetup& ps) {
   M.paired = ps.paired ? 1 : 0;
   M.sequencer = ps.P.sequencer;
   M.err_thr = static_cast<uint32_t>(std::min(4294967295.0, std::floor(ps.P.error_rate * 4294967296.0)));
+  if (ps.P.sequencer == PCS_SEQ_BASIC_RANDOM) {
+    // random quality: a bound no base's error probability exceeds -- the ramp is <= 1.5 and the quality deviate
+    // <= sqrt(-2 ln(2^-33)) = 6.77 (Box-Muller of a 32-bit uniform), taken as 6.9 against float rounding; sigma =
+    // 0.5 (kernels.cu: kQualSigma).  A test word at or above it cannot be an error, so the samplers skip the
+    // quality model for it (kernels.cu: error_bits); 2 % of slack covers u01()'s float rounding of the word.
+    const double bound = ps.P.error_rate * 1.5 * std::exp(0.5 * 6.9 - 0.125) * 1.02 + 1e-7;
+    M.err_thr = bound >= 1.0 ? 4294967295u : static_cast<uint32_t>(std::min(4294967295.0, std::ceil(bound * 4294967296.0)));
+  }
   M.error_rate = static_cast<float>(ps.P.error_rate);
   M.insert_n = static_cast<uint32_t>(ps.insert_alias.size() / 2);
   M.insert_min = ps.kmin;
@@ -1575,10 +1613,20 @@ void simulate_tables(pcs_forest& fo, const pcs_seq_params& P, uint32_t* occ, uin
   }
   unsigned long long* counters = cx.counters_home();
   CUDA_OK(cudaMemcpyAsync(counters, T.counters.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  Lap lap;
   drain_chunks(cx, chunks);
+  lap("  tables copied out (waits for the GPU)");
   CUDA_OK(cudaStreamSynchronize(st));
   CUDA_OK(cudaStreamSynchronize(cs));
-  if (std::getenv("PCS_TIMING")) std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "simulate (plan + kernels + D2H)", now_ms() - t0);
+  lap("  streams drained");
+  if (std::getenv("PCS_TIMING") && T.S > 0) {
+    std::fprintf(stderr, "[pcs host]    %-28s %8.2f ms\n", "simulate (plan + kernels + D2H)", now_ms() - t0);
+    float first = 0, all = 0;  // since the first sampler launch: when the first and the last sampler kernel ended
+    cudaEventElapsedTime(&first, cx.time_ev[0], cx.time_ev[1]);
+    cudaEventElapsedTime(&all, cx.time_ev[0], cx.time_ev[2 * T.S - 1]);
+    std::fprintf(stderr, "[pcs host]      GPU: first sampler %.2f ms, first launch -> last sampler done %.2f ms, kernels summed %.2f ms\n",
+                 first, all, pipelined_kernel_ms(cx, T.S));
+  }
   if (stats) {
     rs.kernel_ms = pipelined_kernel_ms(cx, T.S);
     rs.total_ms = now_ms() - t0;
@@ -2036,6 +2084,19 @@ int pcs_plan_finalize(pcs_plan* pl, const uint32_t* depth, const uint32_t* occur
   return guarded([&] {
     require(pl != nullptr, "plan is NULL");
     finalize_tables(*pl, depth, occurrences, coverage, stats);
+  });
+}
+
+int pcs_plan_finalize_stream(pcs_plan* pl, const uint32_t* depth, uint32_t* coverage, void* stream) {
+  return guarded([&] {
+    require(pl != nullptr, "plan is NULL");
+    pcs_forest& fo = *pl->forest;
+    fo.ctx->bind();
+    const size_t S = pl->host.info.n_out_samples, M = pl->host.info.n_mut, L = pl->host.info.n_loci;
+    require(S * M == 0 || (depth && coverage), "table pointers are NULL");
+    CUDA_OK(pcs::launch_finalize(static_cast<cudaStream_t>(stream), depth, fo.d_row_locus.p, static_cast<uint32_t>(S),
+                                 static_cast<uint32_t>(L), static_cast<uint32_t>(M), coverage));
+    pl->launches_since_read += S * M != 0 ? 1 : 0;
   });
 }
 
@@ -3160,6 +3221,15 @@ int pcs_flat_plan_thinning(const pcs_flat* fl, const pcs_seq_params* params, uin
         if (n_useful) n_useful[i] = t.n_useful;
         ++i;
       }
+  });
+}
+
+int pcs_host_binomial(uint32_t seed, uint64_t n, double p, uint64_t count, uint64_t* out) {
+  return guarded([&] {
+    require(out || count == 0, "bad arguments");
+    require(n < (1ull << 53) && p >= 0.0 && p <= 1.0, "Binomial(n, p): n < 2^53 and 0 <= p <= 1");
+    pcs::PlanRng rng(seed, 0x7e57u, 0u, 0u, 0u);
+    for (uint64_t i = 0; i < count; ++i) out[i] = pcs::binomial(rng, n, p);
   });
 }
 

@@ -423,3 +423,34 @@ def test_thinned_tiles_count_the_useful_offsets_exactly():
     # paired reads and PCS_THIN=0 draw every template
     th = fl.plan_thinning(make_params(coverage=40.0, insert_size_mean=300))
     assert th["thin"].sum() == 0
+
+
+def test_planner_binomial_sampler_matches_scipy_pmf():
+    """csrc/plan_rng.hpp: the planner's Binomial(n, p) draws (inversion below a mean of 10, BTRS above, p > 1/2
+    mirrored) against scipy's pmf -- chi-square over the bins with an expectation >= 10, mean and variance."""
+    from scipy import stats
+    cases = [(5, 0.3), (100, 0.05), (100, 0.5), (1000, 0.2), (139000, 0.2), (139000, 0.8), (8_900_000, 1 / 64),
+             (10 ** 9, 0.37), (10 ** 12, 1e-11), (50, 0.999), (40, 0.25), (2000, 0.006)]
+    n_draws = 400_000
+    pvals = []
+    for i, (n, p) in enumerate(cases):
+        x = L.host_binomial(1000 + i, n, p, n_draws)
+        assert int(x.max()) <= n
+        lo, hi = int(x.min()), int(x.max())
+        obs = np.bincount((x - lo).astype(np.int64), minlength=hi - lo + 1).astype(float)
+        exp = stats.binom.pmf(np.arange(lo, hi + 1), n, p) * n_draws
+        keep = exp >= 10
+        o = np.append(obs[keep], obs[~keep].sum())
+        e = np.append(exp[keep], n_draws - exp[keep].sum())
+        if e[-1] < 5:
+            o[-2] += o[-1]; e[-2] += e[-1]; o, e = o[:-1], e[:-1]
+        pvals.append(stats.chi2.sf(((o - e) ** 2 / e).sum(), len(o) - 1))
+        mean, var = n * p, n * p * (1 - p)
+        assert abs(x.mean() - mean) < 5 * np.sqrt(var / n_draws), (n, p)
+        assert abs(x.var() / var - 1) < 0.02, (n, p)
+    # twelve independent p-values: none absurdly small, and not all small
+    assert min(pvals) > 1e-4, pvals
+    assert np.median(pvals) > 0.1, pvals
+    # degenerate arguments
+    assert L.host_binomial(1, 0, 0.5, 3).tolist() == [0, 0, 0]
+    assert L.host_binomial(1, 17, 0.0, 2).tolist() == [0, 0] and L.host_binomial(1, 17, 1.0, 2).tolist() == [17, 17]
