@@ -13,7 +13,8 @@ import numpy as np
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcs_seq.so")
+# PCS_LIB: another build of the library (kernel experiments: process_b200/csrc/Makefile, `make variants`)
+LIB_PATH = os.environ.get("PCS_LIB") or os.path.join(_HERE, "libpcs_seq.so")
 _LIB = None
 
 EXPORTS = [

@@ -746,18 +746,50 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
         inst[pos++] = {w.germ_lo[g], w.germ_hi[g] - w.germ_lo[g], m, meta};
       }
     };
-    for (uint32_t l = l0; l < l1; ++l) {
-      out.locus_inst_off[l] = static_cast<uint32_t>(pos);
-      const uint32_t row_end = out.locus_first_row[l + 1];
-      for (uint32_t m = out.locus_first_row[l]; m < row_end; ++m) {
-        while (si < s1 && som[si].row == m) inst[pos++] = som[si++];
-        if (listed_once) {
-          const uint8_t mask = row_mask[m].load(std::memory_order_relaxed);
+    if (listed_once) {
+      // the common case, a row at a time with everything a chromosome fixes hoisted out of the loop: the interval
+      // of each allele mask (1, 2, 3 = both), the next somatic row, the row of the next locus
+      const uint32_t* first_row = out.locus_first_row.data();
+      uint32_t* inst_off = out.locus_inst_off.data();
+      const uint8_t* ref_len = d.mut_ref_len;
+      const uint8_t* alt_len = d.mut_alt_len;
+      uint32_t l = l0;
+      const uint32_t m_end = first_row[l1];
+      for (uint32_t m = first_row[l0]; m < m_end;) {
+        const ChrWork& w = work[d.mut_chr[m]];
+        const uint32_t chr_end = std::min(w.row_hi, m_end);
+        const uint32_t bad = 0xffu << d.chr_n_alleles[w.chr];  // mask bits of alleles the chromosome does not have
+        const uint32_t iv_lo[4] = {0u, w.germ_lo[0], w.germ_lo[1], w.germ_lo[0]};
+        const uint32_t iv_n[4] = {0u, w.germ_hi[0] - w.germ_lo[0], w.germ_hi[1] - w.germ_lo[1], w.germ_hi[1] - w.germ_lo[0]};
+        uint32_t any_bad = 0;
+        uint32_t next_som = si < s1 ? som[si].row : 0xffffffffu;
+        uint32_t next_locus_row = first_row[l];
+        for (; m < chr_end; ++m) {
+          if (m == next_locus_row) {
+            inst_off[l] = static_cast<uint32_t>(pos);
+            next_locus_row = first_row[++l];
+          }
+          if (m == next_som) {
+            do inst[pos++] = som[si++]; while (si < s1 && som[si].row == m);
+            next_som = si < s1 ? som[si].row : 0xffffffffu;
+          }
+          const uint32_t mask = row_mask[m].load(std::memory_order_relaxed);
           if (mask) {
-            germline(m, mask);
+            any_bad |= mask & bad;
+            const uint32_t k = mask & 3u;  // bits above the two germline alleles are refused below
+            any_bad |= mask & ~3u;
+            inst[pos++] = {iv_lo[k], iv_n[k], m, static_cast<uint32_t>(ref_len[m]) | (static_cast<uint32_t>(alt_len[m]) << 8)};
             ++gi;
           }
-        } else {
+        }
+        check(any_bad == 0, "germ_allele_mask names a missing allele");
+      }
+    } else {
+      for (uint32_t l = l0; l < l1; ++l) {
+        out.locus_inst_off[l] = static_cast<uint32_t>(pos);
+        const uint32_t row_end = out.locus_first_row[l + 1];
+        for (uint32_t m = out.locus_first_row[l]; m < row_end; ++m) {
+          while (si < s1 && som[si].row == m) inst[pos++] = som[si++];
           while (gi < g1 && g_mut[gi] == m) germline(m, g_mask[gi++]);
         }
       }

@@ -94,12 +94,17 @@ __device__ __forceinline__ uint4 error_block(uint32_t read, uint32_t tile, uint3
   return philox4x32_10(make_uint4(read >> 1, tile, kPurposeErrorBlock, seed));
 }
 
-// the two test words of read `read` in its pair's error block, as "below the model's threshold" bits (bit h:
-// SID hit h).  Constant quality: the outcome.  Random quality: err_thr is an upper bound of every base's error
-// probability (set_model), so a clear bit is "no error" and a set bit is "evaluate the exact test".
-__device__ __forceinline__ uint32_t error_bits(const uint4& e, uint32_t read, uint32_t thr) {
-  const uint32_t t0 = (read & 1u) ? e.z : e.x, t1 = (read & 1u) ? e.w : e.y;
-  return (t0 < thr ? 1u : 0u) | (t1 < thr ? 2u : 0u);
+// The error block of a pair as the walk wants it: two bits per carried SID, in the order a read meets them --
+// 0: no error, count it; 1: an error hides it; 2: ask the queue (ErrDefer).  Bits 0-3: the first two SIDs of the
+// pair's even read, bits 4-7: of its odd read.  A test word at or above the model's threshold is "no error";
+// below it, constant quality: an error (code 1); random quality: err_thr is only an upper bound of every base's
+// error probability (set_model), so the exact test decides (code 2).
+__device__ __forceinline__ uint32_t pair_error_codes(const uint4& e, uint32_t thr, uint32_t below_code) {
+  return (e.x < thr ? below_code : 0u) | (e.y < thr ? below_code << 2 : 0u) | (e.z < thr ? below_code << 4 : 0u) |
+         (e.w < thr ? below_code << 6 : 0u);
+}
+__device__ __forceinline__ uint32_t below_threshold_code(const SeqModel& M) {
+  return M.sequencer == PCS_SEQ_BASIC_CONSTANT ? 1u : 2u;
 }
 
 // the exact test for one base (any base; recomputes the blocks it needs).  *quality: the base's error probability
@@ -148,6 +153,7 @@ __device__ __forceinline__ void add_alt_row(const View& V, uint32_t row, bool ab
 }
 
 struct ErrDraw {  // global-memory kernels and trace mode: every SID tested from scratch
+  static constexpr bool kSnvFirst = false;
   const SeqModel& M;
   uint32_t read, tile;
   uint32_t* mask;  // trace mode: error bits found, else nullptr
@@ -157,16 +163,22 @@ struct ErrDraw {  // global-memory kernels and trace mode: every SID tested from
     if (M.sequencer != PCS_SEQ_ERRORLESS && sid_errors_slow(err_model(M), read, tile, hit, off, n, mask)) return;
     add_alt_row(V, row, abs_row);
   }
+  template <class View, class W, class OffFn>
+  __device__ __forceinline__ void settle(const View& V, uint32_t row, bool abs_row, W& w, uint32_t n, OffFn off) const {
+    count(V, row, abs_row, w.hit, off(), n);
+  }
 };
 
 struct NoErr {
-  template <class View>
-  __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t, uint32_t, uint32_t) const {
+  static constexpr bool kSnvFirst = false;
+  template <class View, class W, class OffFn>
+  __device__ __forceinline__ void settle(const View& V, uint32_t row, bool abs_row, W&, uint32_t, OffFn) const {
     add_alt_row(V, row, abs_row);
   }
 };
 
 struct ErrMaskLookup {
+  static constexpr bool kSnvFirst = false;
   const uint32_t* mask;  // nullptr: no errors
   template <class View>
   __device__ void count(const View& V, uint32_t row, bool abs_row, uint32_t, uint32_t off, uint32_t n) const {
@@ -174,6 +186,10 @@ struct ErrMaskLookup {
       for (uint32_t i = off; i < off + n; ++i)
         if (i < 32u * PCS_ERRMASK_WORDS && ((mask[i >> 5] >> (i & 31)) & 1u)) return;
     add_alt_row(V, row, abs_row);
+  }
+  template <class View, class W, class OffFn>
+  __device__ __forceinline__ void settle(const View& V, uint32_t row, bool abs_row, W& w, uint32_t n, OffFn off) const {
+    count(V, row, abs_row, w.hit, off(), n);
   }
 };
 
@@ -184,6 +200,7 @@ struct ErrMaskLookup {
 // at loci that carry nothing or an SNV.  stop = first position the read cannot reach.
 struct Walk {
   uint32_t q, rem, stop, hit;
+  uint32_t codes;  // staged kernel, error models (ErrDefer): two bits per carried SID still to come
   __device__ __forceinline__ void init(uint32_t x, uint32_t R, uint32_t frag_end) {
     q = x;
     rem = R;
@@ -246,7 +263,7 @@ struct SharedView {
 };
 
 // Staged kernel, error models.  The first two SIDs of a read are settled inside the walk from the two bits of its
-// pair's error block (error_bits) when they are SNVs -- nine carried SIDs in ten.  Whatever needs more draws (a
+// pair's error block (pair_error_codes) when they are SNVs -- nine carried SIDs in ten.  Whatever needs more draws (a
 // third SID, an insertion's further bases, a random-quality test word below the bound) would run inside the walk
 // with the one or two lanes concerned while the others wait, so the walk counts that occurrence at once and
 // queues the carried SID
@@ -264,35 +281,39 @@ __device__ __noinline__ void settle_sid_cold(ErrModel E, uint32_t alt_addr, uint
   asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(alt_addr + row * 4u) : "memory");
 }
 
+// Walk::codes: the read's four bits of pair_error_codes, then "ask the queue" for every later SID; a SID that is
+// not one read base long (an insertion) asks the queue whatever its code.
 struct ErrDefer {
+  static constexpr bool kSnvFirst = true;
   const SeqModel& M;
   uint32_t read, tile;
-  uint32_t bits;        // error_bits of the read
-  uint32_t slots;       // shared address of this warp's kCarriedSlots uint4 slots
-  uint32_t count_addr;  // shared address of the number of waiting items
-  template <class View>
-  __device__ __forceinline__ void count(const View& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
-                                        uint32_t n) const {
-    ErrDraw{M, read, tile, nullptr}.count(V, row, abs_row, hit, off, n);
+  uint32_t slots0;   // shared address of warp 0's kCarriedSlots uint4 slots (warp w: + w * kCarriedSlots * 16)
+  uint32_t counts0;  // shared address of warp 0's number of waiting items (warp w: + 4 w)
+  template <class View, class OffFn>
+  __device__ __forceinline__ void settle(const View& V, uint32_t row, bool abs_row, Walk& w, uint32_t n, OffFn off) const {
+    ErrDraw{M, read, tile, nullptr}.count(V, row, abs_row, w.hit, off(), n);  // past the staged loci: from scratch
   }
-  __device__ __forceinline__ void count(const SharedView& V, uint32_t row, bool abs_row, uint32_t hit, uint32_t off,
-                                        uint32_t n) const {
+  template <class OffFn>
+  __device__ __forceinline__ void settle(const SharedView& V, uint32_t row, bool abs_row, Walk& w, uint32_t n, OffFn off) const {
     const uint32_t rel = abs_row ? row - V.r0 : row;
-    if (n == 0u) {  // nothing of the SID is read (a deletion at the read's last base): no base to get wrong
+    uint32_t c = w.codes & 3u;
+    w.codes = (w.codes >> 2) | 0x80000000u;
+    if (n != 1u) c = 2u;
+    if (c == 0u) {  // nine carried SIDs in ten leave here
       V.add_alt(rel);
       return;
     }
-    if (n == 1u && hit < kErrFastHits) {
-      if (((bits >> hit) & 1u) == 0u) {  // no error
-        V.add_alt(rel);
-        return;
-      }
-      if (M.sequencer == PCS_SEQ_BASIC_CONSTANT) return;  // an error hides it
-      // random quality: the test word is below the bound -- the exact test is the queue's
+    if (c == 1u) return;
+    defer(V, rel, w.hit, off(), n);
+  }
+  __device__ __forceinline__ void defer(const SharedView& V, uint32_t rel, uint32_t hit, uint32_t off, uint32_t n) const {
+    if (n == 0u) {  // nothing of the SID is read: no base to get wrong (cannot happen: alt_len >= 1 and rem_p >= 1)
+      V.add_alt(rel);
+      return;
     }
-    // one slot per carried SID, allocated for all the lanes that are here together with ONE shared atomic (on a
-    // thinned tile nearly every lane carries a SID in the same trip of the walk: thirty-two atomics on one word
-    // would be replayed one after the other)
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t slots = slots0 + warp * (kCarriedSlots * 16u), count_addr = counts0 + warp * 4u;
+    // one slot per carried SID, allocated for all the lanes that are here together with ONE shared atomic
     const uint32_t together = __activemask();
     uint32_t below;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(below));
@@ -317,12 +338,30 @@ struct ErrDefer {
 template <class View, class Err>
 __device__ __forceinline__ bool carried_sid(const View& V, uint32_t p, uint32_t lens, uint32_t row, bool abs_row,
                                             uint32_t R, uint32_t frag_end, Walk& w, const Err& err) {
+  if (Err::kSnvFirst) {
+    // the staged error-model walk: SNVs (nine carried SIDs in ten) leave through the shortest path
+    if ((lens & 0xffffu) == 0x0101u) {  // one read base (the read reaches p, so it has one left), the frame stays
+      err.settle(V, row, abs_row, w, 1u, [&] { return R - (w.rem - (p - w.q)); });
+      ++w.hit;
+      return true;
+    }
+    const uint32_t rem_p = w.rem - (p - w.q);  // bases left when the read reaches p (>= 1)
+    const uint32_t consumed = min((lens >> 8) & 0xffu, rem_p);
+    err.settle(V, row, abs_row, w, consumed, [&] { return R - rem_p; });
+    ++w.hit;
+    w.rem = rem_p - consumed;
+    w.q = p + (lens & 0xffu);
+    w.stop = min(w.q + w.rem, frag_end + 1u);
+    return w.rem != 0;
+  }
+  // One settle() for SNVs and indels alike: lanes that carry an SNV and lanes that carry an indel at the same
+  // trip of the walk run it together (errorless: it is the one red.shared of the occurrence).
   const uint32_t ref_len = lens & 0xffu, alt_len = (lens >> 8) & 0xffu;
   const uint32_t rem_p = w.rem - (p - w.q);  // bases left when the read reaches p (>= 1)
   const uint32_t consumed = min(alt_len, rem_p);
-  err.count(V, row, abs_row, w.hit, R - rem_p, consumed);
+  err.settle(V, row, abs_row, w, consumed, [&] { return R - rem_p; });
   ++w.hit;
-  if ((lens & 0xffffu) != 0x0101u) {
+  if ((lens & 0xffffu) != 0x0101u) {  // an indel moves the read's frame
     w.rem = rem_p - consumed;
     w.q = p + ref_len;
     w.stop = min(w.q + w.rem, frag_end + 1u);
@@ -588,6 +627,17 @@ struct TileReads {
 };
 
 // ---------------------------------------------------- staged sampler kernel
+// Error models: the two reads of a draw block are walked by ONE copy of the walk (a rolled loop): unrolled, the
+// second copy costs the kernel ~60 bytes of spills in the loop (constant quality on C3: 19.5 ms unrolled, 15.7 ms
+// rolled -- profiles/r02_v5_thin_loop_variants.md).  The errorless kernel has the registers and stays unrolled.  Keeping the loop's invariants in shared
+// memory instead of registers (PCS_THIN_STATE_IN_SMEM=1) was measured too and does not pay.
+#ifndef PCS_THIN_UNROLL
+#define PCS_THIN_UNROLL 1
+#endif
+#ifndef PCS_THIN_STATE_IN_SMEM
+#define PCS_THIN_STATE_IN_SMEM 0
+#endif
+constexpr int kThinUnroll = PCS_THIN_UNROLL;
 constexpr int kStagedThreads = 256;
 constexpr int kDefaultMinCtas = 3;
 constexpr uint32_t kQueueSlots = 96;  // per warp: < 32 waiting + <= 64 pushed by one Philox block per lane
@@ -623,7 +673,7 @@ struct StagedTile {
   SharedView SV;
   uint32_t dir;    // shared address of uint2 [buckets]: {index, position} of the first locus at/after the bucket
   uint32_t ent;    // shared address of the tile's entries (16 bytes each)
-  uint32_t carried, carried_n;  // error models: shared addresses of this warp's carried-SID queue and its count
+  uint32_t carried, carried_n;  // error models: shared addresses of warp 0's carried-SID queue and its count
   uint32_t n, stage_end, chr_l1;
   __device__ __forceinline__ uint2 first_locus(uint32_t bucket) const {
     uint2 v;
@@ -654,7 +704,7 @@ struct StagedTile {
 // push and their ballots cost more than the idle lanes of a loop that makes 2.4 trips per drain.)
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
-                                            uint32_t* depth, uint32_t* alt, uint4 item, uint32_t err_bits) {
+                                            uint32_t* depth, uint32_t* alt, uint4 item, uint32_t err_codes) {
   const uint32_t R = M.read_size;
   uint32_t base, lo_addr;
   const uint4 a = S.entry_of(item.y, base, lo_addr);
@@ -664,7 +714,8 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
   w.init(xs, R, frag_end);
   bool done;
   if (ERRORS) {
-    const ErrDefer err{M, read_id, T.id, err_bits, S.carried, S.carried_n};
+    const ErrDefer err{M, read_id, T.id, S.carried, S.carried_n};
+    w.codes = 0xAAAAAAA0u | err_codes;
     done = walk_shared(S.SV, i, S.n, h, R, frag_end, w, err);
     if (!done && w.stop > S.stage_end && T.l1 < S.chr_l1) {
       const GlobalView GV{F.locus_pos, F.locus_inst_off, F.inst, depth + static_cast<size_t>(T.sample) * F.n_loci,
@@ -687,9 +738,10 @@ __device__ __forceinline__ void staged_read(const StagedTile& S, const Tile& T, 
 template <bool ERRORS>
 __device__ __forceinline__ void staged_read_queued(const StagedTile& S, const Tile& T, const DevForest& F, const SeqModel& M,
                                                    uint32_t* depth, uint32_t* alt, uint4 item) {
-  uint32_t bits = 0;
-  if (ERRORS) bits = error_bits(error_block(item.z, T.id, M.seed), item.z, M.err_thr);
-  staged_read<ERRORS>(S, T, F, M, depth, alt, item, bits);
+  uint32_t codes = 0;
+  if (ERRORS)
+    codes = (pair_error_codes(error_block(item.z, T.id, M.seed), M.err_thr, below_threshold_code(M)) >> (4u * (item.z & 1u))) & 15u;
+  staged_read<ERRORS>(S, T, F, M, depth, alt, item, codes);
 }
 
 // Per-warp queue of reads that may span a locus.  Drawing and probing stay converged
@@ -756,6 +808,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   uint32_t* s_depth = reinterpret_cast<uint32_t*>(s_dir + D.max_buckets);
   uint32_t* s_alt = s_depth + D.max_loci;
   __shared__ uint32_t s_safe;
+  __shared__ uint32_t s_dropped;  // thinned tiles: templates that fell off their molecule
+  if (threadIdx.x == 0) s_dropped = 0;
   __shared__ uint32_t s_carried_n[kStagedThreads / 32];
   if (threadIdx.x < kStagedThreads / 32) s_carried_n[threadIdx.x] = 0;
 
@@ -835,8 +889,8 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
                     opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_alt))), F.inst, T.r0};
   S.dir = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_dir)));
   S.ent = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_ent)));
-  S.carried = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried + (ERRORS ? warp * kCarriedSlots : 0u))));
-  S.carried_n = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried_n + warp)));
+  S.carried = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried)));
+  S.carried_n = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_carried_n)));
   S.n = n;
   S.stage_end = T.begin + T.len + M.reach;  // first position whose loci are not staged
   S.chr_l1 = __ldg(F.chr_locus_off + T.chr + 1);
@@ -859,8 +913,9 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   auto flush_carried = [&](bool all) {
     if (!ERRORS) return;
     __syncwarp();  // the walks' pushes (shared atomics of other lanes) are visible
-    const uint32_t waiting = lds32(S.carried_n);
-    if (waiting >= 32u || (all && waiting != 0u)) settle_carried(err_model(M), S.carried, S.carried_n, S.SV.alt, T.id, all);
+    const uint32_t waiting = lds32(S.carried_n + warp * 4u);
+    if (waiting >= 32u || (all && waiting != 0u))
+      settle_carried(err_model(M), S.carried + warp * (kCarriedSlots * 16u), S.carried_n + warp * 4u, S.SV.alt, T.id, all);
   };
   auto drain = [&]() {
     while (Q.tail >= Q.base + 32u * 16u) {
@@ -880,16 +935,39 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
     // fragment) is tested for falling off its fragment and looks its first locus up.
     const uint32_t cum_a = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_cum)));
     const uint32_t slot_a = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_slot)));
-    const uint32_t u_len = T.u_len, n_useful = T.n_useful, last = T.begin + T.len - 1u, limit = T.begin + T.tail_off - 1u;
+#if PCS_THIN_STATE_IN_SMEM
+    // the loop's invariants stay in shared memory and are read where they are used: with the error models the
+    // walk needs the registers (a spilled invariant would be read back from local memory instead)
+    __shared__ uint32_t s_thin[4];
+    if (threadIdx.x == 0) {
+      s_thin[0] = T.u_len;
+      s_thin[1] = T.begin + T.len - 1u;
+      s_thin[2] = T.begin + T.tail_off - 1u;
+      s_thin[3] = s_safe;
+    }
+    __syncthreads();
+    const uint32_t thin_a = opaque(static_cast<uint32_t>(__cvta_generic_to_shared(s_thin)));
+#define THIN_U_LEN (ERRORS ? lds32(thin_a) : u_len_r)
+#define THIN_LAST (ERRORS ? lds32(thin_a + 4u) : last_r)
+#define THIN_LIMIT (ERRORS ? lds32(thin_a + 8u) : limit_r)
+#define THIN_SAFE (ERRORS ? lds32(thin_a + 12u) : safe)
+#else
+#define THIN_U_LEN u_len_r
+#define THIN_LAST last_r
+#define THIN_LIMIT limit_r
+#define THIN_SAFE safe
+#endif
+    const uint32_t u_len_r = T.u_len, n_useful = T.n_useful, last_r = T.begin + T.len - 1u, limit_r = T.begin + T.tail_off - 1u;
     const uint32_t n_blocks = (n_useful + 1u) >> 1;
+    const uint32_t below_code = below_threshold_code(M);
     for (uint32_t j0 = warp * 32u; j0 < n_blocks; j0 += kStagedThreads) {  // warp-uniform trip count
       const uint32_t j = j0 + lane;
       const uint4 u = philox4x32_10(make_uint4(j, T.id, 0u, M.seed));
-      uint4 e = make_uint4(0u, 0u, 0u, 0u);  // the error block of reads 2j and 2j + 1
-      if (ERRORS) e = philox4x32_10(make_uint4(j, T.id, kPurposeErrorBlock, M.seed));
-#pragma unroll
+      uint32_t ecodes = 0;  // pair_error_codes of reads 2j and 2j + 1: all that stays of their error block
+      if (ERRORS) ecodes = pair_error_codes(philox4x32_10(make_uint4(j, T.id, kPurposeErrorBlock, M.seed)), M.err_thr, below_code);
+#pragma unroll (ERRORS ? kThinUnroll : 2)
       for (uint32_t k = 0; k < 2u; ++k) {
-        const uint32_t t = __umulhi(k ? u.z : u.x, u_len), u_hap = k ? u.w : u.y;
+        const uint32_t t = __umulhi(k ? u.z : u.x, THIN_U_LEN), u_hap = k ? u.w : u.y;
         if (2u * j + k < n_useful) {
           uint32_t i;
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(i) : "r"(slot_a + (t >> 6) * 2u));
@@ -898,10 +976,11 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
             ++i;
             c = lds32(cum_a + i * 4u);
           }
-          const uint32_t we = i < n_u ? min(lds32(S.SV.rec + i * 16u), limit) : last;
+          const uint32_t we = i < n_u ? min(lds32(S.SV.rec + i * 16u), THIN_LIMIT) : THIN_LAST;
           const uint32_t xs = useful_position(t, c, we), off = xs - T.begin;
-          if (off >= safe && !fits(u_hap, off, R)) {
-            ++dropped;
+          if (off >= THIN_SAFE && !fits(u_hap, off, R)) {
+            // rare: the last read length of a fragment (error models: counted in shared memory, the walk needs the register)
+            if (ERRORS) atomicAdd(&s_dropped, 1u); else ++dropped;
           } else {
             if (i == n_u) {  // a draw in the tail zone: the first locus at or after the read's start, if any
               uint32_t lo = 0, hi = n;
@@ -911,7 +990,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
               }
               i = lo;
             }
-            staged_read<ERRORS>(S, T, F, M, depth, alt, make_uint4(off, u_hap, 2u * j + k, i), error_bits(e, k, M.err_thr));
+            staged_read<ERRORS>(S, T, F, M, depth, alt, make_uint4(off, u_hap, 2u * j + k, i), (ecodes >> (4u * k)) & 15u);
           }
         }
       }
@@ -973,7 +1052,7 @@ sample_tiles_staged_kernel(const Tile* __restrict__ tiles, const Entry* __restri
   }
   // reads placed = every template of the tile but the dropped ones
   const uint32_t mates = PAIRED ? 2u : 1u;
-  block_sub_u64(static_cast<unsigned long long>(T.n_templates) * mates, dropped * mates, n_reads);
+  block_sub_u64(static_cast<unsigned long long>(T.n_templates) * mates, (dropped + (threadIdx.x == 0 ? s_dropped : 0u)) * mates, n_reads);
 }
 
 // ------------------------------------------- global-memory sampler (fallback, trace)
