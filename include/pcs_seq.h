@@ -268,6 +268,11 @@ int pcs_forest_set_groups(pcs_forest* forest, const uint32_t* leaf_group, uint32
 /* sizes of the flattened view: out[0]=n_loci out[1]=n_instances out[2]=n_haplotypes
  * out[3]=n_fragment_sets out[4]=n_pieces out[5]=device bytes */
 int pcs_forest_info(const pcs_forest* forest, uint64_t out[6]);
+/* the forest's instance table as it lies on the device: inst[4 * n_instances] = {first haplotype, haplotypes, row,
+ * ref_len | alt_len << 8} sorted by row, locus_inst_off[n_loci + 1].  An uploaded forest builds the table on the
+ * device from the germline masks (PCS_DEVICE_INSTANCES=0: on the host); for tests -- pcs_flat_instances is the
+ * host-built twin.  Host pointers. */
+int pcs_forest_instances(pcs_forest* forest, uint32_t* inst, uint32_t* locus_inst_off);
 
 /* tile grid, per-tile template counts (host multinomial), sampling tables -> HBM */
 int pcs_plan_create(pcs_forest* forest, const pcs_seq_params* params, pcs_plan** plan);
@@ -428,6 +433,7 @@ int pcs_flat_hap_rows(const pcs_flat* flat, uint32_t chr, uint32_t hap, uint32_t
  * hap_list.  Lists are in increasing haplotype order and tile hap_list in (group, fragset) order. */
 int pcs_flat_group_list(const pcs_flat* flat, uint32_t group, uint32_t fragset, uint32_t cap, uint32_t* haps,
                         uint32_t* offset, uint32_t* n);
+int pcs_flat_instances(const pcs_flat* flat, uint32_t* inst, uint32_t* locus_inst_off);
 /* host half of pcs_plan_create: tile grid of the shard named in params */
 int pcs_flat_plan(const pcs_flat* flat, const pcs_seq_params* params, pcs_plan_info* info, uint64_t cap,
                   uint32_t* tile_id, uint32_t* tile_templates, uint32_t* tile_sample, uint32_t* tile_chr,

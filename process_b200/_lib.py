@@ -33,7 +33,7 @@ EXPORTS = [
     "pcs_host_gather", "pcs_host_string_column", "pcs_plan_counters", "pcs_memset_u32_stream",
     "pcs_forest_upload_genomes", "pcs_flat_create_genomes", "pcs_plan_coverage_track", "pcs_flat_plan_thinning",
     "pcs_simulate_result", "pcs_plan_result", "pcs_result_info", "pcs_result_fetch", "pcs_result_free",
-    "pcs_host_binomial", "pcs_plan_finalize_stream",
+    "pcs_host_binomial", "pcs_plan_finalize_stream", "pcs_forest_instances", "pcs_flat_instances",
 ]
 
 
@@ -138,6 +138,14 @@ class Flat:
         out = (C.c_uint64 * 6)()
         _ok(lib().pcs_flat_info(self._h, out))
         return dict(n_loci=out[0], n_instances=out[1], n_haplotypes=out[2], n_fragment_sets=out[3], n_pieces=out[4])
+
+    def instances(self):
+        """(inst [n_instances, 4], locus_inst_off [n_loci + 1]) as the host flattener builds them"""
+        i = self.info()
+        inst = np.zeros((i["n_instances"], 4), np.uint32)
+        off = np.zeros(i["n_loci"] + 1, np.uint32)
+        _ok(lib().pcs_flat_instances(self._h, A.ptr(inst, C.c_uint32), A.ptr(off, C.c_uint32)))
+        return inst, off
 
     def cell_haps(self, kind, cell, chrom, cap=4096):
         al = np.zeros(cap, np.uint16); hp = np.zeros(cap, np.uint32); fs = np.zeros(cap, np.uint32)
@@ -327,6 +335,14 @@ class Forest:
         _ok(lib().pcs_forest_info(self._h, out))
         return dict(n_loci=out[0], n_instances=out[1], n_haplotypes=out[2], n_fragment_sets=out[3],
                     n_pieces=out[4], device_bytes=out[5])
+
+    def instances(self):
+        """(inst [n_instances, 4], locus_inst_off [n_loci + 1]) as they lie on the device"""
+        i = self.info()
+        inst = np.zeros((i["n_instances"], 4), np.uint32)
+        off = np.zeros(i["n_loci"] + 1, np.uint32)
+        _ok(lib().pcs_forest_instances(self._h, A.ptr(inst, C.c_uint32), A.ptr(off, C.c_uint32)))
+        return inst, off
 
     # ---- sequences (only needed to write SAM)
     def set_reference(self, chrom, bases: bytes):

@@ -103,6 +103,18 @@ struct FlatForest {
   Table<uint32_t> locus_first_row;       // [L+1]
   Table<Inst> inst;                      // sorted by row; inside a row: somatic placements in DFS order, then germline
 
+  // Deferred instance table (uploads).  The germline's share of `inst` -- 99 % of it on a WGS forest -- is a function
+  // of one allele-mask byte per row and three haplotype intervals per chromosome.  A forest flattened with
+  // defer_instances keeps those instead of `inst` / `locus_inst_off` (both stay empty): the device builds the two
+  // tables from them (kernels.cu: build_instances_kernel) -- 3 bytes per row to write and send instead of 20.
+  bool inst_deferred = false;
+  size_t n_inst = 0;                     // instances of the forest, deferred or not
+  Table<uint8_t> germ_mask;              // [n_mut] germline allele mask of every row (0: not germline)
+  Table<uint16_t> row_meta;              // [n_mut] ref_len | alt_len << 8
+  std::vector<Inst> som;                 // somatic placements, sorted by row (inside a row: DFS order)
+  std::vector<uint32_t> germ_iv;         // [n_chr][8]: first haplotype of allele mask 0..3, haplotypes of mask 0..3
+  std::vector<uint32_t> chr_row_off;     // [n_chr+1] rows of every chromosome
+
   // haplotype leaves, per chromosome (index inside a chromosome = haplotype index)
   std::vector<std::vector<HapRec>> chr_haps;
 
@@ -116,11 +128,13 @@ struct FlatForest {
 
 // throws std::domain_error on malformed input.  A block lent through out.store before the call is kept and used.
 // loci_ready (optional) is called, on the calling thread, once locus_pos / row_locus / chr_locus_off are final.
+// defer_instances: see FlatForest::inst_deferred (ignored -- the host builds the table -- when a germline SID is
+// listed more than once).
 void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
-                    const std::function<void()>& loci_ready = nullptr);
+                    const std::function<void()>& loci_ready = nullptr, bool defer_instances = false);
 // the same view from explicit per-cell genomes (what get_sample_mutations_list() / get_normal_sample() hand over)
 void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads,
-                          const std::function<void()>& loci_ready = nullptr);
+                          const std::function<void()>& loci_ready = nullptr, bool defer_instances = false);
 // bytes of lent memory that are always enough for the tables of `d` (FlatStore::capacity)
 size_t flat_store_bytes(const pcs_forest_desc& d);
 size_t flat_store_bytes(const pcs_cell_genomes_desc& g);

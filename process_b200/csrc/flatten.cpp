@@ -15,6 +15,7 @@
 #include <functional>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <thread>
 #include <unordered_map>
@@ -459,7 +460,7 @@ struct Numbering {
 // tree: flatten_forest; explicit per-cell genomes: flatten_cell_genomes).
 template <class NumberFn>
 void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, const std::function<void()>& loci_ready,
-                  NumberFn&& number) {
+                  bool defer_instances, NumberFn&& number) {
   PhaseTimer timer;
   check(d.n_chr >= 1 && d.n_chr < 65535, "n_chr out of range");
   {
@@ -536,13 +537,19 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   out.locus_first_row = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
   out.locus_first_row[n_loci] = d.n_mut;
   out.locus_inst_off = out.store.table<uint32_t>(static_cast<size_t>(n_loci) + 1);
+  if (defer_instances) {  // what the device builds the instance table from (FlatForest::inst_deferred)
+    out.row_meta = out.store.table<uint16_t>(d.n_mut);
+    out.germ_mask = out.store.table<uint8_t>(static_cast<size_t>(d.n_mut) + 1);
+  }
   {
     const uint16_t* mc = d.mut_chr;
     const uint32_t* mp = d.mut_pos;
     uint32_t* locus_pos = out.locus_pos.data();
     uint32_t* first_row = out.locus_first_row.data();
     uint32_t* row_locus = out.row_locus.data();
-    parallel_for(n_chunks, [&, mc, mp, locus_pos, first_row, row_locus](uint32_t k) {
+    uint16_t* row_meta = out.row_meta.data();  // null unless deferred
+    uint8_t* germ_mask = out.germ_mask.data();
+    parallel_for(n_chunks, [&, mc, mp, locus_pos, first_row, row_locus, row_meta, germ_mask](uint32_t k) {
       const uint32_t lo = chunk_lo(k), hi = chunk_lo(k + 1);
       uint32_t l = chunk_loci[k];  // loci before this chunk
       uint32_t pc = lo ? mc[lo - 1] : 0, pp = lo ? mp[lo - 1] : 0;
@@ -556,6 +563,11 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
         row_locus[m] = l - 1;
         pc = c;
         pp = p;
+      }
+      if (row_meta) {
+        for (uint32_t m = lo; m < hi; ++m)
+          row_meta[m] = static_cast<uint16_t>(d.mut_ref_len[m] | (static_cast<uint16_t>(d.mut_alt_len[m]) << 8));
+        std::memset(germ_mask + lo, 0, (k + 1 == n_chunks ? hi + 1 : hi) - lo);  // the mask bytes start out "not germline"
       }
     });
   }
@@ -578,7 +590,15 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   check(G <= 0xffffffffull, "too many germline SIDs");
   const uint32_t g_chunks = G ? static_cast<uint32_t>(std::min<uint64_t>(4 * n_threads, (G + 65535) / 65536)) : 0;
   // relaxed atomic ORs: a row listed twice may be written by two threads
-  std::unique_ptr<std::atomic<uint8_t>[]> row_mask(new std::atomic<uint8_t>[static_cast<size_t>(d.n_mut) + 1]());
+  static_assert(sizeof(std::atomic<uint8_t>) == 1, "the mask bytes are sent to the device as they lie");
+  std::unique_ptr<std::atomic<uint8_t>[]> row_mask_heap;
+  std::atomic<uint8_t>* row_mask;
+  if (defer_instances) {
+    row_mask = reinterpret_cast<std::atomic<uint8_t>*>(out.germ_mask.data());  // zeroed by the loci pass
+  } else {
+    row_mask_heap.reset(new std::atomic<uint8_t>[static_cast<size_t>(d.n_mut) + 1]());
+    row_mask = row_mask_heap.get();
+  }
   {
     // Threads must not write mask bytes of the same cache line, or the line bounces between cores for every
     // entry.  A list sorted by row is scattered chunk by chunk as it lies; any other order is first partitioned
@@ -676,7 +696,7 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   }
   {
     const std::function<void(uint32_t, const std::function<void(uint32_t)>&)> pf = parallel_for;
-    Numbering nb{d, out, work, row_mask.get(), pf, timer};
+    Numbering nb{d, out, work, row_mask, pf, timer};
     number(nb);
   }
   timer.lap("haplotype numbering");
@@ -693,6 +713,14 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   });
   for (uint32_t k = 0; k < m_chunks; ++k) germ_before[k + 1] += germ_before[k];
   const bool listed_once = germ_before[m_chunks] == G;
+  out.chr_row_off = chr_row_off;
+  out.germ_iv.assign(static_cast<size_t>(d.n_chr) * 8, 0);
+  for (uint32_t c = 0; c < d.n_chr; ++c) {  // haplotype interval of every germline allele mask: 1, 2, 3 = both
+    const ChrWork& w = work[c];
+    uint32_t* iv = out.germ_iv.data() + static_cast<size_t>(c) * 8;
+    iv[1] = w.germ_lo[0]; iv[2] = w.germ_lo[1]; iv[3] = w.germ_lo[0];
+    iv[5] = w.germ_hi[0] - w.germ_lo[0]; iv[6] = w.germ_hi[1] - w.germ_lo[1]; iv[7] = w.germ_hi[1] - w.germ_lo[0];
+  }
   std::vector<uint32_t> g_mut;   // only when a row is listed more than once
   std::vector<uint8_t> g_mask;
   if (!listed_once) {
@@ -724,6 +752,21 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   }
   check(som.size() + G <= 0xffffffffull, "too many SID placements");
   const size_t n_inst = som.size() + G;
+  out.n_inst = n_inst;
+  if (defer_instances && listed_once) {
+    // the device builds inst / locus_inst_off (FlatForest::inst_deferred); what the merge below would have refused
+    // is refused here: a mask naming an allele the chromosome does not have (or one past the two germline alleles)
+    parallel_for(d.n_chr, [&](uint32_t c) {
+      const uint32_t bad = (0xffu << d.chr_n_alleles[c]) | 0xfcu;
+      uint32_t any = 0;
+      for (uint32_t m = chr_row_off[c]; m < chr_row_off[c + 1]; ++m) any |= row_mask[m].load(std::memory_order_relaxed) & bad;
+      check(any == 0, "germ_allele_mask names a missing allele");
+    });
+    out.inst_deferred = true;
+    out.som = std::move(som);
+    out.locus_inst_off = Table<uint32_t>{};
+    timer.lap("instances (deferred)");
+  } else {
   out.inst = out.store.table<Inst>(n_inst);
   out.locus_inst_off[n_loci] = static_cast<uint32_t>(n_inst);
   auto row_less = [](const Inst& in, uint32_t row) { return in.row < row; };
@@ -797,6 +840,7 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
     check(gi == g1 && si == s1 && pos == g1 + s1, "internal: instance merge out of step");
   });
   timer.lap("instances");
+  }
 
   // ---- merge the per-chromosome haplotypes, fragment sets and pieces
   out.chr_haps.resize(d.n_chr);
@@ -833,9 +877,10 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
   timer.lap("merge");
 }
 
-void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, const std::function<void()>& loci_ready) {
+void flatten_forest(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads, const std::function<void()>& loci_ready,
+                    bool defer_instances) {
   check(d.n_nodes >= 1, "the forest has no nodes");
-  flatten_with(d, out, n_threads, loci_ready, [&](Numbering& nb) {
+  flatten_with(d, out, n_threads, loci_ready, defer_instances, [&](Numbering& nb) {
     FlatForest& out = nb.out;
     std::vector<ChrWork>& work = nb.work;
     const std::atomic<uint8_t>* row_mask = nb.row_mask;
@@ -1132,11 +1177,11 @@ pcs_forest_desc common_desc(const pcs_cell_genomes_desc& g) {
 }  // namespace
 
 void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsigned n_threads,
-                          const std::function<void()>& loci_ready) {
+                          const std::function<void()>& loci_ready, bool defer_instances) {
   const pcs_forest_desc d = common_desc(g);
   for (uint32_t c = 0; c < g.n_cells; ++c) check(g.cell_sample[c] < g.n_samples, "cell_sample out of range");
   check(g.n_alleles == 0 || (g.allele_frag_off[0] == 0 && g.allele_sid_off[0] == 0), "allele offsets are not CSR arrays");
-  flatten_with(d, out, n_threads, loci_ready, [&](Numbering& nb) {
+  flatten_with(d, out, n_threads, loci_ready, defer_instances, [&](Numbering& nb) {
     nb.out.n_roots = g.n_normal_preneo;
     std::vector<std::vector<uint64_t>> by_chr(g.n_chr);
     for (uint64_t a = 0; a < g.n_alleles; ++a) {
@@ -1154,15 +1199,15 @@ void flatten_cell_genomes(const pcs_cell_genomes_desc& g, FlatForest& out, unsig
 size_t flat_store_bytes(const pcs_cell_genomes_desc& g) {
   auto padded = [](size_t n, size_t elem) { return (std::max<size_t>(n * elem, 1) + 255) & ~static_cast<size_t>(255); };
   const size_t n_sid = g.n_alleles ? static_cast<size_t>(g.allele_sid_off[g.n_alleles]) : 0;
-  return 2 * padded(g.n_mut, 4) + 2 * padded(static_cast<size_t>(g.n_mut) + 1, 4) +
-         padded(n_sid + static_cast<size_t>(g.n_germline), sizeof(Inst));
+  return 2 * padded(g.n_mut, 4) + 2 * padded(static_cast<size_t>(g.n_mut) + 1, 4) + padded(g.n_mut, 2) +
+         padded(static_cast<size_t>(g.n_mut) + 1, 1) + padded(n_sid + static_cast<size_t>(g.n_germline), sizeof(Inst));
 }
 
 size_t flat_store_bytes(const pcs_forest_desc& d) {
   auto padded = [](size_t n, size_t elem) { return (std::max<size_t>(n * elem, 1) + 255) & ~static_cast<size_t>(255); };
   // loci <= rows; a SID event or a germline entry places at most one instance
-  return 2 * padded(d.n_mut, 4) + 2 * padded(static_cast<size_t>(d.n_mut) + 1, 4) +
-         padded(static_cast<size_t>(d.n_events + d.n_germline), sizeof(Inst));
+  return 2 * padded(d.n_mut, 4) + 2 * padded(static_cast<size_t>(d.n_mut) + 1, 4) + padded(d.n_mut, 2) +
+         padded(static_cast<size_t>(d.n_mut) + 1, 1) + padded(static_cast<size_t>(d.n_events + d.n_germline), sizeof(Inst));
 }
 
 }  // namespace pcs

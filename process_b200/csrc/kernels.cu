@@ -1485,6 +1485,103 @@ cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const ui
   return cudaGetLastError();
 }
 
+// ------------------------------------------------ instance table on the device
+// The flattener of an uploaded forest does not write the instance table (flat.hpp: FlatForest::inst_deferred): 99 %
+// of it is the germline, and a germline instance is {interval of its allele mask on its chromosome, row, lengths}.
+// Built here from one mask byte and one length pair per row, the somatic placements (sorted by row; a few tens of
+// thousands) and eight words per chromosome -- same table, bit for bit, as the host merge
+// (tests/test_gpu_genomes.py::test_device_built_instances_equal_the_host_table): inside a row the somatic
+// placements first, then the germline one; locus_inst_off[l] = first instance of the locus' first row.
+// HBM-bound: reads 7 bytes per row, writes 16 per instance.
+__global__ void __launch_bounds__(kActiveThreads)
+germline_count_kernel(const uint8_t* __restrict__ mask, uint32_t M, uint32_t* __restrict__ block_count) {
+  const uint32_t base = blockIdx.x * kActiveRowsPerBlock;
+  uint32_t n = 0;
+#pragma unroll
+  for (int j = 0; j < kActivePerThread; ++j) {
+    const uint32_t m = base + j * kActiveThreads + threadIdx.x;
+    n += (m < M && mask[m] != 0) ? 1u : 0u;
+  }
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  __shared__ uint32_t s_w[kActiveThreads / 32];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = n;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kActiveThreads / 32; ++w) t += s_w[w];
+    block_count[blockIdx.x] = t;
+  }
+}
+
+// first index of the sorted-by-row somatic placements whose row is >= m
+__device__ __forceinline__ uint32_t somatic_lower_bound(const uint4* __restrict__ som, uint32_t n_som, uint32_t m) {
+  uint32_t lo = 0, hi = n_som;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&som[mid].z) < m) lo = mid + 1u; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kActiveThreads)
+build_instances_kernel(const uint8_t* __restrict__ mask, const uint16_t* __restrict__ meta,
+                       const uint32_t* __restrict__ row_locus, const uint32_t* __restrict__ chr_row_off, uint32_t n_chr,
+                       const uint32_t* __restrict__ germ_iv, const uint4* __restrict__ som, uint32_t n_som,
+                       const uint32_t* __restrict__ block_off, uint32_t M, uint32_t L, uint32_t n_inst,
+                       uint4* __restrict__ inst, uint32_t* __restrict__ locus_inst_off) {
+  __shared__ uint32_t s_w[kActiveThreads / 32];
+  const uint32_t base = blockIdx.x * kActiveRowsPerBlock;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t lanes_below;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanes_below));
+  if (blockIdx.x == 0 && threadIdx.x == 0) locus_inst_off[L] = n_inst;
+  uint32_t running = block_off[blockIdx.x];  // germline rows before this block
+  for (int j = 0; j < kActivePerThread; ++j) {
+    const uint32_t m = base + j * kActiveThreads + threadIdx.x;
+    const uint32_t k = m < M ? mask[m] : 0u;
+    const uint32_t ballot = __ballot_sync(0xffffffffu, k != 0u);
+    if (lane == 0) s_w[warp] = __popc(ballot);
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kActiveThreads / 32; ++w) {
+      const uint32_t c = s_w[w];
+      before += w < static_cast<int>(warp) ? c : 0u;
+      all += c;
+    }
+    if (m < M) {
+      uint32_t si = somatic_lower_bound(som, n_som, m);
+      uint32_t at = running + before + __popc(ballot & lanes_below) + si;  // the instances of every earlier row
+      if (m == 0u || __ldg(row_locus + m) != __ldg(row_locus + m - 1u)) locus_inst_off[__ldg(row_locus + m)] = at;
+      for (; si < n_som && __ldg(&som[si].z) == m; ++si) inst[at++] = __ldg(som + si);
+      if (k != 0u) {
+        uint32_t lo = 0, hi = n_chr;  // the chromosome of the row: last c with chr_row_off[c] <= m
+        while (hi - lo > 1u) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (__ldg(chr_row_off + mid) <= m) lo = mid; else hi = mid;
+        }
+        const uint32_t* iv = germ_iv + lo * 8u;
+        inst[at] = make_uint4(__ldg(iv + (k & 3u)), __ldg(iv + 4u + (k & 3u)), m, meta[m]);
+      }
+    }
+    running += all;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_build_instances(cudaStream_t st, const uint8_t* mask, const uint16_t* meta, const uint32_t* row_locus,
+                                   const uint32_t* chr_row_off, uint32_t n_chr, const uint32_t* germ_iv, const uint4* som,
+                                   uint32_t n_som, uint32_t* block_scratch, uint32_t M, uint32_t L, uint32_t n_inst,
+                                   uint4* inst, uint32_t* locus_inst_off) {
+  const uint32_t nb = active_blocks(M);
+  if (nb == 0) return cudaMemsetAsync(locus_inst_off, 0, sizeof(uint32_t) * (static_cast<size_t>(L) + 1), st);
+  germline_count_kernel<<<nb, kActiveThreads, 0, st>>>(mask, M, block_scratch);
+  active_scan_kernel<<<1, 1024, 0, st>>>(block_scratch, nb, block_scratch + nb);
+  build_instances_kernel<<<nb, kActiveThreads, 0, st>>>(mask, meta, row_locus, chr_row_off, n_chr, germ_iv, som, n_som,
+                                                        block_scratch, M, L, n_inst, inst, locus_inst_off);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------- coverage tracks
 // Binned depth along the genome (the tables behind depth-ratio plots,
 // R/plot_genome_wide_mutations.R:75-108, want depth between the mutations too).  Reads are never materialised,

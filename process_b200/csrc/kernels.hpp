@@ -38,6 +38,12 @@ cudaError_t launch_active_scatter(cudaStream_t st, const uint32_t* occ, const ui
                                   const uint8_t* carried, uint32_t S, uint32_t M, uint32_t L, const uint32_t* block_off,
                                   uint32_t n_active, uint32_t* rows_out, uint32_t* occ_c, uint32_t* cov_c,
                                   double* vaf_c);
+// the instance table of a forest flattened with deferred instances (flat.hpp), built on the device;
+// block_scratch: active_blocks(M) + 1 words
+cudaError_t launch_build_instances(cudaStream_t st, const uint8_t* mask, const uint16_t* meta, const uint32_t* row_locus,
+                                   const uint32_t* chr_row_off, uint32_t n_chr, const uint32_t* germ_iv, const uint4* som,
+                                   uint32_t n_som, uint32_t* block_scratch, uint32_t M, uint32_t L, uint32_t n_inst,
+                                   uint4* inst, uint32_t* locus_inst_off);
 // binned depth track of the plan's reads: track[s][chr_bin_off[chr] + (pos >> bin_shift)] += bases
 cudaError_t launch_coverage_track(cudaStream_t st, const Tile* tiles, uint32_t n_tiles, const Entry* entries,
                                   const DevForest& F, const SeqModel& M, uint32_t bin_shift, uint32_t max_tile_len,

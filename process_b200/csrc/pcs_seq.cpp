@@ -76,6 +76,13 @@ void parallel_copy(void* dst, const void* src, size_t bytes) {
   }, nt);
 }
 
+// PCS_DEVICE_INSTANCES=0: the flattener of an uploaded forest writes the instance table itself and sends it (the
+// round-1 path, kept for A/B runs); default: the device builds it (flat.hpp: FlatForest::inst_deferred)
+bool device_instances() {
+  const char* e = std::getenv("PCS_DEVICE_INSTANCES");
+  return !(e && std::string(e) == "0");
+}
+
 // device buffer from the device's stream-ordered memory pool (cudaMallocAsync): repeated
 // upload / plan / free cycles reuse pooled memory instead of paying cudaMalloc each time
 template <class T>
@@ -257,9 +264,10 @@ struct pcs_ctx {
     cudaEvent_t done = nullptr;
     bool in_flight = false;
   };
-  PlanSlot plan_slots[5];  // [4]: the haplotype lists of a forest's sample groups
+  PlanSlot plan_slots[6];  // [4]: the haplotype lists of a forest's sample groups; [5]: inputs of its device-built instances
   PlanSlot& group_slot(size_t bytes) { return plan_slot(4, bytes); }
-  PlanSlot& plan_slot(size_t k, size_t bytes) {  // k in [0, 4]
+  PlanSlot& instance_slot(size_t bytes) { return plan_slot(5, bytes); }
+  PlanSlot& plan_slot(size_t k, size_t bytes) {  // k in [0, 5]
     PlanSlot& sl = plan_slots[k];
     if (!sl.done) CUDA_OK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
     if (sl.in_flight) {
@@ -311,6 +319,10 @@ struct HostForest {
     flat.store.base = static_cast<char*>(block.p);
     flat.store.capacity = block.bytes;
   }
+  // deferred instance table (flat.inst_deferred): host copies of what the device built, fetched on first use
+  std::mutex inst_mutex;
+  std::vector<pcs::Inst> inst_copy;
+  std::vector<uint32_t> inst_off_copy;
   uint32_t n_groups = 0;
   std::vector<uint32_t> leaf_group;
   std::vector<uint32_t> group_cells;  // tumour cells per group
@@ -507,9 +519,14 @@ struct pcs_forest {
       upload_table(d_locus_pos, F.locus_pos, staged32);
       upload_table(d_row_locus, F.row_locus, staged32);
     }
-    upload_table(d_locus_inst_off, F.locus_inst_off, staged32);
-    upload_table(d_inst, F.inst, staged_inst);
-    if (staged32.empty() && staged_inst.empty()) return;
+    if (!F.inst_deferred) {
+      upload_table(d_locus_inst_off, F.locus_inst_off, staged32);
+      upload_table(d_inst, F.inst, staged_inst);
+    }
+    if (staged32.empty() && staged_inst.empty()) {
+      if (F.inst_deferred) build_instances_on_device();
+      return;
+    }
     auto padded = [](size_t bytes) { return (bytes + 255) & ~static_cast<size_t>(255); };
     size_t total = 0;
     for (const auto& [dst, src] : staged32) total += padded(src->size() * 4);
@@ -520,6 +537,66 @@ struct pcs_forest {
     for (const auto& [dst, src] : staged32) h2d_bytes += dst->upload_staged(*src, st, stage, off);
     for (const auto& [dst, src] : staged_inst) h2d_bytes += dst->upload_staged(*src, st, stage, off);
     CUDA_OK(cudaStreamSynchronize(st));
+    if (F.inst_deferred) build_instances_on_device();
+  }
+  // The instance table of a forest flattened with deferred instances: one mask byte and one length pair per row
+  // go up (from the pinned block, where the flattener wrote them), the somatic placements and the chromosomes'
+  // germline intervals through a pinned slot, and the device writes inst / locus_inst_off (kernels.cu:
+  // build_instances_kernel).  Everything is queued on the context's stream; the temporaries are freed in stream order.
+  void build_instances_on_device() {
+    cudaStream_t st = ctx->stream;
+    const pcs::FlatForest& F = host.flat;
+    const uint32_t M = F.n_mut, L = static_cast<uint32_t>(F.locus_pos.size());
+    d_inst.alloc(F.n_inst, st);
+    d_locus_inst_off.alloc(static_cast<size_t>(L) + 1, st);
+    DevBuf<uint8_t> d_mask;
+    DevBuf<uint16_t> d_meta;
+    DevBuf<pcs::Inst> d_som;
+    DevBuf<uint32_t> d_small, d_scratch;
+    std::vector<std::pair<DevBuf<uint8_t>*, const pcs::Table<uint8_t>*>> st8;
+    std::vector<std::pair<DevBuf<uint16_t>*, const pcs::Table<uint16_t>*>> st16;
+    const pcs::Table<uint8_t> mask_rows{const_cast<uint8_t*>(F.germ_mask.data()), M};  // the table has one spare byte
+    upload_table(d_mask, mask_rows, st8);
+    upload_table(d_meta, F.row_meta, st16);
+    require(st8.empty() && st16.empty(), "internal: the deferred instance inputs are not in the pinned block");
+    // small inputs: [chr_row_off (n_chr + 1) | germ_iv (8 n_chr)] and the somatic placements, through a pinned slot
+    const size_t n_small = F.chr_row_off.size() + F.germ_iv.size();
+    const size_t b_small = n_small * sizeof(uint32_t), b_som = F.som.size() * sizeof(pcs::Inst);
+    const size_t pad_small = (b_small + 255) & ~static_cast<size_t>(255);
+    pcs_ctx::PlanSlot& slot = ctx->instance_slot(pad_small + b_som + 256);
+    std::memcpy(slot.p, F.chr_row_off.data(), F.chr_row_off.size() * sizeof(uint32_t));
+    std::memcpy(slot.p + F.chr_row_off.size() * sizeof(uint32_t), F.germ_iv.data(), F.germ_iv.size() * sizeof(uint32_t));
+    if (b_som) std::memcpy(slot.p + pad_small, F.som.data(), b_som);
+    d_small.alloc(n_small, st);
+    d_som.alloc(F.som.size(), st);
+    CUDA_OK(cudaMemcpyAsync(d_small.p, slot.p, b_small, cudaMemcpyHostToDevice, st));
+    if (b_som) CUDA_OK(cudaMemcpyAsync(d_som.p, slot.p + pad_small, b_som, cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(slot.done, st));
+    slot.in_flight = true;
+    h2d_bytes += b_small + b_som;
+    d_scratch.alloc(static_cast<size_t>(pcs::active_blocks(M)) + 1, st);
+    CUDA_OK(pcs::launch_build_instances(st, d_mask.p, d_meta.p, d_row_locus.p, d_small.p, F.n_chr,
+                                        d_small.p + F.chr_row_off.size(), reinterpret_cast<const uint4*>(d_som.p),
+                                        static_cast<uint32_t>(F.som.size()), d_scratch.p, M, L,
+                                        static_cast<uint32_t>(F.n_inst), reinterpret_cast<uint4*>(d_inst.p),
+                                        d_locus_inst_off.p));
+  }
+  // host copies of the two device-built tables, for the few host paths that read instances (the rows carried by
+  // sequenced cells: include_non_sequenced_mutations): fetched once, on first use
+  void ensure_host_instances() {
+    pcs::FlatForest& F = host.flat;
+    if (!F.inst_deferred) return;
+    std::lock_guard<std::mutex> lock(host.inst_mutex);
+    if (!host.inst_copy.empty() || F.n_inst == 0) return;
+    ctx->bind();
+    host.inst_copy.resize(F.n_inst);
+    host.inst_off_copy.resize(F.locus_pos.size() + 1);
+    CUDA_OK(cudaMemcpyAsync(host.inst_copy.data(), d_inst.p, F.n_inst * sizeof(pcs::Inst), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(host.inst_off_copy.data(), d_locus_inst_off.p, host.inst_off_copy.size() * sizeof(uint32_t),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    F.inst = pcs::Table<pcs::Inst>{host.inst_copy.data(), host.inst_copy.size()};
+    F.locus_inst_off = pcs::Table<uint32_t>{host.inst_off_copy.data(), host.inst_off_copy.size()};
   }
   pcs_forest() = default;
   explicit pcs_forest(const pcs_forest& other, pcs_ctx* cx) : ctx(cx), host_ptr(other.host_ptr), host(*host_ptr) {}
@@ -1694,6 +1771,7 @@ std::unique_ptr<pcs_result> assemble_result(pcs_forest& fo, const uint32_t* d_oc
   if (M == 0 || S == 0) return res;
   DevBuf<uint8_t> d_carried;
   if (include_non_sequenced) {
+    fo.ensure_host_instances();
     const std::vector<uint8_t> carried = carried_rows(fo.host, params);
     d_carried.upload(carried, st);
   }
@@ -1967,7 +2045,7 @@ int pcs_forest_upload(pcs_ctx* cx, const pcs_forest_desc* desc, pcs_forest** out
     fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
     lap("pinned block");
     pcs_forest* early = fo.get();
-    pcs::flatten_forest(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); });
+    pcs::flatten_forest(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); }, device_instances());
     lap("flatten_forest");
     fo->upload_flat();
     lap("upload flat arrays");
@@ -1987,7 +2065,7 @@ int pcs_forest_upload_genomes(pcs_ctx* cx, const pcs_cell_genomes_desc* desc, pc
     Lap lap;
     fo->host.borrow(cx, pcs::flat_store_bytes(*desc));
     pcs_forest* early = fo.get();
-    pcs::flatten_cell_genomes(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); });
+    pcs::flatten_cell_genomes(*desc, fo->host.flat, host_threads(), [early] { early->upload_loci_early(); }, device_instances());
     lap("flatten_cell_genomes");
     fo->upload_flat();
     fo->set_groups(fo->host.flat.leaf_sample.data(), fo->host.flat.n_samples);
@@ -2022,12 +2100,23 @@ int pcs_forest_info(const pcs_forest* fo, uint64_t out[6]) {
     uint64_t haps = 0;
     for (const auto& v : fo->host.flat.chr_haps) haps += v.size();
     out[0] = fo->host.flat.locus_pos.size();
-    out[1] = fo->host.flat.inst.size();
+    out[1] = fo->host.flat.n_inst;
     out[2] = haps;
     out[3] = fo->host.flat.fragsets.size();
     out[4] = fo->host.flat.pieces.size();
     out[5] = fo->d_locus_pos.bytes() + fo->d_chr_locus_off.bytes() + fo->d_locus_inst_off.bytes() +
              fo->d_row_locus.bytes() + fo->d_inst.bytes() + fo->d_hap_list.bytes();
+  });
+}
+
+int pcs_forest_instances(pcs_forest* fo, uint32_t* inst, uint32_t* locus_inst_off) {
+  return guarded([&] {
+    require(fo && inst && locus_inst_off, "bad arguments");
+    fo->ctx->bind();
+    cudaStream_t st = fo->ctx->stream;
+    if (fo->d_inst.n) CUDA_OK(cudaMemcpyAsync(inst, fo->d_inst.p, fo->d_inst.bytes(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaMemcpyAsync(locus_inst_off, fo->d_locus_inst_off.p, fo->d_locus_inst_off.bytes(), cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
   });
 }
 
@@ -2865,7 +2954,10 @@ int pcs_active_rows(pcs_forest* fo, const uint32_t* occ, uint32_t n_out_samples,
     require(fo && occ && rows_out && n_rows, "bad arguments");
     const pcs::FlatForest& F = fo->host.flat;
     std::vector<uint8_t> carried;
-    if (include_non_sequenced) carried = carried_rows(fo->host, params);
+    if (include_non_sequenced) {
+      fo->ensure_host_instances();
+      carried = carried_rows(fo->host, params);
+    }
     uint32_t k = 0;
     for (uint32_t m = 0; m < F.n_mut; ++m) {
       bool on = include_non_sequenced && carried[m];
@@ -3101,7 +3193,7 @@ int pcs_flat_info(const pcs_flat* fl, uint64_t out[6]) {
     uint64_t haps = 0;
     for (const auto& v : F.chr_haps) haps += v.size();
     out[0] = F.locus_pos.size();
-    out[1] = F.inst.size();
+    out[1] = F.n_inst;
     out[2] = haps;
     out[3] = F.fragsets.size();
     out[4] = F.pieces.size();
@@ -3230,6 +3322,15 @@ int pcs_host_binomial(uint32_t seed, uint64_t n, double p, uint64_t count, uint6
     require(n < (1ull << 53) && p >= 0.0 && p <= 1.0, "Binomial(n, p): n < 2^53 and 0 <= p <= 1");
     pcs::PlanRng rng(seed, 0x7e57u, 0u, 0u, 0u);
     for (uint64_t i = 0; i < count; ++i) out[i] = pcs::binomial(rng, n, p);
+  });
+}
+
+int pcs_flat_instances(const pcs_flat* fl, uint32_t* inst, uint32_t* locus_inst_off) {
+  return guarded([&] {
+    require(fl && inst && locus_inst_off, "bad arguments");
+    const pcs::FlatForest& F = fl->host.flat;
+    std::memcpy(inst, F.inst.data(), F.inst.size() * sizeof(pcs::Inst));
+    std::memcpy(locus_inst_off, F.locus_inst_off.data(), F.locus_inst_off.size() * sizeof(uint32_t));
   });
 }
 

@@ -59,3 +59,34 @@ def test_sampling_law_on_the_genome_built_view(ctx):
         z, impossible = CF.z_scores(obs, exp)
         assert impossible == 0
         assert len(z) > 1500 and abs(z.mean()) < 0.1 and 0.9 < z.std() < 1.1 and np.abs(z).max() < 5.5
+
+
+@pytest.mark.parametrize("seed", [0, 3, 7])
+@pytest.mark.parametrize("as_genomes", [False, True])
+def test_device_built_instances_equal_the_host_table(ctx, seed, as_genomes, monkeypatch):
+    """An uploaded forest builds its instance table on the device from one germline mask byte per row
+    (kernels.cu: build_instances_kernel); the host flattener's table (pcs_flat_create; also PCS_DEVICE_INSTANCES=0)
+    is the same table, bit for bit -- rows in order, inside a row the somatic placements then the germline one."""
+    f = synth_forest(small_spec(seed))
+    src = oracle.cell_genomes(f) if as_genomes else f
+    inst_h, off_h = L.Flat(src).instances()
+    assert len(inst_h) > 1000 and (inst_h[:, 3] != 0x0101).any()  # there are indels among them
+    monkeypatch.setenv("PCS_DEVICE_INSTANCES", "1")
+    dev = L.Forest(ctx, src)
+    inst_d, off_d = dev.instances()
+    assert np.array_equal(off_d, off_h) and np.array_equal(inst_d, inst_h)
+    # the rows carried by sequenced cells are computed on the host from a copy fetched on first use
+    P = make_params(coverage=5.0, seed=1)
+    res = dev.simulate_result(P, include_non_sequenced=1)[0]
+    r1 = res.fetch()[0].copy()
+    res.close()
+    assert len(r1) > 1000
+    dev.close()
+    monkeypatch.setenv("PCS_DEVICE_INSTANCES", "0")
+    dev0 = L.Forest(ctx, src)
+    inst_0, off_0 = dev0.instances()
+    assert np.array_equal(off_0, off_h) and np.array_equal(inst_0, inst_h)
+    res0 = dev0.simulate_result(P, include_non_sequenced=1)[0]
+    assert np.array_equal(r1, res0.fetch()[0])
+    res0.close()
+    dev0.close()
