@@ -297,8 +297,14 @@ struct pcs_ctx {
 };
 
 
+namespace {
+struct GridCache;  // the tile geometry of the forest's last call (planner, below)
+std::shared_ptr<GridCache> make_grid_cache();
+}  // namespace
+
 // host half of an uploaded forest: flattened view + output sample groups
 struct HostForest {
+  std::shared_ptr<GridCache> grid_cache = make_grid_cache();
   pcs::FlatForest flat;
   // pinned block lent by a context for flat.store; handed back when the last device copy of the forest dies
   pcs_ctx* lender = nullptr;
@@ -824,9 +830,27 @@ struct PlanSetup {
     std::vector<pcs::Tile> tiles;         // chr, begin, len, l0, l1, r0, n_rows
     std::vector<uint32_t> piece_tile_off; // [pieces of the chromosome + 1]
   };
-  std::vector<ChrGrid> grid;
+  std::shared_ptr<const std::vector<ChrGrid>> grid_ptr;  // kept by the forest: later calls with the same geometry reuse it
+  const std::vector<ChrGrid>& grid_of() const { return *grid_ptr; }
   bool sequenced(uint32_t c) const { return chr_mask.empty() || chr_mask[c]; }
 };
+
+// the tile geometry a forest keeps for its next call: it depends on the forest and on these parameters only
+struct GridKey {
+  uint32_t R = 0, W = 0, lcap = 0;
+  uint64_t reach = 0;
+  bool thin = false;
+  std::vector<uint8_t> chr_mask;
+  bool operator==(const GridKey& o) const {
+    return R == o.R && W == o.W && lcap == o.lcap && reach == o.reach && thin == o.thin && chr_mask == o.chr_mask;
+  }
+};
+struct GridCache {
+  std::mutex m;
+  GridKey key;
+  std::shared_ptr<const std::vector<PlanSetup::ChrGrid>> grid;
+};
+std::shared_ptr<GridCache> make_grid_cache() { return std::make_shared<GridCache>(); }
 
 PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
   PlanSetup ps;
@@ -860,11 +884,22 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
   ps.shards = P.shard_count ? P.shard_count : 1;
   while ((((static_cast<uint64_t>(ps.W) + ps.reach) >> ps.dir_shift) + 1) > 4096) ++ps.dir_shift;
 
-  ps.grid.resize(F.n_chr);
+  GridCache& cache = *fo.grid_cache;
+  GridKey key;
+  key.R = ps.R; key.W = ps.W; key.lcap = ps.lcap; key.reach = ps.reach; key.thin = ps.thin; key.chr_mask = ps.chr_mask;
+  {
+    std::lock_guard<std::mutex> lock(cache.m);
+    if (cache.grid && cache.key == key) {
+      ps.grid_ptr = cache.grid;
+      return ps;
+    }
+  }
+  auto grid_new = std::make_shared<std::vector<PlanSetup::ChrGrid>>(F.n_chr);
+  std::vector<PlanSetup::ChrGrid>& grid = *grid_new;
   Lap lap;
   host_tasks(F.n_chr, [&](size_t ci) {
     const uint32_t c = static_cast<uint32_t>(ci);
-    PlanSetup::ChrGrid& g = ps.grid[c];
+    PlanSetup::ChrGrid& g = grid[c];
     g.piece_tile_off.assign(F.chr_piece_off[c + 1] - F.chr_piece_off[c] + 1, 0);
     if (!ps.sequenced(c)) return;
     const uint32_t* lp = F.locus_pos.data();
@@ -913,10 +948,10 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
     std::vector<std::pair<uint32_t, uint32_t>> chunks;  // (chromosome, first tile)
     constexpr uint32_t kChunk = 128;
     for (uint32_t c = 0; c < F.n_chr; ++c)
-      for (uint32_t i = 0; i < ps.grid[c].tiles.size(); i += kChunk) chunks.emplace_back(c, i);
+      for (uint32_t i = 0; i < grid[c].tiles.size(); i += kChunk) chunks.emplace_back(c, i);
     const uint32_t* lp = F.locus_pos.data();
     host_tasks(chunks.size(), [&](size_t k) {
-      std::vector<pcs::Tile>& tiles = ps.grid[chunks[k].first].tiles;
+      std::vector<pcs::Tile>& tiles = grid[chunks[k].first].tiles;
       const size_t i1 = std::min<size_t>(tiles.size(), chunks[k].second + kChunk);
       for (size_t i = chunks[k].second; i < i1; ++i) {
         pcs::Tile& t = tiles[i];
@@ -925,6 +960,12 @@ PlanSetup plan_setup(const HostForest& fo, const pcs_seq_params& P) {
       }
     });
     lap("    geometry: useful offsets");
+  }
+  ps.grid_ptr = grid_new;
+  {
+    std::lock_guard<std::mutex> lock(cache.m);
+    cache.key = std::move(key);
+    cache.grid = grid_new;
   }
   return ps;
 }
@@ -976,7 +1017,7 @@ void plan_sample_chr(const PlanSetup& ps, uint32_t s, uint32_t c, SampleChrPlan&
   std::vector<pcs::Entry>& entries = task.entries;
   std::vector<pcs::Tile>& all = task.tiles;
   std::vector<double>& tile_w = task.tile_w;
-  const PlanSetup::ChrGrid& g = ps.grid[c];
+  const PlanSetup::ChrGrid& g = ps.grid_of()[c];
   all.reserve(g.tiles.size());
   tile_w.reserve(g.tiles.size());
   // normal cells: every one carries each germline allele whole
@@ -1563,9 +1604,11 @@ struct CallTables {
   size_t S = 0, M = 0, L = 0;
 };
 
-template <class AfterSample>
-void run_pipelined(pcs_forest& fo, const pcs_seq_params& P, bool want_cov, CallTables& T, pcs_run_stats& rs,
-                   AfterSample&& after_sample) {
+// after_part(sample, first row, end row, launches so far): called when the launches that write those rows of the
+// sample's tables are queued
+template <class AfterPart>
+void run_pipelined(pcs_forest& fo, const pcs_seq_params& P, bool want_cov, bool split_last, CallTables& T, pcs_run_stats& rs,
+                   AfterPart&& after_part) {
   pcs_ctx& cx = *fo.ctx;
   cx.bind();
   cudaStream_t st = cx.stream;
@@ -1610,6 +1653,37 @@ void run_pipelined(pcs_forest& fo, const pcs_seq_params& P, bool want_cov, CallT
       at += padded(bytes);
       h2d += bytes;
     };
+    // The LAST sample's tables are the tail of the call: nothing is left to sample while they cross the link.  So
+    // its tiles are launched in `parts` groups of whole chromosomes (rows of a chromosome are contiguous and a tile
+    // never leaves its chromosome): the rows of a group travel while the next group is sampled, and the tail is
+    // one group's tables instead of the sample's.  Same tiles, same counters: the tables do not change.
+    std::vector<uint32_t> part_tile_end{static_cast<uint32_t>(hp.tiles.size())};  // staged tiles of parts 0..k
+    std::vector<uint32_t> part_row_end{static_cast<uint32_t>(M)};
+    // PCS_SPLIT_LAST=force: also on small jobs (tests); PCS_NO_SPLIT: never
+    static const bool force_split = [] {
+      const char* e = std::getenv("PCS_SPLIT_LAST");
+      return e && std::string(e) == "force";
+    }();
+    if (split_last && smp + 1 == S && hp.tiles_global.empty() && F.n_chr >= 2 &&
+        (force_split || (hp.tiles.size() >= 3000 && M >= (1u << 20)))) {
+      constexpr uint32_t kParts = 3;
+      std::vector<uint32_t> chr_part(F.n_chr, kParts - 1);
+      part_row_end.assign(kParts, static_cast<uint32_t>(M));
+      uint32_t c = 0;
+      for (uint32_t k = 0; k + 1 < kParts; ++k) {  // chromosomes up to the one where the rows pass (k + 1) / kParts
+        while (c < F.n_chr && F.locus_first_row[F.chr_locus_off[c + 1]] <= static_cast<uint64_t>(M) * (k + 1) / kParts) chr_part[c++] = k;
+        part_row_end[k] = F.locus_first_row[F.chr_locus_off[c]];
+      }
+      std::vector<pcs::Tile> grouped;
+      grouped.reserve(hp.tiles.size());
+      part_tile_end.assign(kParts, 0);
+      for (uint32_t k = 0; k < kParts; ++k) {  // heaviest first inside every group, as in the whole list
+        for (const pcs::Tile& t : hp.tiles)
+          if (chr_part[t.chr] == k) grouped.push_back(t);
+        part_tile_end[k] = static_cast<uint32_t>(grouped.size());
+      }
+      hp.tiles.swap(grouped);
+    }
     up(d_tiles, hp.tiles, b_tiles);
     up(d_glob, hp.tiles_global, b_glob);
     up(d_ent, hp.entries, b_ent);
@@ -1617,13 +1691,21 @@ void run_pipelined(pcs_forest& fo, const pcs_seq_params& P, bool want_cov, CallT
     CUDA_OK(cudaEventRecord(slot.done, st));
     slot.in_flight = true;
     CUDA_OK(cudaEventRecord(cx.time_event(2 * smp), st));
-    CUDA_OK(pcs::launch_sample_tiles_staged(st, d_tiles.p, static_cast<uint32_t>(hp.tiles.size()), d_ent.p, d_lo.p, DF,
-                                            hp.model, hp.dims, T.depth.p, T.occ.p, T.counters.p));
-    CUDA_OK(pcs::launch_sample_tiles_global(st, d_glob.p, static_cast<uint32_t>(hp.tiles_global.size()), d_ent.p, d_lo.p,
-                                            DF, hp.model, T.depth.p, T.occ.p, T.counters.p));
-    CUDA_OK(cudaEventRecord(cx.time_event(2 * smp + 1), st));
-    launches += (hp.tiles.empty() ? 0 : 1) + (hp.tiles_global.empty() ? 0 : 1);
-    after_sample(smp, launches);
+    uint32_t t0 = 0, r0 = 0;
+    for (size_t k = 0; k < part_tile_end.size(); ++k) {
+      CUDA_OK(pcs::launch_sample_tiles_staged(st, d_tiles.p + t0, part_tile_end[k] - t0, d_ent.p, d_lo.p, DF, hp.model,
+                                              hp.dims, T.depth.p, T.occ.p, T.counters.p));
+      launches += part_tile_end[k] > t0 ? 1 : 0;
+      if (k + 1 == part_tile_end.size()) {
+        CUDA_OK(pcs::launch_sample_tiles_global(st, d_glob.p, static_cast<uint32_t>(hp.tiles_global.size()), d_ent.p, d_lo.p,
+                                                DF, hp.model, T.depth.p, T.occ.p, T.counters.p));
+        launches += hp.tiles_global.empty() ? 0 : 1;
+        CUDA_OK(cudaEventRecord(cx.time_event(2 * smp + 1), st));
+      }
+      after_part(smp, r0, part_row_end[k], launches);
+      t0 = part_tile_end[k];
+      r0 = part_row_end[k];
+    }
     rs.n_templates += hp.info.n_templates;
     if (smp == 0) {
       rs.h2d_bytes = 0;  // filled below
@@ -1664,23 +1746,25 @@ void simulate_tables(pcs_forest& fo, const pcs_seq_params& P, uint32_t* occ, uin
   const size_t M = fo.host.flat.n_mut, L = fo.host.flat.locus_pos.size();
   const size_t row_bytes = M * sizeof(uint32_t);
   uint64_t fin_launches = 0;
-  run_pipelined(fo, P, true, T, rs, [&](uint32_t smp, uint64_t) {
-    if (M == 0) return;
+  size_t n_parts = 0;
+  run_pipelined(fo, P, true, std::getenv("PCS_NO_SPLIT") == nullptr, T, rs, [&](uint32_t smp, uint32_t r0, uint32_t r1, uint64_t) {
+    if (M == 0 || r1 <= r0) return;
     require(occ && cov, "occurrences/coverage output pointers are NULL");
     if (!stage) stage = static_cast<char*>(cx.staging(2 * T.S * row_bytes));
-    CUDA_OK(pcs::launch_finalize(st, T.depth.p + smp * L, fo.d_row_locus.p, 1u, static_cast<uint32_t>(L),
-                                 static_cast<uint32_t>(M), T.cov.p + smp * M));
+    const size_t n_rows = r1 - r0, part_bytes = n_rows * sizeof(uint32_t);
+    CUDA_OK(pcs::launch_finalize(st, T.depth.p + smp * L, fo.d_row_locus.p + r0, 1u, static_cast<uint32_t>(L),
+                                 static_cast<uint32_t>(n_rows), T.cov.p + smp * M + r0));
     ++fin_launches;
-    cudaEvent_t done = cx.chunk_event(2 * T.S + smp);
+    cudaEvent_t done = cx.chunk_event(2 * T.S + 8 + n_parts++);
     CUDA_OK(cudaEventRecord(done, st));
     CUDA_OK(cudaStreamWaitEvent(cs, done, 0));
-    const char* dev_tbl[2] = {reinterpret_cast<const char*>(T.occ.p + smp * M), reinterpret_cast<const char*>(T.cov.p + smp * M)};
-    char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M), reinterpret_cast<char*>(cov + smp * M)};
+    const char* dev_tbl[2] = {reinterpret_cast<const char*>(T.occ.p + smp * M + r0), reinterpret_cast<const char*>(T.cov.p + smp * M + r0)};
+    char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M + r0), reinterpret_cast<char*>(cov + smp * M + r0)};
     for (int t = 0; t < 2; ++t) {
-      char* sp = stage + (2 * smp + t) * row_bytes;
-      CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], row_bytes, cudaMemcpyDeviceToHost, cs));
+      char* sp = stage + (2 * smp + t) * row_bytes + static_cast<size_t>(r0) * sizeof(uint32_t);
+      CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], part_bytes, cudaMemcpyDeviceToHost, cs));
       CUDA_OK(cudaEventRecord(cx.chunk_event(chunks.size()), cs));
-      chunks.push_back({host_tbl[t], sp, row_bytes});
+      chunks.push_back({host_tbl[t], sp, part_bytes});
     }
   });
   if (stats) {
@@ -2979,7 +3063,7 @@ int pcs_simulate_result(pcs_forest* fo, const pcs_seq_params* params, int includ
     const double t0 = now_ms();
     CallTables T;
     pcs_run_stats rs{};
-    run_pipelined(*fo, *params, false, T, rs, [](uint32_t, uint64_t) {});
+    run_pipelined(*fo, *params, false, false, T, rs, [](uint32_t, uint32_t, uint32_t, uint64_t) {});
     uint64_t extra = 0;
     if (stats) {
       CUDA_OK(pcs::launch_sum_u32(st, T.depth.p, T.S * T.L, T.counters.p + 1));

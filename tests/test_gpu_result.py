@@ -68,6 +68,36 @@ def test_pipelined_call_and_device_result_equal_the_one_piece_plan(ctx, kw, incl
     dev.close()
 
 
+def test_last_sample_launched_in_chromosome_groups_gives_the_same_tables():
+    """pcs_simulate() launches the last sample's tiles in groups of whole chromosomes so that a group's rows cross
+    the link while the next group is sampled (big jobs only; PCS_SPLIT_LAST=force: always).  Same tables, bit for bit.
+    The switch is read once per process: a child process runs the forced case."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import sys, numpy as np
+        sys.path.insert(0, %r); sys.path.insert(0, %r)
+        from process_b200 import _abi as A, _lib as L
+        from process_b200.synth import synth_forest
+        from conftest import make_params, small_spec
+        ctx = L.Context(0)
+        for seed, kw in ((4, {}), (2, dict(sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.02)), (1, dict(chr_mask=[0, 1, 1]))):
+            f = synth_forest(small_spec(seed))
+            dev = L.Forest(ctx, f)
+            P = make_params(**{**dict(coverage=9.0, purity=0.7, seed=21), **kw})
+            plan = L.Plan(dev, P)
+            occ, cov, st = plan.run()
+            occ2, cov2, st2 = dev.simulate(P)
+            assert np.array_equal(occ, occ2) and np.array_equal(cov, cov2), "tables differ"
+            assert st2.n_reads == st.n_reads and st2.sum_occurrences == st.sum_occurrences and st2.sum_depth == st.sum_depth
+            assert st2.kernel_launches > st.kernel_launches, (st2.kernel_launches, st.kernel_launches)
+            plan.close(); dev.close()
+        print("split ok")
+    """) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PCS_SPLIT_LAST="force")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "split ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_empty_result_and_shards(ctx):
     f = synth_forest(small_spec(1))
     dev = L.Forest(ctx, f)
