@@ -3,6 +3,7 @@
 // run / trace / injected-count drivers.  No CPU fallback: every compute entry
 // point launches the sm_100a kernels of kernels.cu or fails.
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -81,6 +82,22 @@ void parallel_copy(void* dst, const void* src, size_t bytes) {
 bool device_instances() {
   const char* e = std::getenv("PCS_DEVICE_INSTANCES");
   return !(e && std::string(e) == "0");
+}
+
+// The caller's output tables are usually fresh memory (a new R vector, a new numpy array): the host threads that
+// copy the tables out of pinned memory take a page fault per 4 KB, 35 000 of them for C3's 145 MB -- as long as
+// the tables' trip over the link.  Where the kernel offers transparent huge pages on request (THP mode `madvise`
+// or `always`), ask for them: a fault then maps 2 MB.  Harmless where it does not apply (the call fails or is
+// ignored); PCS_HUGE_OUT=0 skips it.
+void advise_huge_pages(void* p, size_t bytes) {
+  static const bool on = [] {
+    const char* e = std::getenv("PCS_HUGE_OUT");
+    return !(e && std::string(e) == "0");
+  }();
+  if (!on || !p || bytes < (4u << 20)) return;
+  const uintptr_t page = 4096, lo = (reinterpret_cast<uintptr_t>(p) + page - 1) & ~(page - 1),
+                  hi = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(page - 1);
+  if (hi > lo) (void)madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
 }
 
 // device buffer from the device's stream-ordered memory pool (cudaMallocAsync): repeated
@@ -173,7 +190,7 @@ struct pcs_ctx {
       pinned = nullptr;
       pinned_bytes = 0;
       bytes += bytes / 8;  // forests of one study differ a little: do not re-pin for every one of them
-      CUDA_OK(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
+      CUDA_OK(cudaHostAlloc(&pinned, bytes, cudaHostAllocPortable));  // every device of the process may DMA into it
       pinned_bytes = bytes;
     }
     return pinned;
@@ -1567,10 +1584,32 @@ void drain_chunks(pcs_ctx& cx, const std::vector<ChunkCopy>& chunks) {
   for (cudaError_t e : werr) CUDA_OK(e);
 }
 
+// the same with one event per chunk, whatever device recorded it (pcs_simulate_multi: every device sends a slice)
+void drain_chunks_ev(int device, const std::vector<ChunkCopy>& chunks, const std::vector<cudaEvent_t>& done) {
+  if (chunks.empty()) return;
+  const unsigned nt = std::max(1u, std::min(16u, host_threads()));
+  std::vector<cudaError_t> werr(nt, cudaSuccess);
+  pcs::HostPool::get().run(nt, [&](size_t w) {
+    cudaSetDevice(device);
+    for (size_t k = 0; k < chunks.size(); ++k) {
+      const cudaError_t e = cudaEventSynchronize(done[k]);
+      if (e != cudaSuccess) {
+        werr[w] = e;
+        return;
+      }
+      const size_t lo = (chunks[k].bytes * w / nt) & ~static_cast<size_t>(63);
+      const size_t hi = w + 1 == nt ? chunks[k].bytes : (chunks[k].bytes * (w + 1) / nt) & ~static_cast<size_t>(63);
+      if (hi > lo) std::memcpy(chunks[k].dst + lo, chunks[k].src + lo, hi - lo);
+    }
+  }, nt);
+  for (cudaError_t e : werr) CUDA_OK(e);
+}
+
 uint64_t copy_out(pcs_ctx& cx, cudaStream_t st, const std::vector<OutCopy>& items) {
   size_t total = 0;
   for (const auto& it : items) total += (it.bytes + 255) & ~static_cast<size_t>(255);
   if (total == 0) return 0;
+  for (const auto& it : items) advise_huge_pages(it.dst, it.bytes);
   char* stage = static_cast<char*>(cx.staging(total));
   const size_t cb = std::max<size_t>(4u << 20, ((total / 16) + 4095) & ~static_cast<size_t>(4095));
   std::vector<ChunkCopy> chunks;
@@ -1745,6 +1784,11 @@ void simulate_tables(pcs_forest& fo, const pcs_seq_params& P, uint32_t* occ, uin
   char* stage = nullptr;
   const size_t M = fo.host.flat.n_mut, L = fo.host.flat.locus_pos.size();
   const size_t row_bytes = M * sizeof(uint32_t);
+  {
+    size_t n_out = (P.normal_only ? 0 : fo.host.n_groups) + ((P.normal_only || P.with_normal_sample) ? 1 : 0);
+    advise_huge_pages(occ, n_out * row_bytes);
+    advise_huge_pages(cov, n_out * row_bytes);
+  }
   uint64_t fin_launches = 0;
   size_t n_parts = 0;
   run_pipelined(fo, P, true, std::getenv("PCS_NO_SPLIT") == nullptr, T, rs, [&](uint32_t smp, uint32_t r0, uint32_t r1, uint64_t) {
@@ -2440,6 +2484,8 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
     const pcs::FlatForest& F = owner.host.flat;
     const size_t S = ps.samples.size(), M = F.n_mut, L = F.locus_pos.size();
     require(S * M == 0 || (occ && cov), "occurrences/coverage output pointers are NULL");
+    advise_huge_pages(occ, S * M * sizeof(uint32_t));
+    advise_huge_pages(cov, S * M * sizeof(uint32_t));
     for (uint32_t i = 1; i < n; ++i) enable_peer_both_ways(cx0.device, forests[i]->ctx->device);
     // the tables live on the first device.  Plain cudaMalloc, kept by the context: peers cannot reach stream-ordered
     // pool memory through cudaDeviceEnablePeerAccess
@@ -2467,8 +2513,29 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
       if (i) CUDA_OK(cudaStreamWaitEvent(cx.stream, zeroed, 0));
     }
     std::vector<ChunkCopy> chunks;
+    std::vector<cudaEvent_t> chunk_done;
     const size_t row_bytes = M * sizeof(uint32_t);
     char* stage = row_bytes ? static_cast<char*>(cx0.staging(2 * S * row_bytes)) : nullptr;
+    // Row slices of the tables, one per device whose link carries a share.  Default: ONE link, device 0's --
+    // measured on the 8-GPU box (profiles/r02_v5_multi_links.md): with every device sending a slice the call is
+    // 2-3 ms SLOWER (the other devices write into pinned memory of device 0's NUMA node, and the copy-out is bound
+    // by the host's memory system, not by one PCIe link).  PCS_MULTI_LINKS=k: k links; =force: n links whatever the
+    // size of the tables (tests).
+    const uint32_t n_links = [&] {
+      const char* e = std::getenv("PCS_MULTI_LINKS");
+      if (e && std::string(e) == "force") return M >= 128 ? n : 1u;
+      const long v = e ? std::atol(e) : 1;
+      return M < (1u << 16) ? 1u : std::min<uint32_t>(n, static_cast<uint32_t>(std::max(1l, v)));
+    }();
+    auto slice_lo = [&](uint32_t i) { return i >= n_links ? M : (M * static_cast<size_t>(i) / n_links) & ~static_cast<size_t>(63); };
+    size_t slice_cap = 0;
+    for (uint32_t i = 1; i < n_links; ++i) slice_cap = std::max(slice_cap, slice_lo(i + 1) - slice_lo(i));
+    std::vector<uint32_t*> scratch(n, nullptr);
+    for (uint32_t i = 1; i < n_links; ++i) {
+      forests[i]->ctx->bind();
+      scratch[i] = static_cast<uint32_t*>(forests[i]->ctx->peer_table(2 * S * slice_cap * sizeof(uint32_t)));
+    }
+    cx0.bind();
     uint32_t id_base = 0;
     uint64_t templates = 0;
     auto padded = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
@@ -2523,13 +2590,37 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
       CUDA_OK(pcs::launch_finalize(cs0, t_depth + smp * L, owner.d_row_locus.p, 1u, static_cast<uint32_t>(L),
                                    static_cast<uint32_t>(M), t_cov + smp * M));
       ++launches;
+      // The tables go home in n_links row slices: device 0 forwards slice i to device i over NVLink (a few
+      // microseconds) and device i's copy stream sends it to the host; slice 0 goes over device 0's own link.
       const char* dev_tbl[2] = {reinterpret_cast<const char*>(t_occ + smp * M), reinterpret_cast<const char*>(t_cov + smp * M)};
       char* host_tbl[2] = {reinterpret_cast<char*>(occ + smp * M), reinterpret_cast<char*>(cov + smp * M)};
       for (int t = 0; t < 2; ++t) {
+        for (uint32_t i = 1; i < n_links; ++i) {  // the forwards first: they are short and the peers' links start early
+          const size_t r_lo = slice_lo(i), nb = (slice_lo(i + 1) - r_lo) * sizeof(uint32_t);
+          if (nb == 0) continue;
+          uint32_t* scr = scratch[i] + (2 * smp + t) * slice_cap;
+          CUDA_OK(cudaMemcpyPeerAsync(scr, forests[i]->ctx->device, dev_tbl[t] + r_lo * sizeof(uint32_t), cx0.device, nb, cs0));
+          cudaEvent_t fw = cx0.chunk_event(3 * S + 2 + (2 * smp + t) * n_links + i);
+          CUDA_OK(cudaEventRecord(fw, cs0));
+          pcs_ctx& cx = *forests[i]->ctx;
+          cx.bind();
+          cudaStream_t cs = cx.copier();
+          CUDA_OK(cudaStreamWaitEvent(cs, fw, 0));
+          char* sp = stage + (2 * smp + t) * row_bytes + r_lo * sizeof(uint32_t);
+          CUDA_OK(cudaMemcpyAsync(sp, scr, nb, cudaMemcpyDeviceToHost, cs));
+          cudaEvent_t ev = cx.chunk_event(2 * smp + t);
+          CUDA_OK(cudaEventRecord(ev, cs));
+          chunks.push_back({host_tbl[t] + r_lo * sizeof(uint32_t), sp, nb});
+          chunk_done.push_back(ev);
+          cx0.bind();
+        }
+        const size_t nb0 = slice_lo(1) * sizeof(uint32_t);
         char* sp = stage + (2 * smp + t) * row_bytes;
-        CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], row_bytes, cudaMemcpyDeviceToHost, cs0));
-        CUDA_OK(cudaEventRecord(cx0.chunk_event(chunks.size()), cs0));
-        chunks.push_back({host_tbl[t], sp, row_bytes});
+        CUDA_OK(cudaMemcpyAsync(sp, dev_tbl[t], nb0, cudaMemcpyDeviceToHost, cs0));
+        cudaEvent_t ev = cx0.chunk_event(2 * smp + t);
+        CUDA_OK(cudaEventRecord(ev, cs0));
+        chunks.push_back({host_tbl[t], sp, nb0});
+        chunk_done.push_back(ev);
       }
     }
     lap("  plan + launch, all samples");
@@ -2552,11 +2643,12 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
       CUDA_OK(cudaMemcpyAsync(placed[i], d_counters[i].p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, cx.stream));
     }
     cx0.bind();
-    drain_chunks(cx0, chunks);
+    drain_chunks_ev(cx0.device, chunks, chunk_done);
     for (uint32_t i = 0; i < n; ++i) {
       pcs_ctx& cx = *forests[i]->ctx;
       cx.bind();
       CUDA_OK(cudaStreamSynchronize(cx.stream));
+      if (i && i < n_links) CUDA_OK(cudaStreamSynchronize(cx.copier()));
       d_counters[i].release();
       d_alias[i].release();
     }

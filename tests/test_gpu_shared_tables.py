@@ -69,10 +69,13 @@ def test_two_processes_accumulate_into_one_table(tmp_path):
 
 
 @pytest.mark.parametrize("n_ctx", [2, 3])
-def test_one_process_several_contexts(n_ctx):
+@pytest.mark.parametrize("links", ["1", "force"])
+def test_one_process_several_contexts(n_ctx, links, monkeypatch):
     """pcs_simulate_multi: one host process, one context per device (or several on the one GPU there is),
-    shard i on context i, every sampler flushing into the first context's tables."""
+    shard i on context i, every sampler flushing into the first context's tables; the tables go home over the first
+    device's link (PCS_MULTI_LINKS=1) or in row slices over every device's (forced here: the tables are small)."""
     import torch
+    monkeypatch.setenv("PCS_MULTI_LINKS", links)
     f = synth_forest(small_spec(2))
     n_dev = torch.cuda.device_count()
     ctxs = [L.Context(i % n_dev) for i in range(n_ctx)]
