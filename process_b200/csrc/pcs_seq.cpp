@@ -2518,9 +2518,8 @@ int pcs_simulate_multi(pcs_forest* const* forests, uint32_t n, const pcs_seq_par
     char* stage = row_bytes ? static_cast<char*>(cx0.staging(2 * S * row_bytes)) : nullptr;
     // Row slices of the tables, one per device whose link carries a share.  Default: ONE link, device 0's --
     // measured on the 8-GPU box (profiles/r02_v5_multi_links.md): with every device sending a slice the call is
-    // 2-3 ms SLOWER (the other devices write into pinned memory of device 0's NUMA node, and the copy-out is bound
-    // by the host's memory system, not by one PCIe link).  PCS_MULTI_LINKS=k: k links; =force: n links whatever the
-    // size of the tables (tests).
+    // 2-3 ms SLOWER: whatever bounds the copy-out there, it is not one device's PCIe link.  PCS_MULTI_LINKS=k: k
+    // links; =force: n links whatever the size of the tables (tests).
     const uint32_t n_links = [&] {
       const char* e = std::getenv("PCS_MULTI_LINKS");
       if (e && std::string(e) == "force") return M >= 128 ? n : 1u;
