@@ -606,53 +606,61 @@ void flatten_with(const pcs_forest_desc& d, FlatForest& out, unsigned n_threads,
     uint32_t shift = 6;
     while ((d.n_mut >> shift) >= 64) ++shift;
     const uint32_t n_buckets = (d.n_mut >> shift) + 1;
-    std::vector<uint32_t> hist(static_cast<size_t>(g_chunks) * n_buckets, 0);
+    // A list sorted by row (the order a shim's std::map<SID, ...> gives) is validated, checked for its order and
+    // scattered in ONE pass: the listings of one row are neighbours, so a chunk gathers a row's masks in a register
+    // and writes the byte once, with a plain store -- except for its first and its last row, which a neighbouring
+    // chunk may hold listings of as well (atomic OR).  Should a chunk find the list out of order, the masks are
+    // cleared and the general path below starts over.
     std::vector<uint8_t> chunk_sorted(g_chunks, 1);
     parallel_for(g_chunks, [&](uint32_t k) {
       const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
-      uint32_t h[64] = {0};  // on the stack: neighbouring rows of `hist` share cache lines
+      if (lo == hi) return;
+      const uint32_t first_row = d.germ_mut[lo], last_row = d.germ_mut[hi - 1];
+      check(first_row < d.n_mut && last_row < d.n_mut, "germ_mut out of range");
       uint32_t prev = lo ? d.germ_mut[lo - 1] : 0;
-      bool sorted = true;
+      bool sorted = true, in_range = true, named = true;
+      uint32_t row = first_row;
+      uint8_t acc = 0;
+      auto flush = [&]() {
+        if (row == first_row || row == last_row)
+          row_mask[row].fetch_or(acc, std::memory_order_relaxed);
+        else
+          row_mask[row].store(acc, std::memory_order_relaxed);
+      };
       for (uint64_t i = lo; i < hi; ++i) {
         const uint32_t m = d.germ_mut[i];
-        check(m < d.n_mut, "germ_mut out of range");
-        check(d.germ_allele_mask[i] != 0, "germ_allele_mask names a missing allele");
+        if (m >= d.n_mut) {
+          in_range = false;
+          break;
+        }
+        named &= d.germ_allele_mask[i] != 0;
         sorted &= prev <= m;
         prev = m;
-        ++h[m >> shift];
+        if (m != row) {
+          flush();
+          row = m;
+          acc = 0;
+        }
+        acc |= d.germ_allele_mask[i];
       }
+      check(in_range, "germ_mut out of range");
+      check(named, "germ_allele_mask names a missing allele");
+      flush();
       chunk_sorted[k] = sorted;
-      std::copy(h, h + n_buckets, hist.data() + static_cast<size_t>(k) * n_buckets);
     });
-    if (std::find(chunk_sorted.begin(), chunk_sorted.end(), 0) == chunk_sorted.end()) {
-      // chunk k writes rows [germ_mut[lo], germ_mut[hi-1]]: only the two edge bytes can share a line
-      // The list is sorted by row: the listings of one row are neighbours, so a chunk gathers a row's masks in a
-      // register and writes the byte once, with a plain store -- except for its first and its last row, which a
-      // neighbouring chunk may hold listings of as well (atomic OR).
+    if (std::find(chunk_sorted.begin(), chunk_sorted.end(), 0) != chunk_sorted.end()) {
+      // any other order: start over -- count the entries of every bucket per chunk, partition, scatter by bucket
+      parallel_for(g_chunks, [&](uint32_t k) {
+        const size_t lo = (static_cast<size_t>(d.n_mut) + 1) * k / g_chunks, hi = (static_cast<size_t>(d.n_mut) + 1) * (k + 1) / g_chunks;
+        for (size_t m = lo; m < hi; ++m) row_mask[m].store(0, std::memory_order_relaxed);
+      });
+      std::vector<uint32_t> hist(static_cast<size_t>(g_chunks) * n_buckets, 0);
       parallel_for(g_chunks, [&](uint32_t k) {
         const uint64_t lo = G * k / g_chunks, hi = G * (k + 1) / g_chunks;
-        if (lo == hi) return;
-        const uint32_t first_row = d.germ_mut[lo], last_row = d.germ_mut[hi - 1];
-        uint32_t row = first_row;
-        uint8_t acc = 0;
-        auto flush = [&]() {
-          if (row == first_row || row == last_row)
-            row_mask[row].fetch_or(acc, std::memory_order_relaxed);
-          else
-            row_mask[row].store(acc, std::memory_order_relaxed);
-        };
-        for (uint64_t i = lo; i < hi; ++i) {
-          const uint32_t m = d.germ_mut[i];
-          if (m != row) {
-            flush();
-            row = m;
-            acc = 0;
-          }
-          acc |= d.germ_allele_mask[i];
-        }
-        flush();
+        uint32_t h[64] = {0};  // on the stack: neighbouring rows of `hist` share cache lines
+        for (uint64_t i = lo; i < hi; ++i) ++h[d.germ_mut[i] >> shift];
+        std::copy(h, h + n_buckets, hist.data() + static_cast<size_t>(k) * n_buckets);
       });
-    } else {
       // hist -> where chunk k writes its entries of bucket b: buckets in order, chunks in order inside a bucket
       std::vector<uint64_t> bucket_off(n_buckets + 1, 0);
       {
