@@ -564,6 +564,9 @@ def measure_e2e(args, forest, wl_params, ctx, L, world, rank, local, cores, R, b
     dt = time.perf_counter() - t_e
     out.update({"value": reads * R / dt / 1e9, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
                 "ms_per_step": dt * 1e3 / e2e_steps,
+                "h2d_note": "bytes of the forest description the call reads from host memory + the plan's tables; fewer "
+                            "cross the link: the flattened tables are 3-13 bytes per row and the 16-byte instances are "
+                            "built on the device",
                 "what": ("pcs_forest_upload (flatten + H2D) + pcs_simulate (plan, kernels, D2H of the tables), host buffers"
                          if world == 1 else
                          f"one process, {world} GPUs: pcs_forest_upload + pcs_forest_replicate x{world - 1} + pcs_simulate_multi "

@@ -35,6 +35,8 @@ def function_ranges():
                 if line.startswith("sample_tiles_staged_kernel"):
                     name = "kernel: staging + flush"
                 marks.append((no, name))
+            if "// Thinned tile: only the templates whose read can span a locus are drawn" in line:
+                marks.append((no, "kernel: thinned-tile loop (draw -> window -> start)"))
             if "// Philox block j:" in line:
                 marks.append((no, "kernel: draw + probe loop"))
             if "// ---- flush:" in line:

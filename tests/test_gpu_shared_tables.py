@@ -96,3 +96,37 @@ def test_one_process_several_contexts(n_ctx, links, monkeypatch):
         fo.close()
     for c in ctxs:
         c.close()
+
+
+def test_coverage_gather_on_a_side_stream_equals_the_plain_finalize():
+    """pcs_plan_finalize_stream: the owner of shared tables gathers the coverage on a stream of its own, beside the
+    next step's sampler (bench.py at N > 1).  Same coverage table as pcs_plan_finalize on the context's stream."""
+    import torch
+    f = synth_forest(small_spec(3))
+    stream, side = torch.cuda.Stream(), torch.cuda.Stream()
+    ctx = L.Context(0, stream.cuda_stream)
+    dev = L.Forest(ctx, f)
+    plan = L.Plan(dev, make_params(coverage=20.0, purity=0.8, sequencer=A.PCS_SEQ_BASIC_CONSTANT, error_rate=0.01))
+    want_occ, want_cov, want = plan.run()
+    S, M, Lc = plan.info.n_out_samples, plan.info.n_mut, plan.info.n_loci
+    base, _ = ctx.shared_alloc(S * Lc + 2 * S * M)
+    depth_p, occ_p = base, base + 4 * S * Lc
+    cov_a = torch.zeros((S, M), dtype=torch.int32, device="cuda")
+    cov_b = torch.full((S, M), -1, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    plan.counters()  # read and reset what plan.run() counted
+    ctx.memset_u32(base, S * Lc + 2 * S * M)
+    plan.accumulate(depth_p, occ_p, wait=False)
+    plan.finalize(depth_p, occ_p, cov_a.data_ptr(), wait=False)   # on the context's stream
+    side.wait_stream(stream)
+    plan.finalize_on(depth_p, cov_b.data_ptr(), side.cuda_stream)  # on the side stream, behind the sampler
+    torch.cuda.synchronize()
+    got = plan.counters()
+    assert got.n_reads == want.n_reads
+    assert np.array_equal(cov_a.cpu().numpy().astype(np.uint32), want_cov)
+    assert np.array_equal(cov_b.cpu().numpy().astype(np.uint32), want_cov)
+    assert np.array_equal(ctx.to_host(occ_p, S * M).reshape(S, M), want_occ)
+    ctx.shared_free(base)
+    plan.close()
+    dev.close()
+    ctx.close()
