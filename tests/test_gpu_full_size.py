@@ -90,10 +90,30 @@ def test_config2_basic_illumina_200x_purity(ctx):
     occ1, cov1, _ = dev.simulate(make_params(coverage=200.0, purity=1.0, seed=2))
     occ8, cov8, _ = dev.simulate(make_params(coverage=200.0, purity=0.8, seed=2))
     pre = (((f.mut_nature_mask >> A.PCS_NATURE_PRENEOPLASTIC) & 1) == 1) & snv
+    # Closed form (A9/A10): the templates of a chromosome are split over the sample's DNA in proportion to length x
+    # cell weight (tumour cell p / n_T, the normal cell 1 - p), so the reads that carry a tumour-only SID scale by
+    # p L_T / (p L_T + (1 - p) L_N) whatever the locus -- L_T: mean DNA of the sample's tumour cells on the
+    # chromosome (CNAs and WGD included, from the flattened view), L_N = 2 x chr_len.
+    flat = L.Flat(f)
+    frag_len = {}
+    def dna(cell):
+        total = 0
+        for _, _, fs in flat.cell_haps(0, cell, 0):
+            if fs not in frag_len:
+                frag_len[fs] = sum(e - b + 1 for b, e in flat.fragset(fs))
+            total += frag_len[fs]
+        return total
+    L_N = 2.0 * int(f.chr_len[0])
     for s in range(4):
+        cells = np.flatnonzero(f.leaf_sample == s)
+        L_T = float(np.mean([dna(int(c)) for c in cells]))
+        want = 0.8 * L_T / (0.8 * L_T + 0.2 * L_N)
+        got = occ8[s, pre].sum() / occ1[s, pre].sum()
+        assert abs(got / want - 1) < 0.015, (s, got, want, L_T / L_N)
         v1 = occ1[s, pre].sum() / cov1[s, pre].sum()
         v8 = occ8[s, pre].sum() / cov8[s, pre].sum()
-        assert 0.6 * v1 < v8 < 0.95 * v1, (s, v1, v8)
+        assert 0.75 * v1 < v8 < 0.92 * v1, (s, v1, v8)
+    del flat
     assert occ8[-1, pre].sum() == 0
     # simulate_normal_seq: one sample, germline only
     occn, covn, stn = dev.simulate(make_params(coverage=200.0, normal_only=1, with_normal_sample=0,
