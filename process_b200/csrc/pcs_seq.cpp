@@ -1149,7 +1149,7 @@ void set_model(HostPlan& pl, const PlanSetup& ps) {
     // random quality: a bound no base's error probability exceeds -- the ramp is <= 1.5 and the quality deviate
     // <= sqrt(-2 ln(2^-33)) = 6.77 (Box-Muller of a 32-bit uniform), taken as 6.9 against float rounding; sigma =
     // 0.5 (kernels.cu: kQualSigma).  A test word at or above it cannot be an error, so the samplers skip the
-    // quality model for it (kernels.cu: error_bits); 2 % of slack covers u01()'s float rounding of the word.
+    // quality model for it (kernels.cu: pair_error_codes); 2 % of slack covers u01()'s float rounding of the word.
     const double bound = ps.P.error_rate * 1.5 * std::exp(0.5 * 6.9 - 0.125) * 1.02 + 1e-7;
     M.err_thr = bound >= 1.0 ? 4294967295u : static_cast<uint32_t>(std::min(4294967295.0, std::ceil(bound * 4294967296.0)));
   }
