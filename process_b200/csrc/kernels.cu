@@ -781,9 +781,11 @@ __device__ __noinline__ void settle_carried(ErrModel E, uint32_t slots, uint32_t
       for (uint32_t e = 0; e < b && first_error; ++e) first_error = !sid_base_error(E, c.x, tile, c.z, e, o - b + e);
       if (first_error) asm volatile("red.shared.add.u32 [%0], 0xffffffff;" ::"r"(alt_addr + c.y * 4u) : "memory");
     }
-    // insertions: the item goes back for its next base (every lane has read its item: the ballot is the fence)
+    // insertions: the item goes back for its next base, into a slot another lane has just read: the barrier orders
+    // every lane's read before any lane's write (a vote alone synchronises the lanes, not their memory accesses)
     const bool more = (c.w >> 24) != 0u;
     const uint32_t mask = __ballot_sync(0xffffffffu, more);
+    __syncwarp();
     if (more) sts128(first + __popc(mask & lanes_below) * 16u, make_uint4(c.x, c.y, c.z, c.w + 0x00010001u - 0x01000000u));
     waiting += __popc(mask);
     __syncwarp();
