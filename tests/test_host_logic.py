@@ -454,3 +454,45 @@ def test_planner_binomial_sampler_matches_scipy_pmf():
     # degenerate arguments
     assert L.host_binomial(1, 0, 0.5, 3).tolist() == [0, 0, 0]
     assert L.host_binomial(1, 17, 0.0, 2).tolist() == [0, 0] and L.host_binomial(1, 17, 1.0, 2).tolist() == [17, 17]
+
+
+def test_kept_tile_geometry_is_keyed_by_everything_it_depends_on():
+    """The forest keeps the tile geometry of its last call (pcs_seq.cpp: GridCache).  A call with another read size,
+    insert law, chromosome mask or sample grouping must not see the kept grid; the first call repeated must."""
+    f = synth_forest(small_spec(5))
+    fl = L.Flat(f)
+
+    def snapshot(**kw):
+        P = make_params(**{**dict(coverage=30.0, seed=3), **kw})
+        info, tiles = fl.plan(P)
+        th = fl.plan_thinning(P)
+        order = np.argsort(tiles["id"])
+        o2 = np.argsort(th["id"])
+        return (info.n_tiles_total, info.n_templates_total, tuple(tiles["begin"][order]), tuple(tiles["len"][order]),
+                tuple(tiles["templates"][order]), tuple(th["u_len"][o2]), tuple(th["tail_off"][o2]), tuple(th["n_useful"][o2]))
+
+    fresh = {}
+    variants = [dict(), dict(read_size=100), dict(insert_size_mean=300), dict(chr_mask=[1, 0, 1]), dict(read_size=37)]
+    for i, kw in enumerate(variants):  # every variant on a forest that has kept nothing
+        fl_i = L.Flat(f)
+        P = make_params(**{**dict(coverage=30.0, seed=3), **kw})
+        info, tiles = fl_i.plan(P)
+        th = fl_i.plan_thinning(P)
+        order, o2 = np.argsort(tiles["id"]), np.argsort(th["id"])
+        fresh[i] = (info.n_tiles_total, info.n_templates_total, tuple(tiles["begin"][order]), tuple(tiles["len"][order]),
+                    tuple(tiles["templates"][order]), tuple(th["u_len"][o2]), tuple(th["tail_off"][o2]), tuple(th["n_useful"][o2]))
+    # the same variants one after the other, forwards and backwards, on ONE forest: what it kept must never leak
+    for i in list(range(len(variants))) + list(reversed(range(len(variants)))):
+        assert snapshot(**variants[i]) == fresh[i], variants[i]
+    assert fresh[0] != fresh[1] and fresh[0] != fresh[3]
+    # regrouped samples: another number of output samples, possibly another tile width
+    groups = (np.arange(f.n_leaves) % 2).astype(np.uint32)
+    fl.set_groups(groups, 2)
+    a = snapshot()
+    fl2 = L.Flat(f)
+    fl2.set_groups(groups, 2)
+    P = make_params(coverage=30.0, seed=3)
+    info, tiles = fl2.plan(P)
+    assert a[0] == info.n_tiles_total and a[1] == info.n_templates_total
+    fl.set_groups(None, 0)
+    assert snapshot() == fresh[0]
