@@ -496,3 +496,30 @@ def test_kept_tile_geometry_is_keyed_by_everything_it_depends_on():
     assert a[0] == info.n_tiles_total and a[1] == info.n_templates_total
     fl.set_groups(None, 0)
     assert snapshot() == fresh[0]
+
+
+def test_planner_template_counts_follow_the_multinomial_law():
+    """A9: the templates of a (sample, chromosome) are a multinomial over its tiles with weights length x cell weight,
+    drawn as two levels of binomial chains (plan_rng.hpp).  Normal sample only: every tile's weight is its length,
+    so tile i of chromosome c gets Binomial(N_c, len_i / chr_len_c) templates -- z-scores over 300 seeds."""
+    f = synth_forest(small_spec(6))
+    fl = L.Flat(f)
+    R, cov = 100, 400.0
+    z, totals_ok = [], True
+    for seed in range(300):
+        P = make_params(coverage=cov, read_size=R, normal_only=1, with_normal_sample=0, seed=seed)
+        info, t = fl.plan(P)
+        for c in range(f.n_chr):
+            sel = t["chr"] == c
+            n_c = round(cov * int(f.chr_len[c]) / R)
+            totals_ok &= int(t["templates"][sel].sum()) == n_c and int(t["len"][sel].sum()) == int(f.chr_len[c])
+            p = t["len"][sel] / float(f.chr_len[c])
+            z.extend((t["templates"][sel] - n_c * p) / np.sqrt(n_c * p * (1 - p)))
+    z = np.asarray(z)
+    assert totals_ok
+    assert len(z) > 3000 and abs(z.mean()) < 0.06 and abs(z.std() - 1) < 0.05 and np.abs(z).max() < 5.5, (z.mean(), z.std(), np.abs(z).max())
+    # different seeds give different splits, the same seed the same split
+    a = fl.plan(make_params(coverage=cov, read_size=R, normal_only=1, with_normal_sample=0, seed=1))[1]["templates"]
+    b = fl.plan(make_params(coverage=cov, read_size=R, normal_only=1, with_normal_sample=0, seed=1))[1]["templates"]
+    c = fl.plan(make_params(coverage=cov, read_size=R, normal_only=1, with_normal_sample=0, seed=2))[1]["templates"]
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
